@@ -1,0 +1,367 @@
+// capi.cu -- the C ABI of libb200nb.so (declared in include/b200nb.h).
+// Host entry points: H2D copy of R-layout buffers -> device transpose to gene-major -> kernels ->
+// (transpose back) -> D2H.  Device entry points: enqueue only.  No CPU fallback anywhere.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/b200nb.h"
+#include "engine.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// grow-only device workspace of the host entry points (one set per process; calls are serialised)
+enum Slot {
+  S_RAW0, S_RAW1, S_RAW2, S_Y, S_MU, S_W, S_NF, S_X, S_V0, S_V1, S_V2, S_V3, S_OUTD, S_OUTI, S_H, S_MUO, S_HC, S_MUC,
+  S_BETA_IN, S_BETA_OUT, S_BETA_VAR, S_COUNTER, S_NSLOTS
+};
+struct Workspace {
+  void* p[S_NSLOTS] = {};
+  size_t bytes[S_NSLOTS] = {};
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+};
+Workspace g_ws;
+
+int ws_get(Slot s, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 16;
+  if (g_ws.bytes[s] < bytes) {
+    if (g_ws.p[s]) cudaFree(g_ws.p[s]);
+    g_ws.p[s] = nullptr;
+    g_ws.bytes[s] = 0;
+    size_t want = bytes + bytes / 8;
+    CU(cudaMalloc(&g_ws.p[s], want));
+    g_ws.bytes[s] = want;
+  }
+  *out = g_ws.p[s];
+  return 0;
+}
+
+int ws_stream(cudaStream_t* st) {
+  if (!g_ws.stream) CU(cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking));
+  *st = g_ws.stream;
+  return 0;
+}
+
+// device-side work-queue counters: a ring of slots, one per launch, so launches in flight on different
+// streams never share a counter (a slot is reused only after kRing further launches).
+constexpr int kRing = 1024;
+unsigned int* g_counters = nullptr;
+std::atomic<unsigned int> g_counter_next{0};
+int next_counter(unsigned int** out) {
+  if (!g_counters) CU(cudaMalloc(&g_counters, sizeof(unsigned int) * kRing));
+  *out = g_counters + (g_counter_next.fetch_add(1) % kRing);
+  return 0;
+}
+
+int check_dims(int n, int m, int p) {
+  if (n < 0 || m < 1 || p < 1) return fail("bad dimensions n=%d m=%d p=%d", n, m, p);
+  if (p > nb::kMaxSmallP) return fail("p=%d not supported yet by this build (max %d)", p, nb::kMaxSmallP);
+  return 0;
+}
+
+long long ld_for(int m) { return ((long long)m + 3) & ~3LL; }
+
+// copy a column-major host matrix to the device and convert to gene-major
+int upload_matrix(const void* host, int n, int m, int elem, Slot raw, Slot dst, cudaStream_t st, void** out) {
+  void *d_raw, *d_dst;
+  const long long ld = ld_for(m);
+  if (ws_get(raw, (size_t)n * m * elem, &d_raw)) return 1;
+  if (ws_get(dst, (size_t)n * ld * elem + 64, &d_dst)) return 1;
+  CU(cudaMemcpyAsync(d_raw, host, (size_t)n * m * elem, cudaMemcpyHostToDevice, st));
+  CU(nb::launch_to_gene_major(d_raw, d_dst, n, m, ld, elem, st));
+  g_launches++;
+  *out = d_dst;
+  return 0;
+}
+
+int upload_vec(const void* host, size_t bytes, Slot s, cudaStream_t st, void** out) {
+  void* d;
+  if (ws_get(s, bytes, &d)) return 1;
+  CU(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st));
+  *out = d;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200nb_last_error(void) { return g_err; }
+const char* b200nb_version(void) { return "b200nb 0.1 (sm_100a)"; }
+long long b200nb_kernel_launches(void) { return g_launches.load(); }
+
+int b200nb_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return c;
+}
+
+void b200nb_release_workspace(void) {
+  std::lock_guard<std::mutex> lk(g_ws.mu);
+  for (int s = 0; s < S_NSLOTS; s++) {
+    if (g_ws.p[s]) cudaFree(g_ws.p[s]);
+    g_ws.p[s] = nullptr;
+    g_ws.bytes[s] = 0;
+  }
+}
+
+/* ------------------------------------------------------------------ device entry points */
+
+int b200nb_fit_disp_dev(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,
+                        const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
+                        double kappa_0, double tol, int maxit, int use_prior, const double* weights,
+                        int use_weights, double weight_threshold, int use_cr, int n, int m, int p, long long ld,
+                        double* out_log_alpha, int32_t* out_iter, int32_t* out_iter_accept,
+                        double* out_last_change, double* out_initial_lp, double* out_initial_dlp,
+                        double* out_last_lp, double* out_last_dlp, double* out_last_d2lp, void* stream) {
+  if (check_dims(n, m, p)) return 1;
+  if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
+  if (use_weights && !weights) return fail("use_weights set but weights == NULL");
+  unsigned int* ctr;
+  if (next_counter(&ctr)) return 1;
+  nb::DispArgs a{};
+  a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.mu = mu_hat; a.w = use_weights ? weights : nullptr; a.x = x;
+  a.log_alpha_in = log_alpha; a.prior_mean = log_alpha_prior_mean;
+  a.prior_sigmasq = log_alpha_prior_sigmasq; a.min_log_alpha = min_log_alpha; a.kappa_0 = kappa_0; a.tol = tol;
+  a.maxit = maxit; a.use_prior = use_prior; a.use_weights = use_weights; a.use_cr = use_cr;
+  a.weight_threshold = weight_threshold; a.n = n; a.m = m; a.p = p; a.ld = ld;
+  a.log_alpha = out_log_alpha; a.iter = out_iter; a.iter_accept = out_iter_accept; a.last_change = out_last_change;
+  a.initial_lp = out_initial_lp; a.initial_dlp = out_initial_dlp; a.last_lp = out_last_lp; a.last_dlp = out_last_dlp;
+  a.last_d2lp = out_last_d2lp; a.grid = nullptr; a.grid_n = 0; a.counter = ctr;
+  CU(nb::launch_fit_disp(a, (cudaStream_t)stream));
+  if (n > 0) g_launches++;
+  return 0;
+}
+
+int b200nb_fit_disp_grid_dev(const void* y, int y_type, const double* x, const double* mu_hat,
+                             const double* disp_grid, int disp_grid_n, const double* log_alpha_prior_mean,
+                             double log_alpha_prior_sigmasq, int use_prior, const double* weights, int use_weights,
+                             double weight_threshold, int use_cr, int n, int m, int p, long long ld,
+                             double* out_log_alpha, void* stream) {
+  if (check_dims(n, m, p)) return 1;
+  if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
+  if (disp_grid_n < 2) return fail("disp_grid needs at least 2 points");
+  if (use_weights && !weights) return fail("use_weights set but weights == NULL");
+  unsigned int* ctr;
+  if (next_counter(&ctr)) return 1;
+  nb::DispArgs a{};
+  a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.mu = mu_hat; a.w = use_weights ? weights : nullptr; a.x = x;
+  a.log_alpha_in = nullptr; a.prior_mean = log_alpha_prior_mean; a.prior_sigmasq = log_alpha_prior_sigmasq;
+  a.use_prior = use_prior; a.use_weights = use_weights; a.use_cr = use_cr; a.weight_threshold = weight_threshold;
+  a.n = n; a.m = m; a.p = p; a.ld = ld; a.log_alpha = out_log_alpha; a.grid = disp_grid; a.grid_n = disp_grid_n;
+  a.counter = ctr;
+  CU(nb::launch_fit_disp(a, (cudaStream_t)stream));
+  if (n > 0) g_launches++;
+  return 0;
+}
+
+int b200nb_fit_beta_dev(const void* y, int y_type, const double* x, const double* nf, int nf_is_vector,
+                        const double* alpha_hat, const double* contrast, const double* beta_mat,
+                        const double* lambda, const double* weights, int use_weights, double tol, int maxit,
+                        int use_qr, double minmu, int n, int m, int p, long long ld, double* out_beta_mat,
+                        double* out_beta_var_mat, double* out_iter, double* out_hat_diagonals,
+                        double* out_contrast_num, double* out_contrast_denom, double* out_deviance, double* out_mu,
+                        void* stream) {
+  if (check_dims(n, m, p)) return 1;
+  if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
+  if (use_weights && !weights) return fail("use_weights set but weights == NULL");
+  if (maxit < 0) return fail("maxit must be >= 0");
+  unsigned int* ctr;
+  if (next_counter(&ctr)) return 1;
+  nb::BetaArgs a{};
+  a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.nf = nf; a.nf_is_vector = nf_is_vector;
+  a.w = use_weights ? weights : nullptr; a.x = x; a.alpha_hat = alpha_hat; a.contrast = contrast; a.beta_in = beta_mat;
+  a.lambda = lambda; a.use_weights = use_weights; a.tol = tol; a.maxit = maxit; a.use_qr = use_qr; a.minmu = minmu;
+  a.n = n; a.m = m; a.p = p; a.ld = ld; a.beta_out = out_beta_mat; a.beta_var = out_beta_var_mat; a.iter = out_iter;
+  a.hat_diag = out_hat_diagonals; a.mu_out = out_mu; a.contrast_num = out_contrast_num;
+  a.contrast_denom = out_contrast_denom; a.deviance = out_deviance; a.counter = ctr;
+  CU(nb::launch_fit_beta(a, (cudaStream_t)stream));
+  if (n > 0) g_launches++;
+  return 0;
+}
+
+int b200nb_to_gene_major_dev(const void* src, void* dst, int n, int m, long long ld, int elem_size, void* stream) {
+  CU(nb::launch_to_gene_major(src, dst, n, m, ld, elem_size, (cudaStream_t)stream));
+  g_launches++;
+  return 0;
+}
+
+int b200nb_to_col_major_dev(const double* src, double* dst, int n, int m, long long ld, void* stream) {
+  CU(nb::launch_to_col_major(src, dst, n, m, ld, (cudaStream_t)stream));
+  g_launches++;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ host entry points */
+
+int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,
+                    const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
+                    double kappa_0, double tol, int maxit, int use_prior, const double* weights, int use_weights,
+                    double weight_threshold, int use_cr, int n, int m, int p,
+                    double* out_log_alpha, int32_t* out_iter, int32_t* out_iter_accept, double* out_last_change,
+                    double* out_initial_lp, double* out_initial_dlp, double* out_last_lp, double* out_last_dlp,
+                    double* out_last_d2lp) {
+  if (check_dims(n, m, p)) return 1;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ws.mu);
+  cudaStream_t st;
+  if (ws_stream(&st)) return 1;
+  const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
+  const long long ld = ld_for(m);
+  void *d_y, *d_mu, *d_w = nullptr, *d_x, *d_la, *d_pm, *d_outd, *d_outi;
+  if (upload_matrix(y, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
+  if (upload_matrix(mu_hat, n, m, 8, S_RAW1, S_MU, st, &d_mu)) return 1;
+  if (use_weights && upload_matrix(weights, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
+  if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
+  if (upload_vec(log_alpha, sizeof(double) * n, S_V0, st, &d_la)) return 1;
+  if (upload_vec(log_alpha_prior_mean, sizeof(double) * n, S_V1, st, &d_pm)) return 1;
+  if (ws_get(S_OUTD, sizeof(double) * 7 * n, &d_outd)) return 1;
+  if (ws_get(S_OUTI, sizeof(int32_t) * 2 * n, &d_outi)) return 1;
+  double* od = (double*)d_outd;
+  int32_t* oi = (int32_t*)d_outi;
+  if (b200nb_fit_disp_dev(d_y, y_type, (const double*)d_x, (const double*)d_mu, (const double*)d_la,
+                          (const double*)d_pm, log_alpha_prior_sigmasq, min_log_alpha, kappa_0, tol, maxit, use_prior,
+                          (const double*)d_w, use_weights, weight_threshold, use_cr, n, m, p, ld, od, oi, oi + n,
+                          od + n, od + 2 * (size_t)n, od + 3 * (size_t)n, od + 4 * (size_t)n, od + 5 * (size_t)n,
+                          od + 6 * (size_t)n, st))
+    return 1;
+  double* outs[7] = {out_log_alpha, out_last_change, out_initial_lp, out_initial_dlp, out_last_lp, out_last_dlp,
+                     out_last_d2lp};
+  for (int k = 0; k < 7; k++)
+    CU(cudaMemcpyAsync(outs[k], od + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_iter, oi, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_iter_accept, oi + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200nb_fit_disp_grid(const void* y, int y_type, const double* x, const double* mu_hat, const double* disp_grid,
+                         int disp_grid_n, const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq,
+                         int use_prior, const double* weights, int use_weights, double weight_threshold, int use_cr,
+                         int n, int m, int p, double* out_log_alpha) {
+  if (check_dims(n, m, p)) return 1;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ws.mu);
+  cudaStream_t st;
+  if (ws_stream(&st)) return 1;
+  const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
+  const long long ld = ld_for(m);
+  void *d_y, *d_mu, *d_w = nullptr, *d_x, *d_grid, *d_pm, *d_out;
+  if (upload_matrix(y, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
+  if (upload_matrix(mu_hat, n, m, 8, S_RAW1, S_MU, st, &d_mu)) return 1;
+  if (use_weights && upload_matrix(weights, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
+  if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
+  if (upload_vec(disp_grid, sizeof(double) * disp_grid_n, S_V0, st, &d_grid)) return 1;
+  if (upload_vec(log_alpha_prior_mean, sizeof(double) * n, S_V1, st, &d_pm)) return 1;
+  if (ws_get(S_OUTD, sizeof(double) * n, &d_out)) return 1;
+  if (b200nb_fit_disp_grid_dev(d_y, y_type, (const double*)d_x, (const double*)d_mu, (const double*)d_grid,
+                               disp_grid_n, (const double*)d_pm, log_alpha_prior_sigmasq, use_prior,
+                               (const double*)d_w, use_weights, weight_threshold, use_cr, n, m, p, ld, (double*)d_out,
+                               st))
+    return 1;
+  CU(cudaMemcpyAsync(out_log_alpha, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf, const double* alpha_hat,
+                    const double* contrast, const double* beta_mat, const double* lambda, const double* weights,
+                    int use_weights, double tol, int maxit, int use_qr, double minmu, int n, int m, int p,
+                    double* out_beta_mat, double* out_beta_var_mat, double* out_iter, double* out_hat_diagonals,
+                    double* out_contrast_num, double* out_contrast_denom, double* out_deviance, double* out_mu) {
+  if (check_dims(n, m, p)) return 1;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ws.mu);
+  cudaStream_t st;
+  if (ws_stream(&st)) return 1;
+  const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
+  const long long ld = ld_for(m);
+  void *d_y, *d_nf, *d_w = nullptr, *d_x, *d_alpha, *d_contrast, *d_lambda, *d_bin, *d_bout, *d_bvar, *d_outd;
+  void *d_h = nullptr, *d_mu = nullptr, *d_hc = nullptr, *d_muc = nullptr;
+  if (upload_matrix(y, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
+  if (upload_matrix(nf, n, m, 8, S_RAW1, S_NF, st, &d_nf)) return 1;
+  if (use_weights && upload_matrix(weights, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
+  if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
+  if (upload_vec(alpha_hat, sizeof(double) * n, S_V0, st, &d_alpha)) return 1;
+  if (upload_vec(contrast, sizeof(double) * p, S_V1, st, &d_contrast)) return 1;
+  if (upload_vec(lambda, sizeof(double) * p, S_V2, st, &d_lambda)) return 1;
+  if (upload_vec(beta_mat, sizeof(double) * n * p, S_BETA_IN, st, &d_bin)) return 1;
+  if (ws_get(S_BETA_OUT, sizeof(double) * n * p, &d_bout)) return 1;
+  if (ws_get(S_BETA_VAR, sizeof(double) * n * p, &d_bvar)) return 1;
+  if (ws_get(S_OUTD, sizeof(double) * 4 * n, &d_outd)) return 1;
+  if (out_hat_diagonals) {
+    if (ws_get(S_H, sizeof(double) * n * ld, &d_h)) return 1;
+    if (ws_get(S_HC, sizeof(double) * n * m, &d_hc)) return 1;
+  }
+  if (out_mu) {
+    if (ws_get(S_MUO, sizeof(double) * n * ld, &d_mu)) return 1;
+    if (ws_get(S_MUC, sizeof(double) * n * m, &d_muc)) return 1;
+  }
+  double* od = (double*)d_outd;
+  if (b200nb_fit_beta_dev(d_y, y_type, (const double*)d_x, (const double*)d_nf, 0, (const double*)d_alpha,
+                          (const double*)d_contrast, (const double*)d_bin, (const double*)d_lambda,
+                          (const double*)d_w, use_weights, tol, maxit, use_qr, minmu, n, m, p, ld, (double*)d_bout,
+                          (double*)d_bvar, od, (double*)d_h, od + n, od + 2 * (size_t)n, od + 3 * (size_t)n,
+                          (double*)d_mu, st))
+    return 1;
+  if (out_hat_diagonals) {
+    if (b200nb_to_col_major_dev((const double*)d_h, (double*)d_hc, n, m, ld, st)) return 1;
+    CU(cudaMemcpyAsync(out_hat_diagonals, d_hc, sizeof(double) * n * m, cudaMemcpyDeviceToHost, st));
+  }
+  if (out_mu) {
+    if (b200nb_to_col_major_dev((const double*)d_mu, (double*)d_muc, n, m, ld, st)) return 1;
+    CU(cudaMemcpyAsync(out_mu, d_muc, sizeof(double) * n * m, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaMemcpyAsync(out_beta_mat, d_bout, sizeof(double) * n * p, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_beta_var_mat, d_bvar, sizeof(double) * n * p, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_iter, od, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_contrast_num, od + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_contrast_denom, od + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_deviance, od + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200nb_test_special(const double* x, int n, double* out_lgamma, double* out_digamma, double* out_trigamma) {
+  if (n <= 0) return 0;
+  std::lock_guard<std::mutex> lk(g_ws.mu);
+  cudaStream_t st;
+  if (ws_stream(&st)) return 1;
+  void *d_x, *d_o;
+  if (upload_vec(x, sizeof(double) * n, S_V0, st, &d_x)) return 1;
+  if (ws_get(S_OUTD, sizeof(double) * 3 * n, &d_o)) return 1;
+  double* o = (double*)d_o;
+  CU(nb::launch_special_test((const double*)d_x, n, o, o + n, o + 2 * (size_t)n, st));
+  g_launches++;
+  CU(cudaMemcpyAsync(out_lgamma, o, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_digamma, o + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_trigamma, o + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

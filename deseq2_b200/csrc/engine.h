@@ -1,0 +1,90 @@
+// engine.h -- internal launcher interface between the C ABI (capi.cu) and the sm_100a kernels.
+// Device layout ("gene-major"): every n x m matrix is stored one gene per row with the sample axis
+// contiguous, row stride `ld` elements (ld % 4 == 0 so rows start 32-byte aligned for 128-bit loads).
+// The design matrix x stays in R's column-major m x p form (it is tiny and staged into shared memory).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nb {
+
+constexpr int kMaxSmallP = 4;    // register-resident normal equations
+constexpr int kMaxP = 32;        // shared-memory path upper bound
+
+struct DispArgs {
+  // inputs (device pointers)
+  const void* y;        // gene-major counts, int32 or f64
+  int y_is_f64;
+  const double* mu;     // gene-major
+  const double* w;      // gene-major observation weights or nullptr
+  const double* x;      // m x p column-major
+  const double* log_alpha_in;  // n
+  const double* prior_mean;    // n
+  double prior_sigmasq, min_log_alpha, kappa_0, tol;
+  int maxit, use_prior, use_weights, use_cr;
+  double weight_threshold;
+  int n, m, p;
+  long long ld;
+  // outputs (device pointers, length n)
+  double* log_alpha;
+  int32_t* iter;
+  int32_t* iter_accept;
+  double* last_change;
+  double* initial_lp;
+  double* initial_dlp;
+  double* last_lp;
+  double* last_dlp;
+  double* last_d2lp;
+  // grid mode (fitDispGrid): when grid != nullptr the line search is replaced by the two-level grid
+  const double* grid;
+  int grid_n;
+  // work queue counter (device, zeroed by the launcher)
+  unsigned int* counter;
+};
+
+struct BetaArgs {
+  const void* y;
+  int y_is_f64;
+  const double* nf;      // gene-major n x m normalisation factors, or length-m size-factor vector
+  int nf_is_vector;
+  const double* w;       // gene-major weights or nullptr
+  const double* x;       // m x p column-major
+  const double* alpha_hat;   // n
+  const double* contrast;    // p
+  const double* beta_in;     // n x p column-major (R layout), starting values
+  const double* lambda;      // p
+  int use_weights;
+  double tol;
+  int maxit;
+  int use_qr;                // accepted for interface parity; both settings use the equilibrated Cholesky
+  double minmu;
+  int n, m, p;
+  long long ld;
+  // outputs
+  double* beta_out;          // n x p column-major
+  double* beta_var;          // n x p column-major
+  double* iter;              // n (double, as in the reference's NumericVector)
+  double* hat_diag;          // gene-major n x m (ld), may be nullptr
+  double* mu_out;            // gene-major n x m (ld), may be nullptr (fused mu = nf * exp(x beta))
+  double* contrast_num;      // n
+  double* contrast_denom;    // n
+  double* deviance;          // n
+  unsigned int* counter;
+};
+
+// returns cudaSuccess or the launch error; kernels are enqueued on `stream`
+cudaError_t launch_fit_disp(const DispArgs& a, cudaStream_t stream);
+cudaError_t launch_fit_beta(const BetaArgs& a, cudaStream_t stream);
+
+// layout helpers (layout.cu)
+// column-major n x m (R) -> gene-major n x ld.  elem_size 4 or 8.
+cudaError_t launch_to_gene_major(const void* src_colmajor, void* dst, int n, int m, long long ld, int elem_size,
+                                 cudaStream_t stream);
+// gene-major n x ld -> column-major n x m (f64)
+cudaError_t launch_to_col_major(const double* src, double* dst_colmajor, int n, int m, long long ld,
+                                cudaStream_t stream);
+cudaError_t launch_special_test(const double* x, int n, double* lg, double* dg, double* tg, cudaStream_t stream);
+
+int device_sm_count();
+
+}  // namespace nb

@@ -1,0 +1,337 @@
+// fit_beta.cu -- per-gene ridge-penalised NB IRLS on sm_100a, one warp per gene.
+//
+// Behavioural contract (WHAT): /root/reference/src/DESeq2.cpp:283-465 (fitBeta): mu = max(nf*exp(X b), minmu),
+// w = [wt*]mu/(1+alpha*mu), z = log(mu/nf) + (y-mu)/mu, b = argmin ridge WLS, |b|>30 => iter=maxit (diverged b
+// kept), deviance = -2 sum [wt*] log NB(y; mu, 1/alpha), stop when t>0 and |dev-dev_old|/(|dev|+0.1) < tol, NaN =>
+// iter=maxit; post-loop hat diagonal, sandwich covariance, contrast numerator/denominator (:429-455).
+// HOW is new:
+//   * one fused pass per iteration updates mu, the deviance, AND accumulates X'WX / X'Wz for the next solve,
+//     so a gene costs (iterations + 1) passes over its row (held in shared memory) and one warp all-reduce
+//     per pass; the post-loop block reuses the last pass's X'WX (the reference recomputes it three times);
+//   * both reference branches (QR :344-356, normal equations :398) map to one Jacobi-equilibrated Cholesky of
+//     X'WX + Lambda in registers (smallp.cuh) -- algebraically identical, agrees with the QR branch far inside
+//     the 1e-6 contract (tests/test_parity_gpu.py, incl. the badly scaled covariate of test_optim.R);
+//   * log NB is evaluated in the direct form with the mu-independent part
+//     sum [wt*](lgamma(y+r)-lgamma(r)-lgamma(y+1)) hoisted out of the loop and the mu-dependent part written as
+//     y (log mu + log alpha) - (y + r) log1p(mu alpha), r = 1/alpha: one exp and one log1p per sample per
+//     iteration, accurate for every alpha in [1e-8, m];
+//   * log(mu/nf) is never formed: mu = exp(eta + log nf) so log(mu/nf) = eta unless the minmu clamp bites.
+#include "engine.h"
+#include "smallp.cuh"
+
+namespace nb {
+namespace {
+
+struct BetaRow {
+  const double* y;
+  const double* lnf;   // log normalisation factor per sample (CTA-shared when nf is a size-factor vector)
+  double* mu;
+  const double* w;
+  const double* x;     // shared, column-major stride mpad
+  int m, mpad;
+};
+
+// lgamma(y + r) - lgamma(r), accurate for large r (no catastrophic cancellation)
+__device__ __forceinline__ double lgamma_diff(double y, double r, double lg_r) {
+  if (r >= kShift) {
+    const double xr = y + r;
+    const double ixr = rcp_fast(xr), ir = rcp_fast(r);
+    const double tail = stirling_tail(ixr, ixr * ixr) - stirling_tail(ir, ir * ir);
+    return fma(y, log(xr), fma(r - 0.5, log1p(y * ir), -y)) + tail;
+  }
+  return lgamma_pos(y + r) - lg_r;
+}
+
+template <int P, bool USE_W, bool WANT_DEV>
+__device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta)[P], double alpha, double r,
+                                          double log_alpha, double minmu, double log_minmu, int lane, double& dev_var,
+                                          SymP<P>& XtWX, double (&XtWz)[P]) {
+  constexpr int NS = SymP<P>::N;
+  double acc[1 + NS + P];
+#pragma unroll
+  for (int i = 0; i < 1 + NS + P; i++) acc[i] = 0.0;
+#pragma unroll 2
+  for (int j = lane; j < rv.m; j += 32) {
+    double xv[P];
+    double eta = 0.0;
+#pragma unroll
+    for (int k = 0; k < P; k++) {
+      xv[k] = rv.x[k * rv.mpad + j];
+      eta = fma(xv[k], beta[k], eta);
+    }
+    const double lnf = rv.lnf[j];
+    const double le = eta + lnf;
+    double mu = fmax(exp(le), minmu);            // fmax(NaN, minmu) = minmu, as in the reference (:326)
+    const double lmu = (mu == minmu) ? log_minmu : le;
+    rv.mu[j] = mu;
+    const double y = rv.y[j];
+    const double am = mu * alpha;
+    double w = mu * rcp_fast(1.0 + am);
+    double wt = 1.0;
+    if (USE_W) {
+      wt = rv.w[j];
+      w *= wt;
+    }
+    const double z = (lmu - lnf) + fma(y, rcp_fast(mu), -1.0);
+    if (WANT_DEV) {
+      double d = fma(y, lmu + log_alpha, -(y + r) * log1p(am));
+      if (USE_W) d *= wt;
+      acc[0] += d;
+    }
+    const double wz = w * z;
+#pragma unroll
+    for (int a = 0; a < P; a++) {
+      acc[1 + NS + a] = fma(wz, xv[a], acc[1 + NS + a]);
+      const double wx = w * xv[a];
+#pragma unroll
+      for (int b = 0; b <= a; b++) acc[1 + a * (a + 1) / 2 + b] = fma(wx, xv[b], acc[1 + a * (a + 1) / 2 + b]);
+    }
+  }
+  warp_allreduce_sum_n(acc);
+  dev_var = acc[0];
+#pragma unroll
+  for (int i = 0; i < NS; i++) XtWX.v[i] = acc[1 + i];
+#pragma unroll
+  for (int a = 0; a < P; a++) XtWz[a] = acc[1 + NS + a];
+}
+
+template <int P, bool USE_W>
+__global__ void __launch_bounds__(256) fit_beta_kernel(const BetaArgs A, int warps_per_cta, int mpad) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  // per-warp rows: y, mu, [lnf if nf is a matrix], [w]
+  const int nrow = 2 + (A.nf_is_vector ? 0 : 1) + (USE_W ? 1 : 0);
+  double* xs = smem;                                 // P * mpad
+  double* lnf_shared = xs + (size_t)P * mpad;        // mpad (used when nf is a vector)
+  double* rowbase = lnf_shared + mpad + (size_t)warp * nrow * mpad;
+  double* ys = rowbase;
+  double* mus = rowbase + mpad;
+  double* lnfs = A.nf_is_vector ? lnf_shared : rowbase + 2 * mpad;
+  double* wsm = USE_W ? rowbase + (size_t)(A.nf_is_vector ? 2 : 3) * mpad : nullptr;
+
+  for (int idx = threadIdx.x; idx < P * A.m; idx += blockDim.x) {
+    const int k = idx / A.m, j = idx - k * A.m;
+    xs[k * mpad + j] = A.x[idx];
+  }
+  if (A.nf_is_vector)
+    for (int j = threadIdx.x; j < A.m; j += blockDim.x) lnf_shared[j] = log(A.nf[j]);
+  __syncthreads();
+
+  BetaRow rv{ys, lnfs, mus, wsm, xs, A.m, mpad};
+  double lam[P], contrast[P];
+#pragma unroll
+  for (int k = 0; k < P; k++) {
+    lam[k] = A.lambda[k];
+    contrast[k] = A.contrast[k];
+  }
+  const double minmu = A.minmu, log_minmu = log(A.minmu);
+  const double large = 30.0;
+
+  for (;;) {
+    unsigned int g = 0;
+    if (lane == 0) g = atomicAdd(A.counter, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= (unsigned int)A.n) break;
+    const size_t off = (size_t)g * A.ld;
+
+    // ---- stage the row (128-bit loads)
+    for (int j4 = lane * 4; j4 < mpad; j4 += 128) {
+      double yv[4];
+      if (A.y_is_f64) {
+        const double2* p2 = reinterpret_cast<const double2*>(static_cast<const double*>(A.y) + off + j4);
+        const double2 a0 = __ldg(p2), a1 = __ldg(p2 + 1);
+        yv[0] = a0.x; yv[1] = a0.y; yv[2] = a1.x; yv[3] = a1.y;
+      } else {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(static_cast<const int32_t*>(A.y) + off + j4));
+        yv[0] = v.x; yv[1] = v.y; yv[2] = v.z; yv[3] = v.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) ys[j4 + q] = yv[q];
+      if (!A.nf_is_vector) {
+        const double2* n2 = reinterpret_cast<const double2*>(A.nf + off + j4);
+        const double2 n0 = __ldg(n2), n1 = __ldg(n2 + 1);
+        lnfs[j4 + 0] = log(n0.x); lnfs[j4 + 1] = log(n0.y); lnfs[j4 + 2] = log(n1.x); lnfs[j4 + 3] = log(n1.y);
+      }
+      if (USE_W) {
+        const double2* w2 = reinterpret_cast<const double2*>(A.w + off + j4);
+        const double2 w0 = __ldg(w2), w1 = __ldg(w2 + 1);
+        wsm[j4 + 0] = w0.x; wsm[j4 + 1] = w0.y; wsm[j4 + 2] = w1.x; wsm[j4 + 3] = w1.y;
+      }
+    }
+    __syncwarp();
+
+    double beta[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) beta[k] = A.beta_in[(size_t)g + (size_t)A.n * k];
+    const double alpha = A.alpha_hat[g];
+    const double r = 1.0 / alpha;
+    const double log_alpha = log(alpha);
+
+    // mu-independent part of the deviance
+    double devc = 0.0;
+    if (A.maxit > 0) {
+      const double lg_r = lgamma_pos(r);
+      double c = 0.0;
+      for (int j = lane; j < A.m; j += 32) {
+        const double y = ys[j];
+        double t = lgamma_diff(y, r, lg_r) - lgamma_pos(y + 1.0);
+        if (USE_W) t *= wsm[j];
+        c += t;
+      }
+      devc = warp_allreduce_sum(c);
+    }
+
+    SymP<P> XtWX;
+    double XtWz[P];
+    double dv;
+    beta_pass<P, USE_W, false>(rv, beta, alpha, r, log_alpha, minmu, log_minmu, lane, dv, XtWX, XtWz);
+
+    double dev = 0.0, dev_old = 0.0;
+    double it = 0.0;
+    for (int t = 0; t < A.maxit; t++) {
+      it += 1.0;
+      SymP<P> M = XtWX;
+#pragma unroll
+      for (int k = 0; k < P; k++) {
+        M.at(k, k) += lam[k];
+        beta[k] = XtWz[k];
+      }
+      spd_solve_equilibrated<P>(M, beta);
+      bool big = false;
+#pragma unroll
+      for (int k = 0; k < P; k++) big = big || (fabs(beta[k]) > large);
+      if (big) { it = (double)A.maxit; break; }
+      beta_pass<P, USE_W, true>(rv, beta, alpha, r, log_alpha, minmu, log_minmu, lane, dv, XtWX, XtWz);
+      dev = -2.0 * (dv + devc);
+      const double conv_test = fabs(dev - dev_old) / (fabs(dev) + 0.1);
+      if (isnan(conv_test)) { it = (double)A.maxit; break; }
+      if ((t > 0) && (conv_test < A.tol)) break;
+      dev_old = dev;
+    }
+
+    // ---- post-loop block (src/DESeq2.cpp:429-455); XtWX belongs to the mu currently in shared memory
+    SymP<P> M = XtWX, Ainv;
+    double s[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) M.at(k, k) += lam[k];
+#pragma unroll
+    for (int k = 0; k < P; k++) s[k] = rsqrt(M.get(k, k));
+#pragma unroll
+    for (int a = 0; a < P; a++)
+#pragma unroll
+      for (int b = 0; b <= a; b++) M.at(a, b) *= s[a] * s[b];
+    chol_factor<P>(M);
+    chol_inverse<P>(M, Ainv);
+#pragma unroll
+    for (int a = 0; a < P; a++)
+#pragma unroll
+      for (int b = 0; b <= a; b++) Ainv.at(a, b) *= s[a] * s[b];
+
+    __syncwarp();
+    if (A.hat_diag != nullptr || A.mu_out != nullptr) {
+      for (int j = lane; j < A.m; j += 32) {
+        const double mu = mus[j];
+        if (A.mu_out != nullptr) A.mu_out[off + j] = mu;
+        if (A.hat_diag != nullptr) {
+          double w = mu / (1.0 + alpha * mu);
+          if (USE_W) w *= wsm[j];
+          double xv[P];
+#pragma unroll
+          for (int k = 0; k < P; k++) xv[k] = xs[k * mpad + j];
+          double q = 0.0;
+#pragma unroll
+          for (int a = 0; a < P; a++) {
+            q = fma(xv[a] * xv[a], Ainv.get(a, a), q);
+#pragma unroll
+            for (int b = 0; b < a; b++) q = fma(2.0 * xv[a] * xv[b], Ainv.get(a, b), q);
+          }
+          A.hat_diag[off + j] = w * q;
+        }
+      }
+    }
+    // sigma = Ainv * XtWX * Ainv
+    double T[P][P];
+    sym_mul_full<P>(Ainv, XtWX, T);
+    double cn = 0.0, cd = 0.0;
+    double var[P];
+    double sc_[P];   // sigma * contrast
+#pragma unroll
+    for (int a = 0; a < P; a++) sc_[a] = 0.0;
+#pragma unroll
+    for (int a = 0; a < P; a++) {
+#pragma unroll
+      for (int b = 0; b < P; b++) {
+        double sab = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; k++) sab = fma(T[a][k], Ainv.get(k, b), sab);
+        if (a == b) var[a] = sab;
+        sc_[a] = fma(sab, contrast[b], sc_[a]);
+      }
+      cn = fma(contrast[a], beta[a], cn);
+    }
+#pragma unroll
+    for (int a = 0; a < P; a++) cd = fma(contrast[a], sc_[a], cd);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < P; k++) {
+        A.beta_out[(size_t)g + (size_t)A.n * k] = beta[k];
+        A.beta_var[(size_t)g + (size_t)A.n * k] = var[k];
+      }
+      A.iter[g] = it;
+      A.contrast_num[g] = cn;
+      A.contrast_denom[g] = sqrt(cd);
+      A.deviance[g] = dev;
+    }
+    __syncwarp();
+  }
+}
+
+template <int P, bool USE_W>
+cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
+  const int mpad = (a.m + 3) & ~3;
+  const int nrow = 2 + (a.nf_is_vector ? 0 : 1) + (USE_W ? 1 : 0);
+  const size_t fixed = (size_t)(P + 1) * mpad * sizeof(double);
+  const size_t rowbytes = (size_t)nrow * mpad * sizeof(double);
+  const size_t smem_cap = 227 * 1024;
+  int warps = 8;
+  while (warps > 1 && fixed + warps * rowbytes > smem_cap / 2) warps >>= 1;
+  if (fixed + warps * rowbytes > smem_cap) return cudaErrorInvalidValue;
+  const size_t smem = fixed + warps * rowbytes;
+  auto kern = fit_beta_kernel<P, USE_W>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, warps * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+  const int sms = device_sm_count();
+  long long want = ((long long)a.n + warps - 1) / warps;
+  long long grid = (long long)sms * ctas_per_sm;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, warps, mpad);
+  return cudaGetLastError();
+}
+
+template <bool USE_W>
+cudaError_t launch_beta_p(const BetaArgs& a, cudaStream_t stream) {
+  switch (a.p) {
+    case 1: return launch_beta_t<1, USE_W>(a, stream);
+    case 2: return launch_beta_t<2, USE_W>(a, stream);
+    case 3: return launch_beta_t<3, USE_W>(a, stream);
+    case 4: return launch_beta_t<4, USE_W>(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_fit_beta(const BetaArgs& a, cudaStream_t stream) {
+  if (a.n == 0) return cudaSuccess;
+  return a.use_weights ? launch_beta_p<true>(a, stream) : launch_beta_p<false>(a, stream);
+}
+
+}  // namespace nb

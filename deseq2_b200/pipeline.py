@@ -1,0 +1,312 @@
+"""Host-side glue of DESeq()'s default Wald path around the three native calls.
+
+The reference keeps all of this in R (it "stays R" in a real drop-in); R is not in this
+image, so the steps that prepare the inputs of fitDisp / fitBeta and consume their outputs are restated here in
+numpy, one function per R function, same names, so the engine can be driven and measured end to end:
+
+  estimateSizeFactorsForMatrix   R/core.R:535-578   (type="ratio")
+  getBaseMeansAndVariances       R/core.R:2138-2157
+  linearModelMu / roughDispEstimate / momentsDispEstimate   R/core.R:2454-2459, 2422-2437, 2439-2448
+  estimateDispersionsGeneEst     R/core.R:657-860
+  parametricDispersionFit        R/core.R:2166-2189  (Gamma GLM, identity link, glm.fit IRLS restated)
+  dispersionFunction<-           R/methods.R:142-190 (dispFit, varLogDispEsts = mad^2)
+  estimateDispersionsPriorVar    R/core.R:1135-1208  (m - p > 3 branch)
+  estimateDispersionsMAP         R/core.R:943-1131
+  fitNbinomGLMs                  R/fitNbinomGLMs.R:29-236 (without the optim fallback, :203-227)
+  nbinomWaldTest                 R/core.R:1332-1565  (betas, SEs, Wald statistic and p-value)
+  DESeq                          R/core.R:280-432    (test="Wald", fitType="parametric", betaPrior=FALSE)
+
+`engine` is any object with fitDisp / fitDispGrid / fitBeta taking the reference's argument names
+(deseq2_b200.wrappers is the product engine and the default; tests and the bench's CPU baseline pass the
+oracle).  Not restated (out of scope): Cook's distances / outlier replacement, the
+L-BFGS-B fallback for rows with iter == maxit, local / mean trend fits, results()/lfcShrink().
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy import special as _sp
+
+from . import wrappers as _default_engine
+from .wrappers import fitBetaWrapper, fitDispGridWrapper, fitDispWrapper
+
+LN2 = np.log(2.0)
+
+
+def estimateSizeFactorsForMatrix(counts):
+    """R/core.R:535-578, type='ratio', locfunc=median."""
+    counts = np.asarray(counts, dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        logc = np.log(counts)
+    loggeomeans = logc.mean(axis=1)
+    if np.all(np.isinf(loggeomeans)):
+        raise ValueError("every gene contains at least one zero, cannot compute log geometric means")
+    ok = np.isfinite(loggeomeans)
+    sf = np.empty(counts.shape[1])
+    for j in range(counts.shape[1]):
+        sel = ok & (counts[:, j] > 0)
+        sf[j] = np.exp(np.median(logc[sel, j] - loggeomeans[sel]))
+    return sf
+
+
+def getBaseMeansAndVariances(counts, sizeFactors):
+    """R/core.R:2138-2157 (no weights)."""
+    norm = np.asarray(counts, dtype=np.float64) / sizeFactors[None, :]
+    return {"baseMean": norm.mean(axis=1), "baseVar": norm.var(axis=1, ddof=1),
+            "allZero": np.asarray(counts).sum(axis=1) == 0}
+
+
+def linearModelMu(y, x):
+    """R/core.R:2454-2459: (y Q)(x R^-1)'."""
+    Q, R = np.linalg.qr(x)
+    Rinv = np.linalg.inv(R)
+    return (y @ Q) @ (x @ Rinv).T
+
+
+def roughDispEstimate(y, x):
+    """R/core.R:2422-2437."""
+    mu = np.maximum(1.0, linearModelMu(y, x))
+    m, p = x.shape
+    est = (((y - mu) ** 2 - mu) / mu ** 2).sum(axis=1) / (m - p)
+    return np.maximum(est, 0.0)
+
+
+def momentsDispEstimate(baseMean, baseVar, sizeFactors):
+    """R/core.R:2439-2448."""
+    xim = np.mean(1.0 / sizeFactors)
+    return (baseVar - xim * baseMean) / baseMean ** 2
+
+
+def modelMatrixGroups(x):
+    """R/core.R:2450-2452: number of distinct rows of the design."""
+    return len({tuple(r) for r in np.asarray(x)})
+
+
+def nbinomLogLike(counts, mu, disp):
+    """R/core.R:2208-2217 without weights (direct lgamma form; the mu-free part is included)."""
+    size = 1.0 / disp[:, None]
+    y = np.asarray(counts, dtype=np.float64)
+    return (_sp.gammaln(y + size) - _sp.gammaln(size) - _sp.gammaln(y + 1) + size * np.log(size / (size + mu))
+            + y * np.log(mu / (size + mu))).sum(axis=1)
+
+
+def estimateDispersionsGeneEst(counts, sizeFactors, x, engine=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6,
+                               maxit=100, useCR=True, weightThreshold=1e-2, minmu=0.5, mv=None):
+    """R/core.R:657-860 for niter=1, no weights.  `counts` holds only the non-all-zero rows."""
+    engine = engine or _default_engine
+    counts = np.asarray(counts)
+    n, m = counts.shape
+    p = x.shape[1]
+    if mv is None:
+        mv = getBaseMeansAndVariances(counts, sizeFactors)
+    norm = counts / sizeFactors[None, :]
+    roughDisp = roughDispEstimate(norm, x)
+    momentsDisp = momentsDispEstimate(mv["baseMean"], mv["baseVar"], sizeFactors)
+    alpha_hat = np.minimum(roughDisp, momentsDisp)
+    maxDisp = max(10, m)
+    alpha_hat = alpha_init = np.minimum(np.maximum(minDisp, alpha_hat), maxDisp)
+    linearMu = modelMatrixGroups(x) == p
+    nf = np.broadcast_to(sizeFactors[None, :], (n, m))
+    if not linearMu:
+        fit = fitNbinomGLMs(counts, nf, x, alpha_hat, engine=engine)
+        fitMu = fit["mu"]
+    else:
+        fitMu = linearModelMu(norm, x) * nf
+    fitMu = np.maximum(fitMu, minmu)
+    dispRes = fitDispWrapper(ySEXP=counts, xSEXP=x, mu_hatSEXP=fitMu, log_alphaSEXP=np.log(alpha_hat),
+                             log_alpha_prior_meanSEXP=np.log(alpha_hat), log_alpha_prior_sigmasqSEXP=1.0,
+                             min_log_alphaSEXP=np.log(minDisp / 10), kappa_0SEXP=kappa_0, tolSEXP=dispTol,
+                             maxitSEXP=maxit, usePriorSEXP=False, weightsSEXP=None, useWeightsSEXP=False,
+                             weightThresholdSEXP=weightThreshold, useCRSEXP=useCR, engine=engine)
+    dispIter = dispRes["iter"]
+    dispGeneEst = np.minimum(np.exp(dispRes["log_alpha"]), maxDisp)
+    noIncrease = dispRes["last_lp"] < dispRes["initial_lp"] + np.abs(dispRes["initial_lp"]) / 1e6
+    dispGeneEst[noIncrease] = alpha_init[noIncrease]
+    dispGeneEstConv = (dispIter < maxit) & ~(dispIter == 1)
+    refitDisp = ~dispGeneEstConv & (dispGeneEst > minDisp * 10)
+    if refitDisp.sum() > 0:
+        dispGrid = fitDispGridWrapper(y=counts[refitDisp], x=x, mu=fitMu[refitDisp],
+                                      logAlphaPriorMean=np.zeros(int(refitDisp.sum())), logAlphaPriorSigmaSq=1.0,
+                                      usePrior=False, weightsSEXP=None, useWeightsSEXP=False,
+                                      weightThresholdSEXP=weightThreshold, useCRSEXP=useCR, engine=engine)
+        dispGeneEst[refitDisp] = dispGrid
+    dispGeneEst = np.minimum(np.maximum(dispGeneEst, minDisp), maxDisp)
+    return {"dispGeneEst": dispGeneEst, "dispGeneIter": dispIter, "mu": fitMu, "baseMean": mv["baseMean"],
+            "baseVar": mv["baseVar"], "n_refit": int(refitDisp.sum()), "dispRes": dispRes}
+
+
+def _gamma_glm_identity(y, xinv, start, maxit=25, epsilon=1e-8):
+    """glm(y ~ I(1/means), family=Gamma(link='identity'), start=start) via glm.fit's IRLS:
+    eta = mu, working weights 1/mu^2, working response y; converged when |dev-devold|/(|dev|+0.1) < epsilon."""
+    X = np.c_[np.ones_like(xinv), xinv]
+    coef = np.asarray(start, dtype=np.float64)
+    mu = X @ coef
+    dev_old = 2.0 * np.sum(-np.log(y / mu) + (y - mu) / mu)
+    converged = False
+    for _ in range(maxit):
+        w = 1.0 / mu ** 2
+        XtW = X.T * w
+        coef = np.linalg.solve(XtW @ X, XtW @ y)
+        mu = X @ coef
+        if np.any(mu <= 0):
+            raise FloatingPointError("parametric dispersion fit failed")
+        dev = 2.0 * np.sum(-np.log(y / mu) + (y - mu) / mu)
+        if abs(dev - dev_old) / (abs(dev) + 0.1) < epsilon:
+            converged = True
+            break
+        dev_old = dev
+    return coef, converged
+
+
+def parametricDispersionFit(means, disps):
+    """R/core.R:2166-2189.  Returns (asymptDisp, extraPois)."""
+    coefs = np.array([0.1, 1.0])
+    it = 0
+    while True:
+        residuals = disps / (coefs[0] + coefs[1] / means)
+        good = (residuals > 1e-4) & (residuals < 15)
+        oldcoefs = coefs
+        coefs, converged = _gamma_glm_identity(disps[good], 1.0 / means[good], coefs)
+        if not np.all(coefs > 0):
+            raise FloatingPointError("parametric dispersion fit failed")
+        if (np.sum(np.log(coefs / oldcoefs) ** 2) < 1e-6) and converged:
+            break
+        it += 1
+        if it > 10:
+            raise FloatingPointError("dispersion fit did not converge")
+    return coefs
+
+
+def _mad(x):
+    """stats::mad: 1.4826 * median(|x - median(x)|)."""
+    return 1.4826 * np.median(np.abs(x - np.median(x)))
+
+
+def estimateDispersionsFit(dispGeneEst, baseMean, minDisp=1e-8):
+    """R/core.R:864-940 (fitType='parametric') + dispersionFunction<- (R/methods.R:142-190)."""
+    useForFit = dispGeneEst > 100 * minDisp
+    if useForFit.sum() == 0:
+        raise ValueError("all gene-wise dispersion estimates are within 2 orders of magnitude from the minimum value")
+    coefs = parametricDispersionFit(baseMean[useForFit], dispGeneEst[useForFit])
+    dispFit = coefs[0] + coefs[1] / baseMean
+    aboveMinDisp = dispGeneEst >= minDisp * 100
+    dispResiduals = np.log(dispGeneEst) - np.log(dispFit)
+    varLogDispEsts = _mad(dispResiduals[aboveMinDisp]) ** 2
+    return {"dispFit": dispFit, "coefs": coefs, "varLogDispEsts": varLogDispEsts}
+
+
+def estimateDispersionsPriorVar(varLogDispEsts, m, p):
+    """R/core.R:1135-1208, the m - p > 3 branch (the Monte-Carlo branch for 1..3 residual df is not restated)."""
+    if m - p <= 3:
+        raise NotImplementedError("residual df <= 3: the reference uses a Monte-Carlo KL match (R/core.R:1161-1193)")
+    expVarLogDisp = _sp.polygamma(1, (m - p) / 2.0)
+    return max(varLogDispEsts - expVarLogDisp, 0.25)
+
+
+def estimateDispersionsMAP(counts, x, mu, dispGeneEst, dispFit, dispPriorVar, varLogDispEsts, engine=None,
+                           outlierSD=2.0, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, maxit=100, useCR=True,
+                           weightThreshold=1e-2):
+    """R/core.R:943-1131, type='DESeq2', no weights."""
+    engine = engine or _default_engine
+    n, m = np.asarray(counts).shape
+    dispInit = np.where(dispGeneEst > 0.1 * dispFit, dispGeneEst, dispFit)
+    dispResMAP = fitDispWrapper(ySEXP=counts, xSEXP=x, mu_hatSEXP=mu, log_alphaSEXP=np.log(dispInit),
+                                log_alpha_prior_meanSEXP=np.log(dispFit), log_alpha_prior_sigmasqSEXP=dispPriorVar,
+                                min_log_alphaSEXP=np.log(minDisp / 10), kappa_0SEXP=kappa_0, tolSEXP=dispTol,
+                                maxitSEXP=maxit, usePriorSEXP=True, weightsSEXP=None, useWeightsSEXP=False,
+                                weightThresholdSEXP=weightThreshold, useCRSEXP=useCR, engine=engine)
+    dispMAP = np.exp(dispResMAP["log_alpha"])
+    dispIter = dispResMAP["iter"]
+    dispConv = dispIter < maxit
+    refitDisp = ~dispConv
+    if refitDisp.sum() > 0:
+        dispGrid = fitDispGridWrapper(y=np.asarray(counts)[refitDisp], x=x, mu=mu[refitDisp],
+                                      logAlphaPriorMean=np.log(dispFit)[refitDisp], logAlphaPriorSigmaSq=dispPriorVar,
+                                      usePrior=True, weightsSEXP=None, useWeightsSEXP=False,
+                                      weightThresholdSEXP=weightThreshold, useCRSEXP=True, engine=engine)
+        dispMAP[refitDisp] = dispGrid
+    maxDisp = max(10, m)
+    dispMAP = np.minimum(np.maximum(dispMAP, minDisp), maxDisp)
+    dispersionFinal = dispMAP.copy()
+    dispOutlier = np.log(dispGeneEst) > np.log(dispFit) + outlierSD * np.sqrt(varLogDispEsts)
+    dispersionFinal[dispOutlier] = dispGeneEst[dispOutlier]
+    return {"dispersion": dispersionFinal, "dispIter": dispIter, "dispOutlier": dispOutlier, "dispMAP": dispMAP,
+            "n_refit": int(refitDisp.sum()), "dispRes": dispResMAP}
+
+
+def fitNbinomGLMs(counts, nf, x, alpha_hat, lambda_=None, engine=None, betaTol=1e-8, maxit=100, useQR=True,
+                  minmu=0.5):
+    """R/fitNbinomGLMs.R:29-236 without weights and without the optim fallback (:203-227)."""
+    engine = engine or _default_engine
+    counts = np.asarray(counts)
+    n, m = counts.shape
+    p = x.shape[1]
+    if lambda_ is None:
+        lambda_ = np.full(p, 1e-6)
+    norm = counts / nf
+    if np.linalg.matrix_rank(x) == p:
+        Q, R = np.linalg.qr(x)
+        ylog = np.log(norm + 0.1).T
+        beta_mat = np.linalg.solve(R, Q.T @ ylog).T
+    else:
+        beta_mat = np.zeros((n, p))
+        beta_mat[:, 0] = np.log(norm.mean(axis=1))
+    lambdaNatLogScale = np.asarray(lambda_, dtype=np.float64) / LN2 ** 2
+    betaRes = fitBetaWrapper(ySEXP=counts, xSEXP=x, nfSEXP=nf, alpha_hatSEXP=alpha_hat, beta_matSEXP=beta_mat,
+                             lambdaSEXP=lambdaNatLogScale, weightsSEXP=None, useWeightsSEXP=False, tolSEXP=betaTol,
+                             maxitSEXP=maxit, useQRSEXP=useQR, minmuSEXP=minmu, engine=engine)
+    mu = nf * np.exp(betaRes["beta_mat"] @ x.T)
+    logLike = nbinomLogLike(counts, mu, alpha_hat)
+    betaConv = betaRes["iter"] < maxit
+    betaMatrix = betaRes["beta_mat"] / LN2
+    betaSE = np.sqrt(np.maximum(betaRes["beta_var_mat"], 0.0)) / LN2
+    return {"logLike": logLike, "betaConv": betaConv, "betaMatrix": betaMatrix, "betaSE": betaSE, "mu": mu,
+            "betaIter": betaRes["iter"], "hat_diagonals": betaRes["hat_diagonals"], "betaRes": betaRes}
+
+
+def nbinomWaldTest(counts, nf, x, dispersion, engine=None, betaTol=1e-8, maxit=100, useQR=True, minmu=0.5):
+    """R/core.R:1332-1565, betaPrior=FALSE, useT=FALSE; Cook's distances are not restated."""
+    fit = fitNbinomGLMs(counts, nf, x, dispersion, engine=engine, betaTol=betaTol, maxit=maxit, useQR=useQR,
+                        minmu=minmu)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        WaldStatistic = fit["betaMatrix"] / fit["betaSE"]
+    WaldPvalue = 2.0 * _sp.ndtr(-np.abs(WaldStatistic))
+    fit.update({"WaldStatistic": WaldStatistic, "WaldPvalue": WaldPvalue, "deviance": -2.0 * fit["logLike"]})
+    return fit
+
+
+def DESeq(counts, x, sizeFactors=None, engine=None):
+    """R/core.R:280-432 with test='Wald', fitType='parametric', betaPrior=FALSE, no outlier replacement.
+    Returns per-gene vectors over ALL rows; all-zero rows carry NaN (buildDataFrameWithNARows, R/core.R:2232)."""
+    engine = engine or _default_engine
+    counts = np.asarray(counts)
+    N, m = counts.shape
+    p = x.shape[1]
+    if sizeFactors is None:
+        sizeFactors = estimateSizeFactorsForMatrix(counts)
+    mvAll = getBaseMeansAndVariances(counts, sizeFactors)
+    nz = ~mvAll["allZero"]
+    cnz = counts[nz]
+    mv = {k: v[nz] for k, v in mvAll.items()}
+    ge = estimateDispersionsGeneEst(cnz, sizeFactors, x, engine=engine, mv=mv)
+    tf = estimateDispersionsFit(ge["dispGeneEst"], ge["baseMean"])
+    dispPriorVar = estimateDispersionsPriorVar(tf["varLogDispEsts"], m, p)
+    mp = estimateDispersionsMAP(cnz, x, ge["mu"], ge["dispGeneEst"], tf["dispFit"], dispPriorVar,
+                                tf["varLogDispEsts"], engine=engine)
+    nf = np.broadcast_to(sizeFactors[None, :], cnz.shape)
+    wt = nbinomWaldTest(cnz, nf, x, mp["dispersion"], engine=engine)
+
+    def full(v):
+        out = np.full((N,) + v.shape[1:], np.nan)
+        out[nz] = v
+        return out
+
+    return {"sizeFactors": sizeFactors, "baseMean": mvAll["baseMean"], "allZero": mvAll["allZero"],
+            "dispGeneEst": full(ge["dispGeneEst"]), "dispFit": full(tf["dispFit"]), "dispMAP": full(mp["dispMAP"]),
+            "dispersion": full(mp["dispersion"]), "dispOutlier": full(mp["dispOutlier"].astype(float)),
+            "dispPriorVar": dispPriorVar, "trendCoefs": tf["coefs"], "varLogDispEsts": tf["varLogDispEsts"],
+            "betaMatrix": full(wt["betaMatrix"]), "betaSE": full(wt["betaSE"]),
+            "WaldStatistic": full(wt["WaldStatistic"]), "WaldPvalue": full(wt["WaldPvalue"]),
+            "betaConv": full(wt["betaConv"].astype(float)), "betaIter": full(wt["betaIter"]),
+            "deviance": full(wt["deviance"]), "dispGeneIter": full(ge["dispGeneIter"].astype(float)),
+            "dispIter": full(mp["dispIter"].astype(float)),
+            "n_refit_geneest": ge["n_refit"], "n_refit_map": mp["n_refit"]}

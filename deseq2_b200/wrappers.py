@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's R -> native shim for the hot path.
+
+Same function names, argument names, defaults and error behaviour as
+  R/RcppExports.R:4-14   fitDisp / fitBeta / fitDispGrid   (thin .Call stubs)
+  R/wrappers.R:26,63,102 fitDispWrapper / fitDispGridWrapper / fitBetaWrapper (NA screening, default
+                         contrast c(1,0,...), 20-point log-alpha grid, exp() of the grid result)
+but the call lands in libb200nb.so (include/b200nb.h) instead of the Rcpp routines in src/DESeq2.cpp.
+Matrices are numpy arrays shaped like the R objects (genes x samples); they are handed over in
+column-major order, which is what R's .Call would pass.  Results come back as dicts keyed by the
+reference's list member names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_Y_INT32, _Y_F64 = 0, 1
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _ymat(y):
+    y = np.asarray(y)
+    if y.dtype == np.int32:
+        return np.asfortranarray(y), _Y_INT32
+    if np.issubdtype(y.dtype, np.integer):
+        return np.asfortranarray(y.astype(np.int32)), _Y_INT32
+    return np.asfortranarray(y, dtype=np.float64), _Y_F64
+
+
+def _fmat(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _vec(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _weights(weightsSEXP, useWeightsSEXP):
+    if not useWeightsSEXP or weightsSEXP is None:
+        return None
+    return _fmat(weightsSEXP)
+
+
+def fitDisp(ySEXP, xSEXP, mu_hatSEXP, log_alphaSEXP, log_alpha_prior_meanSEXP, log_alpha_prior_sigmasqSEXP,
+            min_log_alphaSEXP, kappa_0SEXP, tolSEXP, maxitSEXP, usePriorSEXP, weightsSEXP, useWeightsSEXP,
+            weightThresholdSEXP, useCRSEXP):
+    """R/RcppExports.R:4 -> src/DESeq2.cpp:164.  Returns the nine-member list of :268-276 as a dict."""
+    L = _lib.lib()
+    _lib.require_device()
+    y, yt = _ymat(ySEXP)
+    x = _fmat(xSEXP)
+    mu = _fmat(mu_hatSEXP)
+    n, m = y.shape
+    p = x.shape[1]
+    if x.shape[0] != m or mu.shape != (n, m):
+        raise ValueError("fitDisp: non-conformable arguments")
+    la = _vec(log_alphaSEXP)
+    pm = _vec(log_alpha_prior_meanSEXP)
+    w = _weights(weightsSEXP, useWeightsSEXP)
+    out = {k: np.empty(n) for k in ("log_alpha", "last_change", "initial_lp", "initial_dlp", "last_lp", "last_dlp",
+                                    "last_d2lp")}
+    out["iter"] = np.empty(n, dtype=np.int32)
+    out["iter_accept"] = np.empty(n, dtype=np.int32)
+    rc = L.b200nb_fit_disp(_ptr(y), yt, _ptr(x), _ptr(mu), _ptr(la), _ptr(pm), float(log_alpha_prior_sigmasqSEXP),
+                           float(min_log_alphaSEXP), float(kappa_0SEXP), float(tolSEXP), int(maxitSEXP),
+                           int(bool(usePriorSEXP)), _ptr(w), int(w is not None), float(weightThresholdSEXP),
+                           int(bool(useCRSEXP)), n, m, p,
+                           _ptr(out["log_alpha"]), _ptr(out["iter"]), _ptr(out["iter_accept"]),
+                           _ptr(out["last_change"]), _ptr(out["initial_lp"]), _ptr(out["initial_dlp"]),
+                           _ptr(out["last_lp"]), _ptr(out["last_dlp"]), _ptr(out["last_d2lp"]))
+    _lib.check(rc, "fitDisp")
+    return out
+
+
+def fitDispGrid(ySEXP, xSEXP, mu_hatSEXP, disp_gridSEXP, log_alpha_prior_meanSEXP, log_alpha_prior_sigmasqSEXP,
+                usePriorSEXP, weightsSEXP, useWeightsSEXP, weightThresholdSEXP, useCRSEXP):
+    """R/RcppExports.R:12 -> src/DESeq2.cpp:469."""
+    L = _lib.lib()
+    _lib.require_device()
+    y, yt = _ymat(ySEXP)
+    x = _fmat(xSEXP)
+    mu = _fmat(mu_hatSEXP)
+    n, m = y.shape
+    p = x.shape[1]
+    grid = _vec(disp_gridSEXP)
+    pm = _vec(log_alpha_prior_meanSEXP)
+    w = _weights(weightsSEXP, useWeightsSEXP)
+    la = np.empty(n)
+    rc = L.b200nb_fit_disp_grid(_ptr(y), yt, _ptr(x), _ptr(mu), _ptr(grid), len(grid), _ptr(pm),
+                                float(log_alpha_prior_sigmasqSEXP), int(bool(usePriorSEXP)), _ptr(w),
+                                int(w is not None), float(weightThresholdSEXP), int(bool(useCRSEXP)), n, m, p,
+                                _ptr(la))
+    _lib.check(rc, "fitDispGrid")
+    return {"log_alpha": la}
+
+
+def fitBeta(ySEXP, xSEXP, nfSEXP, alpha_hatSEXP, contrastSEXP, beta_matSEXP, lambdaSEXP, weightsSEXP,
+            useWeightsSEXP, tolSEXP, maxitSEXP, useQRSEXP, minmuSEXP, return_mu=False):
+    """R/RcppExports.R:8 -> src/DESeq2.cpp:283.  Returns the seven-member list of :458-464 as a dict
+    (plus "mu" when return_mu=True: the fused fitted mean the reference recomputes at R/fitNbinomGLMs.R:180)."""
+    L = _lib.lib()
+    _lib.require_device()
+    y, yt = _ymat(ySEXP)
+    x = _fmat(xSEXP)
+    nf = _fmat(nfSEXP)
+    n, m = y.shape
+    p = x.shape[1]
+    if x.shape[0] != m or nf.shape != (n, m):
+        raise ValueError("fitBeta: non-conformable arguments")
+    alpha = _vec(alpha_hatSEXP)
+    contrast = _vec(contrastSEXP)
+    beta0 = _fmat(np.asarray(beta_matSEXP, dtype=np.float64).reshape(n, p))
+    lam = _vec(lambdaSEXP)
+    w = _weights(weightsSEXP, useWeightsSEXP)
+    beta = np.empty((n, p), order="F")
+    var = np.empty((n, p), order="F")
+    it = np.empty(n)
+    H = np.empty((n, m), order="F")
+    mu = np.empty((n, m), order="F") if return_mu else None
+    cn = np.empty((n, 1))
+    cd = np.empty((n, 1))
+    dev = np.empty(n)
+    rc = L.b200nb_fit_beta(_ptr(y), yt, _ptr(x), _ptr(nf), _ptr(alpha), _ptr(contrast), _ptr(beta0), _ptr(lam),
+                           _ptr(w), int(w is not None), float(tolSEXP), int(maxitSEXP), int(bool(useQRSEXP)),
+                           float(minmuSEXP), n, m, p, _ptr(beta), _ptr(var), _ptr(it), _ptr(H), _ptr(cn), _ptr(cd),
+                           _ptr(dev), _ptr(mu))
+    _lib.check(rc, "fitBeta")
+    out = {"beta_mat": beta, "beta_var_mat": var, "iter": it, "hat_diagonals": H, "contrast_num": cn,
+           "contrast_denom": cd, "deviance": dev}
+    if return_mu:
+        out["mu"] = mu
+    return out
+
+
+# ---------------------------------------------------------------- R/wrappers.R
+
+def _na_check(fname, **kwargs):
+    bad = [k for k, v in kwargs.items() if v is not None and np.any(np.isnan(np.asarray(v, dtype=np.float64)))]
+    if bad:
+        raise ValueError(f"in call to {fname}, the following arguments contain NA: {', '.join(bad)}")
+
+
+def fitDispWrapper(ySEXP, xSEXP, mu_hatSEXP, log_alphaSEXP, log_alpha_prior_meanSEXP, log_alpha_prior_sigmasqSEXP,
+                   min_log_alphaSEXP, kappa_0SEXP, tolSEXP, maxitSEXP, usePriorSEXP, weightsSEXP, useWeightsSEXP,
+                   weightThresholdSEXP, useCRSEXP, engine=None):
+    """R/wrappers.R:26-42."""
+    args = dict(ySEXP=ySEXP, xSEXP=xSEXP, mu_hatSEXP=mu_hatSEXP, log_alphaSEXP=log_alphaSEXP,
+                log_alpha_prior_meanSEXP=log_alpha_prior_meanSEXP,
+                log_alpha_prior_sigmasqSEXP=log_alpha_prior_sigmasqSEXP, min_log_alphaSEXP=min_log_alphaSEXP,
+                kappa_0SEXP=kappa_0SEXP, tolSEXP=tolSEXP, maxitSEXP=maxitSEXP, usePriorSEXP=usePriorSEXP,
+                weightsSEXP=weightsSEXP, useWeightsSEXP=useWeightsSEXP, weightThresholdSEXP=weightThresholdSEXP,
+                useCRSEXP=useCRSEXP)
+    _na_check("fitDisp", **args)
+    return (engine.fitDisp if engine is not None else fitDisp)(**args)
+
+
+def fitDispGridWrapper(y, x, mu, logAlphaPriorMean, logAlphaPriorSigmaSq, usePrior, weightsSEXP, useWeightsSEXP,
+                       weightThresholdSEXP, useCRSEXP, engine=None):
+    """R/wrappers.R:63-83: builds the 20-point grid on [log 1e-8, log max(10, ncol(y))], returns exp(log_alpha)."""
+    _na_check("fitDispGridWrapper", y=y, x=x, mu=mu, logAlphaPriorMean=logAlphaPriorMean,
+              logAlphaPriorSigmaSq=logAlphaPriorSigmaSq, weightsSEXP=weightsSEXP)
+    minLogAlpha = np.log(1e-8)
+    maxLogAlpha = np.log(max(10, np.asarray(y).shape[1]))
+    dispGrid = np.linspace(minLogAlpha, maxLogAlpha, 20)
+    f = engine.fitDispGrid if engine is not None else fitDispGrid
+    logAlpha = f(ySEXP=y, xSEXP=x, mu_hatSEXP=mu, disp_gridSEXP=dispGrid, log_alpha_prior_meanSEXP=logAlphaPriorMean,
+                 log_alpha_prior_sigmasqSEXP=logAlphaPriorSigmaSq, usePriorSEXP=usePrior, weightsSEXP=weightsSEXP,
+                 useWeightsSEXP=useWeightsSEXP, weightThresholdSEXP=weightThresholdSEXP,
+                 useCRSEXP=useCRSEXP)["log_alpha"]
+    return np.exp(logAlpha)
+
+
+def fitBetaWrapper(ySEXP, xSEXP, nfSEXP, alpha_hatSEXP, beta_matSEXP, lambdaSEXP, weightsSEXP, useWeightsSEXP,
+                   tolSEXP, maxitSEXP, useQRSEXP, minmuSEXP, contrastSEXP=None, engine=None, **kw):
+    """R/wrappers.R:102-119: default contrast c(1, 0, ..., 0); NA screening."""
+    if contrastSEXP is None:
+        contrastSEXP = np.r_[1.0, np.zeros(np.asarray(xSEXP).shape[1] - 1)]
+    args = dict(ySEXP=ySEXP, xSEXP=xSEXP, nfSEXP=nfSEXP, alpha_hatSEXP=alpha_hatSEXP, contrastSEXP=contrastSEXP,
+                beta_matSEXP=beta_matSEXP, lambdaSEXP=lambdaSEXP, weightsSEXP=weightsSEXP,
+                useWeightsSEXP=useWeightsSEXP, tolSEXP=tolSEXP, maxitSEXP=maxitSEXP, useQRSEXP=useQRSEXP,
+                minmuSEXP=minmuSEXP)
+    _na_check("fitBeta", **args)
+    return (engine.fitBeta if engine is not None else fitBeta)(**args, **kw)

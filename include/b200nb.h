@@ -1,0 +1,112 @@
+/*
+ * b200nb.h -- C ABI of the B200-native batched negative-binomial GLM engine (libb200nb.so, sm_100a).
+ *
+ * This is the drop-in boundary for the ONE hot path of thelovelab/DESeq2: the three native routines the R
+ * package reaches through .Call (registration table /root/reference/src/RcppExports.cpp:84-94):
+ *
+ *   b200nb_fit_disp       replaces  _DESeq2_fitDisp      src/RcppExports.cpp:16-38, body src/DESeq2.cpp:164-277
+ *   b200nb_fit_disp_grid  replaces  _DESeq2_fitDispGrid  src/RcppExports.cpp:64-82, body src/DESeq2.cpp:469-513
+ *   b200nb_fit_beta       replaces  _DESeq2_fitBeta      src/RcppExports.cpp:41-61, body src/DESeq2.cpp:283-465
+ *
+ * Argument order follows the reference signatures (SEXP list -> plain pointers + explicit dimensions,
+ * named-list members -> caller-allocated output buffers with the reference's member names).  The R-side
+ * .Call shim that re-creates the SEXP interface on top of these symbols is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - matrices are R layout: column-major, genes = rows: y[i + n*j] is gene i, sample j; x is m x p.
+ *   - host entry points take HOST pointers, copy to the current CUDA device, run the kernels, copy the
+ *     results back; they are synchronous.  Inputs are never modified.
+ *   - *_dev entry points take DEVICE pointers in the engine's gene-major layout (one gene per row, sample
+ *     axis contiguous, row stride ld elements, ld % 4 == 0, base 16-byte aligned) and enqueue on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream) without synchronising.
+ *   - every function returns 0 on success, non-zero on failure; b200nb_last_error() then returns a
+ *     message (thread-local).  Per-gene numerical failure is in-band exactly as in the reference
+ *     (iter == maxit sentinel, NaN coefficients), never an error (src/DESeq2.cpp:357-360,375-378).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *   - p (design columns) is limited to B200NB_MAX_P.
+ */
+#ifndef B200NB_H
+#define B200NB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NB_MAX_P 32
+#define B200NB_Y_INT32 0
+#define B200NB_Y_F64 1
+
+/* ---- fitDisp: src/DESeq2.cpp:164.  Outputs = list members at :268-276 (length n each). */
+int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,
+                    const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
+                    double kappa_0, double tol, int maxit, int use_prior, const double* weights, int use_weights,
+                    double weight_threshold, int use_cr, int n, int m, int p,
+                    double* out_log_alpha, int32_t* out_iter, int32_t* out_iter_accept, double* out_last_change,
+                    double* out_initial_lp, double* out_initial_dlp, double* out_last_lp, double* out_last_dlp,
+                    double* out_last_d2lp);
+
+/* ---- fitDispGrid: src/DESeq2.cpp:469.  Output = list member log_alpha (:512). */
+int b200nb_fit_disp_grid(const void* y, int y_type, const double* x, const double* mu_hat, const double* disp_grid,
+                         int disp_grid_n, const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq,
+                         int use_prior, const double* weights, int use_weights, double weight_threshold, int use_cr,
+                         int n, int m, int p, double* out_log_alpha);
+
+/* ---- fitBeta: src/DESeq2.cpp:283.  beta_mat (n x p) is the starting value; outputs = list members at
+ * :458-464: out_beta_mat n x p, out_beta_var_mat n x p, out_iter n (double, NumericVector in the reference),
+ * out_hat_diagonals n x m, out_contrast_num n, out_contrast_denom n, out_deviance n.
+ * nf is the n x m normalisation-factor matrix the reference receives (R/core.R:2221-2228).
+ * out_mu (n x m, may be NULL) is an extension: the fitted mean nf*exp(x beta) clamped at minmu, which the
+ * reference recomputes in R right after the call (R/fitNbinomGLMs.R:180). */
+int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf, const double* alpha_hat,
+                    const double* contrast, const double* beta_mat, const double* lambda, const double* weights,
+                    int use_weights, double tol, int maxit, int use_qr, double minmu, int n, int m, int p,
+                    double* out_beta_mat, double* out_beta_var_mat, double* out_iter, double* out_hat_diagonals,
+                    double* out_contrast_num, double* out_contrast_denom, double* out_deviance, double* out_mu);
+
+/* ---- device-resident variants (gene-major n x ld matrices, see header comment) */
+int b200nb_fit_disp_dev(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,
+                        const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
+                        double kappa_0, double tol, int maxit, int use_prior, const double* weights,
+                        int use_weights, double weight_threshold, int use_cr, int n, int m, int p, long long ld,
+                        double* out_log_alpha, int32_t* out_iter, int32_t* out_iter_accept,
+                        double* out_last_change, double* out_initial_lp, double* out_initial_dlp,
+                        double* out_last_lp, double* out_last_dlp, double* out_last_d2lp, void* stream);
+
+int b200nb_fit_disp_grid_dev(const void* y, int y_type, const double* x, const double* mu_hat,
+                             const double* disp_grid, int disp_grid_n, const double* log_alpha_prior_mean,
+                             double log_alpha_prior_sigmasq, int use_prior, const double* weights, int use_weights,
+                             double weight_threshold, int use_cr, int n, int m, int p, long long ld,
+                             double* out_log_alpha, void* stream);
+
+/* nf_is_vector != 0: nf is the length-m size-factor vector instead of the n x ld matrix.
+ * beta_mat / out_beta_mat / out_beta_var_mat stay column-major n x p.  out_hat_diagonals / out_mu are
+ * gene-major n x ld and may be NULL. */
+int b200nb_fit_beta_dev(const void* y, int y_type, const double* x, const double* nf, int nf_is_vector,
+                        const double* alpha_hat, const double* contrast, const double* beta_mat,
+                        const double* lambda, const double* weights, int use_weights, double tol, int maxit,
+                        int use_qr, double minmu, int n, int m, int p, long long ld, double* out_beta_mat,
+                        double* out_beta_var_mat, double* out_iter, double* out_hat_diagonals,
+                        double* out_contrast_num, double* out_contrast_denom, double* out_deviance, double* out_mu,
+                        void* stream);
+
+/* layout helpers on device buffers: R column-major n x m <-> gene-major n x ld.  elem_size 4 (int32) or 8. */
+int b200nb_to_gene_major_dev(const void* src_colmajor, void* dst, int n, int m, long long ld, int elem_size,
+                             void* stream);
+int b200nb_to_col_major_dev(const double* src, double* dst_colmajor, int n, int m, long long ld, void* stream);
+
+/* ---- housekeeping */
+const char* b200nb_last_error(void);
+int b200nb_device_count(void);            /* number of visible CUDA devices (0 if none / no driver) */
+long long b200nb_kernel_launches(void);   /* kernels this library has launched in this process */
+void b200nb_release_workspace(void);      /* frees cached device / pinned buffers of the host entry points */
+const char* b200nb_version(void);
+
+/* test hook: lgamma / digamma / trigamma of the device math on host arrays x[0..n) (x > 0) */
+int b200nb_test_special(const double* x, int n, double* out_lgamma, double* out_digamma, double* out_trigamma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NB_H */
