@@ -253,6 +253,7 @@ typedef struct {
   double *b, *db, *d2b, *bi, *t1, *t2, *work; /* p*p each */
   int *piv;
   double *yrow, *murow, *wrow; /* m: contiguous copies of the gene's rows */
+  double abs_sum;              /* diagnostics only: sum of |terms| of the last log_posterior() call */
 } disp_ws;
 
 static disp_ws *disp_ws_new(int m, int p, const double *x) {
@@ -311,13 +312,16 @@ static double log_posterior(disp_ws *s, double log_alpha, double prior_mean, dou
   }
   double alpha_neg1 = 1.0 / alpha;
   double lg_an1 = o_lgamma(alpha_neg1);
-  double ll = 0.0;
+  double ll = 0.0, asum = 0.0;
   for (int j = 0; j < m; j++) {
     double y = s->yrow[j], mu = s->murow[j];
-    double t = o_lgamma(y + alpha_neg1) - lg_an1 - y * log(mu + alpha_neg1) - alpha_neg1 * log(1.0 + mu * alpha);
+    double lg1 = o_lgamma(y + alpha_neg1), t2 = y * log(mu + alpha_neg1), t3 = alpha_neg1 * log(1.0 + mu * alpha);
+    double t = lg1 - lg_an1 - t2 - t3;
     ll += useWeights ? s->wrow[j] * t : t;
+    asum += (useWeights ? s->wrow[j] : 1.0) * (fabs(lg1) + fabs(lg_an1) + fabs(t2) + fabs(t3));
   }
   double prior_part = usePrior ? -0.5 * (log_alpha - prior_mean) * (log_alpha - prior_mean) / prior_sigmasq : 0.0;
+  s->abs_sum = asum + fabs(prior_part) + fabs(cr_term);
   return ll + prior_part + cr_term;
 }
 
@@ -412,15 +416,12 @@ static void load_rows(disp_ws *s, const double *y, const double *mu, const doubl
   }
 }
 
-static double rel_margin(double lhs, double rhs) {
-  return fabs(lhs - rhs) / (fabs(lhs) + fabs(rhs) + 1e-300);
-}
-
 /* src/DESeq2.cpp:164-277.  Outputs are the nine named list members (:268-276).
  * `margin` (optional, may be NULL) is NOT part of the reference: it records, per gene, the smallest
- * relative distance |lhs-rhs|/(|lhs|+|rhs|) over every floating-point branch decision of the line
- * search, so tests can tell a knife-edge decision (two valid fp64 evaluations may legitimately
- * disagree) from a real control-flow difference. */
+ * distance |lhs-rhs| over every floating-point branch decision of the line search, in units of the
+ * a-priori rounding-error bound of the log-posterior values entering that decision
+ * (2^-52 * sum of |terms|).  margin >> 1 means no correct fp64 evaluation of the same formulas can take
+ * the other branch; margin ~ 1 is a knife-edge decision.  Tests use it to separate the two. */
 int oracle_fit_disp(const double *y, const double *x, const double *mu_hat, const double *log_alpha_in,
                     const double *log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
                     double kappa_0, double tol, int maxit, int usePrior, const double *weights, int useWeights,
@@ -438,6 +439,7 @@ int oracle_fit_disp(const double *y, const double *x, const double *mu_hat, cons
       double pm = log_alpha_prior_mean[i];
       double a = log_alpha_in[i];
       double lp = log_posterior(s, a, pm, log_alpha_prior_sigmasq, usePrior, useWeights, weightThreshold, useCR);
+      double lp_abs = s->abs_sum;
       double dlp = dlog_posterior(s, a, pm, log_alpha_prior_sigmasq, usePrior, useWeights, weightThreshold, useCR);
       double kappa = kappa_0;
       initial_lp[i] = lp;
@@ -453,9 +455,9 @@ int oracle_fit_disp(const double *y, const double *x, const double *mu_hat, cons
         double theta_kappa = -1.0 * log_posterior(s, a + kappa * dlp, pm, log_alpha_prior_sigmasq, usePrior,
                                                   useWeights, weightThreshold, useCR);
         double theta_hat_kappa = -1.0 * lp - kappa * epsilon * dlp * dlp;
-        /* Armijo margin measured against the scale of the decrease being tested */
-        {
-          double d = fabs(theta_kappa - theta_hat_kappa) / (fabs(theta_kappa) + 1e-300);
+        double prop_abs = s->abs_sum;
+        if (a + kappa * dlp != a) { /* a zero-length step re-evaluates the same point: an exact, implementation-independent tie */
+          double d = fabs(theta_kappa - theta_hat_kappa) / (DBL_EPSILON * (prop_abs + lp_abs));
           if (d < mg) mg = d;
         }
         if (theta_kappa <= theta_hat_kappa) {
@@ -464,16 +466,17 @@ int oracle_fit_disp(const double *y, const double *x, const double *mu_hat, cons
           double lpnew = log_posterior(s, a, pm, log_alpha_prior_sigmasq, usePrior, useWeights, weightThreshold, useCR);
           change = lpnew - lp;
           {
-            double d = fabs(change - tol) / (fabs(lpnew) + 1e-300);
+            double d = fabs(change - tol) / (DBL_EPSILON * (prop_abs + lp_abs));
             if (d < mg) mg = d;
           }
           if (change < tol) { lp = lpnew; break; }
           {
-            double d = rel_margin(a, min_log_alpha);
+            double d = fabs(a - min_log_alpha) / (DBL_EPSILON * 64.0 * (fabs(a) + 1.0));
             if (d < mg) mg = d;
           }
           if (a < min_log_alpha) break;
           lp = lpnew;
+          lp_abs = prop_abs;
           dlp = dlog_posterior(s, a, pm, log_alpha_prior_sigmasq, usePrior, useWeights, weightThreshold, useCR);
           kappa = fmin(kappa * 1.1, kappa_0);
           if (acc % 5 == 0) kappa = kappa / 2.0;
