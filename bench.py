@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- genes/sec of the DESeq2 Wald hot path (fitDisp MLE + fitDisp MAP + fitBeta) on B200.
+
+Contract (see task text): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+  step      one pass of the hot path over one batch of synthetic counts: fitDisp (gene-wise MLE) ->
+            fitDisp (MAP, prior from the fitted trend) -> fitBeta (Wald IRLS), the three native calls of
+            DESeq()'s default Wald path for a linear-mu design.
+  value     genes/sec, kernels only, inputs resident in HBM (gene-major), CUDA events, max over ranks.
+  e2e       the same three calls through the C ABI with HOST buffers in R layout (b200nb_fit_disp x2,
+            b200nb_fit_beta): H2D, layout conversion, kernels, D2H all inside the timed region.
+  roofline  dominant kernel = fit_disp (MLE launch): algorithmic bytes n*(12m+88) / CUDA-event time vs the
+            measured HBM copy bandwidth (MEASURED_PEAKS.json).  The path is FP64-pipe bound, so
+            the HBM fraction is small by construction; it is reported because the contract asks for it.
+  cpu_baseline / --impl reference: the oracle (C restatement of src/DESeq2.cpp, all host threads) on a
+            bounded sample of the same workload.  R is not in this image, so kind = "port".
+N > 1: every rank owns its own shard of n genes (weak scaling); per step the per-gene results
+(beta, SE, dispersion) are all-gathered over NCCL so rank 0 holds them (R/parallel.R:54-66's rbind).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MIN_LOG_ALPHA = float(np.log(1e-8 / 10))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genes", type=int, default=50000, help="genes per GPU (config C2: 50k)")
+    ap.add_argument("--samples", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="genes in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------- workload
+
+def build_workload(n, m, seed, engine):
+    """Synthetic C2 workload + the exact inputs of the three native calls, produced by one untimed run of the
+    host pipeline with `engine` (so MAP/fitBeta inputs are the real downstream values)."""
+    from deseq2_b200 import pipeline, synth
+    d = synth.make_example_counts(n, m, seed=seed)
+    counts = d["counts"]
+    counts = counts[counts.sum(axis=1) > 0]
+    x, sf = d["x"], d["sizeFactors"]
+    ge = pipeline.estimateDispersionsGeneEst(counts, sf, x, engine=engine)
+    tf = pipeline.estimateDispersionsFit(ge["dispGeneEst"], ge["baseMean"])
+    pv = pipeline.estimateDispersionsPriorVar(tf["varLogDispEsts"], m, x.shape[1])
+    mp = pipeline.estimateDispersionsMAP(counts, x, ge["mu"], ge["dispGeneEst"], tf["dispFit"], pv,
+                                         tf["varLogDispEsts"], engine=engine)
+    norm = counts / sf[None, :]
+    rough = pipeline.roughDispEstimate(norm, x)
+    mom = pipeline.momentsDispEstimate(ge["baseMean"], ge["baseVar"], sf)
+    alpha0 = np.minimum(np.maximum(1e-8, np.minimum(rough, mom)), max(10, m))
+    dispInit = np.where(ge["dispGeneEst"] > 0.1 * tf["dispFit"], ge["dispGeneEst"], tf["dispFit"])
+    Q, R = np.linalg.qr(x)
+    beta0 = np.linalg.solve(R, Q.T @ np.log(norm + 0.1).T).T
+    return dict(counts=counts, x=x, sf=sf, mu=ge["mu"], log_alpha0=np.log(alpha0), log_dispInit=np.log(dispInit),
+                log_dispFit=np.log(tf["dispFit"]), priorVar=pv, dispersion=mp["dispersion"], beta0=beta0,
+                lam=np.full(x.shape[1], 1e-6) / np.log(2) ** 2)
+
+
+def three_calls_host(w, engine, sl=slice(None)):
+    """The hot path through the reference-facing API with host buffers (argument names of src/DESeq2.cpp)."""
+    c, x, mu = w["counts"][sl], w["x"], w["mu"][sl]
+    n, m = c.shape
+    common = dict(ySEXP=c, xSEXP=x, mu_hatSEXP=mu, min_log_alphaSEXP=MIN_LOG_ALPHA, kappa_0SEXP=1.0, tolSEXP=1e-6,
+                  maxitSEXP=100, weightsSEXP=None, useWeightsSEXP=False, weightThresholdSEXP=1e-2, useCRSEXP=True)
+    r1 = engine.fitDisp(log_alphaSEXP=w["log_alpha0"][sl], log_alpha_prior_meanSEXP=w["log_alpha0"][sl],
+                        log_alpha_prior_sigmasqSEXP=1.0, usePriorSEXP=False, **common)
+    r2 = engine.fitDisp(log_alphaSEXP=w["log_dispInit"][sl], log_alpha_prior_meanSEXP=w["log_dispFit"][sl],
+                        log_alpha_prior_sigmasqSEXP=w["priorVar"], usePriorSEXP=True, **common)
+    nf = np.broadcast_to(w["sf"][None, :], (n, m))
+    r3 = engine.fitBeta(ySEXP=c, xSEXP=x, nfSEXP=nf, alpha_hatSEXP=w["dispersion"][sl],
+                        contrastSEXP=np.r_[1.0, np.zeros(x.shape[1] - 1)], beta_matSEXP=w["beta0"][sl],
+                        lambdaSEXP=w["lam"], weightsSEXP=None, useWeightsSEXP=False, tolSEXP=1e-8, maxitSEXP=100,
+                        useQRSEXP=True, minmuSEXP=0.5)
+    return r1, r2, r3
+
+
+def host_bytes(n, m, p):
+    h2d = 2 * (4 * n * m + 8 * n * m + 16 * n + 8 * m * p) + (4 * n * m + 8 * n * m + 8 * n + 8 * n * p + 8 * m * p + 16 * p)
+    d2h = 2 * (7 * 8 * n + 2 * 4 * n) + (8 * n * m + 2 * 8 * n * p + 4 * 8 * n)
+    return h2d, d2h
+
+
+# ---------------------------------------------------------------- clocks
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------- reference arm / cpu baseline
+
+def time_oracle(w, n_sample, steps, warmup):
+    from oracle import oracle as O
+    O.build()
+    n = min(n_sample, len(w["counts"]))
+    sl = slice(0, n)
+    for _ in range(warmup):
+        three_calls_host(w, O, sl)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        three_calls_host(w, O, sl)
+    dt = (time.perf_counter() - t0) / steps
+    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    return n / dt, dt, cores, n
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    n, m = a.genes, a.samples
+    cfg = {"workload": f"C2: {n} genes x {m} samples per GPU, ~condition (p=2) Wald: fitDisp(MLE)+fitDisp(MAP)+fitBeta",
+           "genes_per_gpu": n, "samples": m, "p": 2, "parallelism": f"gene-sharded x{world}",
+           "l2": "inputs rotate over 4 device replicas (400 MB working set > 126 MB L2)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import oracle as O
+        w = build_workload(min(n, a.cpu_sample), m, 20260923 + 2, O)
+        v, dt, cores, ns = time_oracle(w, a.cpu_sample, max(1, a.steps), max(0, a.warmup))
+        print(json.dumps({
+            "impl": "reference", "metric": "genes/sec, DESeq2 Wald hot path (fitDisp MLE + fitDisp MAP + fitBeta)",
+            "value": v, "unit": "genes/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (makeExampleDESeqDataSet law, PCG64 seed)", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": "genes/s", "cores": cores, "kind": "port",
+                             "sample": f"first {ns} genes of the workload, oracle C restatement, OpenMP {cores} threads"},
+            "e2e": {"value": v, "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import deseq2_b200
+    from deseq2_b200 import device as D
+    from deseq2_b200 import wrappers as W
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    L = deseq2_b200.lib()
+
+    w = build_workload(n, m, 20260923 + 2 + 1000 * rank, W)
+    ng = len(w["counts"])
+    p = w["x"].shape[1]
+    NREP = 4
+    reps = []
+    xd = D.x_to_device(w["x"], dev)
+    for _ in range(NREP):
+        reps.append(dict(
+            y=D.to_gene_major(w["counts"], dev), mu=D.to_gene_major(w["mu"], dev),
+            la0=torch.as_tensor(w["log_alpha0"], device=dev), lai=torch.as_tensor(w["log_dispInit"], device=dev),
+            lfit=torch.as_tensor(w["log_dispFit"], device=dev), disp=torch.as_tensor(w["dispersion"], device=dev),
+            beta0=torch.as_tensor(np.ascontiguousarray(w["beta0"].T), device=dev)))
+    sfd = torch.as_tensor(w["sf"], device=dev)
+    contrast = np.r_[1.0, np.zeros(p - 1)]
+    outs = [None, None, None]
+    # per-step result exchange (N > 1): beta, beta_var, log dispersion, padded to n genes per rank
+    gathered = torch.empty((world, 2 * p + 1, n), dtype=torch.float64, device=dev) if world > 1 else None
+    packed = torch.zeros((2 * p + 1, n), dtype=torch.float64, device=dev) if world > 1 else None
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    kern_ms = {"fit_disp_mle": 0.0, "fit_disp_map": 0.0, "fit_beta": 0.0}
+
+    def step(i, timed):
+        r = reps[i % NREP]
+        e = [ev() for _ in range(4)] if timed else None
+        if timed:
+            e[0].record()
+        outs[0] = D.fit_disp(r["y"], xd, r["mu"], r["la0"], r["la0"], 1.0, MIN_LOG_ALPHA, 1.0, 1e-6, 100, False,
+                             m=m, out=outs[0])
+        if timed:
+            e[1].record()
+        outs[1] = D.fit_disp(r["y"], xd, r["mu"], r["lai"], r["lfit"], w["priorVar"], MIN_LOG_ALPHA, 1.0, 1e-6, 100,
+                             True, m=m, out=outs[1])
+        if timed:
+            e[2].record()
+        outs[2] = D.fit_beta(r["y"], xd, sfd, r["disp"], contrast, r["beta0"], w["lam"], 1e-8, 100, out=outs[2])
+        if timed:
+            e[3].record()
+        if world > 1:
+            packed[:p, :ng] = outs[2]["beta_mat"]
+            packed[p:2 * p, :ng] = outs[2]["beta_var_mat"]
+            packed[2 * p, :ng] = outs[1]["log_alpha"]
+            dist.all_gather_into_tensor(gathered, packed)
+        return e
+
+    for i in range(max(a.warmup, 3)):
+        step(i, False)
+    torch.cuda.synchronize()
+    launches0 = L.b200nb_kernel_launches()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_start, t_end = ev(), ev()
+    t_start.record()
+    evs = [step(i, True) for i in range(a.steps)]
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = t_start.elapsed_time(t_end)
+    # keep the GPU busy a little longer so the clock sampler sees load even for very short runs
+    clocks = None
+    if rank == 0:
+        t_extra = time.time()
+        i = 0
+        while len(sampler.rows) < 3 and time.time() - t_extra < 3.0:
+            step(i, False)
+            i += 1
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+    launches = L.b200nb_kernel_launches() - launches0
+    for e in evs:
+        kern_ms["fit_disp_mle"] += e[0].elapsed_time(e[1]) / a.steps
+        kern_ms["fit_disp_map"] += e[1].elapsed_time(e[2]) / a.steps
+        kern_ms["fit_beta"] += e[2].elapsed_time(e[3]) / a.steps
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ngt = torch.tensor([ng], dtype=torch.float64, device=dev)
+        dist.all_reduce(ngt, op=dist.ReduceOp.SUM)
+        total_genes = float(ngt.item())
+    else:
+        total_genes = float(ng)
+    total_ms = float(tt.item())
+    ms_per_step = total_ms / a.steps
+    value = total_genes / (ms_per_step * 1e-3)
+
+    # ---- e2e through the C ABI with host buffers (rank-local, then max over ranks)
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(2):
+            three_calls_host(w, W)
+        ke = max(3, min(a.steps, 10))
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            three_calls_host(w, W)
+        dt = (time.perf_counter() - t0) / ke
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d, d2h = host_bytes(ng, m, p)
+        e2e = {"value": total_genes / float(tt.item()), "unit": "genes/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": float(tt.item()) * 1e3,
+               "what": "b200nb_fit_disp x2 + b200nb_fit_beta with host (R-layout, pageable) buffers"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = max(kern_ms, key=kern_ms.get)
+    if dom.startswith("fit_disp"):
+        alg_bytes = ng * (12 * m + 88)
+    else:
+        alg_bytes = ng * (20 * m + 24 * p + 40)
+    achieved = alg_bytes / (kern_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "kernel_ms": kern_ms, "alg_bytes_per_launch": alg_bytes,
+                "note": "fp64 transcendental-bound path (~300 flop/B): HBM fraction is small by construction; "
+                        "see profiles/ for FP64 pipe utilisation"}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        v, dt, cores, ns = time_oracle(w, a.cpu_sample, 2, 1)
+        cpu = {"value": v, "unit": "genes/s", "cores": cores, "kind": "port",
+               "sample": f"first {ns} genes of the workload (3 calls), oracle C restatement of src/DESeq2.cpp, "
+                         f"OpenMP {cores} threads, {dt:.2f} s per pass"}
+
+    line = {"metric": "genes/sec, DESeq2 Wald hot path (fitDisp MLE + fitDisp MAP + fitBeta)", "value": value,
+            "unit": "genes/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (makeExampleDESeqDataSet law, PCG64 seed 20260925)", "config": cfg,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "genes_fitted": total_genes}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
