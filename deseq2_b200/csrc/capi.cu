@@ -74,6 +74,26 @@ int next_counter(unsigned int** out) {
   return 0;
 }
 
+// scratch buffers for fit_disp launches (work queue + per-mode gene lists): a ring of grow-only device buffers,
+// one per launch in flight (slot reuse after kScratchRing further launches; launches on one stream are ordered).
+constexpr int kScratchRing = 16;
+void* g_scratch[kScratchRing] = {};
+size_t g_scratch_bytes[kScratchRing] = {};
+std::atomic<unsigned int> g_scratch_next{0};
+int next_scratch(size_t bytes, unsigned int** out) {
+  const unsigned int s = g_scratch_next.fetch_add(1) % kScratchRing;
+  if (g_scratch_bytes[s] < bytes) {
+    if (g_scratch[s]) CU(cudaFree(g_scratch[s]));
+    g_scratch[s] = nullptr;
+    g_scratch_bytes[s] = 0;
+    const size_t want = bytes + bytes / 4;
+    CU(cudaMalloc(&g_scratch[s], want));
+    g_scratch_bytes[s] = want;
+  }
+  *out = static_cast<unsigned int*>(g_scratch[s]);
+  return 0;
+}
+
 int check_dims(int n, int m, int p) {
   if (n < 0 || m < 1 || p < 1) return fail("bad dimensions n=%d m=%d p=%d", n, m, p);
   if (p > nb::kMaxSmallP) return fail("p=%d not supported yet by this build (max %d)", p, nb::kMaxSmallP);
@@ -141,8 +161,6 @@ int b200nb_fit_disp_dev(const void* y, int y_type, const double* x, const double
   if (check_dims(n, m, p)) return 1;
   if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
   if (use_weights && !weights) return fail("use_weights set but weights == NULL");
-  unsigned int* ctr;
-  if (next_counter(&ctr)) return 1;
   nb::DispArgs a{};
   a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.mu = mu_hat; a.w = use_weights ? weights : nullptr; a.x = x;
   a.log_alpha_in = log_alpha; a.prior_mean = log_alpha_prior_mean;
@@ -151,9 +169,11 @@ int b200nb_fit_disp_dev(const void* y, int y_type, const double* x, const double
   a.weight_threshold = weight_threshold; a.n = n; a.m = m; a.p = p; a.ld = ld;
   a.log_alpha = out_log_alpha; a.iter = out_iter; a.iter_accept = out_iter_accept; a.last_change = out_last_change;
   a.initial_lp = out_initial_lp; a.initial_dlp = out_initial_dlp; a.last_lp = out_last_lp; a.last_dlp = out_last_dlp;
-  a.last_d2lp = out_last_d2lp; a.grid = nullptr; a.grid_n = 0; a.counter = ctr;
+  a.last_d2lp = out_last_d2lp; a.grid = nullptr; a.grid_n = 0;
+  if (n == 0) return 0;
+  if (next_scratch(nb::disp_scratch_bytes(n), &a.scratch)) return 1;
   CU(nb::launch_fit_disp(a, (cudaStream_t)stream));
-  if (n > 0) g_launches++;
+  g_launches += 2;   // classify + line search
   return 0;
 }
 
@@ -166,16 +186,15 @@ int b200nb_fit_disp_grid_dev(const void* y, int y_type, const double* x, const d
   if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
   if (disp_grid_n < 2) return fail("disp_grid needs at least 2 points");
   if (use_weights && !weights) return fail("use_weights set but weights == NULL");
-  unsigned int* ctr;
-  if (next_counter(&ctr)) return 1;
   nb::DispArgs a{};
   a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.mu = mu_hat; a.w = use_weights ? weights : nullptr; a.x = x;
   a.log_alpha_in = nullptr; a.prior_mean = log_alpha_prior_mean; a.prior_sigmasq = log_alpha_prior_sigmasq;
   a.use_prior = use_prior; a.use_weights = use_weights; a.use_cr = use_cr; a.weight_threshold = weight_threshold;
   a.n = n; a.m = m; a.p = p; a.ld = ld; a.log_alpha = out_log_alpha; a.grid = disp_grid; a.grid_n = disp_grid_n;
-  a.counter = ctr;
+  if (n == 0) return 0;
+  if (next_scratch(nb::disp_scratch_bytes(n), &a.scratch)) return 1;
   CU(nb::launch_fit_disp(a, (cudaStream_t)stream));
-  if (n > 0) g_launches++;
+  g_launches++;
   return 0;
 }
 

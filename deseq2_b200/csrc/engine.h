@@ -38,9 +38,16 @@ struct DispArgs {
   // grid mode (fitDispGrid): when grid != nullptr the line search is replaced by the two-level grid
   const double* grid;
   int grid_n;
-  // work queue counter (device, zeroed by the launcher)
+  // device scratch supplied by the caller: (4 + 3 n) 32-bit words
+  // [work-queue counter | 3 per-mode gene counts | 3 per-mode gene lists]; the launcher zeroes the header
+  unsigned int* scratch;
+  // filled by the launcher from `scratch`
   unsigned int* counter;
+  const unsigned int* mode_counts;
+  const int* mode_lists;
 };
+
+inline size_t disp_scratch_bytes(int n) { return (4 + 3 * (size_t)n) * sizeof(unsigned int); }
 
 struct BetaArgs {
   const void* y;

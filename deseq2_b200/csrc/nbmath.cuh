@@ -1,9 +1,14 @@
 // nbmath.cuh -- fp64 device math for the NB-GLM kernels (sm_100a).
 //
 // Own implementations of the special functions the reference pulls from R's nmath
-// (Rf_lgammafn / Rf_digamma / Rf_trigamma, call sites /root/reference/src/DESeq2.cpp:50-58,90-96,139-145).
-// They are written for the GPU's FP64 pipe: one log + one reciprocal per fused lgamma/digamma pair,
-// the rest FMAs, no tables, no divergent slow paths beyond a short predicated shift loop.
+// (Rf_lgammafn / Rf_digamma / Rf_trigamma, call sites /root/reference/src/DESeq2.cpp:50-58,90-96,139-145)
+// and of log() for strictly positive normal arguments.  Written for the GPU's FP64 pipe:
+//   * one log + one reciprocal per fused lgamma/digamma pair, the rest FMAs;
+//   * every polynomial coefficient lives in a __constant__ table so it reaches the DFMA as a uniform-register
+//     operand filled by LDCU.128 (two coefficients per instruction) -- the first profile
+//     (profiles/r01a_fit_disp_sass_hist.txt) showed 30% of issue slots spent on UMOV/IMAD.MOV pairs
+//     materialising 64-bit immediates;
+//   * no special-case branches (callers guarantee positive, finite, normal inputs).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -12,6 +17,23 @@ namespace nb {
 
 constexpr double kHalfLog2Pi = 0.918938533204672741780329736406;  // log(sqrt(2*pi))
 constexpr double kShift = 10.0;  // arguments below this are shifted up before the asymptotic series
+
+// coefficient tables (constant bank)
+//  kLogC[k-1]  = 1 / ((2k+1) 4^k), k = 1..9 : log((1+s)/(1-s)) = t + t^3/12 + t^5/80 + ...,  t = 2s
+//  kStirC[k-1] = B_2k / (2k (2k-1)), k = 1..7
+//  kDigC[k-1]  = B_2k / (2k),        k = 1..7
+//  kTriC[k-1]  = B_2k,               k = 1..7
+__constant__ double kLogC[10] = {1.0 / 12.0,        1.0 / 80.0,         1.0 / 448.0,        1.0 / 2304.0,
+                                 1.0 / 11264.0,     1.0 / 53248.0,      1.0 / 245760.0,     1.0 / 1114112.0,
+                                 1.0 / 4980736.0,   0.0};
+__constant__ double kStirC[8] = {1.0 / 12.0,  -1.0 / 360.0, 1.0 / 1260.0, -1.0 / 1680.0,
+                                 1.0 / 1188.0, -691.0 / 360360.0, 1.0 / 156.0, 0.0};
+__constant__ double kDigC[8] = {1.0 / 12.0, -1.0 / 120.0, 1.0 / 252.0, -1.0 / 240.0,
+                                1.0 / 132.0, -691.0 / 32760.0, 1.0 / 12.0, 0.0};
+__constant__ double kTriC[8] = {1.0 / 6.0, -1.0 / 30.0, 1.0 / 42.0, -1.0 / 30.0,
+                                5.0 / 66.0, -691.0 / 2730.0, 7.0 / 6.0, 0.0};
+// ln2 split: hi has 32 trailing zero bits cleared so e*hi is exact for |e| < 2^11
+__constant__ double kLn2[2] = {6.93147180369123816490e-01, 1.90821492927058770002e-10};
 
 // fast fp64 reciprocal: MUFU.RCP64H seed (~20 bits) + 2 Newton steps (<= 1 ulp for normal inputs).
 // Callers use it only where the operand is known positive, finite and normal.
@@ -25,42 +47,78 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return r;
 }
 
+// log(x) for positive, finite, normal x (no zero / denormal / inf / nan handling).  fdlibm-style:
+// x = 2^e m, m in [sqrt(1/2), sqrt(2)); f = m - 1; t = 2f/(2+f); log m = t + t^3/12 + t^5/80 + ...
+// with the rounding error of t recovered explicitly; result assembled in hi/lo against e*ln2.
+__device__ __forceinline__ double log_pos(double x) {
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  if (hi >= 0x3ff6a09f) {  // m >= ~sqrt(2): halve
+    hi -= 0x00100000;
+    e += 1;
+  }
+  const double m = __hiloint2double(hi, lo);
+  const double f = m - 1.0;
+  const double r = rcp_fast(m + 1.0);
+  double t = f * r;
+  t = fma(f, r, t);                                  // t ~= 2 f / (2 + f)
+  const double z = t * t;
+  const double c = r * fma(f, -t, 2.0 * (f - t));    // exact_t - t
+  double p = kLogC[8];
+  p = fma(p, z, kLogC[7]);
+  p = fma(p, z, kLogC[6]);
+  p = fma(p, z, kLogC[5]);
+  p = fma(p, z, kLogC[4]);
+  p = fma(p, z, kLogC[3]);
+  p = fma(p, z, kLogC[2]);
+  p = fma(p, z, kLogC[1]);
+  p = fma(p, z, kLogC[0]);
+  const double res_lo = fma(t * z, p, c);
+  // (double)e without I2F: 2^52 + 2^31 magic
+  const double de = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
+  const double q = fma(de, kLn2[0], t);
+  const double rem = fma(de, -kLn2[0], q) - t;       // rounding error of q
+  return q + fma(de, kLn2[1], res_lo - rem);
+}
+
 // Stirling tail  sum_{k>=1} B_2k / (2k (2k-1) x^(2k-1))  evaluated as xi * poly(xi^2), x >= kShift
 __device__ __forceinline__ double stirling_tail(double xi, double xi2) {
-  double p = 1.0 / 156.0;                       // k=7
-  p = fma(p, xi2, -691.0 / 360360.0);           // k=6
-  p = fma(p, xi2, 1.0 / 1188.0);                // k=5
-  p = fma(p, xi2, -1.0 / 1680.0);               // k=4
-  p = fma(p, xi2, 1.0 / 1260.0);                // k=3
-  p = fma(p, xi2, -1.0 / 360.0);                // k=2
-  p = fma(p, xi2, 1.0 / 12.0);                  // k=1
+  double p = kStirC[6];
+  p = fma(p, xi2, kStirC[5]);
+  p = fma(p, xi2, kStirC[4]);
+  p = fma(p, xi2, kStirC[3]);
+  p = fma(p, xi2, kStirC[2]);
+  p = fma(p, xi2, kStirC[1]);
+  p = fma(p, xi2, kStirC[0]);
   return p * xi;
 }
 
 // sum_{k>=1} B_2k / (2k x^2k), x >= kShift
 __device__ __forceinline__ double digamma_tail(double xi2) {
-  double p = 1.0 / 12.0;                        // k=7
-  p = fma(p, xi2, -691.0 / 32760.0);            // k=6
-  p = fma(p, xi2, 1.0 / 132.0);                 // k=5
-  p = fma(p, xi2, -1.0 / 240.0);                // k=4
-  p = fma(p, xi2, 1.0 / 252.0);                 // k=3
-  p = fma(p, xi2, -1.0 / 120.0);                // k=2
-  p = fma(p, xi2, 1.0 / 12.0);                  // k=1
+  double p = kDigC[6];
+  p = fma(p, xi2, kDigC[5]);
+  p = fma(p, xi2, kDigC[4]);
+  p = fma(p, xi2, kDigC[3]);
+  p = fma(p, xi2, kDigC[2]);
+  p = fma(p, xi2, kDigC[1]);
+  p = fma(p, xi2, kDigC[0]);
   return p * xi2;
 }
 
 // lgamma(x) for x > 0.
 __device__ __forceinline__ double lgamma_pos(double x) {
   double prod = 1.0;
-  bool shifted = x < kShift;
+  const bool shifted = x < kShift;
   while (x < kShift) {
     prod *= x;
     x += 1.0;
   }
-  double xi = rcp_fast(x);
-  double lx = log(x);
+  const double xi = rcp_fast(x);
+  const double lx = log_pos(x);
   double r = fma(x - 0.5, lx, -x) + kHalfLog2Pi + stirling_tail(xi, xi * xi);
-  if (shifted) r -= log(prod);
+  if (shifted) r -= log_pos(prod);
   return r;
 }
 
@@ -68,21 +126,30 @@ __device__ __forceinline__ double lgamma_pos(double x) {
 __device__ __forceinline__ void lgamma_digamma_pos(double x, double& lg, double& dg) {
   // shift: prod = x (x+1) ... (x+n-1), dprod = d prod / dx
   double prod = 1.0, dprod = 0.0;
-  bool shifted = x < kShift;
+  const bool shifted = x < kShift;
   while (x < kShift) {
     dprod = fma(dprod, x, prod);
     prod *= x;
     x += 1.0;
   }
-  double xi = rcp_fast(x);
-  double xi2 = xi * xi;
-  double lx = log(x);
+  const double xi = rcp_fast(x);
+  const double xi2 = xi * xi;
+  const double lx = log_pos(x);
   lg = fma(x - 0.5, lx, -x) + kHalfLog2Pi + stirling_tail(xi, xi2);
   dg = lx - 0.5 * xi - digamma_tail(xi2);
   if (shifted) {
-    lg -= log(prod);
-    dg -= dprod / prod;
+    lg -= log_pos(prod);
+    dg -= dprod * rcp_fast(prod);
   }
+}
+
+// no-shift variant for x >= kShift (caller guarantees)
+__device__ __forceinline__ void lgamma_digamma_big(double x, double& lg, double& dg) {
+  const double xi = rcp_fast(x);
+  const double xi2 = xi * xi;
+  const double lx = log_pos(x);
+  lg = fma(x - 0.5, lx, -x) + kHalfLog2Pi + stirling_tail(xi, xi2);
+  dg = lx - 0.5 * xi - digamma_tail(xi2);
 }
 
 __device__ __forceinline__ double digamma_pos(double x) {
@@ -95,18 +162,18 @@ __device__ __forceinline__ double digamma_pos(double x) {
 __device__ __forceinline__ double trigamma_pos(double x) {
   double s = 0.0;
   while (x < kShift) {
-    double xi = 1.0 / x;
+    const double xi = 1.0 / x;
     s = fma(xi, xi, s);
     x += 1.0;
   }
-  double xi = 1.0 / x, xi2 = xi * xi;
-  double p = 7.0 / 6.0;                         // B14
-  p = fma(p, xi2, -691.0 / 2730.0);             // B12
-  p = fma(p, xi2, 5.0 / 66.0);                  // B10
-  p = fma(p, xi2, -1.0 / 30.0);                 // B8
-  p = fma(p, xi2, 1.0 / 42.0);                  // B6
-  p = fma(p, xi2, -1.0 / 30.0);                 // B4
-  p = fma(p, xi2, 1.0 / 6.0);                   // B2
+  const double xi = 1.0 / x, xi2 = xi * xi;
+  double p = kTriC[6];
+  p = fma(p, xi2, kTriC[5]);
+  p = fma(p, xi2, kTriC[4]);
+  p = fma(p, xi2, kTriC[3]);
+  p = fma(p, xi2, kTriC[2]);
+  p = fma(p, xi2, kTriC[1]);
+  p = fma(p, xi2, kTriC[0]);
   return s + xi + 0.5 * xi2 + p * xi2 * xi;
 }
 
@@ -117,12 +184,60 @@ __device__ __forceinline__ double warp_allreduce_sum(double v) {
   return v;
 }
 
+__device__ __forceinline__ double warp_allreduce_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 template <int N>
 __device__ __forceinline__ void warp_allreduce_sum_n(double (&v)[N]) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
     for (int i = 0; i < N; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+}
+
+// All-reduce of N per-lane partial sums, N a power of two <= 32, as a butterfly reduce-scatter followed by
+// an all-gather: log2(N) halving exchange rounds (N/2 + N/4 + ... + 1 values shuffled), plain butterflies for
+// the remaining rounds, then N indexed shuffles.  ~2.4x fewer SHFL than N independent butterflies for N = 8.
+// The result is bitwise identical in every lane (each value is reduced along one fixed tree).
+template <int N>
+__device__ __forceinline__ void warp_allreduce_sum_rs(double (&v)[N], int lane) {
+  static_assert(N >= 1 && N <= 32 && (N & (N - 1)) == 0, "N must be a power of two <= 32");
+  int width = N;  // number of live values in v[0 .. width)
+  int o = 16;
+#pragma unroll
+  for (; o > 0 && width > 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+    const int half = width / 2;
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+      if (i < half) {
+        // lower lanes keep v[i], send v[i+half]; upper lanes keep v[i+half], send v[i]
+        const double keep = upper ? v[i + half] : v[i];
+        const double send = upper ? v[i] : v[i + half];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    width = half;
+  }
+#pragma unroll
+  for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+  // value index i (original) now sits in v[0] of the lanes whose upper bits spell i: gather
+  const double mine = v[0];
+  constexpr int LOGN = (N == 1) ? 0 : (N == 2) ? 1 : (N == 4) ? 2 : (N == 8) ? 3 : (N == 16) ? 4 : 5;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    // lane holding original index i: bit (16 >> s) set iff bit (LOGN-1-s) of i ... built below
+    int src = 0;
+#pragma unroll
+    for (int s = 0; s < LOGN; s++) {
+      // round s (offset 16>>s) split the live range in halves: upper lanes kept the upper half
+      if ((i >> (LOGN - 1 - s)) & 1) src |= (16 >> s);
+    }
+    v[i] = __shfl_sync(0xffffffffu, mine, src);
   }
 }
 

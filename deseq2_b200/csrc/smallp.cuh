@@ -135,4 +135,47 @@ __device__ __forceinline__ bool spd_solve_equilibrated(SymP<P>& A, double (&b)[P
   return ok;
 }
 
+// Cox-Reid pieces for B = X'WX (SPD): det(B), and tr(B^-1 dB) when WANT_TR.
+// p = 1, 2, 3 use the adjugate (no square roots, one reciprocal); larger p the Cholesky factor.
+template <int P, bool WANT_TR>
+__device__ __forceinline__ void cr_det_trace(const SymP<P>& B, const SymP<P>& dB, double& det, double& tr) {
+  tr = 0.0;
+  if constexpr (P == 1) {
+    det = B.v[0];
+    if (WANT_TR) tr = dB.v[0] * rcp_fast(det);
+  } else if constexpr (P == 2) {
+    const double b00 = B.v[0], b10 = B.v[1], b11 = B.v[2];
+    det = fma(b00, b11, -b10 * b10);
+    if (WANT_TR) tr = (fma(b11, dB.v[0], fma(b00, dB.v[2], -2.0 * b10 * dB.v[1]))) * rcp_fast(det);
+  } else if constexpr (P == 3) {
+    const double b00 = B.v[0], b10 = B.v[1], b11 = B.v[2], b20 = B.v[3], b21 = B.v[4], b22 = B.v[5];
+    // cofactors (symmetric adjugate)
+    const double c00 = fma(b11, b22, -b21 * b21);
+    const double c10 = fma(b21, b20, -b10 * b22);
+    const double c20 = fma(b10, b21, -b11 * b20);
+    const double c11 = fma(b00, b22, -b20 * b20);
+    const double c21 = fma(b10, b20, -b00 * b21);
+    const double c22 = fma(b00, b11, -b10 * b10);
+    det = fma(b00, c00, fma(b10, c10, b20 * c20));
+    if (WANT_TR) {
+      double t = c00 * dB.v[0];
+      t = fma(c11, dB.v[2], t);
+      t = fma(c22, dB.v[5], t);
+      t = fma(2.0 * c10, dB.v[1], t);
+      t = fma(2.0 * c20, dB.v[3], t);
+      t = fma(2.0 * c21, dB.v[4], t);
+      tr = t * rcp_fast(det);
+    }
+  } else {
+    SymP<P> L = B;
+    chol_factor<P>(L);
+    det = chol_det<P>(L);
+    if (WANT_TR) {
+      SymP<P> Bi;
+      chol_inverse<P>(L, Bi);
+      tr = sym_trace_prod<P>(Bi, dB);
+    }
+  }
+}
+
 }  // namespace nb

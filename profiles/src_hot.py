@@ -20,13 +20,19 @@ lo = starts[which]; hi = starts[which + 1] if which + 1 < len(starts) else len(t
 agg = collections.Counter(); stall = collections.Counter(); src = {}; total = 0; nsass = 0
 for fp, hdr, body in tables[lo:hi]:
     ie = hdr.index("Instructions Executed"); ss = hdr.index("Warp Stall Sampling (All Samples)")
+    cur = None
+    ai = hdr.index("Address")
     for r in body:
+        if r[0]:
+            cur = (fp.split("/")[-1], r[0]); src[cur] = r[1].strip()
+            continue            # the source-line row itself only repeats the sum of its SASS rows
+        if not r[ai]:
+            continue
         try:
             n = int(r[ie] or 0); s = int(r[ss] or 0)
         except ValueError:
             continue
-        key = (fp.split("/")[-1], r[0]); agg[key] += n; stall[key] += s; total += n; nsass += 1
-        if r[1]: src[key] = r[1].strip()
+        key = cur; agg[key] += n; stall[key] += s; total += n; nsass += 1
 print("SASS instructions:", nsass, " warp-instructions executed:", total, " stall samples:", sum(stall.values()))
 print("%-16s %6s %7s %7s  %s" % ("file", "line", "inst%", "stall%", "source"))
 for key, n in agg.most_common(45):
