@@ -1,0 +1,84 @@
+"""The C-ABI library loads without a GPU and exports exactly the symbols include/b200nb.h declares; the product
+has no CPU fallback (compute calls fail loudly without a device) and never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "b200nb.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200nb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported_and_bound():
+    import deseq2_b200
+    from deseq2_b200 import _lib
+    lib = deseq2_b200.lib()
+    syms = _header_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b200nb.h but not exported by libb200nb.so"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in deseq2_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == syms
+    out = subprocess.run(["nm", "-D", "--defined-only", deseq2_b200.lib_path()], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r"\b(b200nb_[a-z0-9_]+)\b", out)))
+    assert exported == syms, "exported b200nb_* symbols differ from the header"
+    assert lib.b200nb_version().startswith(b"b200nb")
+    assert lib.b200nb_kernel_launches() >= 0
+
+
+def test_no_cpu_fallback():
+    import deseq2_b200
+    from deseq2_b200 import wrappers
+    if deseq2_b200.lib().b200nb_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    y = np.ones((4, 6), dtype=np.int32)
+    x = np.c_[np.ones(6), np.r_[0, 0, 0, 1, 1, 1.0]]
+    with pytest.raises(deseq2_b200.EngineError):
+        wrappers.fitDisp(y, x, np.ones((4, 6)), np.zeros(4), np.zeros(4), 1.0, -20.0, 1.0, 1e-6, 10, False, None, False,
+                         1e-2, True)
+    with pytest.raises(deseq2_b200.EngineError):
+        wrappers.fitBeta(y, x, np.ones((4, 6)), np.ones(4), [1, 0], np.zeros((4, 2)), [1e-6, 1e-6], None, False, 1e-8,
+                         10, True, 0.5)
+
+
+def test_argument_errors_are_reported():
+    import deseq2_b200
+    lib = deseq2_b200.lib()
+    rc = lib.b200nb_fit_disp(None, 0, None, None, None, None, 1.0, -20.0, 1.0, 1e-6, 10, 0, None, 0, 1e-2, 1, 5, 0, 2,
+                             *([None] * 9))
+    assert rc != 0 and b"bad dimensions" in lib.b200nb_last_error()
+    rc = lib.b200nb_fit_beta(None, 0, None, None, None, None, None, None, None, 0, 1e-8, 10, 1, 0.5, 5, 6, 64,
+                             *([None] * 8))
+    assert rc != 0 and b"not supported" in lib.b200nb_last_error()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "deseq2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "nbglm_oracle" not in txt, f
+
+
+def test_na_screening_mirrors_r_wrappers():
+    """R/wrappers.R:30-34,109-113: NA in any argument is an error raised before the native call."""
+    from deseq2_b200 import wrappers
+    y = np.ones((3, 4))
+    x = np.c_[np.ones(4), [0, 0, 1, 1.0]]
+    mu = np.ones((3, 4))
+    mu[1, 2] = np.nan
+    with pytest.raises(ValueError, match="mu_hatSEXP"):
+        wrappers.fitDispWrapper(y, x, mu, np.zeros(3), np.zeros(3), 1.0, -20, 1.0, 1e-6, 10, False, None, False, 1e-2, True)
+    with pytest.raises(ValueError, match="alpha_hatSEXP"):
+        wrappers.fitBetaWrapper(y, x, np.ones((3, 4)), np.array([1.0, np.nan, 1.0]), np.zeros((3, 2)), [1e-6, 1e-6], None,
+                                False, 1e-8, 10, True, 0.5)

@@ -124,3 +124,166 @@ def test_fit_beta_maxit0_contrast(engine, oracle):
     g, o = engine.fitBeta(**a), oracle.fitBeta(**a)
     assert np.all(g["iter"] == 0)
     _compare_beta(g, o, "maxit0")
+
+
+# ---------------------------------------------------------------- evaluation modes, weights, designs
+
+def test_fit_disp_big_and_mixed_counts(engine, oracle):
+    """High-count genes (BIG mode: every count >= 10), mixed genes (GEN mode: max >= 256 and min < 10) and
+    low-count genes (TAB mode) in one call."""
+    c = make_case(1200, 48, seed=41, interceptMean=8.0, interceptSD=3.0)
+    y = c["counts"]
+    big = np.flatnonzero(y.max(axis=1) >= 256)[:80]          # force GEN mode: a few tiny counts in high-count genes
+    y[big, :3] = np.arange(3 * len(big)).reshape(len(big), 3) % 7
+    assert (y.min(axis=1) >= 10).sum() > 100 and ((y.max(axis=1) >= 256) & (y.min(axis=1) < 10)).sum() > 20
+    assert (y.max(axis=1) < 256).sum() > 50
+    a = disp_args(c, c["mu"], np.log(c["alpha0"]))
+    _compare_disp(engine.fitDisp(**a), oracle.fitDisp(**a, with_margin=True), "modes", min_robust=0.85)
+
+
+def test_fit_disp_non_integer_counts(engine, oracle):
+    c = make_case(300, 16, seed=42)
+    y = c["counts"].astype(np.float64) + 0.25
+    a = disp_args(c, c["mu"], np.log(c["alpha0"]), y=y)
+    _compare_disp(engine.fitDisp(**a), oracle.fitDisp(**a, with_margin=True), "non-integer y", min_robust=0.8)
+
+
+def _weights_for(c, seed, p_small=0.08):
+    rng = np.random.default_rng(seed)
+    w = rng.uniform(0.3, 1.0, c["counts"].shape)
+    w[rng.random(w.shape) < p_small] = 1e-3          # below the Cox-Reid weightThreshold (1e-2)
+    return np.maximum(w / w.max(axis=1, keepdims=True), 1e-6)
+
+
+@pytest.mark.parametrize("design,seed", [("condition", 51), ("batch", 52), ("factor4", 53)])
+def test_fit_disp_weights_and_designs(engine, oracle, design, seed):
+    from deseq2_b200 import synth
+    m = 24
+    x = {"condition": synth.design_condition(m), "batch": synth.design_batch_condition(m, 2),
+         "factor4": synth.design_factor(m, 4)}[design]
+    c = make_case(500, m, x=x, seed=seed)
+    alpha = np.clip(0.1 + 4 / c["baseMean"], 1e-8, m)
+    mu = c["mu"] if c["mu"] is not None else np.maximum(
+        c["nf"] * np.exp(oracle.fitBeta(**beta_args(c, alpha))["beta_mat"] @ x.T), 0.5)
+    w = _weights_for(c, seed)
+    a = disp_args(c, mu, np.log(c["alpha0"]), prior_mean=np.log(alpha), sigmasq=0.8, usePrior=True, weights=w,
+                  useWeights=True)
+    _compare_disp(engine.fitDisp(**a), oracle.fitDisp(**a, with_margin=True), f"weights/{design}", min_robust=0.85)
+
+
+def test_fit_disp_weights_drop_a_design_column(engine, oracle):
+    """Cox-Reid column removal (src/DESeq2.cpp:41-43): every sample of the second group below the weight
+    threshold -> that design column is all zero on the kept rows and is dropped."""
+    from deseq2_b200 import synth
+    m = 12
+    c = make_case(200, m, x=synth.design_condition(m), seed=54)
+    w = np.ones(c["counts"].shape)
+    w[:, m // 2:] = 5e-3
+    a = disp_args(c, c["mu"], np.log(c["alpha0"]), weights=w, useWeights=True)
+    _compare_disp(engine.fitDisp(**a), oracle.fitDisp(**a, with_margin=True), "dropped column", min_robust=0.8)
+
+
+@pytest.mark.parametrize("design,seed,useQR", [("batch", 61, True), ("factor4", 62, False), ("intercept", 63, True)])
+def test_fit_beta_designs_weights_nf_matrix(engine, oracle, design, seed, useQR):
+    from deseq2_b200 import synth
+    m = 24
+    x = {"batch": synth.design_batch_condition(m, 2), "factor4": synth.design_factor(m, 4),
+         "intercept": np.ones((m, 1))}[design]
+    c = make_case(600, m, x=x if design != "intercept" else None, seed=seed)
+    if design == "intercept":
+        c["x"] = x
+        c["beta0"] = np.log(c["baseMean"])[:, None]
+    rng = np.random.default_rng(seed)
+    nf = c["nf"] * np.exp(rng.normal(0, 0.2, c["nf"].shape))          # gene-specific normalisation factors
+    nf /= np.exp(np.mean(np.log(nf), axis=1, keepdims=True))
+    alpha = np.clip(0.1 + 4 / c["baseMean"], 1e-8, m)
+    w = _weights_for(c, seed, p_small=0.0)
+    p = x.shape[1]
+    lam = np.full(p, 1e-6) / np.log(2) ** 2
+    if p > 1:
+        lam[-1] = 0.3
+    a = beta_args(c, alpha, nf=nf, weights=w, useWeights=True, useQR=useQR, lam=lam, x=x,
+                  contrast=np.r_[np.zeros(p - 1), 1.0])
+    _compare_beta(engine.fitBeta(**a), oracle.fitBeta(**a), f"beta/{design}")
+
+
+def test_fit_beta_badly_scaled_covariate(engine, oracle):
+    """test_optim.R:2-26: a continuous covariate with sd 1000 -- the equilibrated Cholesky must track the QR branch."""
+    rng = np.random.default_rng(71)
+    m = 20
+    x = np.c_[np.ones(m), rng.normal(0, 1000, m)]
+    c = make_case(300, m, seed=72)
+    c["x"] = x
+    Q, R = np.linalg.qr(x)
+    c["beta0"] = np.linalg.solve(R, Q.T @ np.log(c["counts"] / c["nf"] + 0.1).T).T
+    alpha = np.clip(0.1 + 4 / c["baseMean"], 1e-8, m)
+    a = beta_args(c, alpha, x=x)
+    g, o = engine.fitBeta(**a), oracle.fitBeta(**a)
+    conv = o["iter"] < 100
+    assert np.array_equal(g["iter"][conv], o["iter"][conv])
+    assert np.nanmax(rel_err(g["beta_mat"][conv], o["beta_mat"][conv], floor=1e-9)) < TOL
+    assert np.nanmax(rel_err(np.sqrt(g["beta_var_mat"][conv]), np.sqrt(o["beta_var_mat"][conv]))) < TOL
+
+
+def test_fit_beta_divergence_sentinel(engine):
+    """test_optim.R:29-39 on the engine: the 0/1000 row must report iter == maxit."""
+    y = np.array([[0, 0, 0, 0, 0, 1000, 1000, 0, 0, 0], [5, 7, 6, 4, 5, 9, 11, 8, 10, 12]], dtype=np.int32)
+    x = np.c_[np.ones(10), np.r_[np.zeros(5), np.ones(5)]]
+    r = engine.fitBeta(y, x, np.ones((2, 10)), [0.1, 0.1], [1, 0], np.ones((2, 2)), np.full(2, 1e-6) / np.log(2) ** 2,
+                       None, False, 1e-8, 100, True, 0.5)
+    assert r["iter"][0] == 100 and r["iter"][1] < 100
+
+
+def test_fit_beta_weight_zero_equals_dropped_sample(engine):
+    c = make_case(200, 10, seed=73)
+    alpha = np.clip(0.1 + 4 / c["baseMean"], 1e-8, 10)
+    w = np.ones(c["counts"].shape)
+    w[:, 0] = 0.0
+    a = engine.fitBeta(**beta_args(c, alpha, weights=w, useWeights=True))
+    sub = dict(c)
+    sub["counts"], sub["nf"], sub["x"] = c["counts"][:, 1:], c["nf"][:, 1:], c["x"][1:]
+    b = engine.fitBeta(**beta_args(sub, alpha))
+    assert np.allclose(a["beta_mat"], b["beta_mat"], atol=1e-8)
+    assert np.allclose(a["beta_var_mat"], b["beta_var_mat"], rtol=1e-7)
+    assert np.allclose(a["deviance"], b["deviance"], rtol=1e-9)
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE.json config 2)
+
+def test_c2_full_size_properties(engine, oracle):
+    """50k x 100 is too slow to check gene by gene against the oracle in a test; use size-independent properties:
+    chunked == whole, restart-from-optimum is a fixed point, maxit=0 reproduces the covariance block, and an
+    oracle spot check on a random 1% of the genes."""
+    c = make_case(50000, 100, seed=20260923 + 2)
+    n = len(c["counts"])
+    a = disp_args(c, c["mu"], np.log(c["alpha0"]))
+    g = engine.fitDisp(**a)
+    # chunked == whole (bitwise: genes are independent and the kernels are deterministic)
+    sl = slice(12345, 13345)
+    sub = {k: (v[sl] if isinstance(v, np.ndarray) and v.shape[:1] == (n,) else v) for k, v in a.items()}
+    gs = engine.fitDisp(**sub)
+    for k in DISP_KEYS + ("iter", "iter_accept"):
+        assert np.array_equal(gs[k], g[k][sl]), k
+    # restart from the optimum with a tiny tolerance: the first accepted step must already satisfy change < tol
+    conv = (g["iter"] < 100) & (g["log_alpha"] > np.log(1e-7))
+    a2 = disp_args(c, c["mu"], g["log_alpha"])
+    g2 = engine.fitDisp(**a2)
+    assert np.max(np.abs(g2["log_alpha"][conv] - g["log_alpha"][conv])) < 5e-2
+    assert np.all(g2["last_lp"][conv] >= g["last_lp"][conv] - 1e-6 * (1 + np.abs(g["last_lp"][conv])))
+    # oracle spot check
+    rng = np.random.default_rng(0)
+    idx = np.sort(rng.choice(n, 500, replace=False))
+    subo = {k: (v[idx] if isinstance(v, np.ndarray) and v.shape[:1] == (n,) else v) for k, v in a.items()}
+    o = oracle.fitDisp(**subo, with_margin=True)
+    gsub = {k: v[idx] for k, v in g.items()}
+    _compare_disp(gsub, o, "c2 spot check")
+    # fitBeta: maxit = 0 from the fitted coefficients reproduces variance / hat diagonal / contrast
+    alpha = np.clip(np.exp(g["log_alpha"]), 1e-8, 100)
+    fb = engine.fitBeta(**beta_args(c, alpha))
+    fb0 = engine.fitBeta(**beta_args(c, alpha, beta0=fb["beta_mat"], maxit=0))
+    for k in ("beta_var_mat", "hat_diagonals", "contrast_num", "contrast_denom"):
+        assert np.nanmax(rel_err(fb0[k], fb[k], floor=1e-12)) < 1e-9, k
+    # hat diagonals sum to the effective number of parameters (trace of the hat matrix <= p)
+    tr = fb["hat_diagonals"].sum(axis=1)
+    ok = fb["iter"] < 100
+    assert np.all(tr[ok] <= 2 + 1e-9) and np.median(tr[ok]) > 1.99
