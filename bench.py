@@ -164,6 +164,7 @@ def time_oracle(w, n_sample, steps, warmup):
 
 def main():
     a = parse()
+    os.environ["NCCL_DEBUG"] = os.environ.get("B200NB_NCCL_DEBUG", "WARN")   # keep NCCL's banner off stdout
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -202,7 +203,14 @@ def main():
     L = deseq2_b200.lib()
 
     w = build_workload(n, m, 20260923 + 2 + 1000 * rank, W)
-    ng = len(w["counts"])
+    ng = len(w["counts"])           # genes with a non-zero row sum: the ones that count for `value`
+    if world > 1 and ng < n:
+        # equal shard shapes for the all-gather: top the shard up to n rows by repeating its first genes
+        # (extra work that is NOT counted in `value`)
+        idx = np.r_[np.arange(ng), np.arange(n - ng) % ng]
+        for k in ("counts", "mu", "nf", "log_alpha0", "log_dispInit", "log_dispFit", "dispersion", "beta0"):
+            w[k] = np.asfortranarray(w[k][idx])
+    nrow = len(w["counts"])
     p = w["x"].shape[1]
     NREP = 4
     reps = []
@@ -217,9 +225,18 @@ def main():
     contrast = np.r_[1.0, np.zeros(p - 1)]
     outs = [None, None, None]
     # per-step result exchange (N > 1): beta, beta_var, log dispersion, padded to n genes per rank
-    gathered = torch.empty((world, 2 * p + 1, n), dtype=torch.float64, device=dev) if world > 1 else None
-    packed = torch.zeros((2 * p + 1, n), dtype=torch.float64, device=dev) if world > 1 else None
+    # the kernels write beta (p x n), Var beta (p x n) and the MAP log-dispersion (n) straight into `packed`
+    gathered = torch.empty((world, 2 * p + 1, nrow), dtype=torch.float64, device=dev) if world > 1 else None
+    packed = torch.zeros((2 * p + 1, nrow), dtype=torch.float64, device=dev) if world > 1 else None
 
+    if world > 1:
+        f64 = lambda *sh: torch.empty(sh, dtype=torch.float64, device=dev)
+        outs[1] = {k: f64(nrow) for k in ("last_change", "initial_lp", "initial_dlp", "last_lp", "last_dlp", "last_d2lp")}
+        outs[1].update(log_alpha=packed[2 * p], iter=torch.empty(nrow, dtype=torch.int32, device=dev),
+                       iter_accept=torch.empty(nrow, dtype=torch.int32, device=dev))
+        ldd = D.ld_for(m)
+        outs[2] = dict(beta_mat=packed[:p], beta_var_mat=packed[p:2 * p], iter=f64(nrow), contrast_num=f64(nrow),
+                       contrast_denom=f64(nrow), deviance=f64(nrow), hat_diagonals=f64(nrow, ldd), mu=f64(nrow, ldd))
     ev = lambda: torch.cuda.Event(enable_timing=True)
     kern_ms = {"fit_disp_mle": 0.0, "fit_disp_map": 0.0, "fit_beta": 0.0}
 
@@ -240,9 +257,6 @@ def main():
         if timed:
             e[3].record()
         if world > 1 and comm:
-            packed[:p, :ng] = outs[2]["beta_mat"]
-            packed[p:2 * p, :ng] = outs[2]["beta_var_mat"]
-            packed[2 * p, :ng] = outs[1]["log_alpha"]
             dist.all_gather_into_tensor(gathered, packed)
         return e
 

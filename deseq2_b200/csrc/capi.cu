@@ -5,8 +5,11 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/b200nb.h"
 #include "engine.h"
@@ -181,9 +184,85 @@ int next_scratch(size_t bytes, unsigned int** out) {
   return 0;
 }
 
+// ---------------------------------------------------------------- design analysis for the general-p kernels
+// Distinct rows of the design matrix (what R/core.R:2450 modelMatrixGroups computes) and a row id per sample.
+// <= 32 distinct rows: GROUPED (xg = G x ps); otherwise SAMPLEWISE (xg = all m rows, gid[j] = j).
+bool use_generic(int p) {
+  static const bool force = getenv("B200NB_FORCE_GENERIC") != nullptr;
+  return force || p > nb::kMaxSmallP;
+}
+
+struct DesignDev {
+  const double* xg;
+  const int* gid;
+  int G, grouped;
+};
+constexpr int kDesignRing = 16;
+void* g_design[kDesignRing] = {};
+size_t g_design_bytes[kDesignRing] = {};
+std::atomic<unsigned int> g_design_next{0};
+
+// x_host: m x p column-major.  Uploads xg / gid on `st`.
+int prepare_design(const double* x_host, int m, int p, cudaStream_t st, DesignDev* out) {
+  const int ps = p | 1;
+  std::vector<int> gid(m), rep;
+  for (int j = 0; j < m; j++) {
+    int found = -1;
+    for (size_t g = 0; g < rep.size() && found < 0; g++) {
+      bool same = true;
+      for (int k = 0; k < p && same; k++) same = (x_host[j + (size_t)m * k] == x_host[rep[g] + (size_t)m * k]);
+      if (same) found = (int)g;
+    }
+    if (found < 0) {
+      if (rep.size() > 32) break;   // too many distinct rows: samplewise
+      found = (int)rep.size();
+      rep.push_back(j);
+    }
+    gid[j] = found;
+  }
+  const bool grouped = rep.size() <= 32;
+  const int rows = grouped ? (int)rep.size() : m;
+  std::vector<double> xg((size_t)rows * ps, 0.0);
+  for (int r = 0; r < rows; r++) {
+    const int j = grouped ? rep[r] : r;
+    for (int k = 0; k < p; k++) xg[(size_t)r * ps + k] = x_host[j + (size_t)m * k];
+  }
+  if (!grouped)
+    for (int j = 0; j < m; j++) gid[j] = j;
+  const size_t xbytes = xg.size() * sizeof(double), gbytes = (size_t)m * sizeof(int);
+  const size_t need = ((xbytes + 15) & ~(size_t)15) + gbytes;
+  const unsigned int s = g_design_next.fetch_add(1) % kDesignRing;
+  if (g_design_bytes[s] < need) {
+    if (g_design[s]) CU(cudaFree(g_design[s]));
+    g_design[s] = nullptr;
+    g_design_bytes[s] = 0;
+    CU(cudaMalloc(&g_design[s], need + need / 4));
+    g_design_bytes[s] = need + need / 4;
+  }
+  char* base = static_cast<char*>(g_design[s]);
+  // pageable H2D copies are staged before cudaMemcpyAsync returns, so the vectors may die at scope exit
+  CU(cudaMemcpyAsync(base, xg.data(), xbytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(base + ((xbytes + 15) & ~(size_t)15), gid.data(), gbytes, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  out->xg = reinterpret_cast<const double*>(base);
+  out->gid = reinterpret_cast<const int*>(base + ((xbytes + 15) & ~(size_t)15));
+  out->G = grouped ? (int)rep.size() : m;
+  out->grouped = grouped ? 1 : 0;
+  return 0;
+}
+
+// design matrix given as a DEVICE pointer (the *_dev entry points): fetch it (m*p doubles) and analyse.
+// This synchronises `st`; it only happens on the general-p path.
+int prepare_design_from_device(const double* x_dev, int m, int p, cudaStream_t st, DesignDev* out) {
+  std::vector<double> xh((size_t)m * p);
+  CU(cudaMemcpyAsync(xh.data(), x_dev, xh.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return prepare_design(xh.data(), m, p, st, out);
+}
+
 int check_dims(int n, int m, int p) {
   if (n < 0 || m < 1 || p < 1) return fail("bad dimensions n=%d m=%d p=%d", n, m, p);
-  if (p > nb::kMaxSmallP) return fail("p=%d not supported yet by this build (max %d)", p, nb::kMaxSmallP);
+  if (p > nb::kMaxP) return fail("p=%d not supported (max %d design columns)", p, nb::kMaxP);
   return 0;
 }
 
@@ -267,6 +346,14 @@ int b200nb_fit_disp_dev(const void* y, int y_type, const double* x, const double
   a.last_d2lp = out_last_d2lp; a.grid = nullptr; a.grid_n = 0;
   if (n == 0) return 0;
   if (next_scratch(nb::disp_scratch_bytes(n), &a.scratch)) return 1;
+  if (use_generic(p)) {
+    DesignDev dd;
+    if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
+    a.xg = dd.xg; a.gid = dd.gid; a.G = dd.G; a.grouped = dd.grouped;
+    CU(nb::launch_fit_disp_generic(a, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+  }
   CU(nb::launch_fit_disp(a, (cudaStream_t)stream));
   g_launches += 2;   // classify + line search
   return 0;
@@ -288,6 +375,14 @@ int b200nb_fit_disp_grid_dev(const void* y, int y_type, const double* x, const d
   a.n = n; a.m = m; a.p = p; a.ld = ld; a.log_alpha = out_log_alpha; a.grid = disp_grid; a.grid_n = disp_grid_n;
   if (n == 0) return 0;
   if (next_scratch(nb::disp_scratch_bytes(n), &a.scratch)) return 1;
+  if (use_generic(p)) {
+    DesignDev dd;
+    if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
+    a.xg = dd.xg; a.gid = dd.gid; a.G = dd.G; a.grouped = dd.grouped;
+    CU(nb::launch_fit_disp_generic(a, (cudaStream_t)stream));
+    g_launches++;
+    return 0;
+  }
   CU(nb::launch_fit_disp(a, (cudaStream_t)stream));
   g_launches++;
   return 0;
@@ -313,6 +408,15 @@ int b200nb_fit_beta_dev(const void* y, int y_type, const double* x, const double
   a.n = n; a.m = m; a.p = p; a.ld = ld; a.beta_out = out_beta_mat; a.beta_var = out_beta_var_mat; a.iter = out_iter;
   a.hat_diag = out_hat_diagonals; a.mu_out = out_mu; a.contrast_num = out_contrast_num;
   a.contrast_denom = out_contrast_denom; a.deviance = out_deviance; a.counter = ctr;
+  if (use_generic(p)) {
+    if (n == 0) return 0;
+    DesignDev dd;
+    if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
+    a.xg = dd.xg; a.gid = dd.gid; a.G = dd.G; a.grouped = dd.grouped;
+    CU(nb::launch_fit_beta_generic(a, (cudaStream_t)stream));
+    g_launches++;
+    return 0;
+  }
   CU(nb::launch_fit_beta(a, (cudaStream_t)stream));
   if (n > 0) g_launches++;
   return 0;

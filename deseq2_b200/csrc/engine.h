@@ -38,6 +38,10 @@ struct DispArgs {
   // grid mode (fitDispGrid): when grid != nullptr the line search is replaced by the two-level grid
   const double* grid;
   int grid_n;
+  // general-p path (fit_generic.cu): distinct design rows and per-sample row ids, prepared by the C-ABI layer
+  const double* xg;   // G x (p|1) (grouped) or m x (p|1) (samplewise)
+  const int* gid;     // m
+  int G, grouped;
   // device scratch supplied by the caller: (4 + 3 n) 32-bit words
   // [work-queue counter | 3 per-mode gene counts | 3 per-mode gene lists]; the launcher zeroes the header
   unsigned int* scratch;
@@ -77,11 +81,18 @@ struct BetaArgs {
   double* contrast_denom;    // n
   double* deviance;          // n
   unsigned int* counter;
+  // general-p path (fit_generic.cu)
+  const double* xg;
+  const int* gid;
+  int G, grouped;
 };
 
 // returns cudaSuccess or the launch error; kernels are enqueued on `stream`
 cudaError_t launch_fit_disp(const DispArgs& a, cudaStream_t stream);
 cudaError_t launch_fit_beta(const BetaArgs& a, cudaStream_t stream);
+// any p <= kMaxP (shared-memory normal equations, grouped design); used for p > kMaxSmallP
+cudaError_t launch_fit_disp_generic(const DispArgs& a, cudaStream_t stream);
+cudaError_t launch_fit_beta_generic(const BetaArgs& a, cudaStream_t stream);
 
 // layout helpers (layout.cu)
 // column-major n x m (R) -> gene-major n x ld.  elem_size 4 or 8.

@@ -287,3 +287,75 @@ def test_c2_full_size_properties(engine, oracle):
     tr = fb["hat_diagonals"].sum(axis=1)
     ok = fb["iter"] < 100
     assert np.all(tr[ok] <= 2 + 1e-9) and np.median(tr[ok]) > 1.99
+
+
+# ---------------------------------------------------------------- general p (5 <= p <= 32): shared-memory path
+
+def _mu_from_fit(oracle, c, x, alpha, lam=None, beta0=None):
+    fit = oracle.fitBeta(**beta_args(c, alpha, x=x, lam=lam, beta0=beta0))
+    return np.maximum(c["nf"] * np.exp(fit["beta_mat"] @ x.T), 0.5)
+
+
+@pytest.mark.parametrize("kind,seed", [("factor10", 81), ("expanded11", 82), ("covariates7", 83)])
+def test_general_p_parity(engine, oracle, kind, seed):
+    """BASELINE.json config 4 shapes (10-level factor: p=10 MLE pass, 11-column expanded matrix with ridge) and a
+    design with continuous covariates (> 32 distinct rows -> samplewise normal equations)."""
+    from deseq2_b200 import synth
+    rng = np.random.default_rng(seed)
+    m = 60
+    if kind == "factor10":
+        x = synth.design_factor(m, 10)
+        lam = np.full(10, 1e-6) / np.log(2) ** 2
+    elif kind == "expanded11":
+        x = synth.design_factor_expanded(m, 10)
+        lam = np.r_[1e-6, np.full(10, 1.0 / 0.7)] / np.log(2) ** 2
+    else:
+        x = np.c_[synth.design_batch_condition(m, 3), rng.normal(0, 1, (m, 3))]
+        lam = np.full(7, 1e-6) / np.log(2) ** 2
+    p = x.shape[1]
+    xgen = synth.design_factor(m, 10) if kind == "expanded11" else x
+    c = make_case(400, m, x=xgen, seed=seed, betaSD=0.5)
+    c["x"] = x
+    n = len(c["counts"])
+    if kind == "expanded11":
+        beta0 = np.zeros((n, p))
+        beta0[:, 0] = np.log(c["baseMean"])
+    else:
+        Q, R = np.linalg.qr(x)
+        beta0 = np.linalg.solve(R, Q.T @ np.log(c["counts"] / c["nf"] + 0.1).T).T
+    alpha = np.clip(0.1 + 4 / c["baseMean"], 1e-8, m)
+    a = beta_args(c, alpha, x=x, lam=lam, beta0=beta0, contrast=np.r_[np.zeros(p - 1), 1.0])
+    g, o = engine.fitBeta(**a), oracle.fitBeta(**a)
+    _compare_beta(g, o, f"beta/{kind}", tol=2e-6 if kind == "expanded11" else TOL)
+    mu = np.maximum(c["nf"] * np.exp(o["beta_mat"] @ x.T), 0.5)
+    xd = xgen if kind == "expanded11" else x       # dispersion fits always use the full-rank matrix
+    c["x"] = xd
+    d = disp_args(c, mu, np.log(c["alpha0"]), prior_mean=np.log(alpha), sigmasq=0.7, usePrior=True)
+    _compare_disp(engine.fitDisp(**d), oracle.fitDisp(**d, with_margin=True), f"disp/{kind}", min_robust=0.85)
+    w = _weights_for(c, seed)
+    d = disp_args(c, mu, np.log(c["alpha0"]), weights=w, useWeights=True)
+    _compare_disp(engine.fitDisp(**d), oracle.fitDisp(**d, with_margin=True), f"disp-w/{kind}", min_robust=0.85)
+    grid = np.linspace(np.log(1e-8), np.log(m), 20)
+    sel = slice(0, 40)
+    kw = dict(ySEXP=c["counts"][sel], xSEXP=xd, mu_hatSEXP=mu[sel], disp_gridSEXP=grid,
+              log_alpha_prior_meanSEXP=np.log(alpha)[sel], log_alpha_prior_sigmasqSEXP=0.5, usePriorSEXP=True,
+              weightsSEXP=None, useWeightsSEXP=False, weightThresholdSEXP=1e-2, useCRSEXP=True)
+    gg, og = engine.fitDispGrid(**kw)["log_alpha"], oracle.fitDispGrid(**kw)["log_alpha"]
+    assert np.mean(np.abs(gg - og) < 1e-9) > 0.9
+
+
+def test_generic_kernels_on_small_p_designs():
+    """Cross-check: force the general-p (shared-memory) kernels onto the p <= 4 cases above in a fresh process
+    (the switch is read once per process) -- both kernel families must agree with the oracle on the same inputs."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("B200NB_FORCE_GENERIC"):
+        pytest.skip("already running with the generic kernels forced")
+    env = dict(os.environ, B200NB_FORCE_GENERIC="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_parity_gpu.py"), "-q", "-m", "gpu", "-k",
+                        "mle_parity or map_parity or fit_beta_parity or weights_and_designs or designs_weights_nf "
+                        "or maxit0 or grid_parity or drop_a_design"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
