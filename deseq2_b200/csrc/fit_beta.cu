@@ -37,57 +37,69 @@ __device__ __forceinline__ double lgamma_diff(double y, double r, double lg_r) {
     const double xr = y + r;
     const double ixr = rcp_fast(xr), ir = rcp_fast(r);
     const double tail = stirling_tail(ixr, ixr * ixr) - stirling_tail(ir, ir * ir);
-    return fma(y, log(xr), fma(r - 0.5, log1p(y * ir), -y)) + tail;
+    return fma(y, log_pos(xr), fma(r - 0.5, log1p_pos(y * ir), -y)) + tail;
   }
   return lgamma_pos(y + r) - lg_r;
 }
 
-template <int P, bool USE_W, bool WANT_DEV>
+constexpr int pow2_ceil_b(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+// One fused IRLS pass: mu (stored to shared memory), mu-dependent part of the deviance, X'WX and X'Wz.
+// Four samples per lane per trip (clamped index + validity factor) for instruction-level parallelism.
+template <int P, bool USE_W>
 __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta)[P], double alpha, double r,
                                           double log_alpha, double minmu, double log_minmu, int lane, double& dev_var,
                                           SymP<P>& XtWX, double (&XtWz)[P]) {
   constexpr int NS = SymP<P>::N;
-  double acc[1 + NS + P];
+  constexpr int NA = pow2_ceil_b(1 + NS + P);
+  double acc[NA];
 #pragma unroll
-  for (int i = 0; i < 1 + NS + P; i++) acc[i] = 0.0;
-#pragma unroll 2
-  for (int j = lane; j < rv.m; j += 32) {
-    double xv[P];
-    double eta = 0.0;
+  for (int i = 0; i < NA; i++) acc[i] = 0.0;
+  const int mlast = rv.m - 1;
+  for (int j0 = lane; j0 < rv.m; j0 += 128) {
 #pragma unroll
-    for (int k = 0; k < P; k++) {
-      xv[k] = rv.x[k * rv.mpad + j];
-      eta = fma(xv[k], beta[k], eta);
-    }
-    const double lnf = rv.lnf[j];
-    const double le = eta + lnf;
-    double mu = fmax(exp(le), minmu);            // fmax(NaN, minmu) = minmu, as in the reference (:326)
-    const double lmu = (mu == minmu) ? log_minmu : le;
-    rv.mu[j] = mu;
-    const double y = rv.y[j];
-    const double am = mu * alpha;
-    double w = mu * rcp_fast(1.0 + am);
-    double wt = 1.0;
-    if (USE_W) {
-      wt = rv.w[j];
-      w *= wt;
-    }
-    const double z = (lmu - lnf) + fma(y, rcp_fast(mu), -1.0);
-    if (WANT_DEV) {
-      double d = fma(y, lmu + log_alpha, -(y + r) * log1p(am));
-      if (USE_W) d *= wt;
-      acc[0] += d;
-    }
-    const double wz = w * z;
+    for (int u = 0; u < 4; u++) {
+      const int jr = j0 + 32 * u;
+      const int j = min(jr, mlast);
+      double vw = (jr < rv.m) ? 1.0 : 0.0;
+      double xv[P];
+      double eta = 0.0;
 #pragma unroll
-    for (int a = 0; a < P; a++) {
-      acc[1 + NS + a] = fma(wz, xv[a], acc[1 + NS + a]);
-      const double wx = w * xv[a];
+      for (int k = 0; k < P; k++) {
+        xv[k] = rv.x[k * rv.mpad + j];
+        eta = fma(xv[k], beta[k], eta);
+      }
+      const double lnf = rv.lnf[j];
+      const double le = eta + lnf;
+      // fmax(NaN, minmu) = minmu, as in the reference (:326); huge |eta| takes libm's exp for inf / 0
+      double mu = fmax((fabs(le) < 700.0) ? exp_fast(le) : exp(le), minmu);
+      const double lmu = (mu == minmu) ? log_minmu : le;
+      if (jr < rv.m) rv.mu[j] = mu;
+      const double y = rv.y[j];
+      const double am = mu * alpha;
+      const double u1 = 1.0 + am;
+      const double iu1 = rcp_fast(u1);
+      double w = mu * iu1 * vw;
+      if (USE_W) {
+        const double wt = rv.w[j];
+        w *= wt;
+        vw *= wt;
+      }
+      const double z = (lmu - lnf) + fma(y, rcp_fast(mu), -1.0);
+      // log1p(am) = log(u1) + (am - (u1 - 1)) / u1
+      const double l1p = log_pos(u1) + (am - (u1 - 1.0)) * iu1;
+      acc[0] = fma(vw, fma(y, lmu + log_alpha, -(y + r) * l1p), acc[0]);
+      const double wz = w * z;
 #pragma unroll
-      for (int b = 0; b <= a; b++) acc[1 + a * (a + 1) / 2 + b] = fma(wx, xv[b], acc[1 + a * (a + 1) / 2 + b]);
+      for (int a = 0; a < P; a++) {
+        acc[1 + NS + a] = fma(wz, xv[a], acc[1 + NS + a]);
+        const double wx = w * xv[a];
+#pragma unroll
+        for (int b = 0; b <= a; b++) acc[1 + a * (a + 1) / 2 + b] = fma(wx, xv[b], acc[1 + a * (a + 1) / 2 + b]);
+      }
     }
   }
-  warp_allreduce_sum_n(acc);
+  warp_allreduce_sum_rs<NA>(acc, lane);
   dev_var = acc[0];
 #pragma unroll
   for (int i = 0; i < NS; i++) XtWX.v[i] = acc[1 + i];
@@ -96,7 +108,7 @@ __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta
 }
 
 template <int P, bool USE_W>
-__global__ void __launch_bounds__(256) fit_beta_kernel(const BetaArgs A, int warps_per_cta, int mpad) {
+__global__ void __launch_bounds__(256, 2) fit_beta_kernel(const BetaArgs A, int warps_per_cta, int mpad) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -185,24 +197,26 @@ __global__ void __launch_bounds__(256) fit_beta_kernel(const BetaArgs A, int war
     SymP<P> XtWX;
     double XtWz[P];
     double dv;
-    beta_pass<P, USE_W, false>(rv, beta, alpha, r, log_alpha, minmu, log_minmu, lane, dv, XtWX, XtWz);
-
     double dev = 0.0, dev_old = 0.0;
     double it = 0.0;
-    for (int t = 0; t < A.maxit; t++) {
-      it += 1.0;
-      SymP<P> M = XtWX;
+    // t = -1: the pass at the starting values (mu, weights for the first solve); t >= 0: IRLS iterations
+    for (int t = -1; t < A.maxit; t++) {
+      if (t >= 0) {
+        it += 1.0;
+        SymP<P> M = XtWX;
 #pragma unroll
-      for (int k = 0; k < P; k++) {
-        M.at(k, k) += lam[k];
-        beta[k] = XtWz[k];
+        for (int k = 0; k < P; k++) {
+          M.at(k, k) += lam[k];
+          beta[k] = XtWz[k];
+        }
+        spd_solve_equilibrated<P>(M, beta);
+        bool big = false;
+#pragma unroll
+        for (int k = 0; k < P; k++) big = big || (fabs(beta[k]) > large);
+        if (big) { it = (double)A.maxit; break; }
       }
-      spd_solve_equilibrated<P>(M, beta);
-      bool big = false;
-#pragma unroll
-      for (int k = 0; k < P; k++) big = big || (fabs(beta[k]) > large);
-      if (big) { it = (double)A.maxit; break; }
-      beta_pass<P, USE_W, true>(rv, beta, alpha, r, log_alpha, minmu, log_minmu, lane, dv, XtWX, XtWz);
+      beta_pass<P, USE_W>(rv, beta, alpha, r, log_alpha, minmu, log_minmu, lane, dv, XtWX, XtWz);
+      if (t < 0) continue;
       dev = -2.0 * (dv + devc);
       const double conv_test = fabs(dev - dev_old) / (fabs(dev) + 0.1);
       if (isnan(conv_test)) { it = (double)A.maxit; break; }
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(256) fit_beta_kernel(const BetaArgs A, int war
         const double mu = mus[j];
         if (A.mu_out != nullptr) A.mu_out[off + j] = mu;
         if (A.hat_diag != nullptr) {
-          double w = mu / (1.0 + alpha * mu);
+          double w = mu * rcp_fast(fma(alpha, mu, 1.0));
           if (USE_W) w *= wsm[j];
           double xv[P];
 #pragma unroll

@@ -83,6 +83,40 @@ __device__ __forceinline__ double log_pos(double x) {
   return q + fma(de, kLn2[1], res_lo - rem);
 }
 
+// 1/k!, k = 2..13 (exp_fast)
+__constant__ double kExpC[12] = {1.0 / 2.0,          1.0 / 6.0,           1.0 / 24.0,           1.0 / 120.0,
+                                 1.0 / 720.0,        1.0 / 5040.0,        1.0 / 40320.0,        1.0 / 362880.0,
+                                 1.0 / 3628800.0,    1.0 / 39916800.0,    1.0 / 479001600.0,    1.0 / 6227020800.0};
+
+// exp(x) for |x| < 700 (no overflow / underflow / nan handling): x = k ln2 + r, |r| <= ln2/2, Taylor to r^13,
+// scaled by 2^k through the exponent field.  < 1 ulp-ish (checked on the device against mpmath in tests).
+__device__ __forceinline__ double exp_fast(double x) {
+  const double kf = rint(x * 1.4426950408889634);
+  const double r = fma(kf, -kLn2[1], fma(kf, -kLn2[0], x));
+  double p = kExpC[11];
+  p = fma(p, r, kExpC[10]);
+  p = fma(p, r, kExpC[9]);
+  p = fma(p, r, kExpC[8]);
+  p = fma(p, r, kExpC[7]);
+  p = fma(p, r, kExpC[6]);
+  p = fma(p, r, kExpC[5]);
+  p = fma(p, r, kExpC[4]);
+  p = fma(p, r, kExpC[3]);
+  p = fma(p, r, kExpC[2]);
+  p = fma(p, r, kExpC[1]);
+  p = fma(p, r, kExpC[0]);
+  p = fma(p * r, r, r);          // r + r^2 * poly
+  const double e = 1.0 + p;
+  const int k = (int)kf;
+  return __hiloint2double(__double2hiint(e) + (k << 20), __double2loint(e));
+}
+
+// log1p(x) for x >= 0 (finite): log(u) + (x - (u - 1)) / u with u = 1 + x recovers the bits 1 + x rounds away
+__device__ __forceinline__ double log1p_pos(double x) {
+  const double u = 1.0 + x;
+  return log_pos(u) + (x - (u - 1.0)) * rcp_fast(u);
+}
+
 // Stirling tail  sum_{k>=1} B_2k / (2k (2k-1) x^(2k-1))  evaluated as xi * poly(xi^2), x >= kShift
 __device__ __forceinline__ double stirling_tail(double xi, double xi2) {
   double p = kStirC[6];
