@@ -104,45 +104,72 @@ def host_bytes(n, m, p):
 # ---------------------------------------------------------------- clocks
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle-reason sampler for the timed region.  Uses NVML in-process (pynvml: ~50 us per sample,
+    no fork) -- spawning nvidia-smi from the benchmark process stalls the launching thread for tens of ms, which
+    is longer than the whole timed region here.  Falls back to one nvidia-smi call if NVML is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.index = index
-        self.rows = []
+    def __init__(self, index, period=0.02):
+        self.index, self.period = index, period
+        self.sm, self.mask, self.max_sm = [], 0, None
         self._stop = threading.Event()
         self._t = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _sample(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            try:
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+            except Exception:
+                pass
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([s.strip() for s in out.split(",")])
+                self._sample()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(self.period)
+
+    @property
+    def rows(self):
+        return self.sm
 
     def start(self):
+        if self._h is None:
+            return
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
 
     def stop(self):
         self._stop.set()
         if self._t:
-            self._t.join(timeout=6)
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+            self._t.join(timeout=2)
+        if self._h is None:   # fallback: a single nvidia-smi query after the timed region
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(v) for v in out.strip().split(",")[:2]]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi (after)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
+        reasons = sorted(n for bit, n in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
 
 
 # ---------------------------------------------------------------- reference arm / cpu baseline
@@ -284,7 +311,7 @@ def main():
     if rank == 0:
         t_extra = time.time()
         i = 0
-        while len(sampler.rows) < 3 and time.time() - t_extra < 3.0:
+        while sampler._h is not None and len(sampler.rows) < 5 and time.time() - t_extra < 2.0:
             step(i, False, comm=False)   # rank-local only: no collectives outside the lock-step region
             i += 1
         torch.cuda.synchronize()

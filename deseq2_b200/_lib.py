@@ -6,7 +6,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libb200nb.so")
+_SO = os.environ.get("B200NB_LIB") or os.path.join(_HERE, "libb200nb.so")   # B200NB_LIB: experiment builds
 _lib = None
 
 

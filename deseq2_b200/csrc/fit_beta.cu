@@ -107,8 +107,12 @@ __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta
   for (int a = 0; a < P; a++) XtWz[a] = acc[1 + NS + a];
 }
 
+#ifndef NB_LB_THREADS
+#define NB_LB_THREADS 256
+#define NB_LB_CTAS 2
+#endif
 template <int P, bool USE_W>
-__global__ void __launch_bounds__(256, 2) fit_beta_kernel(const BetaArgs A, int warps_per_cta, int mpad) {
+__global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_beta_kernel(const BetaArgs A, int warps_per_cta, int mpad) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -308,7 +312,7 @@ cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
   const size_t fixed = (size_t)(P + 1) * mpad * sizeof(double);
   const size_t rowbytes = (size_t)nrow * mpad * sizeof(double);
   const size_t smem_cap = 227 * 1024;
-  int warps = 8;
+  int warps = NB_LB_THREADS / 32;
   while (warps > 1 && fixed + warps * rowbytes > smem_cap / 2) warps >>= 1;
   if (fixed + warps * rowbytes > smem_cap) return cudaErrorInvalidValue;
   const size_t smem = fixed + warps * rowbytes;

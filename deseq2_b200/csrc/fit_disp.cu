@@ -434,8 +434,12 @@ __device__ __forceinline__ void line_search_gene(const DispArgs& A, const DispRo
   }
 }
 
+#ifndef NB_LB_THREADS
+#define NB_LB_THREADS 256
+#define NB_LB_CTAS 2
+#endif
 template <int P, bool USE_W>
-__global__ void __launch_bounds__(256, 2) fit_disp_kernel(const DispArgs A, int warps_per_cta, int mpad) {
+__global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(const DispArgs A, int warps_per_cta, int mpad) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -540,7 +544,7 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
   const size_t xbytes = (size_t)P * mpad * sizeof(double);
   const size_t rowbytes = ((size_t)NROW * mpad + kTabMax) * sizeof(double);
   const size_t smem_cap = 227 * 1024;
-  int warps = 8;
+  int warps = NB_LB_THREADS / 32;
   while (warps > 1 && xbytes + warps * rowbytes > smem_cap / 2) warps >>= 1;   // aim for >= 2 CTAs/SM
   if (xbytes + warps * rowbytes > smem_cap) return cudaErrorInvalidValue;
   const size_t smem = xbytes + warps * rowbytes;

@@ -66,15 +66,16 @@ __device__ __forceinline__ double log_pos(double x) {
   t = fma(f, r, t);                                  // t ~= 2 f / (2 + f)
   const double z = t * t;
   const double c = r * fma(f, -t, 2.0 * (f - t));    // exact_t - t
-  double p = kLogC[8];
-  p = fma(p, z, kLogC[7]);
-  p = fma(p, z, kLogC[6]);
-  p = fma(p, z, kLogC[5]);
-  p = fma(p, z, kLogC[4]);
-  p = fma(p, z, kLogC[3]);
-  p = fma(p, z, kLogC[2]);
-  p = fma(p, z, kLogC[1]);
-  p = fma(p, z, kLogC[0]);
+  // Estrin evaluation of the degree-8 polynomial in z: dependency depth 4 instead of 8
+  const double z2 = z * z;
+  const double a0 = fma(kLogC[1], z, kLogC[0]);
+  const double a1 = fma(kLogC[3], z, kLogC[2]);
+  const double a2 = fma(kLogC[5], z, kLogC[4]);
+  const double a3 = fma(kLogC[7], z, kLogC[6]);
+  const double z4 = z2 * z2;
+  const double b0 = fma(a1, z2, a0);
+  const double b1 = fma(a3, z2, a2);
+  const double p = fma(fma(kLogC[8], z4, b1), z4, b0);
   const double res_lo = fma(t * z, p, c);
   // (double)e without I2F: 2^52 + 2^31 magic
   const double de = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
@@ -93,18 +94,19 @@ __constant__ double kExpC[12] = {1.0 / 2.0,          1.0 / 6.0,           1.0 / 
 __device__ __forceinline__ double exp_fast(double x) {
   const double kf = rint(x * 1.4426950408889634);
   const double r = fma(kf, -kLn2[1], fma(kf, -kLn2[0], x));
-  double p = kExpC[11];
-  p = fma(p, r, kExpC[10]);
-  p = fma(p, r, kExpC[9]);
-  p = fma(p, r, kExpC[8]);
-  p = fma(p, r, kExpC[7]);
-  p = fma(p, r, kExpC[6]);
-  p = fma(p, r, kExpC[5]);
-  p = fma(p, r, kExpC[4]);
-  p = fma(p, r, kExpC[3]);
-  p = fma(p, r, kExpC[2]);
-  p = fma(p, r, kExpC[1]);
-  p = fma(p, r, kExpC[0]);
+  // Estrin: 12 coefficients (1/2! .. 1/13!) in r
+  const double r2 = r * r;
+  const double e0 = fma(kExpC[1], r, kExpC[0]);
+  const double e1 = fma(kExpC[3], r, kExpC[2]);
+  const double e2 = fma(kExpC[5], r, kExpC[4]);
+  const double e3 = fma(kExpC[7], r, kExpC[6]);
+  const double e4 = fma(kExpC[9], r, kExpC[8]);
+  const double e5 = fma(kExpC[11], r, kExpC[10]);
+  const double r4 = r2 * r2;
+  const double f0 = fma(e1, r2, e0);
+  const double f1 = fma(e3, r2, e2);
+  const double f2 = fma(e5, r2, e4);
+  double p = fma(fma(f2, r4, f1), r4, f0);
   p = fma(p * r, r, r);          // r + r^2 * poly
   const double e = 1.0 + p;
   const int k = (int)kf;
