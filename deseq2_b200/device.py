@@ -100,7 +100,8 @@ def fit_disp_grid(y, x, mu_hat, disp_grid, log_alpha_prior_mean, log_alpha_prior
     n, ld = y.shape
     xd = _x_dev(x, y.device)
     p, m = xd.shape
-    grid = torch.as_tensor(np.asarray(disp_grid, dtype=np.float64), device=y.device)
+    grid = disp_grid if isinstance(disp_grid, torch.Tensor) else torch.as_tensor(
+        np.asarray(disp_grid, dtype=np.float64), device=y.device)
     la = torch.empty(n, dtype=F64, device=y.device)
     rc = L.b200nb_fit_disp_grid_dev(_p(y), _ytype(y), _p(xd), _p(mu_hat), _p(grid), grid.numel(),
                                     _p(log_alpha_prior_mean), float(log_alpha_prior_sigmasq), int(bool(usePrior)),
@@ -120,8 +121,10 @@ def fit_beta(y, x, nf, alpha_hat, contrast, beta_mat, lambda_, tol, maxit, useQR
     p, m = xd.shape
     dev = y.device
     nf_is_vector = int(nf.dim() == 1)
-    contrast = torch.as_tensor(np.asarray(contrast, dtype=np.float64), device=dev)
-    lam = torch.as_tensor(np.asarray(lambda_, dtype=np.float64), device=dev)
+    # pass device tensors to keep the call asynchronous (a numpy argument costs a synchronous pageable H2D copy)
+    if not isinstance(contrast, torch.Tensor):
+        contrast = torch.as_tensor(np.asarray(contrast, dtype=np.float64), device=dev)
+    lam = lambda_ if isinstance(lambda_, torch.Tensor) else torch.as_tensor(np.asarray(lambda_, dtype=np.float64), device=dev)
     if out is None:
         out = {"beta_mat": torch.empty((p, n), dtype=F64, device=dev),
                "beta_var_mat": torch.empty((p, n), dtype=F64, device=dev),
