@@ -80,10 +80,17 @@ int next_counter(unsigned int** out) {
 // ---------------------------------------------------------------- pinned staging for pageable host buffers
 // R hands over ordinary (pageable) memory.  cudaMemcpy from pageable memory runs at ~9 GB/s on the GPU box;
 // staging through a ring of pinned buffers filled by a few host threads while the previous chunk is in flight
-// reaches PCIe speed.  kStageThreads OpenMP workers do the host-side memcpy.
+// reaches PCIe speed.  B200NB_STAGE_THREADS (default 8; 4..16 measure the same) OpenMP workers do the host-side memcpy.
 constexpr size_t kStageChunk = 16u << 20;
 constexpr int kStageRing = 3;
-constexpr int kStageThreads = 8;
+int stage_threads() {
+  static int t = [] {
+    const char* e = getenv("B200NB_STAGE_THREADS");
+    int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 64 ? 64 : v);
+  }();
+  return t;
+}
 struct Staging {
   void* buf[kStageRing] = {};
   cudaEvent_t ev[kStageRing] = {};
@@ -106,9 +113,10 @@ void par_memcpy(void* dst, const void* src, size_t bytes) {
     memcpy(dst, src, bytes);
     return;
   }
-#pragma omp parallel for num_threads(kStageThreads) schedule(static)
-  for (int t = 0; t < kStageThreads; t++) {
-    const size_t lo = bytes * t / kStageThreads, hi = bytes * (t + 1) / kStageThreads;
+  const int T = stage_threads();
+#pragma omp parallel for num_threads(T) schedule(static)
+  for (int t = 0; t < T; t++) {
+    const size_t lo = bytes * t / T, hi = bytes * (t + 1) / T;
     memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
   }
 }

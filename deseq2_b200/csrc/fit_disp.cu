@@ -4,14 +4,14 @@
 // ascent on log alpha, accept / reject / kappa schedule replicated decision for decision), :31-158
 // (log posterior and its first two derivatives, Cox-Reid term with weight-threshold row/column
 // subsetting) and :469-513 (fitDispGrid).  HOW is new:
-//   * the gene's row (counts, mu, 1/mu, weights) is staged once into shared memory with 128-bit loads;
+//   * the gene's row (counts, mu, weights) is staged once into shared memory with 128-bit loads;
 //     every lane owns samples lane, lane+32, ...; all per-gene scalars are warp-uniform;
 //   * one fused pass per proposal evaluates the log posterior AND its derivative (they share
 //     log(1+mu*alpha) and 1/(1/mu+alpha)), so an accepted step costs one pass instead of the reference's
 //     three (theta(kappa), lpnew, dlp) -- the values are the same because the reference re-evaluates the
 //     same function at the same point (:225 vs :233);
 //   * the identities log(mu+1/alpha) = log(1+mu*alpha) - log(alpha), mu*alpha/(1+mu*alpha) = alpha*wd,
-//     y/(mu+1/alpha) = y*alpha*wd/mu (wd = 1/(1/mu+alpha)) remove two logs/divisions per sample;
+//     y/(mu+1/alpha) = y*alpha/(1+mu*alpha) (wd = mu/(1+mu*alpha)) remove two logs/divisions per sample;
 //   * counts are integers, so sum_j [lgamma(y_j + r) - lgamma(r)] = sum_k c_k log(r + k) and
 //     sum_j [digamma(y_j + r) - digamma(r)] = sum_k c_k / (r + k) with c_k = sum_j w_j [y_j > k]:
 //     for a gene whose largest count is below kTabMax the warp builds the c_k table once (shared-memory
@@ -37,7 +37,6 @@ enum DispMode { MODE_TAB = 0, MODE_BIG = 1, MODE_GEN = 2 };
 struct DispRow {
   const double* y;
   const double* mu;
-  const double* imu;
   const double* w;    // only read when USE_W
   const double* x;    // shared, column-major with stride mpad
   const double* tab;  // c_k, k = 0 .. ntab-1 (TAB mode)
@@ -84,21 +83,23 @@ __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal
       const int jr = j0 + 32 * u;
       const int j = min(jr, mlast);
       double vw = (jr < rv.m) ? 1.0 : 0.0;
-      const double y = rv.y[j], mu = rv.mu[j], imu = rv.imu[j];
-      const double wd = rcp_fast(imu + alpha);
+      const double y = rv.y[j], mu = rv.mu[j];
+      // wd = 1/(1/mu + alpha) = mu/(1 + mu alpha); alpha wd (y/mu - 1) = alpha (y - mu)/(1 + mu alpha): 1/mu never needed
       const double onema = fma(mu, alpha, 1.0);
+      const double wi = rcp_fast(onema);
+      const double wd = mu * wi;
       const double l2 = log_pos(onema);
       const double xr = y + r;
       double t, d;
       if (MODE == MODE_TAB) {
         t = -xr * l2;
-        d = l2 + alpha * wd * fma(y, imu, -1.0);
+        d = l2 + alpha * (y - mu) * wi;
       } else {
         double lg, dg;
         if (MODE == MODE_BIG) lgamma_digamma_big(xr, lg, dg);
         else lgamma_digamma_pos(xr, lg, dg);
         t = (lg - lg_r) - xr * l2;
-        d = (dg_r - dg) + l2 + alpha * wd * fma(y, imu, -1.0);
+        d = (dg_r - dg) + l2 + alpha * (y - mu) * wi;
       }
       double wdm = wd * vw;
       if (USE_W) {
@@ -190,14 +191,14 @@ __device__ __forceinline__ double disp_d2(const DispRow& rv, const DispScal& sc,
     }
   }
   for (int j = lane; j < rv.m; j += 32) {
-    const double y = rv.y[j], mu = rv.mu[j], imu = rv.imu[j];
-    const double wd = rcp_fast(imu + alpha);
+    const double y = rv.y[j], mu = rv.mu[j];
     const double onema = fma(mu, alpha, 1.0);
+    const double wi = rcp_fast(onema);
+    const double wd = mu * wi;
     const double l2 = log_pos(onema);
     const double xr = y + r;
     // t1 = dg_r + l2 - mu a/(1+mu a) - psi(y+r) + y/(mu+r);  t2 = -r2 tg_r + mu^2 a/(1+mu a)^2 + r2 psi'(y+r) + r2 y/(mu+r)^2
-    double t1 = l2 + alpha * wd * fma(y, imu, -1.0);
-    const double wi = wd * imu;
+    double t1 = l2 + alpha * (y - mu) * wi;
     double t2 = wd * wd * alpha + y * wi * wi;
     if (mode != MODE_TAB) {
       t1 += dg_r - digamma_pos(xr);
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const void* y, int y_is_f
 }
 
 struct DispWarpSmem {
-  double *ys, *mus, *imus, *wsm, *tab;
+  double *ys, *mus, *wsm, *tab;
 };
 
 // stage one gene row into the warp's shared-memory slice (128-bit loads); returns sum_j w_j y_j and max y
@@ -332,7 +333,6 @@ __device__ __forceinline__ void stage_row(const DispArgs& A, unsigned int g, int
       const int j = j4 + q;
       S.ys[j] = yv[q];
       S.mus[j] = mv[q];
-      S.imus[j] = 1.0 / mv[q];
       if (USE_W) S.wsm[j] = wv[q];
       if (j < A.m) {
         sum_wy_l += wv[q] * yv[q];
@@ -443,11 +443,10 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(con
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  constexpr int NROW = USE_W ? 4 : 3;
+  constexpr int NROW = USE_W ? 3 : 2;
   double* xs = smem;                                   // P * mpad
   double* rowbase = smem + (size_t)P * mpad + (size_t)warp * ((size_t)NROW * mpad + kTabMax);
-  DispWarpSmem S{rowbase, rowbase + mpad, rowbase + 2 * mpad, USE_W ? rowbase + 3 * mpad : nullptr,
-                 rowbase + (size_t)NROW * mpad};
+  DispWarpSmem S{rowbase, rowbase + mpad, USE_W ? rowbase + 2 * mpad : nullptr, rowbase + (size_t)NROW * mpad};
 
   // stage the design matrix (column-major m x p -> column-major with padded stride)
   for (int idx = threadIdx.x; idx < P * A.m; idx += blockDim.x) {
@@ -456,7 +455,7 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(con
   }
   __syncthreads();
 
-  DispRow rv{S.ys, S.mus, S.imus, S.wsm, xs, S.tab, A.m, mpad, 0};
+  DispRow rv{S.ys, S.mus, S.wsm, xs, S.tab, A.m, mpad, 0};
   const DispScal sc{A.prior_sigmasq, 1.0 / A.prior_sigmasq, A.weight_threshold, A.use_prior, A.use_cr};
   const unsigned int n0 = A.mode_counts[MODE_TAB], n1 = A.mode_counts[MODE_BIG];
 
@@ -493,17 +492,16 @@ __global__ void __launch_bounds__(256, 2) fit_disp_grid_kernel(const DispArgs A,
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  constexpr int NROW = USE_W ? 4 : 3;
+  constexpr int NROW = USE_W ? 3 : 2;
   double* xs = smem;
   double* rowbase = smem + (size_t)P * mpad + (size_t)warp * ((size_t)NROW * mpad + kTabMax);
-  DispWarpSmem S{rowbase, rowbase + mpad, rowbase + 2 * mpad, USE_W ? rowbase + 3 * mpad : nullptr,
-                 rowbase + (size_t)NROW * mpad};
+  DispWarpSmem S{rowbase, rowbase + mpad, USE_W ? rowbase + 2 * mpad : nullptr, rowbase + (size_t)NROW * mpad};
   for (int idx = threadIdx.x; idx < P * A.m; idx += blockDim.x) {
     const int k = idx / A.m, j = idx - k * A.m;
     xs[k * mpad + j] = A.x[idx];
   }
   __syncthreads();
-  DispRow rv{S.ys, S.mus, S.imus, S.wsm, xs, S.tab, A.m, mpad, 0};
+  DispRow rv{S.ys, S.mus, S.wsm, xs, S.tab, A.m, mpad, 0};
   const DispScal sc{A.prior_sigmasq, 1.0 / A.prior_sigmasq, A.weight_threshold, A.use_prior, A.use_cr};
   for (;;) {
     unsigned int g = 0;
@@ -540,7 +538,7 @@ template <int P, bool USE_W>
 cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
   DispArgs a = a0;
   const int mpad = (a.m + 3) & ~3;
-  constexpr int NROW = USE_W ? 4 : 3;
+  constexpr int NROW = USE_W ? 3 : 2;
   const size_t xbytes = (size_t)P * mpad * sizeof(double);
   const size_t rowbytes = ((size_t)NROW * mpad + kTabMax) * sizeof(double);
   const size_t smem_cap = 227 * 1024;

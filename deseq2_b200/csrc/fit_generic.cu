@@ -123,21 +123,23 @@ struct GenWarp {
   double *v0, *v1, *v2, *v3;          // length-32 vectors
 };
 
+// nrow = number of m-length rows: 2 (y, mu) or 3 (y, lnf, mu) plus 1 when weights are used; `three` selects r2
 __host__ __device__ inline size_t gen_warp_doubles(int mpad, int p, int ps, int G, int grouped, int nrow) {
   const size_t terms = grouped ? (size_t)G : (size_t)mpad;
   const size_t acc = grouped ? (size_t)G * 32 : (size_t)mpad;
   return (size_t)nrow * mpad + kTabMaxG + 3 * acc + (grouped ? 3 * terms : 0) + terms + 4 * (size_t)p * ps + 4 * 32;
 }
 
-__device__ __forceinline__ GenWarp carve(double* base, int mpad, int p, int ps, int G, int grouped, int nrow) {
+__device__ __forceinline__ GenWarp carve(double* base, int mpad, int p, int ps, int G, int grouped, int nrow,
+                                         bool three, bool use_w) {
   GenWarp S;
   const size_t terms = grouped ? (size_t)G : (size_t)mpad;
   const size_t acc = grouped ? (size_t)G * 32 : (size_t)mpad;
   double* q = base;
   S.ys = q; q += mpad;
   S.r1 = q; q += mpad;
-  S.r2 = q; q += mpad;
-  S.wsm = (nrow > 3) ? q : nullptr; q += (nrow > 3) ? mpad : 0;
+  S.r2 = three ? q : nullptr; q += three ? mpad : 0;
+  S.wsm = use_w ? q : nullptr; q += use_w ? mpad : 0;
   S.tab = q; q += kTabMaxG;
   S.accA = q; q += acc;
   S.accB = q; q += acc;
@@ -207,17 +209,17 @@ __device__ __forceinline__ void gdisp_eval(const GDispCtx& C, double a, double p
   }
   const double* ys = S.ys;
   const double* mus = S.r1;
-  const double* imus = S.r2;
-#pragma unroll 2
+#pragma unroll 4
   for (int j = lane; j < D.m; j += 32) {
-    const double y = ys[j], mu = mus[j], imu = imus[j];
-    const double wd = rcp_fast(imu + alpha);
+    const double y = ys[j], mu = mus[j];
+    // wd = 1/(1/mu + alpha) = mu/(1 + mu alpha); 1/mu never needed: y/mu - 1 = (y - mu)/mu cancels against wd
     const double onema = fma(mu, alpha, 1.0);
+    const double wi = rcp_fast(onema);
+    const double wd = mu * wi;
     const double l2 = log_pos(onema);
     const double xr = y + r;
     double t = -xr * l2;
-    double d = l2 + alpha * wd * fma(y, imu, -1.0);
-    const double wi = wd * imu;
+    double d = l2 + alpha * (y - mu) * wi;
     double d2 = wd * wd * alpha + y * wi * wi;
     if (!C.tab_mode) {
       double lg, dg;
@@ -334,7 +336,6 @@ __device__ __forceinline__ void gstage_disp(const DispArgs& A, unsigned int g, i
     }
     S.ys[j] = y;
     S.r1[j] = mu;
-    S.r2[j] = 1.0 / mu;
     if (A.use_weights) S.wsm[j] = w;
   }
   sum_wy = warp_allreduce_sum(swy);
@@ -373,7 +374,7 @@ __device__ __forceinline__ void gbuild_table(const GenWarp& S, int m, bool use_w
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(128) fit_disp_generic_kernel(const DispArgs A, int mpad, int ps, size_t warp_doubles) {
+__global__ void __launch_bounds__(256) fit_disp_generic_kernel(const DispArgs A, int mpad, int ps, size_t warp_doubles) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -384,10 +385,10 @@ __global__ void __launch_bounds__(128) fit_disp_generic_kernel(const DispArgs A,
   for (int i = threadIdx.x; i < xrows * ps; i += blockDim.x) xg[i] = A.xg[i];
   for (int i = threadIdx.x; i < A.m; i += blockDim.x) gid[i] = A.gid[i];
   __syncthreads();
-  const int nrow = A.use_weights ? 4 : 3;
+  const int nrow = A.use_weights ? 3 : 2;
   GDispCtx C;
   C.D = Design{xg, gid, A.p, ps, A.G, A.grouped, A.m};
-  C.S = carve(wbase, mpad, A.p, ps, A.G, A.grouped, nrow);
+  C.S = carve(wbase, mpad, A.p, ps, A.G, A.grouped, nrow, false, A.use_weights != 0);
   C.prior_sigmasq = A.prior_sigmasq;
   C.inv_sigmasq = 1.0 / A.prior_sigmasq;
   C.weight_threshold = A.weight_threshold;
@@ -563,7 +564,7 @@ __device__ __forceinline__ double lgamma_diff_g(double y, double r, double lg_r)
   return lgamma_pos(y + r) - lg_r;
 }
 
-__global__ void __launch_bounds__(128) fit_beta_generic_kernel(const BetaArgs A, int mpad, int ps, size_t warp_doubles) {
+__global__ void __launch_bounds__(256) fit_beta_generic_kernel(const BetaArgs A, int mpad, int ps, size_t warp_doubles) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(128) fit_beta_generic_kernel(const BetaArgs A,
   const int nrow = A.use_weights ? 4 : 3;
   GBetaCtx C;
   C.D = Design{xg, gid, p, ps, A.G, A.grouped, A.m};
-  C.S = carve(wbase, mpad, p, ps, A.G, A.grouped, nrow);
+  C.S = carve(wbase, mpad, p, ps, A.G, A.grouped, nrow, true, A.use_weights != 0);
   C.use_w = A.use_weights;
   C.minmu = A.minmu;
   C.log_minmu = log(A.minmu);
@@ -755,8 +756,8 @@ bool plan(int m, int p, int G, int grouped, int nrow, size_t extra_doubles, GenL
   out.warp_doubles = gen_warp_doubles(out.mpad, p, out.ps, G, grouped, nrow);
   const size_t fixed = ((size_t)(grouped ? G : m) * out.ps + (m + 1) / 2 + extra_doubles) * sizeof(double);
   const size_t cap = 227 * 1024;
-  int warps = 4;
-  while (warps > 1 && fixed + warps * out.warp_doubles * sizeof(double) > cap) warps >>= 1;
+  int warps = 8;
+  while (warps > 1 && fixed + warps * out.warp_doubles * sizeof(double) > cap) warps--;
   out.warps = warps;
   out.smem = fixed + warps * out.warp_doubles * sizeof(double);
   return out.smem <= cap;
@@ -767,7 +768,7 @@ bool plan(int m, int p, int G, int grouped, int nrow, size_t extra_doubles, GenL
 cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
   DispArgs a = a0;
   GenLaunch L;
-  if (!plan(a.m, a.p, a.G, a.grouped, a.use_weights ? 4 : 3, 0, L)) return cudaErrorInvalidValue;
+  if (!plan(a.m, a.p, a.G, a.grouped, a.use_weights ? 3 : 2, 0, L)) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(fit_disp_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
   if (e != cudaSuccess) return e;
   int ctas_per_sm = 0;
