@@ -442,6 +442,31 @@ int b200nb_to_col_major_dev(const double* src, double* dst, int n, int m, long l
   return 0;
 }
 
+int b200nb_prep_dev(const void* y, int y_type, const double* x, const double* proj, const double* size_factors,
+                    double xim, double min_disp, double max_disp, double minmu, int n, int m, int p, long long ld,
+                    double* base_mean, double* base_var, int32_t* all_zero, double* alpha0, double* mu_lin,
+                    double* beta0, void* stream) {
+  if (check_dims(n, m, p)) return 1;
+  if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
+  if (m <= p) return fail("prep needs m > p (m=%d, p=%d)", m, p);
+  nb::PrepArgs a{};
+  a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.x = x; a.proj = proj; a.size_factors = size_factors; a.xim = xim;
+  a.min_disp = min_disp; a.max_disp = max_disp; a.minmu = minmu; a.n = n; a.m = m; a.p = p; a.ld = ld;
+  a.base_mean = base_mean; a.base_var = base_var; a.all_zero = all_zero; a.alpha0 = alpha0; a.mu_lin = mu_lin;
+  a.beta0 = beta0;
+  CU(nb::launch_prep(a, (cudaStream_t)stream));
+  if (n > 0) g_launches++;
+  return 0;
+}
+
+int b200nb_trend_fit_dev(const double* means, const double* disps, int n, double min_disp, double* out4,
+                         void* stream) {
+  if (n < 1) return fail("trend fit needs at least one gene");
+  CU(nb::launch_trend_fit(means, disps, n, min_disp, out4, (cudaStream_t)stream));
+  g_launches++;
+  return 0;
+}
+
 /* ------------------------------------------------------------------ host entry points */
 
 int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,

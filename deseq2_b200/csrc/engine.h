@@ -87,6 +87,28 @@ struct BetaArgs {
   int G, grouped;
 };
 
+// per-gene pre-steps (pipeline_kernels.cu)
+struct PrepArgs {
+  const void* y;
+  int y_is_f64;
+  const double* x;             // m x p column-major
+  const double* proj;          // p x m row-major: (X'X)^-1 X'
+  const double* size_factors;  // m
+  double xim;                  // mean(1 / size factor)
+  double min_disp, max_disp, minmu;
+  int n, m, p;
+  long long ld;
+  double* base_mean;           // n
+  double* base_var;            // n
+  int32_t* all_zero;           // n
+  double* alpha0;              // n: min(rough, moments) dispersion, clamped
+  double* mu_lin;              // gene-major n x ld or nullptr: linear-model mu * size factor, clamped at minmu
+  double* beta0;               // n x p column-major or nullptr: least-squares start values on log(K/s + 0.1)
+};
+cudaError_t launch_prep(const PrepArgs& a, cudaStream_t stream);
+cudaError_t launch_trend_fit(const double* means, const double* disps, int n, double min_disp, double* out4,
+                             cudaStream_t stream);
+
 // returns cudaSuccess or the launch error; kernels are enqueued on `stream`
 cudaError_t launch_fit_disp(const DispArgs& a, cudaStream_t stream);
 cudaError_t launch_fit_beta(const BetaArgs& a, cudaStream_t stream);

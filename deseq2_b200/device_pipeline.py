@@ -1,0 +1,166 @@
+"""Device-resident DESeq() Wald path: counts go in once (gene-major, on the GPU), every per-gene step runs on the
+device, only a handful of scalars ever reach the host.
+
+Same sequence as deseq2_b200/pipeline.py (the numpy restatement of R/core.R:280-432 with test="Wald",
+fitType="parametric", betaPrior=FALSE, no weights, no outlier replacement), but
+  * the pre-steps (base mean/variance, rough + moments dispersion, linear-model mu, IRLS start values) are one
+    CUDA kernel (b200nb_prep_dev, csrc/pipeline_kernels.cu),
+  * the parametric dispersion-trend fit is one single-CTA kernel (b200nb_trend_fit_dev),
+  * fitDisp / fitDispGrid / fitBeta are the engine's device entry points,
+  * the elementwise rules between them (noIncrease, convergence flags, clamps, outlier rule, MAD, Wald statistic
+    and p-value) are a few torch tensor ops -- plumbing, not the product.
+This is SURVEY.md section 8(f) rows 2-3 (pre-steps and Wald statistics on device) layered on rows (a)-(e).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import device as D
+from .pipeline import modelMatrixGroups
+
+F64 = torch.float64
+LN2 = float(np.log(2.0))
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prep(y, x, sizeFactors, minDisp=1e-8, minmu=0.5, want_mu=True, want_beta0=True):
+    """b200nb_prep_dev.  y: gene-major (n, ld) int32/float64 device tensor; x: (m, p) numpy; sizeFactors: (m,) numpy."""
+    L = _lib.lib()
+    dev = y.device
+    n, ld = y.shape
+    x = np.asarray(x, dtype=np.float64)
+    m, p = x.shape
+    proj = np.linalg.solve(x.T @ x, x.T)                       # (X'X)^-1 X', p x m
+    xd = D.x_to_device(x, dev)
+    projd = torch.as_tensor(np.ascontiguousarray(proj), device=dev)
+    sfd = torch.as_tensor(np.asarray(sizeFactors, dtype=np.float64), device=dev)
+    out = {"baseMean": torch.empty(n, dtype=F64, device=dev), "baseVar": torch.empty(n, dtype=F64, device=dev),
+           "allZero": torch.empty(n, dtype=torch.int32, device=dev), "alpha0": torch.empty(n, dtype=F64, device=dev),
+           "mu_lin": torch.empty((n, ld), dtype=F64, device=dev) if want_mu else None,
+           "beta0": torch.empty((p, n), dtype=F64, device=dev) if want_beta0 else None}
+    rc = L.b200nb_prep_dev(_p(y), 0 if y.dtype == torch.int32 else 1, _p(xd), _p(projd), _p(sfd),
+                           float(np.mean(1.0 / np.asarray(sizeFactors))), float(minDisp), float(max(10, m)),
+                           float(minmu), n, m, p, ld, _p(out["baseMean"]), _p(out["baseVar"]), _p(out["allZero"]),
+                           _p(out["alpha0"]), _p(out["mu_lin"]), _p(out["beta0"]), _stream())
+    _lib.check(rc, "prep_dev")
+    out["xd"], out["sfd"] = xd, sfd
+    return out
+
+
+def trend_fit(means, disps, minDisp=1e-8):
+    """parametricDispersionFit on device: returns a 4-vector tensor (asymptDisp, extraPois, status, rounds)."""
+    L = _lib.lib()
+    out = torch.empty(4, dtype=F64, device=means.device)
+    _lib.check(L.b200nb_trend_fit_dev(_p(means), _p(disps), means.numel(), float(minDisp), _p(out), _stream()),
+               "trend_fit_dev")
+    return out
+
+
+def _median(v):
+    """R's median (mean of the two middle order statistics for even length)."""
+    s, _ = torch.sort(v)
+    k = s.numel()
+    return s[k // 2] if k % 2 else 0.5 * (s[k // 2 - 1] + s[k // 2])
+
+
+def _grid_refit(y, xd, mu, sel, m, prior_mean, prior_sigmasq, usePrior):
+    """fitDispGridWrapper (R/wrappers.R:63-83) on the genes flagged in boolean `sel`; returns (idx, alpha)."""
+    idx = torch.nonzero(sel).squeeze(1)
+    if idx.numel() == 0:
+        return idx, None
+    grid = np.linspace(np.log(1e-8), np.log(max(10, m)), 20)
+    pm = prior_mean[idx] if prior_mean is not None else torch.zeros(idx.numel(), dtype=F64, device=y.device)
+    la = D.fit_disp_grid(y[idx].contiguous(), xd, mu[idx].contiguous(), grid, pm, prior_sigmasq, usePrior)["log_alpha"]
+    return idx, torch.exp(la)
+
+
+def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, maxit=100, betaTol=1e-8, minmu=0.5,
+                 outlierSD=2.0):
+    """y: gene-major (N, ld) device tensor of counts (int32 or float64).  Returns a dict of device tensors over the
+    rows with a non-zero sum (`idx` maps them back to the N input rows) plus the trend / prior scalars."""
+    dev = y.device
+    x = np.asarray(x, dtype=np.float64)
+    m, p = x.shape
+    if m - p <= 3:
+        raise NotImplementedError("residual df <= 3: the reference's Monte-Carlo prior-variance branch is not restated")
+    maxDisp = float(max(10, m))
+    linearMu = modelMatrixGroups(x) == p
+    pr = prep(y, x, sizeFactors, minDisp=minDisp, minmu=minmu, want_mu=linearMu)
+    xd, sfd = pr["xd"], pr["sfd"]
+    idx = torch.nonzero(pr["allZero"] == 0).squeeze(1)
+    ynz = y[idx].contiguous()
+    bm = pr["baseMean"][idx]
+    alpha0 = pr["alpha0"][idx]
+    beta0 = pr["beta0"][:, idx].contiguous()
+    n = idx.numel()
+    contrast = torch.zeros(p, dtype=F64, device=dev)
+    contrast[0] = 1.0
+    lam = torch.full((p,), 1e-6 / LN2 ** 2, dtype=F64, device=dev)
+    min_log_alpha = float(np.log(minDisp / 10))
+
+    # ---- estimateDispersionsGeneEst (R/core.R:657-860)
+    if linearMu:
+        mu = pr["mu_lin"][idx].contiguous()
+    else:
+        mu = D.fit_beta(ynz, xd, sfd, alpha0, contrast, beta0, lam, betaTol, maxit, minmu=minmu, want_hat=False)["mu"]
+    la0 = torch.log(alpha0)
+    r = D.fit_disp(ynz, xd, mu, la0, la0, 1.0, min_log_alpha, kappa_0, dispTol, maxit, False)
+    dge = torch.clamp(torch.exp(r["log_alpha"]), max=maxDisp)
+    noIncrease = r["last_lp"] < r["initial_lp"] + r["initial_lp"].abs() / 1e6
+    dge = torch.where(noIncrease, alpha0, dge)
+    conv = (r["iter"] < maxit) & (r["iter"] != 1)
+    gi, ga = _grid_refit(ynz, xd, mu, (~conv) & (dge > minDisp * 10), m, None, 1.0, False)
+    if ga is not None:
+        dge[gi] = ga
+    dge = torch.clamp(dge, minDisp, maxDisp)
+    n_refit_geneest = int(gi.numel())
+
+    # ---- estimateDispersionsFit + dispersionFunction<- + PriorVar (R/core.R:864-940, R/methods.R:142-190, R/core.R:1135-1208)
+    tr = trend_fit(bm, dge, minDisp)
+    dispFit = tr[0] + tr[1] / bm
+    above = dge >= minDisp * 100
+    resid = (torch.log(dge) - torch.log(dispFit))[above]
+    med = _median(resid)
+    varLogDispEsts = (1.4826 * _median((resid - med).abs())) ** 2
+    expVar = torch.special.polygamma(1, torch.tensor((m - p) / 2.0, dtype=F64, device=dev))
+    dispPriorVar = float(torch.clamp(varLogDispEsts - expVar, min=0.25).item())
+    status = tr[2].item()
+    if status != 0:
+        raise FloatingPointError(f"parametric dispersion fit failed on device (status {int(status)})")
+
+    # ---- estimateDispersionsMAP (R/core.R:943-1131)
+    dispInit = torch.where(dge > 0.1 * dispFit, dge, dispFit)
+    logFit = torch.log(dispFit)
+    rm = D.fit_disp(ynz, xd, mu, torch.log(dispInit), logFit, dispPriorVar, min_log_alpha, kappa_0, dispTol, maxit, True)
+    dispMAP = torch.exp(rm["log_alpha"])
+    gi2, ga2 = _grid_refit(ynz, xd, mu, rm["iter"] >= maxit, m, logFit, dispPriorVar, True)
+    if ga2 is not None:
+        dispMAP[gi2] = ga2
+    dispMAP = torch.clamp(dispMAP, minDisp, maxDisp)
+    dispOutlier = torch.log(dge) > logFit + outlierSD * torch.sqrt(varLogDispEsts)
+    dispersion = torch.where(dispOutlier, dge, dispMAP)
+
+    # ---- nbinomWaldTest (R/core.R:1332-1565) via fitNbinomGLMs (R/fitNbinomGLMs.R:29-236)
+    fb = D.fit_beta(ynz, xd, sfd, dispersion, contrast, beta0, lam, betaTol, maxit, minmu=minmu)
+    betaMatrix = fb["beta_mat"] / LN2                      # (p, n)
+    betaSE = torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0.0)) / LN2
+    stat = betaMatrix / betaSE
+    pval = 2.0 * torch.special.ndtr(-stat.abs())
+    return {"idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
+            "dispersion": dispersion, "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"],
+            "betaMatrix": betaMatrix.T, "betaSE": betaSE.T, "WaldStatistic": stat.T, "WaldPvalue": pval.T,
+            "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": fb["deviance"], "mu": fb["mu"],
+            "H": fb["hat_diagonals"], "trendCoefs": tr[:2], "varLogDispEsts": varLogDispEsts,
+            "dispPriorVar": dispPriorVar, "n_refit_geneest": n_refit_geneest, "n_refit_map": int(gi2.numel()),
+            "allZero": pr["allZero"]}

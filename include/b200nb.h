@@ -96,6 +96,22 @@ int b200nb_to_gene_major_dev(const void* src_colmajor, void* dst, int n, int m, 
                              void* stream);
 int b200nb_to_col_major_dev(const double* src, double* dst_colmajor, int n, int m, long long ld, void* stream);
 
+/* ---- pre-steps of the hot path on device buffers (the R glue around the native calls)
+ * b200nb_prep_dev: per gene, from the counts (gene-major n x ld) and size factors:
+ *   base_mean, base_var, all_zero      getBaseMeansAndVariances   R/core.R:2138-2157
+ *   alpha0 = clamp(min(roughDispEstimate, momentsDispEstimate), min_disp, max_disp)   R/core.R:2422-2448, 716, 727
+ *   mu_lin (optional) = linearModelMuNormalized clamped at minmu                      R/core.R:2454-2467, 764
+ *   beta0 (optional, n x p column-major) = QR least squares of log(K/s + 0.1) on X    R/fitNbinomGLMs.R:139-145
+ * x is m x p column-major; proj is (X'X)^-1 X' as p x m row-major; xim = mean(1/size_factor).
+ * b200nb_trend_fit_dev: parametricDispersionFit (R/core.R:2166-2189) over genes with disps > 100*min_disp;
+ *   out4 = {asymptDisp, extraPois, status (0 ok, 1 not converged, 2 non-positive, 3 no usable genes), rounds}. */
+int b200nb_prep_dev(const void* y, int y_type, const double* x, const double* proj, const double* size_factors,
+                    double xim, double min_disp, double max_disp, double minmu, int n, int m, int p, long long ld,
+                    double* base_mean, double* base_var, int32_t* all_zero, double* alpha0, double* mu_lin,
+                    double* beta0, void* stream);
+int b200nb_trend_fit_dev(const double* means, const double* disps, int n, double min_disp, double* out4,
+                         void* stream);
+
 /* ---- housekeeping */
 const char* b200nb_last_error(void);
 int b200nb_device_count(void);            /* number of visible CUDA devices (0 if none / no driver) */
