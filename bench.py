@@ -37,7 +37,7 @@ MIN_LOG_ALPHA = float(np.log(1e-8 / 10))
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genes", type=int, default=50000, help="genes per GPU (config C2: 50k)")
@@ -104,73 +104,63 @@ def host_bytes(n, m, p):
 # ---------------------------------------------------------------- clocks
 
 class ClockSampler:
-    """SM clock / throttle-reason sampler for the timed region.  Uses NVML in-process (pynvml: ~50 us per sample,
-    no fork) -- spawning nvidia-smi from the benchmark process stalls the launching thread for tens of ms, which
-    is longer than the whole timed region here.  Falls back to one nvidia-smi call if NVML is unavailable."""
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+    """SM clock / throttle-reason log for the timed region, the way /opt/skills/guides/B200_PROFILING.md does it: a
+    separate `nvidia-smi -lms` process started BEFORE the warm-up and stopped after the run (in-process NVML polling
+    was measured to stall the launching thread by 0.3-3 ms per query; a forked nvidia-smi per sample by far more).
+    Rows are attributed to the timed region by their timestamps; the GPU is kept under the same load until at least
+    two rows fall inside [start of timed region, now]."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index, period=0.02):
-        self.index, self.period = index, period
-        self.sm, self.mask, self.max_sm = [], 0, None
-        self._stop = threading.Event()
-        self._t = None
-        self._h = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
-            self._nv = pynvml
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
-            self._sample()          # resolve NVML entry points now, not inside the timed region
-            self.sm, self.mask = [], 0
-        except Exception:
-            self._h = None
-
-    def _sample(self):
-        nv = self._nv
-        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-        try:
-            self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
-        except Exception:
-            try:
-                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
-            except Exception:
-                pass
-
-    def _run(self):
-        while not self._stop.wait(self.period):
-            try:
-                self._sample()
-            except Exception:
-                pass
-
-    @property
-    def rows(self):
-        return self.sm
+    def __init__(self, index, period_ms=50):
+        self.index, self.period_ms = index, period_ms
+        self.proc, self.window, self._buf, self._t = None, None, [], None
 
     def start(self):
-        if self._h is None:
-            return
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = vis.split(",")[self.index] if vis else str(self.index)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          str(self.period_ms), "-i", phys], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self._t = threading.Thread(target=self._reader, daemon=True)
+            self._t.start()
+        except Exception:
+            self.proc = None
+
+    def _reader(self):
+        for line in self.proc.stdout:
+            self._buf.append((time.time(), line))
+
+    def rows_since(self, t0):
+        return [r for r in self._buf if r[0] >= t0]
 
     def stop(self):
-        self._stop.set()
-        if self._t:
-            self._t.join(timeout=2)
-        if self._h is None:   # fallback: a single nvidia-smi query after the timed region
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        rows = self._buf
+        if self.window is not None:
+            inside = [r for r in rows if self.window[0] <= r[0] <= self.window[1]]
+            rows = inside if inside else rows[-2:]
+        sm, mx, reasons = [], [], set()
+        for _, line in rows:
+            f = [v.strip() for v in line.split(",")]
             try:
-                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout
-                a, b = [float(v) for v in out.strip().split(",")[:2]]
-                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi (after)"}
+                sm.append(float(f[1])); mx.append(float(f[2]))
             except Exception:
-                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "unavailable"}
-        reasons = sorted(n for bit, n in self.REASONS.items() if self.mask & bit)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
-                "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
+                continue
+            for k, nm in enumerate(self.NAMES):
+                if len(f) > 3 + k and f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm),
+                "source": f"nvidia-smi -lms {self.period_ms}, rows from the start of the timed region while the same steps keep running"}
 
 
 # ---------------------------------------------------------------- reference arm / cpu baseline
@@ -289,21 +279,25 @@ def main():
             dist.all_gather_into_tensor(gathered, packed)
         return e
 
+    # the sampler thread is started BEFORE the warm-up so its start-up (GIL hand-over) cannot delay the first timed
+    # launches; samples are attributed to the timed region by timestamp afterwards
+    sampler = ClockSampler(local_rank)
+    if rank == 0 and not os.environ.get("B200NB_NO_SAMPLER"):
+        sampler.start()
     for i in range(max(a.warmup, 3)):
         step(i, True)            # warm-up includes the event records the timed steps make
     torch.cuda.synchronize()
     launches0 = L.b200nb_kernel_launches()
-    sampler = ClockSampler(local_rank)
-    if rank == 0 and not os.environ.get("B200NB_NO_SAMPLER"):
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t_start, t_end = ev(), ev()
+    w0 = time.perf_counter()
     t_start.record()
     evs = [step(i, True) for i in range(a.steps)]
     t_end.record()
     torch.cuda.synchronize()
+    w0_wall = time.time() - (time.perf_counter() - w0)
     if world > 1:
         dist.barrier()
     total_ms = t_start.elapsed_time(t_end)
@@ -313,10 +307,13 @@ def main():
     if rank == 0:
         t_extra = time.time()
         i = 0
-        while sampler._h is not None and len(sampler.rows) < 5 and time.time() - t_extra < 2.0:
+        while sampler.proc is not None and len(sampler.rows_since(w0_wall)) < 2 and time.time() - t_extra < 1.5:
             step(i, False, comm=False)   # rank-local only: no collectives outside the lock-step region
             i += 1
+            if i % 8 == 0:
+                torch.cuda.synchronize()
         torch.cuda.synchronize()
+        sampler.window = (w0_wall, time.time())
         clocks = sampler.stop()
     if os.environ.get("B200NB_BENCH_DEBUG") and rank == 0:
         print("per-step ms:", [[round(e[k].elapsed_time(e[k + 1]), 3) for k in range(3)] for e in evs], file=sys.stderr)
@@ -355,6 +352,30 @@ def main():
         e2e = {"value": total_genes / float(tt.item()), "unit": "genes/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": float(tt.item()) * 1e3,
                "what": "b200nb_fit_disp x2 + b200nb_fit_beta with host (R-layout, pageable) buffers"}
+
+    # ---- the whole DESeq() Wald path on the device (pre-steps, both dispersion fits, trend, grid refits, Wald fit and
+    # statistics; counts resident in HBM): reported next to `value`, which stays the three hot-path calls
+    full = None
+    try:
+        from deseq2_b200 import device_pipeline as DP
+        yfull = D.to_gene_major(np.ascontiguousarray(w["counts"][:ng]), dev)
+        for _ in range(2):
+            DP.DESeq_device(yfull, w["x"], w["sf"])
+        torch.cuda.synchronize()
+        kf = 5
+        t0 = time.perf_counter()
+        for _ in range(kf):
+            DP.DESeq_device(yfull, w["x"], w["sf"])
+        torch.cuda.synchronize()
+        dtf = (time.perf_counter() - t0) / kf
+        tt = torch.tensor([dtf], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        full = {"value": total_genes / float(tt.item()), "unit": "genes/s", "ms_per_step": float(tt.item()) * 1e3,
+                "what": "device_pipeline.DESeq_device: prep kernel + fitDisp MLE + grid refit + trend kernel + fitDisp MAP "
+                        "+ grid refit + fitBeta + Wald statistics, counts resident in HBM, wall clock incl. host syncs"}
+    except Exception as ex:  # pragma: no cover
+        full = {"error": repr(ex)[:200]}
 
     if rank != 0:
         if world > 1:
@@ -398,7 +419,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (makeExampleDESeqDataSet law, PCG64 seed 20260925)", "config": cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "genes_fitted": total_genes}
+            "full_pipeline": full, "genes_fitted": total_genes}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -55,7 +55,7 @@ template <int P, bool USE_W, bool WANT_D, int MODE>
 __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal& sc, double a, double pm,
                                                double sum_wy, int lane, double& lp, double& dlp) {
   constexpr int NS = SymP<P>::N;
-  const double alpha = exp(a);
+  const double alpha = exp_fast(a);   // a is confined to [-30, 10] by the line search / grid
   const double r = rcp_fast(alpha);
   double lg_r = 0.0, dg_r = 0.0;
   if (MODE != MODE_TAB) lgamma_digamma_pos(r, lg_r, dg_r);
@@ -171,7 +171,7 @@ __device__ __forceinline__ void disp_eval(const DispRow& rv, const DispScal& sc,
 template <int P, bool USE_W>
 __device__ __forceinline__ double disp_d2(const DispRow& rv, const DispScal& sc, int mode, double a, int lane) {
   constexpr int NS = SymP<P>::N;
-  const double alpha = exp(a);
+  const double alpha = exp_fast(a);   // a is confined to [-30, 10] by the line search / grid
   const double r = rcp_fast(alpha);
   const double r2 = r * r;
   double dg_r = 0.0, tg_r = 0.0;

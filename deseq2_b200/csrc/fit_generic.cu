@@ -183,7 +183,7 @@ __device__ __forceinline__ void gdisp_eval(const GDispCtx& C, double a, double p
                                            double& lp, double& dlp, double& d2lp) {
   const Design& D = C.D;
   const GenWarp& S = C.S;
-  const double alpha = exp(a);
+  const double alpha = exp_fast(a);   // a is confined to [-30, 10] by the line search / grid
   const double r = rcp_fast(alpha);
   const double r2 = r * r;
   double lg_r = 0.0, dg_r = 0.0, tg_r = 0.0;
