@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <math.h>
 #include <stdlib.h>
 
 #include <atomic>
@@ -204,6 +205,8 @@ struct DesignDev {
   const double* xg;
   const int* gid;
   int G, grouped;
+  int saturated;       // G == p and the distinct rows form an invertible p x p matrix
+  double sat_logdet;   // 2 log|det X_g|
 };
 constexpr int kDesignRing = 16;
 void* g_design[kDesignRing] = {};
@@ -256,6 +259,33 @@ int prepare_design(const double* x_host, int m, int p, cudaStream_t st, DesignDe
   out->gid = reinterpret_cast<const int*>(base + ((xbytes + 15) & ~(size_t)15));
   out->G = grouped ? (int)rep.size() : m;
   out->grouped = grouped ? 1 : 0;
+  out->saturated = 0;
+  out->sat_logdet = 0.0;
+  if (grouped && (int)rep.size() == p) {
+    // log|det| of the p x p matrix of distinct rows (partial-pivot LU)
+    std::vector<double> a((size_t)p * p);
+    for (int r = 0; r < p; r++)
+      for (int k = 0; k < p; k++) a[(size_t)r * p + k] = xg[(size_t)r * ps + k];
+    double logdet = 0.0;
+    bool ok = true;
+    for (int c = 0; c < p && ok; c++) {
+      int pr = c;
+      for (int r = c + 1; r < p; r++)
+        if (fabs(a[(size_t)r * p + c]) > fabs(a[(size_t)pr * p + c])) pr = r;
+      if (fabs(a[(size_t)pr * p + c]) < 1e-12) { ok = false; break; }
+      if (pr != c)
+        for (int k = 0; k < p; k++) { double t = a[(size_t)c * p + k]; a[(size_t)c * p + k] = a[(size_t)pr * p + k]; a[(size_t)pr * p + k] = t; }
+      logdet += log(fabs(a[(size_t)c * p + c]));
+      for (int r = c + 1; r < p; r++) {
+        const double f = a[(size_t)r * p + c] / a[(size_t)c * p + c];
+        for (int k = c; k < p; k++) a[(size_t)r * p + k] -= f * a[(size_t)c * p + k];
+      }
+    }
+    if (ok) {
+      out->saturated = 1;
+      out->sat_logdet = 2.0 * logdet;
+    }
+  }
   return 0;
 }
 
@@ -358,6 +388,7 @@ int b200nb_fit_disp_dev(const void* y, int y_type, const double* x, const double
     DesignDev dd;
     if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
     a.xg = dd.xg; a.gid = dd.gid; a.G = dd.G; a.grouped = dd.grouped;
+    a.saturated = dd.saturated && !use_weights; a.sat_logdet = dd.sat_logdet;
     CU(nb::launch_fit_disp_generic(a, (cudaStream_t)stream));
     g_launches += 1;
     return 0;
@@ -387,6 +418,7 @@ int b200nb_fit_disp_grid_dev(const void* y, int y_type, const double* x, const d
     DesignDev dd;
     if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
     a.xg = dd.xg; a.gid = dd.gid; a.G = dd.G; a.grouped = dd.grouped;
+    a.saturated = dd.saturated && !use_weights; a.sat_logdet = dd.sat_logdet;
     CU(nb::launch_fit_disp_generic(a, (cudaStream_t)stream));
     g_launches++;
     return 0;

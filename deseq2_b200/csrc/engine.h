@@ -42,6 +42,10 @@ struct DispArgs {
   const double* xg;   // G x (p|1) (grouped) or m x (p|1) (samplewise)
   const int* gid;     // m
   int G, grouped;
+  // saturated design (G == p, distinct rows X_g invertible): X'WX = X_g' diag(W_g) X_g, so
+  // log det = 2 log|det X_g| + sum_g log W_g and tr(B^-1 dB) = sum_g dW_g / W_g -- no p x p algebra at all
+  int saturated;
+  double sat_logdet;  // 2 log|det X_g|
   // device scratch supplied by the caller: (4 + 3 n) 32-bit words
   // [work-queue counter | 3 per-mode gene counts | 3 per-mode gene lists]; the launcher zeroes the header
   unsigned int* scratch;

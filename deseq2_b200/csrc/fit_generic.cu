@@ -175,6 +175,8 @@ struct GDispCtx {
   double prior_sigmasq, inv_sigmasq, weight_threshold;
   int use_prior, use_cr, use_w;
   int tab_mode, ntab;
+  int saturated;
+  double sat_logdet;
   double sum_wy;
 };
 
@@ -253,7 +255,33 @@ __device__ __forceinline__ void gdisp_eval(const GDispCtx& C, double a, double p
   double red[3] = {s_ll, s_dl, s_d2};
   warp_allreduce_sum_n(red);
   double cr = 0.0, dcr = 0.0, cr2 = 0.0;
-  if (C.use_cr) {
+  if (C.use_cr && C.saturated) {
+    // saturated design: lane g owns group g.  log det B = 2 log|det X_g| + sum log W_g,
+    // tr(B^-1 dB) = sum dW/W, tr(B^-1 dB B^-1 dB) = sum (dW/W)^2, tr(B^-1 d2B) = sum d2W/W
+    double lw = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    for (int g = lane; g < D.G; g += 32) {
+      double W = 0.0, dW = 0.0, d2W = 0.0;
+      for (int l = 0; l < 32; l++) {
+        const int sl = g * 32 + ((l + lane) & 31);
+        W += S.accA[sl];
+        if (want_d) dW += S.accB[sl];
+        if (want2) d2W += S.accC[sl];
+      }
+      lw += log_pos(W);
+      if (want_d) {
+        const double iw = rcp_fast(W);
+        const double q = dW * iw;
+        t1 += q;
+        t2 = fma(q, q, t2);
+        if (want2) t3 = fma(d2W, iw, t3);
+      }
+    }
+    double rr[4] = {lw, t1, t2, t3};
+    warp_allreduce_sum_n(rr);
+    cr = -0.5 * (rr[0] + C.sat_logdet);
+    dcr = -0.5 * rr[1];
+    if (want2) cr2 = 0.5 * rr[1] * rr[1] - 0.5 * (rr[1] * rr[1] - rr[2] + rr[3]);
+  } else if (C.use_cr) {
     if (D.grouped) {
       reduce_group_acc(S.accA, S.WA, D.G, lane);
       if (want_d) reduce_group_acc(S.accB, S.WB, D.G, lane);
@@ -395,6 +423,8 @@ __global__ void __launch_bounds__(256) fit_disp_generic_kernel(const DispArgs A,
   C.use_prior = A.use_prior;
   C.use_cr = A.use_cr;
   C.use_w = A.use_weights;
+  C.saturated = A.saturated && A.grouped && A.G == A.p && !A.use_weights;
+  C.sat_logdet = A.sat_logdet;
   const double epsilon = 1.0e-4;
 
   for (;;) {
