@@ -14,6 +14,7 @@ numpy, one function per R function, same names, so the engine can be driven and 
   estimateDispersionsMAP         R/core.R:943-1131
   fitNbinomGLMs                  R/fitNbinomGLMs.R:29-236 (without the optim fallback, :203-227)
   nbinomWaldTest                 R/core.R:1332-1565  (betas, SEs, Wald statistic and p-value)
+  nbinomLRT                      R/core.R:1787-2012  (full vs reduced fit, 2 (l_full - l_reduced), chi-square p-value)
   DESeq                          R/core.R:280-432    (test="Wald", fitType="parametric", betaPrior=FALSE)
 
 `engine` is any object with fitDisp / fitDispGrid / fitBeta taking the reference's argument names
@@ -272,6 +273,42 @@ def nbinomWaldTest(counts, nf, x, dispersion, engine=None, betaTol=1e-8, maxit=1
     WaldPvalue = 2.0 * _sp.ndtr(-np.abs(WaldStatistic))
     fit.update({"WaldStatistic": WaldStatistic, "WaldPvalue": WaldPvalue, "deviance": -2.0 * fit["logLike"]})
     return fit
+
+
+def _fit_intercept_only(counts, nf, alpha_hat):
+    """R/fitNbinomGLMs.R:99-137: reduced model ~1 with the default wide prior needs no IRLS (no native call)."""
+    norm = counts / nf
+    betaMatrix = np.log2(norm.mean(axis=1))[:, None]
+    mu = nf * (2.0 ** betaMatrix)
+    logLike = nbinomLogLike(counts, mu, alpha_hat)
+    w = 1.0 / (1.0 / mu + alpha_hat[:, None])
+    xtwx = w.sum(axis=1)
+    return {"logLike": logLike, "betaConv": np.ones(len(counts), bool), "betaMatrix": betaMatrix,
+            "betaSE": (np.sqrt(1.0 / xtwx) / LN2)[:, None], "mu": mu, "betaIter": np.ones(len(counts)),
+            "hat_diagonals": w / xtwx[:, None]}
+
+
+def nbinomLRT(counts, nf, full, reduced, dispersion, engine=None, betaTol=1e-8, maxit=100, useQR=True, minmu=0.5):
+    """R/core.R:1787-2012 with user-supplied model matrices, betaPrior=FALSE; Cook's distances are not restated.
+    `full` / `reduced` are m x p model matrices (reduced nested in full)."""
+    from scipy import stats as _st
+    counts = np.asarray(counts)
+    if reduced.shape[1] >= full.shape[1]:
+        raise ValueError("less than one degree of freedom, perhaps full and reduced models are not in the correct order")
+    fullModel = fitNbinomGLMs(counts, nf, full, dispersion, engine=engine, betaTol=betaTol, maxit=maxit, useQR=useQR,
+                              minmu=minmu)
+    if reduced.shape[1] == 1 and np.all(reduced == 1):
+        reducedModel = _fit_intercept_only(counts, nf, dispersion)
+    else:
+        reducedModel = fitNbinomGLMs(counts, nf, reduced, dispersion, engine=engine, betaTol=betaTol, maxit=maxit,
+                                     useQR=useQR, minmu=minmu)
+    df = full.shape[1] - reduced.shape[1]
+    LRTStatistic = 2.0 * (fullModel["logLike"] - reducedModel["logLike"])
+    LRTPvalue = _st.chi2.sf(LRTStatistic, df)
+    return {"LRTStatistic": LRTStatistic, "LRTPvalue": LRTPvalue, "deviance": -2.0 * fullModel["logLike"],
+            "betaMatrix": fullModel["betaMatrix"], "betaSE": fullModel["betaSE"], "fullBetaConv": fullModel["betaConv"],
+            "reducedBetaConv": reducedModel["betaConv"], "betaIter": fullModel["betaIter"], "mu": fullModel["mu"],
+            "hat_diagonals": fullModel["hat_diagonals"], "df": df}
 
 
 def DESeq(counts, x, sizeFactors=None, engine=None):

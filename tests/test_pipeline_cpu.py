@@ -35,3 +35,35 @@ def test_linear_mu_matches_group_means():
     mu = pipeline.linearModelMu(norm, d["x"])
     assert np.allclose(mu[:, :4], norm[:, :4].mean(axis=1, keepdims=True))
     assert np.allclose(mu[:, 4:], norm[:, 4:].mean(axis=1, keepdims=True))
+
+
+def test_lrt_full_vs_reduced(oracle):
+    """BASELINE.json config 5 shape (nbinomLRT ~batch+condition vs ~batch), small, oracle engine: the LRT statistic is
+    2 (l_full - l_reduced) >= 0 and genes with a true condition effect get small p-values."""
+    m = 24
+    full = synth.design_batch_condition(m, 2)            # intercept, batch, condition  (p = 3)
+    reduced = full[:, :2]                                 # ~batch
+    d = synth.make_example_counts(600, m, x=full, seed=31, betaSD=1.0)
+    counts = d["counts"][d["counts"].sum(axis=1) > 0]
+    sf = d["sizeFactors"]
+    nf = np.broadcast_to(sf[None, :], counts.shape)
+    alpha = np.clip(0.1 + 4 / (counts / sf).mean(axis=1), 1e-8, m)
+    r = pipeline.nbinomLRT(counts, nf, full, reduced, alpha, engine=oracle)
+    # low-count genes are excluded: fitBeta clamps mu at minmu = 0.5 during the fit while the log-likelihood is
+    # evaluated at the unclamped mu (R/fitNbinomGLMs.R:180-182), so nesting need not hold there -- in R either
+    ok = r["fullBetaConv"] & r["reducedBetaConv"] & ((counts / sf).mean(axis=1) > 5)
+    # both fits stop at a relative deviance change of 1e-8, so the statistic is only non-negative up to that
+    assert r["df"] == 1 and np.all(r["LRTStatistic"][ok] > -1e-6 * np.abs(r["deviance"][ok]))
+    truth = np.abs(d["trueBeta"][d["counts"].sum(axis=1) > 0][:, 2])
+    hi = ok & ((counts / sf).mean(axis=1) > 50)
+    assert np.median(r["LRTPvalue"][hi & (truth > 1.5)]) < 1e-3 < np.median(r["LRTPvalue"][hi & (truth < 0.1)])
+    # reduced = ~1 takes the closed-form branch (R/fitNbinomGLMs.R:99-137): the mean of normalised counts, which is
+    # the NB MLE only for equal size factors -- close to, not equal to, an explicit IRLS fit
+    ones = np.ones((m, 1))
+    a = pipeline._fit_intercept_only(counts, nf, alpha)
+    b = pipeline.fitNbinomGLMs(counts, nf, ones, alpha, engine=oracle)
+    conv = b["betaConv"] & ((counts / sf).min(axis=1) > 2)
+    assert np.allclose(a["betaMatrix"][conv], b["betaMatrix"][conv], atol=0.1)
+    assert np.all(a["logLike"][conv] <= b["logLike"][conv] + 1e-6 * np.abs(b["logLike"][conv]))
+    r1 = pipeline.nbinomLRT(counts, nf, full, ones, alpha, engine=oracle)
+    assert r1["df"] == 2 and np.all(np.isfinite(r1["LRTPvalue"][ok]))
