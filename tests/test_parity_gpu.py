@@ -359,3 +359,47 @@ def test_generic_kernels_on_small_p_designs():
                         "or maxit0 or grid_parity or drop_a_design"], env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+# ---------------------------------------------------------------- edge shapes (test_edge_case.R:5-19 analogues)
+
+@pytest.mark.parametrize("n,m", [(1, 4), (3, 5), (7, 33), (2, 3000)])
+def test_edge_shapes(engine, oracle, n, m):
+    """One gene (test_edge_case.R:5-11), m not a multiple of 4 / 32, a single trip of the sample loop, a very
+    long row; intercept-only and two-group designs; an all-zero row passes through without crashing."""
+    rng = np.random.default_rng(n * 1000 + m)
+    x = np.c_[np.ones(m), (np.arange(m) % 2).astype(float)]
+    mu_true = rng.uniform(5, 200, (n, 1)) * np.exp(0.5 * x[:, 1])[None, :]
+    y = rng.negative_binomial(5.0, 5.0 / (5.0 + mu_true)).astype(np.int32)
+    if n > 2:
+        y[-1] = 0                                       # all-zero gene
+    mu = np.maximum(mu_true, 0.5)
+    la = np.log(np.full(n, 0.2))
+    kw = dict(ySEXP=y, xSEXP=x, mu_hatSEXP=mu, log_alphaSEXP=la, log_alpha_prior_meanSEXP=la,
+              log_alpha_prior_sigmasqSEXP=1.0, min_log_alphaSEXP=np.log(1e-9), kappa_0SEXP=1.0, tolSEXP=1e-6,
+              maxitSEXP=100, usePriorSEXP=False, weightsSEXP=None, useWeightsSEXP=False, weightThresholdSEXP=1e-2,
+              useCRSEXP=True)
+    g, o = engine.fitDisp(**kw), oracle.fitDisp(**kw, with_margin=True)
+    ok = (o["margin"] > ROBUST) & np.isfinite(o["last_lp"])
+    assert np.array_equal(g["iter"][ok], o["iter"][ok])
+    assert np.all(rel_err(g["log_alpha"][ok], o["log_alpha"][ok], floor=1e-9) < TOL)
+    for xx in (x, np.ones((m, 1))):
+        p = xx.shape[1]
+        kb = dict(ySEXP=y, xSEXP=xx, nfSEXP=np.ones((n, m)), alpha_hatSEXP=np.full(n, 0.2),
+                  contrastSEXP=np.r_[1.0, np.zeros(p - 1)], beta_matSEXP=np.tile(np.r_[3.0, np.zeros(p - 1)], (n, 1)),
+                  lambdaSEXP=np.full(p, 1e-6) / np.log(2) ** 2, weightsSEXP=None, useWeightsSEXP=False, tolSEXP=1e-8,
+                  maxitSEXP=100, useQRSEXP=True, minmuSEXP=0.5)
+        gb, ob = engine.fitBeta(**kb), oracle.fitBeta(**kb)
+        assert np.array_equal(gb["iter"], ob["iter"])
+        assert np.nanmax(rel_err(gb["beta_mat"], ob["beta_mat"], floor=1e-7)) < TOL
+        assert np.nanmax(rel_err(gb["hat_diagonals"], ob["hat_diagonals"], floor=1e-9)) < TOL
+
+
+def test_empty_input_is_a_no_op(engine):
+    x = np.c_[np.ones(6), np.r_[0, 0, 0, 1, 1, 1.0]]
+    r = engine.fitDisp(np.zeros((0, 6), np.int32), x, np.zeros((0, 6)), np.zeros(0), np.zeros(0), 1.0, -20.0, 1.0, 1e-6,
+                       10, False, None, False, 1e-2, True)
+    assert r["log_alpha"].shape == (0,)
+    b = engine.fitBeta(np.zeros((0, 6), np.int32), x, np.zeros((0, 6)), np.zeros(0), [1, 0], np.zeros((0, 2)),
+                       [1e-6, 1e-6], None, False, 1e-8, 10, True, 0.5)
+    assert b["beta_mat"].shape == (0, 2)
