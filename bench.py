@@ -113,7 +113,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index, period_ms=50):
+    def __init__(self, index, period_ms=100):
         self.index, self.period_ms = index, period_ms
         self.proc, self.window, self._buf, self._t = None, None, [], None
 
@@ -126,6 +126,11 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self._t = threading.Thread(target=self._reader, daemon=True)
             self._t.start()
+            # nvidia-smi's own start-up (NVML init over every GPU of the box) holds driver locks for 100s of ms and was
+            # measured to stall our kernels: wait for its first row before any timed work is enqueued
+            t0 = time.time()
+            while not self._buf and time.time() - t0 < 10.0 and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 

@@ -36,8 +36,8 @@ int fail(const char* fmt, ...) {
 
 // grow-only device workspace of the host entry points (one set per process; calls are serialised)
 enum Slot {
-  S_RAW0, S_RAW1, S_RAW2, S_Y, S_MU, S_W, S_NF, S_X, S_V0, S_V1, S_V2, S_V3, S_OUTD, S_OUTI, S_H, S_MUO, S_HC, S_MUC,
-  S_BETA_IN, S_BETA_OUT, S_BETA_VAR, S_COUNTER, S_NSLOTS
+  S_RAW0, S_RAW1, S_RAW2, S_Y, S_MU, S_W, S_NF, S_X, S_V0, S_V1, S_V2, S_OUTD, S_OUTI, S_H, S_MUO, S_HC, S_MUC,
+  S_BETA_IN, S_BETA_OUT, S_BETA_VAR, S_NSLOTS
 };
 struct Workspace {
   void* p[S_NSLOTS] = {};

@@ -114,6 +114,7 @@ __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta
 template <int P, bool USE_W>
 __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_beta_kernel(const BetaArgs A, int warps_per_cta, int mpad) {
   extern __shared__ __align__(16) double smem[];
+  init_log_table();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   // per-warp rows: y, mu, [lnf if nf is a matrix], [w]

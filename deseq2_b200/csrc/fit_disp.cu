@@ -158,14 +158,6 @@ __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal
   if (WANT_D) dlp = (r * r * acc[1] + dcr) * alpha + dprior;
 }
 
-template <int P, bool USE_W, bool WANT_D>
-__device__ __forceinline__ void disp_eval(const DispRow& rv, const DispScal& sc, int mode, double a, double pm,
-                                          double sum_wy, int lane, double& lp, double& dlp) {
-  if (mode == MODE_TAB) disp_eval_mode<P, USE_W, WANT_D, MODE_TAB>(rv, sc, a, pm, sum_wy, lane, lp, dlp);
-  else if (mode == MODE_BIG) disp_eval_mode<P, USE_W, WANT_D, MODE_BIG>(rv, sc, a, pm, sum_wy, lane, lp, dlp);
-  else disp_eval_mode<P, USE_W, WANT_D, MODE_GEN>(rv, sc, a, pm, sum_wy, lane, lp, dlp);
-}
-
 // second derivative at `a` (once per gene): src/DESeq2.cpp:111-158.  In TAB mode the digamma / trigamma
 // differences come from the factor table: psi(y+r)-psi(r) = sum_{k<y} 1/(r+k), psi'(y+r)-psi'(r) = -sum 1/(r+k)^2.
 template <int P, bool USE_W>
@@ -441,6 +433,7 @@ __device__ __forceinline__ void line_search_gene(const DispArgs& A, const DispRo
 template <int P, bool USE_W>
 __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(const DispArgs A, int warps_per_cta, int mpad) {
   extern __shared__ __align__(16) double smem[];
+  init_log_table();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   constexpr int NROW = USE_W ? 3 : 2;
@@ -490,6 +483,7 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(con
 template <int P, bool USE_W>
 __global__ void __launch_bounds__(256, 2) fit_disp_grid_kernel(const DispArgs A, int warps_per_cta, int mpad) {
   extern __shared__ __align__(16) double smem[];
+  init_log_table();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   constexpr int NROW = USE_W ? 3 : 2;

@@ -404,6 +404,7 @@ __device__ __forceinline__ void gbuild_table(const GenWarp& S, int m, bool use_w
 
 __global__ void __launch_bounds__(256) fit_disp_generic_kernel(const DispArgs A, int mpad, int ps, size_t warp_doubles) {
   extern __shared__ __align__(16) double smem[];
+  init_log_table();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int xrows = A.grouped ? A.G : A.m;
@@ -596,6 +597,7 @@ __device__ __forceinline__ double lgamma_diff_g(double y, double r, double lg_r)
 
 __global__ void __launch_bounds__(256) fit_beta_generic_kernel(const BetaArgs A, int mpad, int ps, size_t warp_doubles) {
   extern __shared__ __align__(16) double smem[];
+  init_log_table();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int p = A.p;

