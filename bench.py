@@ -113,7 +113,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index, period_ms=100):
+    def __init__(self, index, period_ms=200):
         self.index, self.period_ms = index, period_ms
         self.proc, self.window, self._buf, self._t = None, None, [], None
 
@@ -269,6 +269,7 @@ def main():
         outs_b = [(dict(shared1, log_alpha=pk[2 * p]), dict(shared2, beta_mat=pk[:p], beta_var_mat=pk[p:2 * p]))
                   for pk in packs]
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    cpu_times = []
     kern_ms = {"fit_disp_mle": 0.0, "fit_disp_map": 0.0, "fit_beta": 0.0}
 
     def step(i, timed, comm=True):
@@ -280,17 +281,22 @@ def main():
                 pending[b] = None
             outs[1], outs[2] = outs_b[b]
         e = [ev() for _ in range(4)] if timed else None
+        cpu_t = [time.perf_counter()]
         if timed:
             e[0].record()
         outs[0] = D.fit_disp(r["y"], xd, r["mu"], r["la0"], r["la0"], 1.0, MIN_LOG_ALPHA, 1.0, 1e-6, 100, False,
                              m=m, out=outs[0])
+        cpu_t.append(time.perf_counter())
         if timed:
             e[1].record()
         outs[1] = D.fit_disp(r["y"], xd, r["mu"], r["lai"], r["lfit"], w["priorVar"], MIN_LOG_ALPHA, 1.0, 1e-6, 100,
                              True, m=m, out=outs[1])
+        cpu_t.append(time.perf_counter())
         if timed:
             e[2].record()
         outs[2] = D.fit_beta(r["y"], xd, sfd, r["disp"], contrast, r["beta0"], lamd, 1e-8, 100, out=outs[2])
+        cpu_t.append(time.perf_counter())
+        cpu_times.append(cpu_t)
         if timed:
             e[3].record()
         if world > 1 and comm:
@@ -312,13 +318,17 @@ def main():
     t_start, t_end = ev(), ev()
     w0 = time.perf_counter()
     t_start.record()
-    evs = [step(i, True) for i in range(a.steps)]
+    no_ev = bool(os.environ.get("B200NB_NO_STEP_EVENTS"))
+    evs = [step(i, not no_ev) for i in range(a.steps)]
     for b_ in range(NBUF if world > 1 else 0):   # the timed region ends when every gather has landed
         if pending[b_] is not None:
             pending[b_].wait()
             pending[b_] = None
     t_end.record()
+    cpu_enq_ms = 1e3 * (time.perf_counter() - w0)
     torch.cuda.synchronize()
+    if os.environ.get("B200NB_BENCH_DEBUG") and rank == 0:
+        print("cpu enqueue of the timed region: %.2f ms" % cpu_enq_ms, file=sys.stderr)
     w0_wall = time.time() - (time.perf_counter() - w0)
     if world > 1:
         dist.barrier()
@@ -337,7 +347,14 @@ def main():
         torch.cuda.synchronize()
         sampler.window = (w0_wall, time.time())
         clocks = sampler.stop()
-    if os.environ.get("B200NB_BENCH_DEBUG") and rank == 0:
+    if no_ev:
+        evs = []
+        kern_ms = {"fit_disp_mle": 1e-9, "fit_disp_map": 1e-9, "fit_beta": 1e-9}
+    if os.environ.get("B200NB_BENCH_DEBUG") and rank == 0 and not no_ev:
+        ct = cpu_times[max(a.warmup, 3):max(a.warmup, 3) + a.steps]
+        print("cpu enqueue ms per call (max over steps):", [round(1e3 * max(c[k + 1] - c[k] for c in ct), 3) for k in range(3)],
+              "cpu total enqueue ms:", round(1e3 * (ct[-1][3] - ct[0][0]), 2), "gpu ms:", round(total_ms, 2), file=sys.stderr)
+        print("cpu per-step [mle,map,beta] ms:", [[round(1e3 * (c[k + 1] - c[k]), 2) for k in range(3)] for c in ct], file=sys.stderr)
         print("per-step ms:", [[round(e[k].elapsed_time(e[k + 1]), 3) for k in range(3)] for e in evs], file=sys.stderr)
     for e in evs:
         kern_ms["fit_disp_mle"] += e[0].elapsed_time(e[1]) / a.steps

@@ -318,12 +318,22 @@ cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
   if (fixed + warps * rowbytes > smem_cap) return cudaErrorInvalidValue;
   const size_t smem = fixed + warps * rowbytes;
   auto kern = fit_beta_kernel<P, USE_W>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, warps * 32, smem);
-  if (e != cudaSuccess) return e;
-  if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+  // the attribute / occupancy queries are made once per (kernel, shared-memory size) and cached
+  static size_t cached_smem[2] = {0, 0};
+  static int cached_ctas[2] = {0, 0};
+  const int slot = 0;
+  cudaError_t e = cudaSuccess;
+  if (cached_smem[slot] != smem || cached_ctas[slot] < 1) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int c = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern, warps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (c < 1) return cudaErrorLaunchOutOfResources;
+    cached_smem[slot] = smem;
+    cached_ctas[slot] = c;
+  }
+  const int ctas_per_sm = cached_ctas[slot];
   const int sms = device_sm_count();
   long long want = ((long long)a.n + warps - 1) / warps;
   long long grid = (long long)sms * ctas_per_sm;

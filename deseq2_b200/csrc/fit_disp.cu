@@ -542,12 +542,22 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
   const size_t smem = xbytes + warps * rowbytes;
   const bool grid_mode = a.grid != nullptr;
   auto kern = grid_mode ? fit_disp_grid_kernel<P, USE_W> : fit_disp_kernel<P, USE_W>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int ctas_per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, warps * 32, smem);
-  if (e != cudaSuccess) return e;
-  if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+  // the attribute / occupancy queries are made once per (kernel, shared-memory size) and cached
+  static size_t cached_smem[2] = {0, 0};
+  static int cached_ctas[2] = {0, 0};
+  const int slot = (grid_mode ? 1 : 0);
+  cudaError_t e = cudaSuccess;
+  if (cached_smem[slot] != smem || cached_ctas[slot] < 1) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int c = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern, warps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (c < 1) return cudaErrorLaunchOutOfResources;
+    cached_smem[slot] = smem;
+    cached_ctas[slot] = c;
+  }
+  const int ctas_per_sm = cached_ctas[slot];
   const int sms = device_sm_count();
   long long want = ((long long)a.n + warps - 1) / warps;
   long long grid = (long long)sms * ctas_per_sm;   // persistent: one resident wave, genes come from the queue
