@@ -499,6 +499,21 @@ int b200nb_trend_fit_dev(const double* means, const double* disps, int n, double
   return 0;
 }
 
+int b200nb_cooks_dev(const void* y, int y_type, const double* mu, const double* hat, const double* size_factors,
+                     const int32_t* cell_ptr, const int32_t* cell_samples, int ncell, int n, int m, int p,
+                     long long ld, double* cooks, double* max_cooks, double* robust_disp, void* stream) {
+  if (check_dims(n, m, p)) return 1;
+  if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
+  if (ncell < 1 || ncell > m) return fail("bad number of design cells %d", ncell);
+  nb::CooksArgs a{};
+  a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.mu = mu; a.hat = hat; a.size_factors = size_factors;
+  a.cell_ptr = cell_ptr; a.cell_samples = cell_samples; a.ncell = ncell; a.n = n; a.m = m; a.p = p; a.ld = ld;
+  a.cooks = cooks; a.max_cooks = max_cooks; a.robust_disp = robust_disp;
+  CU(nb::launch_cooks(a, (cudaStream_t)stream));
+  if (n > 0) g_launches++;
+  return 0;
+}
+
 /* ------------------------------------------------------------------ host entry points */
 
 int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,

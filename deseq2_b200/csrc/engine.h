@@ -110,6 +110,23 @@ struct PrepArgs {
   double* beta0;               // n x p column-major or nullptr: least-squares start values on log(K/s + 0.1)
 };
 cudaError_t launch_prep(const PrepArgs& a, cudaStream_t stream);
+
+// Cook's distances (pipeline_kernels.cu)
+struct CooksArgs {
+  const void* y;
+  int y_is_f64;
+  const double* mu;            // gene-major fitted means
+  const double* hat;           // gene-major hat diagonals
+  const double* size_factors;  // m
+  const int* cell_ptr;         // ncell + 1: samples of cell c are cell_samples[cell_ptr[c] .. cell_ptr[c+1])
+  const int* cell_samples;     // m: a permutation of 0..m-1 grouped by cell
+  int ncell, n, m, p;
+  long long ld;
+  double* cooks;               // gene-major n x ld or nullptr
+  double* max_cooks;           // n
+  double* robust_disp;         // n
+};
+cudaError_t launch_cooks(const CooksArgs& a, cudaStream_t stream);
 cudaError_t launch_trend_fit(const double* means, const double* disps, int n, double min_disp, double* out4,
                              cudaStream_t stream);
 

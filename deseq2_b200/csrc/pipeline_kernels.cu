@@ -203,3 +203,161 @@ cudaError_t launch_trend_fit(const double* means, const double* disps, int n, do
 }
 
 }  // namespace nb
+
+// ================================================================ Cook's distances
+// R/core.R:2277-2359: robustMethodOfMomentsDisp (per-cell trimmed mean, trimmed mean of squared errors, max over
+// cells), Cook's distance from the hat diagonal, and the per-gene maximum over samples with >= 3 replicates in
+// their cell.  One warp per gene.  The trimmed means need the floor(n*trim) smallest and largest values of a cell:
+// they are extracted one at a time with a warp arg-min / arg-max over the lanes' unmarked candidates (cells have
+// tens to hundreds of samples, floor(n/8) extractions), which avoids a full sort.
+namespace nb {
+namespace {
+
+struct ArgVal {
+  double v;
+  int idx;
+};
+
+__device__ __forceinline__ ArgVal warp_argmin(double v, int idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  return ArgVal{v, idx};
+}
+
+// sum of vals[list[0..n)] minus its k smallest and k largest entries (k = floor(n * trim)); `taken` is an n-length
+// scratch (one byte per candidate) in shared memory.  Returns the trimmed mean.  trim < 0.5.
+__device__ __forceinline__ double trimmed_mean_list(const double* vals, const int* list, int n, int k,
+                                                    unsigned char* taken, int lane) {
+  double tot = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    tot += vals[list[i]];
+    taken[i] = 0;
+  }
+  tot = warp_allreduce_sum(tot);
+  __syncwarp();
+  double removed = 0.0;
+  for (int round = 0; round < 2 * k; round++) {
+    const bool want_min = round < k;
+    double best = want_min ? 1e308 : -1e308;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < n; i += 32) {
+      if (taken[i]) continue;
+      const double v = vals[list[i]];
+      if (want_min ? (v < best) : (v > best)) { best = v; bi = i; }
+    }
+    const ArgVal r = warp_argmin(want_min ? best : -best, bi);
+    removed += want_min ? r.v : -r.v;
+    if (lane == (r.idx & 31)) taken[r.idx] = 1;   // candidate i is owned by lane i % 32
+    __syncwarp();
+  }
+  return (tot - removed) / (double)(n - 2 * k);
+}
+
+__device__ __forceinline__ int trim_bin(int n) { return n <= 3 ? 0 : (n <= 23 ? 1 : 2); }
+
+__global__ void __launch_bounds__(128) cooks_kernel(const CooksArgs A) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int mpad = (A.m + 3) & ~3;
+  int* cell_ptr = reinterpret_cast<int*>(smem);                 // ncell + 1
+  int* cell_samples = cell_ptr + A.ncell + 1;                   // m
+  double* sf = smem + ((A.ncell + 1 + A.m + 1) / 2 + 1);        // mpad
+  double* wbase = sf + mpad + (size_t)warp * (2 * mpad + (mpad + 7) / 8);
+  double* vn = wbase;                                           // normalised counts
+  double* sq = wbase + mpad;                                    // squared errors
+  unsigned char* taken = reinterpret_cast<unsigned char*>(wbase + 2 * mpad);
+  for (int i = threadIdx.x; i <= A.ncell; i += blockDim.x) cell_ptr[i] = A.cell_ptr[i];
+  for (int i = threadIdx.x; i < A.m; i += blockDim.x) {
+    cell_samples[i] = A.cell_samples[i];
+    sf[i] = A.size_factors[i];
+  }
+  __syncthreads();
+  const double trimratio[3] = {1.0 / 3.0, 1.0 / 4.0, 1.0 / 8.0};
+  const double scale_c[3] = {2.04, 1.86, 1.51};
+  const int g = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (g >= A.n) return;
+  const size_t off = (size_t)g * A.ld;
+  double s = 0.0;
+  for (int j = lane; j < A.m; j += 32) {
+    const double y = A.y_is_f64 ? static_cast<const double*>(A.y)[off + j] : (double)static_cast<const int32_t*>(A.y)[off + j];
+    const double v = y / sf[j];
+    vn[j] = v;
+    s += v;
+  }
+  const double mean = warp_allreduce_sum(s) / (double)A.m;
+  __syncwarp();
+  double vmax = -1e308;
+  bool any3 = false;
+  for (int c = 0; c < A.ncell; c++) {
+    const int lo = cell_ptr[c], nc = cell_ptr[c + 1] - lo;
+    if (nc < 3) continue;
+    any3 = true;
+    const int tb = trim_bin(nc);
+    const int k = (int)floor((double)nc * trimratio[tb]);
+    const double cm = trimmed_mean_list(vn, cell_samples + lo, nc, k, taken, lane);
+    for (int i = lane; i < nc; i += 32) {
+      const int j = cell_samples[lo + i];
+      const double d = vn[j] - cm;
+      sq[j] = d * d;
+    }
+    __syncwarp();
+    const double ve = scale_c[tb] * trimmed_mean_list(sq, cell_samples + lo, nc, k, taken, lane);
+    vmax = fmax(vmax, ve);
+  }
+  if (!any3) {
+    // trimmedVariance over all samples (R/core.R:2327-2332); cell_samples is a permutation of 0..m-1
+    const int k = (int)floor((double)A.m / 8.0);
+    const double rm = trimmed_mean_list(vn, cell_samples, A.m, k, taken, lane);
+    for (int j = lane; j < A.m; j += 32) {
+      const double d = vn[j] - rm;
+      sq[j] = d * d;
+    }
+    __syncwarp();
+    vmax = 1.51 * trimmed_mean_list(sq, cell_samples, A.m, k, taken, lane);
+  }
+  const double alpha_r = fmax((vmax - mean) / (mean * mean), 0.04);
+  // Cook's distance and its maximum over samples in cells with >= 3 replicates
+  double mx = -1e308;
+  for (int c = 0; c < A.ncell; c++) {
+    const int lo = cell_ptr[c], nc = cell_ptr[c + 1] - lo;
+    for (int i = lane; i < nc; i += 32) {
+      const int j = cell_samples[lo + i];
+      const double y = A.y_is_f64 ? static_cast<const double*>(A.y)[off + j] : (double)static_cast<const int32_t*>(A.y)[off + j];
+      const double mu = A.mu[off + j], h = A.hat[off + j];
+      const double V = mu + alpha_r * mu * mu;
+      const double d = y - mu;
+      const double ck = d * d / V / (double)A.p * h / ((1.0 - h) * (1.0 - h));
+      if (A.cooks != nullptr) A.cooks[off + j] = ck;
+      if (nc >= 3) mx = fmax(mx, ck);
+    }
+  }
+  mx = warp_allreduce_max(mx);
+  if (lane == 0) {
+    A.robust_disp[g] = alpha_r;
+    A.max_cooks[g] = (any3 && A.m > A.p) ? mx : nan("");
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_cooks(const CooksArgs& a, cudaStream_t stream) {
+  if (a.n == 0) return cudaSuccess;
+  const int mpad = (a.m + 3) & ~3;
+  int warps = 4;
+  auto bytes = [&](int w) {
+    return (((size_t)(a.ncell + 1 + a.m + 1) / 2 + 1) + mpad + (size_t)w * (2 * mpad + (mpad + 7) / 8)) * sizeof(double);
+  };
+  while (warps > 1 && bytes(warps) > 200 * 1024) warps >>= 1;
+  const size_t smem = bytes(warps);
+  cudaError_t e = cudaFuncSetAttribute(cooks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cooks_kernel<<<(a.n + warps - 1) / warps, warps * 32, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace nb

@@ -67,6 +67,29 @@ def trend_fit(means, disps, minDisp=1e-8):
     return out
 
 
+def cooks(y, mu, hat, x, sizeFactors, want_matrix=True):
+    """b200nb_cooks_dev: Cook's distances, their per-gene maximum and the robust moments dispersion."""
+    from .pipeline import designCells
+    L = _lib.lib()
+    dev = y.device
+    n, ld = y.shape
+    x = np.asarray(x, dtype=np.float64)
+    m, p = x.shape
+    cells, sizes = designCells(x)
+    order = np.argsort(cells, kind="stable").astype(np.int32)
+    ptr = np.r_[0, np.cumsum(sizes)].astype(np.int32)
+    ptrd = torch.as_tensor(ptr, device=dev)
+    ordd = torch.as_tensor(order, device=dev)
+    sfd = torch.as_tensor(np.asarray(sizeFactors, dtype=np.float64), device=dev)
+    out = {"cooks": torch.empty((n, ld), dtype=F64, device=dev) if want_matrix else None,
+           "maxCooks": torch.empty(n, dtype=F64, device=dev), "robustDisp": torch.empty(n, dtype=F64, device=dev)}
+    rc = L.b200nb_cooks_dev(_p(y), 0 if y.dtype == torch.int32 else 1, _p(mu), _p(hat), _p(sfd), _p(ptrd), _p(ordd),
+                            len(sizes), n, m, p, ld, _p(out["cooks"]), _p(out["maxCooks"]), _p(out["robustDisp"]),
+                            _stream())
+    _lib.check(rc, "cooks_dev")
+    return out
+
+
 def _median(v):
     """R's median (mean of the two middle order statistics for even length)."""
     s, _ = torch.sort(v)
@@ -157,7 +180,8 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
     betaSE = torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0.0)) / LN2
     stat = betaMatrix / betaSE
     pval = 2.0 * torch.special.ndtr(-stat.abs())
-    return {"idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
+    ck = cooks(ynz, fb["mu"], fb["hat_diagonals"], x, sizeFactors, want_matrix=False)   # R/core.R:1457-1460
+    return {"maxCooks": ck["maxCooks"], "idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
             "dispersion": dispersion, "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"],
             "betaMatrix": betaMatrix.T, "betaSE": betaSE.T, "WaldStatistic": stat.T, "WaldPvalue": pval.T,
             "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": fb["deviance"], "mu": fb["mu"],

@@ -15,6 +15,7 @@ numpy, one function per R function, same names, so the engine can be driven and 
   fitNbinomGLMs                  R/fitNbinomGLMs.R:29-236 (without the optim fallback, :203-227)
   nbinomWaldTest                 R/core.R:1332-1565  (betas, SEs, Wald statistic and p-value)
   nbinomLRT                      R/core.R:1787-2012  (full vs reduced fit, 2 (l_full - l_reduced), chi-square p-value)
+  robustMethodOfMomentsDisp / trimmedCellVariance / calculateCooksDistance / recordMaxCooks   R/core.R:2277-2359
   DESeq                          R/core.R:280-432    (test="Wald", fitType="parametric", betaPrior=FALSE)
 
 `engine` is any object with fitDisp / fitDispGrid / fitBeta taking the reference's argument names
@@ -273,6 +274,88 @@ def nbinomWaldTest(counts, nf, x, dispersion, engine=None, betaTol=1e-8, maxit=1
     WaldPvalue = 2.0 * _sp.ndtr(-np.abs(WaldStatistic))
     fit.update({"WaldStatistic": WaldStatistic, "WaldPvalue": WaldPvalue, "deviance": -2.0 * fit["logLike"]})
     return fit
+
+
+def _r_trimmed_mean(x, trim):
+    """R's mean(x, trim=) along the last axis: drop floor(n*trim) order statistics from each end."""
+    x = np.sort(np.asarray(x, dtype=np.float64), axis=-1)
+    n = x.shape[-1]
+    if trim >= 0.5:
+        return np.median(x, axis=-1)
+    lo = int(np.floor(n * trim))
+    return x[..., lo:n - lo].mean(axis=-1)
+
+
+def _trimfn(n):
+    """as.integer(cut(n, breaks=c(0, 3.5, 23.5, Inf))) - 1  (R/core.R:2306)."""
+    return 0 if n <= 3.5 else (1 if n <= 23.5 else 2)
+
+
+_TRIMRATIO = (1.0 / 3.0, 1.0 / 4.0, 1.0 / 8.0)
+_SCALE_C = (2.04, 1.86, 1.51)
+
+
+def designCells(x):
+    """Cell (distinct design row) id per sample, in order of first appearance, and the cell sizes."""
+    seen, ids = {}, []
+    for r in np.asarray(x):
+        ids.append(seen.setdefault(tuple(r), len(seen)))
+    ids = np.asarray(ids)
+    return ids, np.bincount(ids)
+
+
+def trimmedCellVariance(cnts, cells):
+    """R/core.R:2302-2325."""
+    levels = np.unique(cells)
+    cellMeans = np.empty((cnts.shape[0], len(levels)))
+    for k, lvl in enumerate(levels):
+        sel = cells == lvl
+        cellMeans[:, k] = _r_trimmed_mean(cnts[:, sel], _TRIMRATIO[_trimfn(sel.sum())])
+    qmat = cellMeans[:, np.searchsorted(levels, cells)]
+    sqerror = (cnts - qmat) ** 2
+    varEst = np.empty_like(cellMeans)
+    for k, lvl in enumerate(levels):
+        sel = cells == lvl
+        t = _trimfn(sel.sum())
+        varEst[:, k] = _SCALE_C[t] * _r_trimmed_mean(sqerror[:, sel], _TRIMRATIO[t])
+    return varEst.max(axis=1)
+
+
+def trimmedVariance(x):
+    """R/core.R:2327-2332."""
+    rm = _r_trimmed_mean(x, 1.0 / 8.0)
+    return 1.51 * _r_trimmed_mean((x - rm[:, None]) ** 2, 1.0 / 8.0)
+
+
+def robustMethodOfMomentsDisp(counts, sizeFactors, x):
+    """R/core.R:2277-2300."""
+    cnts = np.asarray(counts, dtype=np.float64) / sizeFactors[None, :]
+    cells, sizes = designCells(x)
+    three = sizes[cells] >= 3
+    if three.any():
+        v = trimmedCellVariance(cnts[:, three], cells[three])
+    else:
+        v = trimmedVariance(cnts)
+    m = cnts.mean(axis=1)
+    return np.maximum((v - m) / m ** 2, 0.04)
+
+
+def calculateCooksDistance(counts, mu, H, sizeFactors, x):
+    """R/core.R:2333-2340."""
+    p = x.shape[1]
+    disp = robustMethodOfMomentsDisp(counts, sizeFactors, x)
+    V = mu + disp[:, None] * mu ** 2
+    return (np.asarray(counts, dtype=np.float64) - mu) ** 2 / V / p * H / (1 - H) ** 2
+
+
+def recordMaxCooks(x, cooks):
+    """R/core.R:2349-2359: max Cook's distance over the samples that have >= 3 replicates in their cell."""
+    cells, sizes = designCells(x)
+    samplesForCooks = sizes[cells] >= 3
+    m, p = x.shape
+    if m > p and samplesForCooks.any():
+        return cooks[:, samplesForCooks].max(axis=1)
+    return np.full(cooks.shape[0], np.nan)
 
 
 def _fit_intercept_only(counts, nf, alpha_hat):

@@ -112,6 +112,13 @@ int b200nb_prep_dev(const void* y, int y_type, const double* x, const double* pr
 int b200nb_trend_fit_dev(const double* means, const double* disps, int n, double min_disp, double* out4,
                          void* stream);
 
+/* b200nb_cooks_dev: calculateCooksDistance + recordMaxCooks + robustMethodOfMomentsDisp (R/core.R:2277-2359).
+ * cells = distinct design rows: cell_ptr (ncell+1) / cell_samples (m, sample indices grouped by cell), device ints.
+ * cooks (gene-major n x ld) may be NULL; max_cooks[n] is NaN when no cell has >= 3 replicates or m <= p. */
+int b200nb_cooks_dev(const void* y, int y_type, const double* mu, const double* hat, const double* size_factors,
+                     const int32_t* cell_ptr, const int32_t* cell_samples, int ncell, int n, int m, int p,
+                     long long ld, double* cooks, double* max_cooks, double* robust_disp, void* stream);
+
 /* ---- housekeeping */
 const char* b200nb_last_error(void);
 int b200nb_device_count(void);            /* number of visible CUDA devices (0 if none / no driver) */

@@ -81,3 +81,40 @@ def test_device_pipeline_matches_host_pipeline(engine, design, n, m):
     assert np.all((pv[conv] >= 0) & (pv[conv] <= 1))
     se = rel_err(dv["betaSE"].cpu().numpy()[conv], host["betaSE"][idx][conv])
     assert np.mean(se < 1e-5) > 0.97
+
+
+@pytest.mark.parametrize("design,m", [("condition", 12), ("condition", 60), ("batch", 36), ("covariate", 20),
+                                      ("factor10", 200)])
+def test_cooks_kernel_matches_numpy(engine, design, m):
+    """robust moments dispersion (per-cell trimmed means), Cook's distances and their maximum
+    (R/core.R:2277-2359) on device vs the numpy restatement."""
+    import torch
+    from deseq2_b200 import device as D, device_pipeline as DP, pipeline, synth
+    rng = np.random.default_rng(5)
+    if design == "condition":
+        x = synth.design_condition(m)
+    elif design == "batch":
+        x = synth.design_batch_condition(m, 3)
+    elif design == "factor10":
+        x = synth.design_factor(m, 10)
+    else:
+        x = np.c_[np.ones(m), rng.normal(0, 1, m)]          # every sample its own cell -> trimmedVariance branch
+    d = synth.make_example_counts(800, m, x=x if design != "covariate" else None, seed=17)
+    counts = d["counts"][d["counts"].sum(axis=1) > 0]
+    counts[::7, 0] *= 30                                    # planted outliers (test_outlier.R:33-55 idea)
+    sf = d["sizeFactors"]
+    n = len(counts)
+    mu = np.maximum((counts / sf).mean(axis=1, keepdims=True) * sf[None, :] * rng.uniform(0.8, 1.25, (n, m)), 0.5)
+    H = rng.uniform(0.01, 0.6, (n, m))
+    dev = torch.device("cuda")
+    out = DP.cooks(D.to_gene_major(counts, dev), D.to_gene_major(mu, dev), D.to_gene_major(H, dev), x, sf)
+    ref_disp = pipeline.robustMethodOfMomentsDisp(counts, sf, x)
+    ref_cooks = pipeline.calculateCooksDistance(counts, mu, H, sf, x)
+    ref_max = pipeline.recordMaxCooks(x, ref_cooks)
+    assert np.max(rel_err(out["robustDisp"].cpu().numpy(), ref_disp)) < 1e-10
+    assert np.max(rel_err(out["cooks"].cpu().numpy()[:, :m], ref_cooks, floor=1e-12)) < 1e-9
+    got_max = out["maxCooks"].cpu().numpy()
+    if np.all(np.isnan(ref_max)):
+        assert np.all(np.isnan(got_max))
+    else:
+        assert np.max(rel_err(got_max, ref_max, floor=1e-12)) < 1e-9
