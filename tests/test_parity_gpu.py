@@ -403,3 +403,46 @@ def test_empty_input_is_a_no_op(engine):
     b = engine.fitBeta(np.zeros((0, 6), np.int32), x, np.zeros((0, 6)), np.zeros(0), [1, 0], np.zeros((0, 2)),
                        [1e-6, 1e-6], None, False, 1e-8, 10, True, 0.5)
     assert b["beta_mat"].shape == (0, 2)
+
+
+# ---------------------------------------------------------------- BASELINE.json config shapes (3, 4, 5), spot checks
+
+@pytest.mark.parametrize("name,n,m", [("C3", 1500, 500), ("C4", 400, 1000), ("C5", 1500, 200)])
+def test_config_shapes_spot_check(engine, oracle, name, n, m):
+    """The sample counts and designs of BASELINE.json configs 3-5 at a reduced gene count (genes are independent, so
+    the per-gene arithmetic is the full-size arithmetic): C3 ~batch+condition (3x2, p=4, m=500), C4 10-level factor
+    (p=10) plus its 11-column expanded matrix with ridge (m=1000), C5 full ~batch+condition (2x2, p=3) and reduced
+    ~batch (p=2) for the LRT (m=200)."""
+    from deseq2_b200 import synth
+    if name == "C3":
+        x = synth.design_batch_condition(m, 3)
+        fits = [(x, None)]
+    elif name == "C4":
+        x = synth.design_factor(m, 10)
+        xe = synth.design_factor_expanded(m, 10)
+        fits = [(x, None), (xe, np.r_[1e-6, np.full(10, 1.0 / 0.5)] / np.log(2) ** 2)]
+    else:
+        x = synth.design_batch_condition(m, 2)
+        fits = [(x, None), (x[:, :2], None)]
+    c = make_case(n, m, x=x, seed={"C3": 303, "C4": 404, "C5": 505}[name], betaSD=0.5)
+    alpha = np.clip(0.1 + 4 / c["baseMean"], 1e-8, m)
+    betas = None
+    for xf, lam in fits:
+        p = xf.shape[1]
+        if np.linalg.matrix_rank(xf) == p:
+            Q, R = np.linalg.qr(xf)
+            b0 = np.linalg.solve(R, Q.T @ np.log(c["counts"] / c["nf"] + 0.1).T).T
+        else:
+            b0 = np.zeros((len(c["counts"]), p))
+            b0[:, 0] = np.log(c["baseMean"])
+        a = beta_args(c, alpha, x=xf, lam=lam, beta0=b0)
+        g, o = engine.fitBeta(**a), oracle.fitBeta(**a)
+        _compare_beta(g, o, f"{name} beta p={p}", tol=2e-6 if lam is not None else TOL)
+        if betas is None:
+            betas = o["beta_mat"]
+    mu = np.maximum(c["nf"] * np.exp(betas @ x.T), 0.5)
+    d = disp_args(c, mu, np.log(c["alpha0"]))
+    gd = engine.fitDisp(**d)
+    _compare_disp(gd, oracle.fitDisp(**d, with_margin=True), f"{name} disp mle", min_robust=0.8)
+    d2 = disp_args(c, mu, gd["log_alpha"], prior_mean=np.log(alpha), sigmasq=0.5, usePrior=True)
+    _compare_disp(engine.fitDisp(**d2), oracle.fitDisp(**d2, with_margin=True), f"{name} disp map", min_robust=0.8)
