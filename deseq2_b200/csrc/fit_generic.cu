@@ -123,31 +123,36 @@ struct GenWarp {
   double *v0, *v1, *v2, *v3;          // length-32 vectors
 };
 
-// nrow = number of m-length rows: 2 (y, mu) or 3 (y, lnf, mu) plus 1 when weights are used; `three` selects r2
-__host__ __device__ inline size_t gen_warp_doubles(int mpad, int p, int ps, int G, int grouped, int nrow) {
+// per-warp shared-memory layout.  Rows of length mpad: y, r1 (optional), r2 (optional), weights (optional);
+// factor table (optional); `nacc` accumulator sets (3 for the dispersion kernel, 2 for IRLS).
+struct GenShape {
+  int has_r1, has_r2, use_w, has_tab, nacc;
+};
+__host__ __device__ inline size_t gen_warp_doubles(int mpad, int p, int ps, int G, int grouped, GenShape sh) {
   const size_t terms = grouped ? (size_t)G : (size_t)mpad;
   const size_t acc = grouped ? (size_t)G * 32 : (size_t)mpad;
-  return (size_t)nrow * mpad + kTabMaxG + 3 * acc + (grouped ? 3 * terms : 0) + terms + 4 * (size_t)p * ps + 4 * 32;
+  const size_t rows = 1 + sh.has_r1 + sh.has_r2 + sh.use_w;
+  return rows * mpad + (sh.has_tab ? kTabMaxG : 0) + sh.nacc * acc + (grouped ? sh.nacc * terms : 0) + terms +
+         4 * (size_t)p * ps + 4 * 32;
 }
 
-__device__ __forceinline__ GenWarp carve(double* base, int mpad, int p, int ps, int G, int grouped, int nrow,
-                                         bool three, bool use_w) {
+__device__ __forceinline__ GenWarp carve(double* base, int mpad, int p, int ps, int G, int grouped, GenShape sh) {
   GenWarp S;
   const size_t terms = grouped ? (size_t)G : (size_t)mpad;
   const size_t acc = grouped ? (size_t)G * 32 : (size_t)mpad;
   double* q = base;
   S.ys = q; q += mpad;
-  S.r1 = q; q += mpad;
-  S.r2 = three ? q : nullptr; q += three ? mpad : 0;
-  S.wsm = use_w ? q : nullptr; q += use_w ? mpad : 0;
-  S.tab = q; q += kTabMaxG;
+  S.r1 = sh.has_r1 ? q : nullptr; q += sh.has_r1 ? mpad : 0;
+  S.r2 = sh.has_r2 ? q : nullptr; q += sh.has_r2 ? mpad : 0;
+  S.wsm = sh.use_w ? q : nullptr; q += sh.use_w ? mpad : 0;
+  S.tab = sh.has_tab ? q : nullptr; q += sh.has_tab ? kTabMaxG : 0;
   S.accA = q; q += acc;
   S.accB = q; q += acc;
-  S.accC = q; q += acc;
+  S.accC = (sh.nacc > 2) ? q : nullptr; q += (sh.nacc > 2) ? acc : 0;
   if (grouped) {
     S.WA = q; q += terms;
     S.WB = q; q += terms;
-    S.WC = q; q += terms;
+    S.WC = (sh.nacc > 2) ? q : nullptr; q += (sh.nacc > 2) ? terms : 0;
   } else {
     S.WA = S.accA; S.WB = S.accB; S.WC = S.accC;
   }
@@ -414,10 +419,9 @@ __global__ void __launch_bounds__(256) fit_disp_generic_kernel(const DispArgs A,
   for (int i = threadIdx.x; i < xrows * ps; i += blockDim.x) xg[i] = A.xg[i];
   for (int i = threadIdx.x; i < A.m; i += blockDim.x) gid[i] = A.gid[i];
   __syncthreads();
-  const int nrow = A.use_weights ? 3 : 2;
   GDispCtx C;
   C.D = Design{xg, gid, A.p, ps, A.G, A.grouped, A.m};
-  C.S = carve(wbase, mpad, A.p, ps, A.G, A.grouped, nrow, false, A.use_weights != 0);
+  C.S = carve(wbase, mpad, A.p, ps, A.G, A.grouped, GenShape{1, 0, A.use_weights != 0, 1, 3});
   C.prior_sigmasq = A.prior_sigmasq;
   C.inv_sigmasq = 1.0 / A.prior_sigmasq;
   C.weight_threshold = A.weight_threshold;
@@ -617,10 +621,9 @@ __global__ void __launch_bounds__(256) fit_beta_generic_kernel(const BetaArgs A,
     contrast[k] = A.contrast[k];
   }
   __syncthreads();
-  const int nrow = A.use_weights ? 4 : 3;
   GBetaCtx C;
   C.D = Design{xg, gid, p, ps, A.G, A.grouped, A.m};
-  C.S = carve(wbase, mpad, p, ps, A.G, A.grouped, nrow, true, A.use_weights != 0);
+  C.S = carve(wbase, mpad, p, ps, A.G, A.grouped, GenShape{A.nf_is_vector ? 0 : 1, 1, A.use_weights != 0, 0, 2});
   C.use_w = A.use_weights;
   C.minmu = A.minmu;
   C.log_minmu = log(A.minmu);
@@ -782,10 +785,10 @@ struct GenLaunch {
   size_t warp_doubles, smem;
 };
 
-bool plan(int m, int p, int G, int grouped, int nrow, size_t extra_doubles, GenLaunch& out) {
+bool plan(int m, int p, int G, int grouped, GenShape sh, size_t extra_doubles, GenLaunch& out) {
   out.mpad = (m + 3) & ~3;
   out.ps = p | 1;
-  out.warp_doubles = gen_warp_doubles(out.mpad, p, out.ps, G, grouped, nrow);
+  out.warp_doubles = gen_warp_doubles(out.mpad, p, out.ps, G, grouped, sh);
   const size_t fixed = ((size_t)(grouped ? G : m) * out.ps + (m + 1) / 2 + extra_doubles) * sizeof(double);
   const size_t cap = 227 * 1024;
   int warps = 8;
@@ -800,7 +803,7 @@ bool plan(int m, int p, int G, int grouped, int nrow, size_t extra_doubles, GenL
 cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
   DispArgs a = a0;
   GenLaunch L;
-  if (!plan(a.m, a.p, a.G, a.grouped, a.use_weights ? 3 : 2, 0, L)) return cudaErrorInvalidValue;
+  if (!plan(a.m, a.p, a.G, a.grouped, GenShape{1, 0, a.use_weights != 0, 1, 3}, 0, L)) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(fit_disp_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
   if (e != cudaSuccess) return e;
   int ctas_per_sm = 0;
@@ -821,7 +824,8 @@ cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
 cudaError_t launch_fit_beta_generic(const BetaArgs& a, cudaStream_t stream) {
   GenLaunch L;
   const int mpad = (a.m + 3) & ~3;
-  if (!plan(a.m, a.p, a.G, a.grouped, a.use_weights ? 4 : 3, (size_t)mpad + 64, L)) return cudaErrorInvalidValue;
+  if (!plan(a.m, a.p, a.G, a.grouped, GenShape{a.nf_is_vector ? 0 : 1, 1, a.use_weights != 0, 0, 2}, (size_t)mpad + 64, L))
+    return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(fit_beta_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
   if (e != cudaSuccess) return e;
   int ctas_per_sm = 0;

@@ -108,6 +108,32 @@ def _grid_refit(y, xd, mu, sel, m, prior_mean, prior_sigmasq, usePrior):
     return idx, torch.exp(la)
 
 
+def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e-8, maxit=100, minmu=0.5):
+    """nbinomLRT (R/core.R:1787-2012) on device tensors: two IRLS fits, LRT statistic 2 (l_full - l_reduced) and its
+    chi-square p-value.  The kernel's deviance is -2 log-likelihood at the fitted (minmu-clamped) mean, i.e. what
+    R/fitNbinomGLMs.R:180-182 recomputes in R whenever no fitted mean sits on the clamp."""
+    dev = ynz.device
+    sfd = torch.as_tensor(np.asarray(sizeFactors, dtype=np.float64), device=dev)
+    res = {}
+    for name, x in (("full", x_full), ("reduced", x_reduced)):
+        x = np.asarray(x, dtype=np.float64)
+        m, p = x.shape
+        pr = prep(ynz, x, sizeFactors, minmu=minmu, want_mu=False)
+        contrast = torch.zeros(p, dtype=F64, device=dev)
+        contrast[0] = 1.0
+        lam = torch.full((p,), 1e-6 / LN2 ** 2, dtype=F64, device=dev)
+        res[name] = D.fit_beta(ynz, pr["xd"], sfd, dispersion, contrast, pr["beta0"], lam, betaTol, maxit, minmu=minmu,
+                               want_hat=(name == "full"), want_mu=(name == "full"))
+    df = x_full.shape[1] - x_reduced.shape[1]
+    stat = res["reduced"]["deviance"] - res["full"]["deviance"]
+    pval = torch.special.gammaincc(torch.tensor(df / 2.0, dtype=F64, device=dev), torch.clamp(stat, min=0.0) / 2.0)
+    return {"LRTStatistic": stat, "LRTPvalue": pval, "deviance": res["full"]["deviance"], "df": df,
+            "betaMatrix": (res["full"]["beta_mat"] / LN2).T,
+            "betaSE": (torch.sqrt(torch.clamp(res["full"]["beta_var_mat"], min=0.0)) / LN2).T,
+            "fullBetaConv": res["full"]["iter"] < maxit, "reducedBetaConv": res["reduced"]["iter"] < maxit,
+            "mu": res["full"]["mu"], "H": res["full"]["hat_diagonals"]}
+
+
 def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, maxit=100, betaTol=1e-8, minmu=0.5,
                  outlierSD=2.0):
     """y: gene-major (N, ld) device tensor of counts (int32 or float64).  Returns a dict of device tensors over the

@@ -118,3 +118,27 @@ def test_cooks_kernel_matches_numpy(engine, design, m):
         assert np.all(np.isnan(got_max))
     else:
         assert np.max(rel_err(got_max, ref_max, floor=1e-12)) < 1e-9
+
+
+def test_lrt_device_matches_host(engine):
+    """BASELINE.json config 5's call sequence (nbinomLRT ~batch+condition vs ~batch) on device vs the host glue."""
+    import torch
+    from deseq2_b200 import device as D, device_pipeline as DP, pipeline, synth
+    m = 40
+    full = synth.design_batch_condition(m, 2)
+    reduced = full[:, :2]
+    d = synth.make_example_counts(3000, m, x=full, seed=41, betaSD=0.7)
+    counts = d["counts"][d["counts"].sum(axis=1) > 0]
+    sf = d["sizeFactors"]
+    nf = np.broadcast_to(sf[None, :], counts.shape)
+    alpha = np.clip(0.1 + 4 / (counts / sf).mean(axis=1), 1e-8, m)
+    host = pipeline.nbinomLRT(counts, nf, full, reduced, alpha, engine=engine)
+    dev = torch.device("cuda")
+    got = DP.nbinomLRT_device(D.to_gene_major(counts, dev), full, reduced, sf, torch.as_tensor(alpha, device=dev))
+    ok = host["fullBetaConv"] & host["reducedBetaConv"] & ((counts / sf).min(axis=1) > 2)   # away from the minmu clamp
+    st = got["LRTStatistic"].cpu().numpy()
+    assert np.max(np.abs(st[ok] - host["LRTStatistic"][ok]) / (1 + np.abs(host["deviance"][ok]))) < 1e-9
+    pv = got["LRTPvalue"].cpu().numpy()
+    big = ok & (host["LRTPvalue"] > 1e-12)
+    assert np.max(rel_err(pv[big], host["LRTPvalue"][big])) < 1e-6
+    assert np.max(rel_err(got["betaMatrix"].cpu().numpy()[ok], host["betaMatrix"][ok], floor=1e-6)) < 1e-6
