@@ -170,10 +170,31 @@ class ClockSampler:
 
 # ---------------------------------------------------------------- reference arm / cpu baseline
 
-def time_oracle(w, n_sample, steps, warmup):
+def _set_omp_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must still use the host's cores."""
+    import ctypes
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+        return int(n)
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", 1))
+
+
+def time_oracle(w, n_sample, steps, warmup, budget_s=120.0):
+    """Oracle (CPU restatement of src/DESeq2.cpp) on the first n genes of the workload, all host threads
+    (OpenMP over gene chunks = BiocParallel emulation).  The sample is shrunk if the requested steps would not fit
+    the time budget."""
     from oracle import oracle as O
     O.build()
+    O.lib()
+    cores = _set_omp_threads(int(os.environ.get("B200NB_REF_THREADS", os.cpu_count() or 1)))
     n = min(n_sample, len(w["counts"]))
+    t0 = time.perf_counter()
+    three_calls_host(w, O, slice(0, min(n, 2000)))          # probe (also first-touch / thread start-up)
+    per_gene = (time.perf_counter() - t0) / min(n, 2000)
+    total_passes = max(1, steps + warmup)
+    if per_gene * n * total_passes > budget_s:
+        n = max(500, int(budget_s / (per_gene * total_passes)))
     sl = slice(0, n)
     for _ in range(warmup):
         three_calls_host(w, O, sl)
@@ -181,7 +202,6 @@ def time_oracle(w, n_sample, steps, warmup):
     for _ in range(steps):
         three_calls_host(w, O, sl)
     dt = (time.perf_counter() - t0) / steps
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     return n / dt, dt, cores, n
 
 
@@ -200,6 +220,9 @@ def main():
         if rank != 0:
             return
         from oracle import oracle as O
+        O.build()
+        O.lib()
+        _set_omp_threads(int(os.environ.get("B200NB_REF_THREADS", os.cpu_count() or 1)))
         w = build_workload(min(n, a.cpu_sample), m, 20260923 + 2, O)
         v, dt, cores, ns = time_oracle(w, a.cpu_sample, max(1, a.steps), max(0, a.warmup))
         print(json.dumps({
