@@ -7,7 +7,7 @@
 //   * the gene's row (counts, mu, weights) is staged once into shared memory with 128-bit loads;
 //     every lane owns samples lane, lane+32, ...; all per-gene scalars are warp-uniform;
 //   * one fused pass per proposal evaluates the log posterior AND its derivative (they share
-//     log(1+mu*alpha) and 1/(1/mu+alpha)), so an accepted step costs one pass instead of the reference's
+//     log(1+mu*alpha) and 1/(1+mu*alpha)), so an accepted step costs one pass instead of the reference's
 //     three (theta(kappa), lpnew, dlp) -- the values are the same because the reference re-evaluates the
 //     same function at the same point (:225 vs :233);
 //   * the identities log(mu+1/alpha) = log(1+mu*alpha) - log(alpha), mu*alpha/(1+mu*alpha) = alpha*wd,
