@@ -51,18 +51,22 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs A) {
   s2 = warp_allreduce_sum(s2);
   const double bv = s2 / (double)(A.m - 1);
   __syncwarp();
-  // coef = P v  (lane k owns coefficient k)
-  if (lane < A.p) {
+  // coef = P v: lanes stride over samples (coalesced reads of P), one warp reduction per coefficient
+  for (int k = 0; k < A.p; k++) {
+    const double* Pk = A.proj + (size_t)k * A.m;
     double c = 0.0, cl = 0.0;
-    const double* Pk = A.proj + (size_t)lane * A.m;
-    for (int j = 0; j < A.m; j++) {
+    for (int j = lane; j < A.m; j += 32) {
       const double pk = __ldg(Pk + j);
       c = fma(pk, vn[j], c);
       cl = fma(pk, vl[j], cl);
     }
-    coef[lane] = c;
-    coefl[lane] = cl;
-    if (A.beta0 != nullptr) A.beta0[(size_t)g + (size_t)A.n * lane] = cl;
+    c = warp_allreduce_sum(c);
+    cl = warp_allreduce_sum(cl);
+    if (lane == 0) {
+      coef[k] = c;
+      coefl[k] = cl;
+      if (A.beta0 != nullptr) A.beta0[(size_t)g + (size_t)A.n * k] = cl;
+    }
   }
   __syncwarp();
   // fitted = X coef; rough dispersion; linear mu
@@ -213,23 +217,10 @@ cudaError_t launch_trend_fit(const double* means, const double* disps, int n, do
 namespace nb {
 namespace {
 
-struct ArgVal {
-  double v;
-  int idx;
-};
-
-__device__ __forceinline__ ArgVal warp_argmin(double v, int idx) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-  }
-  return ArgVal{v, idx};
-}
-
-// sum of vals[list[0..n)] minus its k smallest and k largest entries (k = floor(n * trim)); `taken` is an n-length
-// scratch (one byte per candidate) in shared memory.  Returns the trimmed mean.  trim < 0.5.
+// mean of vals[list[0..n)] after removing its k smallest and k largest entries (k = floor(n * trim), trim < 0.5).
+// Each round removes the current minimum AND the current maximum among the unmarked candidates (one scan, two
+// interleaved warp arg-reductions; ties: lowest index for the minimum, highest for the maximum, so the two are
+// distinct while at least two candidates remain).  `taken`: n-byte scratch in shared memory.
 __device__ __forceinline__ double trimmed_mean_list(const double* vals, const int* list, int n, int k,
                                                     unsigned char* taken, int lane) {
   double tot = 0.0;
@@ -240,18 +231,27 @@ __device__ __forceinline__ double trimmed_mean_list(const double* vals, const in
   tot = warp_allreduce_sum(tot);
   __syncwarp();
   double removed = 0.0;
-  for (int round = 0; round < 2 * k; round++) {
-    const bool want_min = round < k;
-    double best = want_min ? 1e308 : -1e308;
-    int bi = 0x7fffffff;
+  for (int round = 0; round < k; round++) {
+    double lo = 1e308, hi = -1e308;
+    int ilo = 0x7fffffff, ihi = -1;
     for (int i = lane; i < n; i += 32) {
       if (taken[i]) continue;
       const double v = vals[list[i]];
-      if (want_min ? (v < best) : (v > best)) { best = v; bi = i; }
+      if (v < lo) { lo = v; ilo = i; }
+      if (v >= hi) { hi = v; ihi = i; }
     }
-    const ArgVal r = warp_argmin(want_min ? best : -best, bi);
-    removed += want_min ? r.v : -r.v;
-    if (lane == (r.idx & 31)) taken[r.idx] = 1;   // candidate i is owned by lane i % 32
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double olo = __shfl_xor_sync(0xffffffffu, lo, o);
+      const int oilo = __shfl_xor_sync(0xffffffffu, ilo, o);
+      const double ohi = __shfl_xor_sync(0xffffffffu, hi, o);
+      const int oihi = __shfl_xor_sync(0xffffffffu, ihi, o);
+      if (olo < lo || (olo == lo && oilo < ilo)) { lo = olo; ilo = oilo; }
+      if (ohi > hi || (ohi == hi && oihi > ihi)) { hi = ohi; ihi = oihi; }
+    }
+    removed += lo + hi;
+    if (lane == (ilo & 31)) taken[ilo] = 1;   // candidate i is owned by lane i % 32
+    if (lane == (ihi & 31)) taken[ihi] = 1;
     __syncwarp();
   }
   return (tot - removed) / (double)(n - 2 * k);

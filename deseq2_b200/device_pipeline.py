@@ -143,6 +143,19 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
     m, p = x.shape
     if m - p <= 3:
         raise NotImplementedError("residual df <= 3: the reference's Monte-Carlo prior-variance branch is not restated")
+    import os
+    import time
+    stage_ms = {}
+    _t = [time.perf_counter()]
+    debug = bool(os.environ.get("B200NB_PIPE_DEBUG"))
+
+    def mark(name):
+        if debug:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            stage_ms[name] = round((now - _t[0]) * 1e3, 3)
+            _t[0] = now
+
     maxDisp = float(max(10, m))
     linearMu = modelMatrixGroups(x) == p
     pr = prep(y, x, sizeFactors, minDisp=minDisp, minmu=minmu, want_mu=linearMu)
@@ -152,6 +165,7 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
     bm = pr["baseMean"][idx]
     alpha0 = pr["alpha0"][idx]
     beta0 = pr["beta0"][:, idx].contiguous()
+    mark("prep+compact")
     n = idx.numel()
     contrast = torch.zeros(p, dtype=F64, device=dev)
     contrast[0] = 1.0
@@ -164,7 +178,9 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
     else:
         mu = D.fit_beta(ynz, xd, sfd, alpha0, contrast, beta0, lam, betaTol, maxit, minmu=minmu, want_hat=False)["mu"]
     la0 = torch.log(alpha0)
+    mark("mu")
     r = D.fit_disp(ynz, xd, mu, la0, la0, 1.0, min_log_alpha, kappa_0, dispTol, maxit, False)
+    mark("fit_disp_mle")
     dge = torch.clamp(torch.exp(r["log_alpha"]), max=maxDisp)
     noIncrease = r["last_lp"] < r["initial_lp"] + r["initial_lp"].abs() / 1e6
     dge = torch.where(noIncrease, alpha0, dge)
@@ -174,6 +190,7 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
         dge[gi] = ga
     dge = torch.clamp(dge, minDisp, maxDisp)
     n_refit_geneest = int(gi.numel())
+    mark("rules+grid_mle")
 
     # ---- estimateDispersionsFit + dispersionFunction<- + PriorVar (R/core.R:864-940, R/methods.R:142-190, R/core.R:1135-1208)
     tr = trend_fit(bm, dge, minDisp)
@@ -187,11 +204,13 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
     status = tr[2].item()
     if status != 0:
         raise FloatingPointError(f"parametric dispersion fit failed on device (status {int(status)})")
+    mark("trend+priorvar")
 
     # ---- estimateDispersionsMAP (R/core.R:943-1131)
     dispInit = torch.where(dge > 0.1 * dispFit, dge, dispFit)
     logFit = torch.log(dispFit)
     rm = D.fit_disp(ynz, xd, mu, torch.log(dispInit), logFit, dispPriorVar, min_log_alpha, kappa_0, dispTol, maxit, True)
+    mark("fit_disp_map")
     dispMAP = torch.exp(rm["log_alpha"])
     gi2, ga2 = _grid_refit(ynz, xd, mu, rm["iter"] >= maxit, m, logFit, dispPriorVar, True)
     if ga2 is not None:
@@ -199,15 +218,18 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
     dispMAP = torch.clamp(dispMAP, minDisp, maxDisp)
     dispOutlier = torch.log(dge) > logFit + outlierSD * torch.sqrt(varLogDispEsts)
     dispersion = torch.where(dispOutlier, dge, dispMAP)
+    mark("rules+grid_map")
 
     # ---- nbinomWaldTest (R/core.R:1332-1565) via fitNbinomGLMs (R/fitNbinomGLMs.R:29-236)
     fb = D.fit_beta(ynz, xd, sfd, dispersion, contrast, beta0, lam, betaTol, maxit, minmu=minmu)
+    mark("fit_beta")
     betaMatrix = fb["beta_mat"] / LN2                      # (p, n)
     betaSE = torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0.0)) / LN2
     stat = betaMatrix / betaSE
     pval = 2.0 * torch.special.ndtr(-stat.abs())
     ck = cooks(ynz, fb["mu"], fb["hat_diagonals"], x, sizeFactors, want_matrix=False)   # R/core.R:1457-1460
-    return {"maxCooks": ck["maxCooks"], "idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
+    mark("wald_stats+cooks")
+    return {"stage_ms": stage_ms, "maxCooks": ck["maxCooks"], "idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
             "dispersion": dispersion, "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"],
             "betaMatrix": betaMatrix.T, "betaSE": betaSE.T, "WaldStatistic": stat.T, "WaldPvalue": pval.T,
             "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": fb["deviance"], "mu": fb["mu"],

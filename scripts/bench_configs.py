@@ -18,7 +18,7 @@ from deseq2_b200 import device as D, pipeline, synth  # noqa: E402
 MINLA = float(np.log(1e-9))
 
 
-def run(name, n, m, x, x_fit=None, lam=None, reps=3):
+def run(name, n, m, x, x_fit=None, lam=None, reps=3, lrt_reduced=None):
     dev = torch.device("cuda")
     d = synth.make_example_counts(n, m, x=x, seed=11, betaSD=0.5)
     counts = d["counts"]
@@ -74,6 +74,28 @@ def run(name, n, m, x, x_fit=None, lam=None, reps=3):
     bytes_disp = n * (12 * m + 88)
     res["fit_disp_hbm_GBs"] = bytes_disp / (res["fit_disp_mle_ms"] * 1e-3) / 1e9
     res["fit_beta_hbm_GBs"] = n * (20 * m + 24 * pf + 40) / (res["fit_beta_ms"] * 1e-3) / 1e9
+    # the whole device-resident analysis on this shape (prep, both dispersion fits, trend, grid refits, Wald fit +
+    # statistics + Cook's; wall clock incl. the few host syncs).  LRT configs add the reduced fit.
+    try:
+        from deseq2_b200 import device_pipeline as DP
+        import time
+        DP.DESeq_device(y, x, sf)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out_p = DP.DESeq_device(y, x, sf)
+        torch.cuda.synchronize()
+        res["device_pipeline_wald_ms"] = (time.perf_counter() - t0) * 1e3
+        res["device_pipeline_wald_genes_per_s"] = n / (res["device_pipeline_wald_ms"] * 1e-3)
+        if lrt_reduced is not None:
+            ynz = y[out_p["idx"]].contiguous()
+            DP.nbinomLRT_device(ynz, x, lrt_reduced, sf, out_p["dispersion"])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            DP.nbinomLRT_device(ynz, x, lrt_reduced, sf, out_p["dispersion"])
+            torch.cuda.synchronize()
+            res["device_lrt_ms"] = (time.perf_counter() - t0) * 1e3
+    except Exception as ex:
+        res["device_pipeline_error"] = repr(ex)[:200]
     print(json.dumps(res), flush=True)
 
 
@@ -87,5 +109,6 @@ if __name__ == "__main__":
     run("C4 50k x 1000 10-level factor p=10 (MLE pass)", int(50000 * s), 1000, synth.design_factor(1000, 10))
     run("C4 50k x 1000 expanded p=11 ridge (MAP pass)", int(50000 * s), 1000, synth.design_factor(1000, 10),
         x_fit=synth.design_factor_expanded(1000, 10), lam=np.r_[1e-6, np.full(10, 1 / 0.7)] / np.log(2) ** 2)
-    run("C5 shard 125k x 200 ~batch+condition(2x2) p=3", int(125000 * s), 200, synth.design_batch_condition(200, 2))
+    run("C5 shard 125k x 200 ~batch+condition(2x2) p=3", int(125000 * s), 200, synth.design_batch_condition(200, 2),
+        lrt_reduced=synth.design_batch_condition(200, 2)[:, :2])
     run("C5 reduced ~batch p=2", int(125000 * s), 200, synth.design_condition(200))
