@@ -433,7 +433,7 @@ int oracle_fit_disp(const double *y, const double *x, const double *mu_hat, cons
 #pragma omp parallel
   {
     disp_ws *s = disp_ws_new(m, p, x);
-#pragma omp for schedule(dynamic, 64)
+#pragma omp for schedule(dynamic, 8)
     for (int i = 0; i < n; i++) {
       load_rows(s, y, mu_hat, weights, n, i);
       double pm = log_alpha_prior_mean[i];
@@ -509,7 +509,7 @@ int oracle_fit_disp_grid(const double *y, const double *x, const double *mu_hat,
     disp_ws *s = disp_ws_new(m, p, x);
     double *lpv = (double *)malloc(sizeof(double) * grid_n);
     double *fine = (double *)malloc(sizeof(double) * grid_n);
-#pragma omp for schedule(dynamic, 16)
+#pragma omp for schedule(dynamic, 4)
     for (int i = 0; i < n; i++) {
       load_rows(s, y, mu_hat, weights, n, i);
       double pm = log_alpha_prior_mean[i];
@@ -595,7 +595,7 @@ int oracle_fit_beta(const double *y, const double *x, const double *nf, const do
     double *Ainv = (double *)malloc(sizeof(double) * pp), *work = (double *)malloc(sizeof(double) * pp);
     double *T1 = (double *)malloc(sizeof(double) * pp), *sigma = (double *)malloc(sizeof(double) * pp);
     int *piv = (int *)malloc(sizeof(int) * p);
-#pragma omp for schedule(dynamic, 64)
+#pragma omp for schedule(dynamic, 8)
     for (int i = 0; i < n; i++) {
       for (int j = 0; j < m; j++) {
         yrow[j] = y[i + (size_t)n * j];
