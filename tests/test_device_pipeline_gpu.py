@@ -57,10 +57,11 @@ def test_trend_kernel_matches_numpy(engine):
     assert np.max(rel_err(out[:2], ref)) < 1e-8
 
 
-@pytest.mark.parametrize("design,n,m", [("condition", 6000, 40), ("batch", 3000, 36)])
+@pytest.mark.parametrize("design,n,m", [("condition", 6000, 40), ("batch", 3000, 36), ("factor10", 1500, 120)])
 def test_device_pipeline_matches_host_pipeline(engine, design, n, m):
     from deseq2_b200 import device_pipeline as DP, pipeline, synth
-    x = synth.design_condition(m) if design == "condition" else synth.design_batch_condition(m, 3)
+    x = {"condition": synth.design_condition(m), "batch": synth.design_batch_condition(m, 3),
+         "factor10": synth.design_factor(m, 10)}[design]
     d, y = _setup(n, m, x=x, seed=11)
     host = pipeline.DESeq(d["counts"], x, sizeFactors=d["sizeFactors"], engine=engine)
     dv = DP.DESeq_device(y, x, d["sizeFactors"])
