@@ -173,23 +173,30 @@ int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   return 0;
 }
 
-// scratch buffers for fit_disp launches (work queue + per-mode gene lists): a ring of grow-only device buffers,
-// one per launch in flight (slot reuse after kScratchRing further launches; launches on one stream are ordered).
+// scratch buffers for fit_disp launches (work queue + per-mode gene lists): ONE device arena cut into a ring of
+// equal slots, one slot per launch in flight (slot reuse after kScratchRing further launches; launches on one stream
+// are ordered).  The arena is (re)allocated only when a call needs a larger slot than any before -- a per-slot
+// cudaFree/cudaMalloc was measured to stall the pipeline by up to 80 ms whenever the gene count changed, and a
+// lazily allocated ring stalled the first 8 steps of every run.
 constexpr int kScratchRing = 16;
-void* g_scratch[kScratchRing] = {};
-size_t g_scratch_bytes[kScratchRing] = {};
+void* g_scratch_arena = nullptr;
+size_t g_scratch_slot = 0;
 std::atomic<unsigned int> g_scratch_next{0};
 int next_scratch(size_t bytes, unsigned int** out) {
-  const unsigned int s = g_scratch_next.fetch_add(1) % kScratchRing;
-  if (g_scratch_bytes[s] < bytes) {
-    if (g_scratch[s]) CU(cudaFree(g_scratch[s]));
-    g_scratch[s] = nullptr;
-    g_scratch_bytes[s] = 0;
-    const size_t want = bytes + bytes / 4;
-    CU(cudaMalloc(&g_scratch[s], want));
-    g_scratch_bytes[s] = want;
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (g_scratch_slot < bytes) {
+    if (g_scratch_arena) {
+      CU(cudaDeviceSynchronize());
+      CU(cudaFree(g_scratch_arena));
+    }
+    g_scratch_arena = nullptr;
+    g_scratch_slot = 0;
+    const size_t slot = (bytes + bytes / 2 + 4095) & ~(size_t)4095;
+    CU(cudaMalloc(&g_scratch_arena, slot * kScratchRing));
+    g_scratch_slot = slot;
   }
-  *out = static_cast<unsigned int*>(g_scratch[s]);
+  const unsigned int s = g_scratch_next.fetch_add(1) % kScratchRing;
+  *out = reinterpret_cast<unsigned int*>(static_cast<char*>(g_scratch_arena) + (size_t)s * g_scratch_slot);
   return 0;
 }
 
@@ -209,9 +216,26 @@ struct DesignDev {
   double sat_logdet;   // 2 log|det X_g|
 };
 constexpr int kDesignRing = 16;
-void* g_design[kDesignRing] = {};
-size_t g_design_bytes[kDesignRing] = {};
+void* g_design_arena = nullptr;
+size_t g_design_slot = 0;
 std::atomic<unsigned int> g_design_next{0};
+int next_design_slot(size_t need, char** out) {
+  need = (need + 255) & ~(size_t)255;
+  if (g_design_slot < need) {
+    if (g_design_arena) {
+      CU(cudaDeviceSynchronize());
+      CU(cudaFree(g_design_arena));
+    }
+    g_design_arena = nullptr;
+    g_design_slot = 0;
+    const size_t slot = (need + need / 2 + 4095) & ~(size_t)4095;
+    CU(cudaMalloc(&g_design_arena, slot * kDesignRing));
+    g_design_slot = slot;
+  }
+  const unsigned int s = g_design_next.fetch_add(1) % kDesignRing;
+  *out = static_cast<char*>(g_design_arena) + (size_t)s * g_design_slot;
+  return 0;
+}
 
 // x_host: m x p column-major.  Uploads xg / gid on `st`.
 int prepare_design(const double* x_host, int m, int p, cudaStream_t st, DesignDev* out) {
@@ -242,15 +266,8 @@ int prepare_design(const double* x_host, int m, int p, cudaStream_t st, DesignDe
     for (int j = 0; j < m; j++) gid[j] = j;
   const size_t xbytes = xg.size() * sizeof(double), gbytes = (size_t)m * sizeof(int);
   const size_t need = ((xbytes + 15) & ~(size_t)15) + gbytes;
-  const unsigned int s = g_design_next.fetch_add(1) % kDesignRing;
-  if (g_design_bytes[s] < need) {
-    if (g_design[s]) CU(cudaFree(g_design[s]));
-    g_design[s] = nullptr;
-    g_design_bytes[s] = 0;
-    CU(cudaMalloc(&g_design[s], need + need / 4));
-    g_design_bytes[s] = need + need / 4;
-  }
-  char* base = static_cast<char*>(g_design[s]);
+  char* base = nullptr;
+  if (next_design_slot(need, &base)) return 1;
   // pageable H2D copies are staged before cudaMemcpyAsync returns, so the vectors may die at scope exit
   CU(cudaMemcpyAsync(base, xg.data(), xbytes, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(base + ((xbytes + 15) & ~(size_t)15), gid.data(), gbytes, cudaMemcpyHostToDevice, st));

@@ -559,19 +559,24 @@ __device__ __forceinline__ double gbeta_pass(const GBetaCtx& C, const double* be
     const int t = D.grouped ? D.gid[j] : j;
     const double lnf = C.lnf[j];
     const double le = S.q[t] + lnf;
-    const double mu = fmax(exp(le), C.minmu);
+    const double mu = fmax((fabs(le) < 700.0) ? exp_fast(le) : exp(le), C.minmu);
     const double lmu = (mu == C.minmu) ? C.log_minmu : le;
     mus[j] = mu;
     const double y = S.ys[j];
     const double am = mu * alpha;
-    double w = mu * rcp_fast(1.0 + am);
+    const double u1 = 1.0 + am;
+    const double iu1 = rcp_fast(u1);
+    double w = mu * iu1;
     double wt = 1.0;
     if (C.use_w) {
       wt = S.wsm[j];
       w *= wt;
     }
     const double z = (lmu - lnf) + fma(y, rcp_fast(mu), -1.0);
-    if (want_dev) dev = fma(wt, fma(y, lmu + log_alpha, -(y + r) * log1p(am)), dev);
+    if (want_dev) {
+      const double l1p = log_pos(u1) + (am - (u1 - 1.0)) * iu1;   // log1p(am)
+      dev = fma(wt, fma(y, lmu + log_alpha, -(y + r) * l1p), dev);
+    }
     if (D.grouped) {
       const int slot = t * 32 + lane;
       S.accA[slot] += w;
@@ -594,7 +599,7 @@ __device__ __forceinline__ double lgamma_diff_g(double y, double r, double lg_r)
     const double xr = y + r;
     const double ixr = rcp_fast(xr), ir = rcp_fast(r);
     const double tail = stirling_tail(ixr, ixr * ixr) - stirling_tail(ir, ir * ir);
-    return fma(y, log_pos(xr), fma(r - 0.5, log1p(y * ir), -y)) + tail;
+    return fma(y, log_pos(xr), fma(r - 0.5, log1p_pos(y * ir), -y)) + tail;
   }
   return lgamma_pos(y + r) - lg_r;
 }
@@ -738,7 +743,7 @@ __global__ void __launch_bounds__(256) fit_beta_generic_kernel(const BetaArgs A,
         const double mu = S.r2[j];
         if (A.mu_out != nullptr) A.mu_out[off + j] = mu;
         if (A.hat_diag != nullptr) {
-          double w = mu / (1.0 + alpha * mu);
+          double w = mu * rcp_fast(fma(alpha, mu, 1.0));
           if (A.use_weights) w *= S.wsm[j];
           A.hat_diag[off + j] = w * S.q[C.D.grouped ? gid[j] : j];
         }

@@ -34,6 +34,21 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_WS = {}
+
+
+def _ws(name, shape, dtype, dev):
+    """Reusable n x ld work matrices (fitted means, hat diagonals): at 20k x 1000 a fresh 160 MB torch allocation per
+    call was measured to cost tens of ms in allocator / cudaMalloc churn, far more than the kernels that fill it.
+    The tensors returned by DESeq_device under "mu" / "H" are views of this workspace: valid until the next call."""
+    key = (name, str(dev))
+    t = _WS.get(key)
+    if t is None or t.shape != tuple(shape) or t.dtype != dtype:
+        t = torch.empty(shape, dtype=dtype, device=dev)
+        _WS[key] = t
+    return t
+
+
 def prep(y, x, sizeFactors, minDisp=1e-8, minmu=0.5, want_mu=True, want_beta0=True):
     """b200nb_prep_dev.  y: gene-major (n, ld) int32/float64 device tensor; x: (m, p) numpy; sizeFactors: (m,) numpy."""
     L = _lib.lib()
@@ -47,7 +62,7 @@ def prep(y, x, sizeFactors, minDisp=1e-8, minmu=0.5, want_mu=True, want_beta0=Tr
     sfd = torch.as_tensor(np.asarray(sizeFactors, dtype=np.float64), device=dev)
     out = {"baseMean": torch.empty(n, dtype=F64, device=dev), "baseVar": torch.empty(n, dtype=F64, device=dev),
            "allZero": torch.empty(n, dtype=torch.int32, device=dev), "alpha0": torch.empty(n, dtype=F64, device=dev),
-           "mu_lin": torch.empty((n, ld), dtype=F64, device=dev) if want_mu else None,
+           "mu_lin": _ws("mu_lin", (n, ld), F64, dev) if want_mu else None,
            "beta0": torch.empty((p, n), dtype=F64, device=dev) if want_beta0 else None}
     rc = L.b200nb_prep_dev(_p(y), 0 if y.dtype == torch.int32 else 1, _p(xd), _p(projd), _p(sfd),
                            float(np.mean(1.0 / np.asarray(sizeFactors))), float(minDisp), float(max(10, m)),
@@ -158,14 +173,14 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
 
     maxDisp = float(max(10, m))
     linearMu = modelMatrixGroups(x) == p
-    pr = prep(y, x, sizeFactors, minDisp=minDisp, minmu=minmu, want_mu=linearMu)
+    # rows with a zero sum are dropped before anything else (R/core.R:706), so every later array is aligned
+    idx = torch.nonzero(y[:, :m].sum(dim=1) != 0).squeeze(1)
+    ynz = y if idx.numel() == y.shape[0] else y[idx].contiguous()
+    pr = prep(ynz, x, sizeFactors, minDisp=minDisp, minmu=minmu, want_mu=linearMu)
     xd, sfd = pr["xd"], pr["sfd"]
-    idx = torch.nonzero(pr["allZero"] == 0).squeeze(1)
-    ynz = y[idx].contiguous()
-    bm = pr["baseMean"][idx]
-    alpha0 = pr["alpha0"][idx]
-    beta0 = pr["beta0"][:, idx].contiguous()
-    mark("prep+compact")
+    bm = pr["baseMean"]
+    alpha0 = pr["alpha0"]
+    beta0 = pr["beta0"]
     n = idx.numel()
     contrast = torch.zeros(p, dtype=F64, device=dev)
     contrast[0] = 1.0
@@ -174,9 +189,15 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
 
     # ---- estimateDispersionsGeneEst (R/core.R:657-860)
     if linearMu:
-        mu = pr["mu_lin"][idx].contiguous()
+        mu = pr["mu_lin"]
     else:
-        mu = D.fit_beta(ynz, xd, sfd, alpha0, contrast, beta0, lam, betaTol, maxit, minmu=minmu, want_hat=False)["mu"]
+        nn0 = ynz.shape[0]
+        vec = lambda: torch.empty(nn0, dtype=F64, device=dev)
+        out0 = {"beta_mat": torch.empty((p, nn0), dtype=F64, device=dev),
+                "beta_var_mat": torch.empty((p, nn0), dtype=F64, device=dev), "iter": vec(), "contrast_num": vec(),
+                "contrast_denom": vec(), "deviance": vec(), "hat_diagonals": None,
+                "mu": _ws("mu_glm", tuple(ynz.shape), F64, dev)}
+        mu = D.fit_beta(ynz, xd, sfd, alpha0, contrast, beta0, lam, betaTol, maxit, minmu=minmu, out=out0)["mu"]
     la0 = torch.log(alpha0)
     mark("mu")
     r = D.fit_disp(ynz, xd, mu, la0, la0, 1.0, min_log_alpha, kappa_0, dispTol, maxit, False)
@@ -221,7 +242,12 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
     mark("rules+grid_map")
 
     # ---- nbinomWaldTest (R/core.R:1332-1565) via fitNbinomGLMs (R/fitNbinomGLMs.R:29-236)
-    fb = D.fit_beta(ynz, xd, sfd, dispersion, contrast, beta0, lam, betaTol, maxit, minmu=minmu)
+    nn, ldd = ynz.shape
+    outb = {"beta_mat": torch.empty((p, nn), dtype=F64, device=dev), "beta_var_mat": torch.empty((p, nn), dtype=F64, device=dev),
+            "iter": torch.empty(nn, dtype=F64, device=dev), "contrast_num": torch.empty(nn, dtype=F64, device=dev),
+            "contrast_denom": torch.empty(nn, dtype=F64, device=dev), "deviance": torch.empty(nn, dtype=F64, device=dev),
+            "hat_diagonals": _ws("H", (nn, ldd), F64, dev), "mu": _ws("mu_fit", (nn, ldd), F64, dev)}
+    fb = D.fit_beta(ynz, xd, sfd, dispersion, contrast, beta0, lam, betaTol, maxit, minmu=minmu, out=outb)
     mark("fit_beta")
     betaMatrix = fb["beta_mat"] / LN2                      # (p, n)
     betaSE = torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0.0)) / LN2
@@ -235,4 +261,4 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
             "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": fb["deviance"], "mu": fb["mu"],
             "H": fb["hat_diagonals"], "trendCoefs": tr[:2], "varLogDispEsts": varLogDispEsts,
             "dispPriorVar": dispPriorVar, "n_refit_geneest": n_refit_geneest, "n_refit_map": int(gi2.numel()),
-            "allZero": pr["allZero"]}
+            "n_input_rows": y.shape[0]}
