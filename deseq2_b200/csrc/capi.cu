@@ -315,9 +315,24 @@ int prepare_design_from_device(const double* x_dev, int m, int p, cudaStream_t s
   return prepare_design(xh.data(), m, p, st, out);
 }
 
+// The library keeps per-process device state (work-queue arenas, workspace, pinned staging): one process drives one
+// GPU, as in the one-process-per-GPU deployment the engine is built for.  A second device in the same process is
+// refused loudly instead of silently using buffers that live on the first one.
+int g_bound_device = -1;
+int check_device() {
+  int dev = -1;
+  CU(cudaGetDevice(&dev));
+  if (g_bound_device < 0) g_bound_device = dev;
+  if (dev != g_bound_device)
+    return fail("libb200nb is bound to CUDA device %d in this process (current device is %d): use one process per GPU",
+                g_bound_device, dev);
+  return 0;
+}
+
 int check_dims(int n, int m, int p) {
   if (n < 0 || m < 1 || p < 1) return fail("bad dimensions n=%d m=%d p=%d", n, m, p);
   if (p > nb::kMaxP) return fail("p=%d not supported (max %d design columns)", p, nb::kMaxP);
+  if (n > 0 && check_device()) return 1;
   return 0;
 }
 
