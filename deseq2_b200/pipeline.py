@@ -16,6 +16,8 @@ numpy, one function per R function, same names, so the engine can be driven and 
   nbinomWaldTest                 R/core.R:1332-1565  (betas, SEs, Wald statistic and p-value)
   nbinomLRT                      R/core.R:1787-2012  (full vs reduced fit, 2 (l_full - l_reduced), chi-square p-value)
   robustMethodOfMomentsDisp / trimmedCellVariance / calculateCooksDistance / recordMaxCooks   R/core.R:2277-2359
+  fitGLMsWithPrior / estimateBetaPriorVar / Hmisc.wtd.quantile / addAllContrasts / averagePriorsOverLevels /
+  makeExpandedModelMatrix (additive factor designs)   R/fitNbinomGLMs.R:242-337, R/core.R:1601-1689, 2762-2803, R/expanded.R
   DESeq                          R/core.R:280-432    (test="Wald", fitType="parametric", betaPrior=FALSE)
 
 `engine` is any object with fitDisp / fitDispGrid / fitBeta taking the reference's argument names
@@ -392,6 +394,109 @@ def nbinomLRT(counts, nf, full, reduced, dispersion, engine=None, betaTol=1e-8, 
             "betaMatrix": fullModel["betaMatrix"], "betaSE": fullModel["betaSE"], "fullBetaConv": fullModel["betaConv"],
             "reducedBetaConv": reducedModel["betaConv"], "betaIter": fullModel["betaIter"], "mu": fullModel["mu"],
             "hat_diagonals": fullModel["hat_diagonals"], "df": df}
+
+
+# ---------------------------------------------------------------- beta prior (config 4: betaPrior=TRUE, expanded matrix)
+
+def factorDesign(factors, expanded=False):
+    """Model matrix of an additive design of factors, ~f1 + f2 + ... (no interactions).
+    factors: list of integer level-code vectors (0 = reference level).  standard: intercept + one indicator per
+    non-reference level (model.matrix treatment contrasts); expanded: intercept + one indicator for EVERY level
+    (makeExpandedModelMatrix, R/expanded.R:1-18).  Returns (matrix, names, factor index per column (-1 = intercept),
+    level per column)."""
+    factors = [np.asarray(f) for f in factors]
+    m = len(factors[0])
+    cols, names, fidx, lvl = [np.ones(m)], ["Intercept"], [-1], [-1]
+    for k, f in enumerate(factors):
+        for l in range(0 if expanded else 1, int(f.max()) + 1):
+            cols.append((f == l).astype(np.float64))
+            names.append(f"f{k}{l}")
+            fidx.append(k)
+            lvl.append(l)
+    return np.stack(cols, axis=1), names, np.asarray(fidx), np.asarray(lvl)
+
+
+def wtd_quantile(x, weights, prob):
+    """Hmisc.wtd.quantile(x, weights, prob, type='quantile', normwt=TRUE)  (R/core.R:2762-2803)."""
+    x = np.asarray(x, dtype=np.float64)
+    w = np.asarray(weights, dtype=np.float64)
+    keep = ~(np.isnan(w) | (w == 0))
+    x, w = x[keep], w[keep]
+    w = w * len(x) / w.sum()                       # normwt
+    order = np.argsort(x, kind="stable")
+    xs, ws = x[order], w[order]
+    ux, inv = np.unique(xs, return_inverse=True)   # wtd.table: sum of weights per distinct x
+    wts = np.bincount(inv, weights=ws)
+    n = wts.sum()
+    o = 1 + (n - 1) * prob
+    low = max(np.floor(o), 1.0)
+    high = min(low + 1, n)
+    frac = o % 1
+    cum = np.cumsum(wts)
+
+    def at(v):      # approx(cumsum(wts), x, xout=v, method='constant', f=1, rule=2): smallest x with cum >= v
+        i = np.searchsorted(cum, v - 1e-12 * max(1.0, v), side="left")
+        return ux[min(i, len(ux) - 1)]
+
+    return (1 - frac) * at(low) + frac * at(high)
+
+
+def matchWeightedUpperQuantileForVariance(x, weights, upperQuantile=0.05):
+    """R/core.R:2416-2419."""
+    from scipy import stats as _st
+    sdEst = wtd_quantile(np.abs(x), weights, 1 - upperQuantile) / _st.norm.ppf(1 - upperQuantile / 2)
+    return sdEst ** 2
+
+
+def estimateBetaPriorVar(betaMatrix, names, fidx, baseMean, dispFit, expandedType=True, upperQuantile=0.05):
+    """R/core.R:1601-1689 (betaPriorMethod='weighted').  betaMatrix: MLE log2 fold changes on the STANDARD matrix
+    (columns described by names / fidx from factorDesign(expanded=False)).  Returns the prior variances for the
+    standard columns and, when expandedType, for the expanded matrix columns (averagePriorsOverLevels,
+    R/expanded.R:20-73) given `levels_per_factor` inferred from fidx."""
+    weights = 1.0 / (1.0 / baseMean + dispFit)
+    cols = {nm: betaMatrix[:, k] for k, nm in enumerate(names)}
+    colsets = [(nm, betaMatrix[:, k], fidx[k]) for k, nm in enumerate(names)]
+    if expandedType:                                # addAllContrasts (R/expanded.R:76-100)
+        for f in sorted(set(int(v) for v in fidx if v >= 0)):
+            M = betaMatrix[:, fidx == f]
+            nlev = M.shape[1]
+            for j in range(nlev - 1):
+                for i in range(j + 1, nlev):
+                    colsets.append((f"f{f}Cntrst", M[:, i] - M[:, j], f))
+
+    def one(x):
+        fin = np.abs(x) < 10
+        if fin.sum() == 0:
+            return 1e6
+        return matchWeightedUpperQuantileForVariance(x[fin], weights[fin], upperQuantile)
+
+    pv = [(nm, one(x) if nm != "Intercept" else 1e6, f) for nm, x, f in colsets]
+    std = np.array([v for (nm, v, f) in pv[:len(names)]])
+    if not expandedType:
+        return std, None
+    mean_by_factor = {}
+    for f in sorted(set(int(v) for v in fidx if v >= 0)):
+        mean_by_factor[f] = float(np.mean([v for (nm, v, ff) in pv if ff == f]))
+    return std, mean_by_factor
+
+
+def fitGLMsWithPrior(counts, nf, factors, dispersion, baseMean, dispFit, engine=None, betaTol=1e-8, maxit=100,
+                     useQR=True, minmu=0.5):
+    """R/fitNbinomGLMs.R:242-337 for an additive factor design with the expanded model matrix (the default when
+    betaPrior=TRUE): MLE fit on the standard matrix -> estimateBetaPriorVar -> MAP fit on the expanded matrix with
+    lambda = 1 / betaPriorVar."""
+    x_std, names, fidx, _ = factorDesign(factors, expanded=False)
+    mle = fitNbinomGLMs(counts, nf, x_std, dispersion, engine=engine, betaTol=betaTol, maxit=maxit, useQR=useQR,
+                        minmu=minmu)
+    _, mean_by_factor = estimateBetaPriorVar(mle["betaMatrix"], names, fidx, baseMean, dispFit, expandedType=True)
+    x_exp, enames, efidx, _ = factorDesign(factors, expanded=True)
+    betaPriorVar = np.array([1e6 if f < 0 else mean_by_factor[int(f)] for f in efidx])
+    if np.any(betaPriorVar == 0):
+        raise ValueError("beta prior variances are equal to zero for some variables")
+    fit = fitNbinomGLMs(counts, nf, x_exp, dispersion, lambda_=1.0 / betaPriorVar, engine=engine, betaTol=betaTol,
+                        maxit=maxit, useQR=useQR, minmu=minmu)
+    return {"fit": fit, "H": mle["hat_diagonals"], "mu": mle["mu"], "betaPriorVar": betaPriorVar,
+            "modelMatrix": x_exp, "mleBetaMatrix": mle["betaMatrix"], "names": enames, "mle": mle}
 
 
 def DESeq(counts, x, sizeFactors=None, engine=None):

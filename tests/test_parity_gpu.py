@@ -446,3 +446,25 @@ def test_config_shapes_spot_check(engine, oracle, name, n, m):
     _compare_disp(gd, oracle.fitDisp(**d, with_margin=True), f"{name} disp mle", min_robust=0.8)
     d2 = disp_args(c, mu, gd["log_alpha"], prior_mean=np.log(alpha), sigmasq=0.5, usePrior=True)
     _compare_disp(engine.fitDisp(**d2), oracle.fitDisp(**d2, with_margin=True), f"{name} disp map", min_robust=0.8)
+
+
+def test_beta_prior_sequence_engine_vs_oracle(engine, oracle):
+    """BASELINE.json config 4's call sequence (betaPrior: MLE fit p=10, prior variance, MAP fit on the 11-column
+    expanded matrix) through the same host glue with the CUDA engine and with the oracle."""
+    from deseq2_b200 import pipeline, synth
+    m, levels = 120, 10
+    g = (np.arange(m) * levels) // m
+    d = synth.make_example_counts(600, m, x=synth.design_factor(m, levels), seed=61, betaSD=0.8)
+    counts = d["counts"][d["counts"].sum(axis=1) > 0]
+    sf = d["sizeFactors"]
+    nf = np.broadcast_to(sf[None, :], counts.shape)
+    bm = (counts / sf).mean(axis=1)
+    dispFit = 0.1 + 4 / bm
+    disp = np.clip(dispFit, 1e-8, m)
+    a = pipeline.fitGLMsWithPrior(counts, nf, [g], disp, bm, dispFit, engine=engine)
+    b = pipeline.fitGLMsWithPrior(counts, nf, [g], disp, bm, dispFit, engine=oracle)
+    assert np.max(rel_err(a["betaPriorVar"], b["betaPriorVar"])) < 1e-6
+    assert np.array_equal(a["fit"]["betaIter"], b["fit"]["betaIter"])
+    conv = b["fit"]["betaConv"]
+    assert np.max(np.abs(a["fit"]["betaMatrix"][conv] - b["fit"]["betaMatrix"][conv])) < 2e-6
+    assert np.max(rel_err(a["fit"]["betaSE"][conv], b["fit"]["betaSE"][conv])) < 2e-6

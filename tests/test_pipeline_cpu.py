@@ -67,3 +67,44 @@ def test_lrt_full_vs_reduced(oracle):
     assert np.all(a["logLike"][conv] <= b["logLike"][conv] + 1e-6 * np.abs(b["logLike"][conv]))
     r1 = pipeline.nbinomLRT(counts, nf, full, ones, alpha, engine=oracle)
     assert r1["df"] == 2 and np.all(np.isfinite(r1["LRTPvalue"][ok]))
+
+
+def test_weighted_quantile_reduces_to_plain_quantile():
+    """Hmisc.wtd.quantile with equal weights is R's type-7 quantile."""
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=501)
+    for p in (0.5, 0.9, 0.95):
+        assert abs(pipeline.wtd_quantile(x, np.ones_like(x), p) - np.quantile(x, p)) < 1e-12
+    # a heavy weight drags the quantile towards its value
+    w = np.ones_like(x)
+    w[np.argmax(x)] = 200.0
+    assert pipeline.wtd_quantile(x, w, 0.9) > np.quantile(x, 0.9)
+
+
+def test_beta_prior_pipeline_config4_shape(oracle):
+    """BASELINE.json config 4's call sequence at a small size: 10-level factor, MLE pass on the standard matrix
+    (p = 10), estimateBetaPriorVar, MAP pass on the 11-column expanded matrix with lambda = 1/betaPriorVar."""
+    m, levels = 60, 10
+    g = (np.arange(m) * levels) // m
+    x = synth.design_factor(m, levels)
+    d = synth.make_example_counts(500, m, x=x, seed=51, betaSD=0.8)
+    counts = d["counts"][d["counts"].sum(axis=1) > 0]
+    sf = d["sizeFactors"]
+    nf = np.broadcast_to(sf[None, :], counts.shape)
+    bm = (counts / sf).mean(axis=1)
+    dispFit = 0.1 + 4 / bm
+    xs, names, fidx, _ = pipeline.factorDesign([g], expanded=False)
+    assert np.array_equal(xs, x)
+    r = pipeline.fitGLMsWithPrior(counts, nf, [g], np.clip(dispFit, 1e-8, m), bm, dispFit, engine=oracle)
+    assert r["modelMatrix"].shape == (m, 11) and np.linalg.matrix_rank(r["modelMatrix"]) == 10
+    pv = r["betaPriorVar"]
+    assert pv[0] == 1e6 and np.allclose(pv[1:], pv[1]) and 0.05 < pv[1] < 5.0     # truth: betaSD^2 = 0.64 (log2)
+    fit = r["fit"]
+    conv = fit["betaConv"] & r["mle"]["betaConv"] & (bm > 20)
+    # level effects of the MAP fit sum to ~0 within a gene (symmetric ridge on a rank-deficient design) ...
+    assert np.max(np.abs(fit["betaMatrix"][conv, 1:].sum(axis=1))) < 1e-3
+    # ... and are shrunken versions of the MLE contrasts
+    mle_c = r["mleBetaMatrix"][conv, 1:]                       # level l vs level 1
+    map_c = fit["betaMatrix"][conv, 2:] - fit["betaMatrix"][conv, 1:2]
+    assert np.median(np.abs(map_c)) < np.median(np.abs(mle_c))
+    assert np.corrcoef(map_c.ravel(), mle_c.ravel())[0, 1] > 0.98
