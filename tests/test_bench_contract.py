@@ -1,0 +1,47 @@
+"""bench.py contract checks that need no GPU: the reference arm (oracle on the host cores) prints exactly one JSON
+line with the keys the driver reads, and the workload builder produces R-layout (column-major) host buffers."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    env = dict(os.environ, OMP_NUM_THREADS="1")          # what torchrun exports; the arm must still use the cores
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
+                        "--warmup", "0", "--genes", "800", "--cpu-sample", "800"], capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "genes/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_workload_is_r_layout(oracle):
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.build_workload(300, 12, 5, oracle)
+    for k in ("counts", "mu", "nf", "beta0"):
+        assert w[k].flags["F_CONTIGUOUS"], k
+    assert w["counts"].dtype == np.int32
+    h2d, d2h = bench.host_bytes(len(w["counts"]), 12, 2)
+    assert h2d > d2h > 0
