@@ -484,7 +484,9 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "kernel_ms": kern_ms, "alg_bytes_per_launch": alg_bytes,
                 "fp64_pipe_active_pct_ncu": {"fit_disp_kernel": 41.8, "fit_beta_kernel": 45.0, "issue_active_pct": 54.3,
-                                             "source": "profiles/r01e_*_ncu_summary.txt (sm__pipe_fp64_cycles_active)"},
+                                             "fit_disp_fp64_tflops": 10.7, "fp64_peak_tflops_ncu": 37.2,
+                                             "source": "profiles/r01e_*_ncu_summary.txt (sm__pipe_fp64_cycles_active), "
+                                                       "profiles/r01e_fit_disp_sass_hist.txt"},
                 "note": "fp64 transcendental-bound path (~300 flop/B): HBM fraction is small by construction; the "
                         "binding unit is the FP64 pipe (see fp64_pipe_active_pct_ncu)"}
 
