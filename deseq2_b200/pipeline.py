@@ -12,7 +12,7 @@ numpy, one function per R function, same names, so the engine can be driven and 
   dispersionFunction<-           R/methods.R:142-190 (dispFit, varLogDispEsts = mad^2)
   estimateDispersionsPriorVar    R/core.R:1135-1208  (m - p > 3 branch)
   estimateDispersionsMAP         R/core.R:943-1131
-  fitNbinomGLMs                  R/fitNbinomGLMs.R:29-236 (without the optim fallback, :203-227)
+  fitNbinomGLMs / fitNbinomGLMsOptim   R/fitNbinomGLMs.R:29-236, 340-407 (L-BFGS-B fallback opt-in: useOptim=True)
   nbinomWaldTest                 R/core.R:1332-1565  (betas, SEs, Wald statistic and p-value)
   nbinomLRT                      R/core.R:1787-2012  (full vs reduced fit, 2 (l_full - l_reduced), chi-square p-value)
   robustMethodOfMomentsDisp / trimmedCellVariance / calculateCooksDistance / recordMaxCooks   R/core.R:2277-2359
@@ -22,8 +22,8 @@ numpy, one function per R function, same names, so the engine can be driven and 
 
 `engine` is any object with fitDisp / fitDispGrid / fitBeta taking the reference's argument names
 (deseq2_b200.wrappers is the product engine and the default; tests and the bench's CPU baseline pass the
-oracle).  Not restated (out of scope): Cook's distances / outlier replacement, the
-L-BFGS-B fallback for rows with iter == maxit, local / mean trend fits, results()/lfcShrink().
+oracle).  Not restated (out of scope): outlier replacement / refit, local / mean trend fits,
+observation weights in the glue, results()/lfcShrink().
 """
 from __future__ import annotations
 
@@ -237,9 +237,50 @@ def estimateDispersionsMAP(counts, x, mu, dispGeneEst, dispFit, dispPriorVar, va
             "n_refit": int(refitDisp.sum()), "dispRes": dispResMAP}
 
 
+def fitNbinomGLMsOptim(counts, nf, x, lambda_, rowsForOptim, rowStable, alpha_hat, betaMatrix, betaSE, betaConv,
+                       beta_mat, mu, logLike, minmu=0.5):
+    """R/fitNbinomGLMs.R:340-407: L-BFGS-B on the penalised NB log-likelihood (log2 scale, box [-30, 30]) for the rows
+    the IRLS left unconverged / unstable; standard errors from the sandwich at the optimum.  No weights."""
+    from scipy import optimize as _so
+    counts = np.asarray(counts, dtype=np.float64)
+    lam = np.asarray(lambda_, dtype=np.float64)
+    lamNat = lam / LN2 ** 2
+    large = 30.0
+    betaMatrix, betaSE, betaConv, mu, logLike = (betaMatrix.copy(), betaSE.copy(), betaConv.copy(), mu.copy(),
+                                                 logLike.copy())
+    for row in rowsForOptim:
+        betaRow = betaMatrix[row] if (rowStable[row] and np.all(np.abs(betaMatrix[row]) < large)) else beta_mat[row]
+        nfr, k, alpha = nf[row], counts[row], alpha_hat[row]
+
+        def objective(p_):
+            mu_row = nfr * 2.0 ** (x @ p_)
+            ll = nbinomLogLike(k[None, :], mu_row[None, :], np.array([alpha]))[0]
+            logPrior = np.sum(-0.5 * np.log(2 * np.pi / lam) - 0.5 * lam * p_ ** 2)   # dnorm(p, 0, sqrt(1/lambda), log=TRUE)
+            v = -(ll + logPrior)
+            return v if np.isfinite(v) else 1e300
+
+        o = _so.minimize(objective, np.asarray(betaRow, dtype=np.float64), method="L-BFGS-B",
+                         bounds=[(-large, large)] * x.shape[1])
+        if o.status == 0:
+            betaConv[row] = True
+        betaMatrix[row] = o.x
+        mu_row = nfr * 2.0 ** (x @ o.x)
+        mu[row] = mu_row
+        mu_row = np.maximum(mu_row, minmu)
+        w = 1.0 / (1.0 / mu_row + alpha)
+        xtwx = (x.T * w) @ x
+        inv = np.linalg.inv(xtwx + np.diag(lamNat))
+        sigma = inv @ xtwx @ inv
+        betaSE[row] = np.sqrt(np.maximum(np.diag(sigma), 0.0)) / LN2
+        logLike[row] = nbinomLogLike(k[None, :], mu_row[None, :], np.array([alpha]))[0]
+    return {"betaMatrix": betaMatrix, "betaSE": betaSE, "betaConv": betaConv, "mu": mu, "logLike": logLike}
+
+
 def fitNbinomGLMs(counts, nf, x, alpha_hat, lambda_=None, engine=None, betaTol=1e-8, maxit=100, useQR=True,
-                  minmu=0.5):
-    """R/fitNbinomGLMs.R:29-236 without weights and without the optim fallback (:203-227)."""
+                  minmu=0.5, useOptim=False, forceOptim=False):
+    """R/fitNbinomGLMs.R:29-236 without weights.  useOptim=True adds the reference's L-BFGS-B fallback for rows that
+    did not converge / are unstable / have non-positive variance (:203-227; the reference's default is TRUE, the
+    default here is FALSE so that the engine's raw output is what the parity tests and the bench see)."""
     engine = engine or _default_engine
     counts = np.asarray(counts)
     n, m = counts.shape
@@ -263,6 +304,15 @@ def fitNbinomGLMs(counts, nf, x, alpha_hat, lambda_=None, engine=None, betaTol=1
     betaConv = betaRes["iter"] < maxit
     betaMatrix = betaRes["beta_mat"] / LN2
     betaSE = np.sqrt(np.maximum(betaRes["beta_var_mat"], 0.0)) / LN2
+    if useOptim or forceOptim:
+        rowStable = ~np.isnan(betaRes["beta_mat"]).any(axis=1)
+        rowVarPositive = ~(betaRes["beta_var_mat"] <= 0).any(axis=1)
+        rows = np.arange(n) if forceOptim else np.flatnonzero(~betaConv | ~rowStable | ~rowVarPositive)
+        if rows.size:
+            o = fitNbinomGLMsOptim(counts, np.broadcast_to(nf, counts.shape), x, lambda_, rows, rowStable, alpha_hat,
+                                   betaMatrix, betaSE, betaConv, beta_mat / LN2, mu, logLike, minmu=minmu)
+            betaMatrix, betaSE, betaConv, mu, logLike = (o["betaMatrix"], o["betaSE"], o["betaConv"], o["mu"],
+                                                         o["logLike"])
     return {"logLike": logLike, "betaConv": betaConv, "betaMatrix": betaMatrix, "betaSE": betaSE, "mu": mu,
             "betaIter": betaRes["iter"], "hat_diagonals": betaRes["hat_diagonals"], "betaRes": betaRes}
 

@@ -108,3 +108,29 @@ def test_beta_prior_pipeline_config4_shape(oracle):
     map_c = fit["betaMatrix"][conv, 2:] - fit["betaMatrix"][conv, 1:2]
     assert np.median(np.abs(map_c)) < np.median(np.abs(mle_c))
     assert np.corrcoef(map_c.ravel(), mle_c.ravel())[0, 1] > 0.98
+
+
+def test_optim_fallback_matches_irls_and_rescues_divergence(oracle):
+    """test_optim.R:2-39: forceOptim (L-BFGS-B on every row) agrees with IRLS on beta and SE for a badly scaled
+    covariate, and the 0/1000 row that IRLS abandons (iter == maxit) gets a finite optim estimate."""
+    rng = np.random.default_rng(7)
+    m = 20
+    x = np.c_[np.ones(m), rng.normal(0, 1000, m)]
+    d = synth.make_example_counts(40, m, seed=77)
+    counts = d["counts"][d["counts"].min(axis=1) > 3]
+    nf = np.ones(counts.shape)
+    alpha = np.full(len(counts), 0.1)
+    a = pipeline.fitNbinomGLMs(counts, nf, x, alpha, engine=oracle)
+    b = pipeline.fitNbinomGLMs(counts, nf, x, alpha, engine=oracle, forceOptim=True)
+    conv = a["betaConv"]
+    assert conv.mean() > 0.8
+    assert np.allclose(a["betaMatrix"][conv, 0], b["betaMatrix"][conv, 0], atol=1e-4)
+    assert np.allclose(a["betaMatrix"][conv, 1] * 1000, b["betaMatrix"][conv, 1] * 1000, atol=5e-3)
+    assert np.allclose(a["betaSE"][conv], b["betaSE"][conv], rtol=1e-2)
+    y = np.array([[0, 0, 0, 0, 0, 1000, 1000, 0, 0, 0]], dtype=np.int32)
+    x2 = np.c_[np.ones(10), np.r_[np.zeros(5), np.ones(5)]]
+    r0 = pipeline.fitNbinomGLMs(y, np.ones((1, 10)), x2, np.array([0.1]), engine=oracle)
+    r1 = pipeline.fitNbinomGLMs(y, np.ones((1, 10)), x2, np.array([0.1]), engine=oracle, useOptim=True)
+    assert r0["betaIter"][0] == 100 and not r0["betaConv"][0]
+    assert np.all(np.isfinite(r1["betaMatrix"])) and np.all(np.abs(r1["betaMatrix"]) <= 30)
+    assert r1["logLike"][0] >= r0["logLike"][0] - 1e-6
