@@ -7,8 +7,9 @@
  *
  *     R CMD SHLIB -o DESeq2.so deseq2_b200_shim.c -L<repo>/deseq2_b200 -lb200nb -Wl,-rpath,<repo>/deseq2_b200
  *
- * (needs R's headers; they are NOT available in the build image of this repository, so this file ships as
- * source only and is not compiled by __graft_entry__.build()).  The R code of the package is unchanged:
+ * (needs R's headers; they are NOT available in the build image of this repository, so __graft_entry__.build()
+ * does not compile this file; tests/test_r_shim.py compiles it unchanged against the mock R API in tests/mock_r/
+ * and exercises every entry point).  The R code of the package is unchanged:
  * R/RcppExports.R:4-14 keeps calling .Call('_DESeq2_fitDisp', PACKAGE = 'DESeq2', ...).
  *
  * Semantics kept from the reference: inputs are never modified; outputs are fresh R objects in a named list with
