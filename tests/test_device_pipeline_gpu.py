@@ -7,21 +7,23 @@ from helpers import rel_err
 
 pytestmark = pytest.mark.gpu
 
+DEV = "cuda"      # tests/test_emulated_kernels.py re-runs these functions with DEV = "cpu" on the emulated engine
+
 
 def _setup(n, m, x=None, seed=1):
     import torch
     from deseq2_b200 import device as D, synth
     d = synth.make_example_counts(n, m, x=x, seed=seed)
-    y = D.to_gene_major(d["counts"], torch.device("cuda"))
+    y = D.to_gene_major(d["counts"], torch.device(DEV))
     return d, y
 
 
 @pytest.mark.parametrize("design", ["condition", "batch"])
-def test_prep_kernel_matches_numpy(engine, design):
+def test_prep_kernel_matches_numpy(engine, design, n=2000):
     from deseq2_b200 import device_pipeline as DP, pipeline, synth
     m = 30
     x = synth.design_condition(m) if design == "condition" else synth.design_batch_condition(m, 3)
-    d, y = _setup(2000, m, x=x, seed=3)
+    d, y = _setup(n, m, x=x, seed=3)
     sf = d["sizeFactors"]
     pr = DP.prep(y, x, sf)
     counts = d["counts"]
@@ -42,16 +44,16 @@ def test_prep_kernel_matches_numpy(engine, design):
     assert np.max(np.abs(pr["beta0"].cpu().numpy().T[nz] - b0)) < 1e-10
 
 
-def test_trend_kernel_matches_numpy(engine):
+def test_trend_kernel_matches_numpy(engine, n=20000):
     import torch
     from deseq2_b200 import device_pipeline as DP, pipeline
     rng = np.random.default_rng(0)
-    means = 10 ** rng.uniform(0, 4, 20000)
-    disps = (0.1 + 4 / means) * rng.gamma(8, 1 / 8, 20000)
-    disps[rng.random(20000) < 0.02] = 1e-8          # genes at the floor are excluded from the fit
-    disps[rng.random(20000) < 0.01] *= 40           # outliers trimmed by the residual rule
+    means = 10 ** rng.uniform(0, 4, n)
+    disps = (0.1 + 4 / means) * rng.gamma(8, 1 / 8, n)
+    disps[rng.random(n) < 0.02] = 1e-8              # genes at the floor are excluded from the fit
+    disps[rng.random(n) < 0.01] *= 40               # outliers trimmed by the residual rule
     ref = pipeline.parametricDispersionFit(means[disps > 1e-6], disps[disps > 1e-6])
-    dev = torch.device("cuda")
+    dev = torch.device(DEV)
     out = DP.trend_fit(torch.as_tensor(means, device=dev), torch.as_tensor(disps, device=dev)).cpu().numpy()
     assert out[2] == 0
     assert np.max(rel_err(out[:2], ref)) < 1e-8
@@ -86,7 +88,7 @@ def test_device_pipeline_matches_host_pipeline(engine, design, n, m):
 
 @pytest.mark.parametrize("design,m", [("condition", 12), ("condition", 60), ("batch", 36), ("covariate", 20),
                                       ("factor10", 200)])
-def test_cooks_kernel_matches_numpy(engine, design, m):
+def test_cooks_kernel_matches_numpy(engine, design, m, n=800):
     """robust moments dispersion (per-cell trimmed means), Cook's distances and their maximum
     (R/core.R:2277-2359) on device vs the numpy restatement."""
     import torch
@@ -100,14 +102,14 @@ def test_cooks_kernel_matches_numpy(engine, design, m):
         x = synth.design_factor(m, 10)
     else:
         x = np.c_[np.ones(m), rng.normal(0, 1, m)]          # every sample its own cell -> trimmedVariance branch
-    d = synth.make_example_counts(800, m, x=x if design != "covariate" else None, seed=17)
+    d = synth.make_example_counts(n, m, x=x if design != "covariate" else None, seed=17)
     counts = d["counts"][d["counts"].sum(axis=1) > 0]
     counts[::7, 0] *= 30                                    # planted outliers (test_outlier.R:33-55 idea)
     sf = d["sizeFactors"]
     n = len(counts)
     mu = np.maximum((counts / sf).mean(axis=1, keepdims=True) * sf[None, :] * rng.uniform(0.8, 1.25, (n, m)), 0.5)
     H = rng.uniform(0.01, 0.6, (n, m))
-    dev = torch.device("cuda")
+    dev = torch.device(DEV)
     out = DP.cooks(D.to_gene_major(counts, dev), D.to_gene_major(mu, dev), D.to_gene_major(H, dev), x, sf)
     ref_disp = pipeline.robustMethodOfMomentsDisp(counts, sf, x)
     ref_cooks = pipeline.calculateCooksDistance(counts, mu, H, sf, x)
@@ -121,20 +123,20 @@ def test_cooks_kernel_matches_numpy(engine, design, m):
         assert np.max(rel_err(got_max, ref_max, floor=1e-12)) < 1e-9
 
 
-def test_lrt_device_matches_host(engine):
+def test_lrt_device_matches_host(engine, n=3000):
     """BASELINE.json config 5's call sequence (nbinomLRT ~batch+condition vs ~batch) on device vs the host glue."""
     import torch
     from deseq2_b200 import device as D, device_pipeline as DP, pipeline, synth
     m = 40
     full = synth.design_batch_condition(m, 2)
     reduced = full[:, :2]
-    d = synth.make_example_counts(3000, m, x=full, seed=41, betaSD=0.7)
+    d = synth.make_example_counts(n, m, x=full, seed=41, betaSD=0.7)
     counts = d["counts"][d["counts"].sum(axis=1) > 0]
     sf = d["sizeFactors"]
     nf = np.broadcast_to(sf[None, :], counts.shape)
     alpha = np.clip(0.1 + 4 / (counts / sf).mean(axis=1), 1e-8, m)
     host = pipeline.nbinomLRT(counts, nf, full, reduced, alpha, engine=engine)
-    dev = torch.device("cuda")
+    dev = torch.device(DEV)
     got = DP.nbinomLRT_device(D.to_gene_major(counts, dev), full, reduced, sf, torch.as_tensor(alpha, device=dev))
     ok = host["fullBetaConv"] & host["reducedBetaConv"] & ((counts / sf).min(axis=1) > 2)   # away from the minmu clamp
     st = got["LRTStatistic"].cpu().numpy()

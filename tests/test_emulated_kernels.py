@@ -1,0 +1,148 @@
+"""The product's CUDA kernels, executed on the CPU by the SIMT emulator (tests/simt_emu/), against the oracle.
+
+tests/simt_emu/build_emu.py compiles deseq2_b200/csrc/*.cu -- the very sources nvcc compiles for sm_100a, with three
+mechanical rewrites (launch syntax, `extern __shared__`, one PTX statement) -- into libb200nb_emu.so, which exports
+the same C ABI (include/b200nb.h).  This module points the ctypes loader at that library and runs the parity cases of
+tests/test_parity_gpu.py / tests/test_golden.py (the -m gpu tests) at reduced gene counts, with the same acceptance
+rules.  What it buys: kernel control flow, indexing, shared-memory layout, warp synchronisation (the emulator does
+not run lanes in lock step and reports collectives that not every named lane reaches) and use of uninitialised
+memory (poisoned) are checked on every CPU run, before any GPU time is spent.  What it does not: performance, and
+bit-identity with the GPU's arithmetic (tolerances are those of the GPU tests).
+
+This is a CHECK of the product source, never a product path: the emulated library exists only under tests/, and
+only this module (or an explicit B200NB_LIB=... in the environment of a test run) loads it.
+The whole -m gpu parity suite can be run the same way on a machine without a GPU (about 8 minutes):
+
+    B200NB_LIB=tests/simt_emu/_build/libb200nb_emu.so python -m pytest tests/test_parity_gpu.py tests/test_golden.py \\
+        tests/test_r_shim.py -m gpu --deselect tests/test_parity_gpu.py::test_c2_full_size_properties
+"""
+import ctypes as C
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "simt_emu"))
+
+
+@pytest.fixture(scope="module")
+def emu(oracle):
+    """deseq2_b200.wrappers bound to the emulated library for the duration of this module."""
+    import build_emu
+    from deseq2_b200 import _lib, wrappers
+    lib = C.CDLL(build_emu.build())
+    for name, argt in _lib.SIGNATURES.items():
+        f = getattr(lib, name)
+        f.argtypes = argt
+        f.restype = _lib._RESTYPE.get(name, C.c_int)
+    saved = _lib._lib
+    _lib._lib = lib
+    try:
+        yield wrappers
+    finally:
+        _lib._lib = saved
+
+
+def test_emulated_library_exports_the_c_abi(emu):
+    from deseq2_b200 import _lib
+    lib = _lib.lib()
+    assert lib.b200nb_version().startswith(b"b200nb") and lib.b200nb_device_count() == 1
+    before = lib.simt_emu_launches()
+    x = np.array([0.3, 1.0, 7.5, 123.0])
+    lg, dg, tg = np.empty(4), np.empty(4), np.empty(4)
+    assert lib.b200nb_test_special(x.ctypes.data, 4, lg.ctypes.data, dg.ctypes.data, tg.ctypes.data) == 0
+    assert lib.simt_emu_launches() > before            # the kernels really ran inside the emulator
+
+
+import test_golden as TG          # noqa: E402
+import test_parity_gpu as TP      # noqa: E402
+
+CASES = [
+    ("special functions", lambda e, o: TP.test_device_special_functions(e)),
+    ("fitDisp MLE 800x37", lambda e, o: TP.test_fit_disp_mle_parity(e, o, 800, 37, 13)),
+    ("fitDisp MLE m=6", lambda e, o: TP.test_fit_disp_mle_parity(e, o, 300, 6, 12)),
+    ("fitDisp MAP m=100", lambda e, o: TP.test_fit_disp_map_parity(e, o, n=400)),
+    ("fitDisp f64 counts, no CR", lambda e, o: TP.test_fit_disp_f64_counts_and_no_cr(e, o)),
+    ("fitDisp TAB/BIG/GEN modes", lambda e, o: TP.test_fit_disp_big_and_mixed_counts(e, o, n=360)),
+    ("fitDisp non-integer counts", lambda e, o: TP.test_fit_disp_non_integer_counts(e, o)),
+    ("fitDisp weights ~condition", lambda e, o: TP.test_fit_disp_weights_and_designs(e, o, "condition", 51)),
+    ("fitDisp weights ~batch+condition", lambda e, o: TP.test_fit_disp_weights_and_designs(e, o, "batch", 52)),
+    ("fitDisp weights 4-level factor", lambda e, o: TP.test_fit_disp_weights_and_designs(e, o, "factor4", 53)),
+    ("fitDisp CR column drop", lambda e, o: TP.test_fit_disp_weights_drop_a_design_column(e, o)),
+    ("fitDispGrid", lambda e, o: TP.test_fit_disp_grid_parity(e, o)),
+    ("fitBeta QR m=6", lambda e, o: TP.test_fit_beta_parity(e, o, 1500, 6, 32, True)),
+    ("fitBeta normal equations m=37", lambda e, o: TP.test_fit_beta_parity(e, o, 800, 37, 33, False)),
+    ("fitBeta maxit=0 contrast", lambda e, o: TP.test_fit_beta_maxit0_contrast(e, o)),
+    ("fitBeta ~batch+condition, weights, nf matrix", lambda e, o: TP.test_fit_beta_designs_weights_nf_matrix(e, o, "batch", 61, True)),
+    ("fitBeta 4-level factor", lambda e, o: TP.test_fit_beta_designs_weights_nf_matrix(e, o, "factor4", 62, False)),
+    ("fitBeta intercept only", lambda e, o: TP.test_fit_beta_designs_weights_nf_matrix(e, o, "intercept", 63, True)),
+    ("fitBeta badly scaled covariate", lambda e, o: TP.test_fit_beta_badly_scaled_covariate(e, o)),
+    ("fitBeta divergence sentinel", lambda e, o: TP.test_fit_beta_divergence_sentinel(e)),
+    ("fitBeta weight 0 == dropped sample", lambda e, o: TP.test_fit_beta_weight_zero_equals_dropped_sample(e)),
+    ("general p: 10-level factor", lambda e, o: TP.test_general_p_parity(e, o, "factor10", 81, n=60)),
+    ("general p: expanded 11 columns + ridge", lambda e, o: TP.test_general_p_parity(e, o, "expanded11", 82, n=60)),
+    ("general p: continuous covariates", lambda e, o: TP.test_general_p_parity(e, o, "covariates7", 83, n=60)),
+    ("config 4 shape m=1000", lambda e, o: TP.test_config_shapes_spot_check(e, o, "C4", 48, 1000)),
+    ("config 3 shape m=500", lambda e, o: TP.test_config_shapes_spot_check(e, o, "C3", 60, 500)),
+    ("edge 1x4", lambda e, o: TP.test_edge_shapes(e, o, 1, 4)),
+    ("edge 3x5", lambda e, o: TP.test_edge_shapes(e, o, 3, 5)),
+    ("edge 7x33", lambda e, o: TP.test_edge_shapes(e, o, 7, 33)),
+    ("edge 2x3000", lambda e, o: TP.test_edge_shapes(e, o, 2, 3000)),
+    ("empty input", lambda e, o: TP.test_empty_input_is_a_no_op(e)),
+]
+
+
+@pytest.mark.parametrize("name,run", CASES, ids=[c[0] for c in CASES])
+def test_emulated_kernel_parity(emu, oracle, name, run):
+    run(emu, oracle)
+
+
+@pytest.fixture()
+def emu_device(emu, monkeypatch):
+    """deseq2_b200.device / device_pipeline on CPU torch tensors: in the emulator "device" pointers are host pointers
+    and there are no streams, so the torch plumbing runs unchanged with device = "cpu"."""
+    import test_device_pipeline_gpu as TD
+    from deseq2_b200 import device as D, device_pipeline as DP
+    null_stream = lambda: C.c_void_p(0)
+    monkeypatch.setattr(D, "_stream", null_stream)
+    monkeypatch.setattr(DP, "_stream", null_stream)
+    monkeypatch.setattr(TD, "DEV", "cpu")
+    DP._ws.clear() if hasattr(DP._ws, "clear") else None
+    return TD
+
+
+DEVICE_CASES = [
+    ("prep ~condition", lambda T, e: T.test_prep_kernel_matches_numpy(e, "condition", n=300)),
+    ("prep ~batch+condition", lambda T, e: T.test_prep_kernel_matches_numpy(e, "batch", n=300)),
+    ("trend fit", lambda T, e: T.test_trend_kernel_matches_numpy(e, n=3000)),
+    ("cooks m=12", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "condition", 12, n=200)),
+    ("cooks ~batch+condition", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "batch", 36, n=150)),
+    ("cooks covariate (one cell per sample)", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "covariate", 20, n=150)),
+    ("cooks 10-level factor", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "factor10", 200, n=60)),
+    ("DESeq on device ~condition", lambda T, e: T.test_device_pipeline_matches_host_pipeline(e, "condition", 240, 40)),
+    ("DESeq on device ~batch+condition", lambda T, e: T.test_device_pipeline_matches_host_pipeline(e, "batch", 160, 36)),
+    ("LRT on device", lambda T, e: T.test_lrt_device_matches_host(e, n=250)),
+]
+
+
+@pytest.mark.parametrize("name,run", DEVICE_CASES, ids=[c[0] for c in DEVICE_CASES])
+def test_emulated_device_pipeline(emu, emu_device, name, run):
+    run(emu_device, emu)
+
+
+def test_emulated_engine_through_R_boundary(emu, oracle, tmp_path):
+    """The R .Call shim linked against the emulated engine: R-shaped arguments in, the CUDA kernels' source executed,
+    named R list out -- the complete drop-in path of INTEGRATION.md, minus R and minus the GPU."""
+    import build_emu
+    import test_r_shim as TR
+    bdir = os.path.dirname(build_emu.build())
+    so = TR._build(str(tmp_path), "DESeq2_emu.so", [], ["-L" + bdir, "-lb200nb_emu", "-Wl,-rpath," + bdir])
+    TR.test_engine_through_R_boundary(TR.MockR(so), oracle)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))), ids=os.path.basename)
+def test_emulated_engine_matches_golden(emu, path):
+    TG.test_engine_matches_golden(emu, path)

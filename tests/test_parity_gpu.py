@@ -70,8 +70,8 @@ def test_fit_disp_mle_parity(engine, oracle, n, m, seed):
     _compare_disp(g, o, f"mle {n}x{m}", min_robust=0.9 if m >= 30 else 0.3)
 
 
-def test_fit_disp_map_parity(engine, oracle):
-    c = make_case(3000, 100, seed=21)
+def test_fit_disp_map_parity(engine, oracle, n=3000):
+    c = make_case(n, 100, seed=21)
     a0 = disp_args(c, c["mu"], np.log(c["alpha0"]))
     mle = oracle.fitDisp(**a0)
     fit = 0.1 + 4.0 / c["baseMean"]
@@ -128,15 +128,15 @@ def test_fit_beta_maxit0_contrast(engine, oracle):
 
 # ---------------------------------------------------------------- evaluation modes, weights, designs
 
-def test_fit_disp_big_and_mixed_counts(engine, oracle):
+def test_fit_disp_big_and_mixed_counts(engine, oracle, n=1200):
     """High-count genes (BIG mode: every count >= 10), mixed genes (GEN mode: max >= 256 and min < 10) and
     low-count genes (TAB mode) in one call."""
-    c = make_case(1200, 48, seed=41, interceptMean=8.0, interceptSD=3.0)
+    c = make_case(n, 48, seed=41, interceptMean=8.0, interceptSD=3.0)
     y = c["counts"]
-    big = np.flatnonzero(y.max(axis=1) >= 256)[:80]          # force GEN mode: a few tiny counts in high-count genes
+    big = np.flatnonzero(y.max(axis=1) >= 256)[:n // 15]     # force GEN mode: a few tiny counts in high-count genes
     y[big, :3] = np.arange(3 * len(big)).reshape(len(big), 3) % 7
-    assert (y.min(axis=1) >= 10).sum() > 100 and ((y.max(axis=1) >= 256) & (y.min(axis=1) < 10)).sum() > 20
-    assert (y.max(axis=1) < 256).sum() > 50
+    assert (y.min(axis=1) >= 10).sum() > n // 12 and ((y.max(axis=1) >= 256) & (y.min(axis=1) < 10)).sum() > n // 60
+    assert (y.max(axis=1) < 256).sum() > n // 24
     a = disp_args(c, c["mu"], np.log(c["alpha0"]))
     _compare_disp(engine.fitDisp(**a), oracle.fitDisp(**a, with_margin=True), "modes", min_robust=0.85)
 
@@ -297,7 +297,7 @@ def _mu_from_fit(oracle, c, x, alpha, lam=None, beta0=None):
 
 
 @pytest.mark.parametrize("kind,seed", [("factor10", 81), ("expanded11", 82), ("covariates7", 83)])
-def test_general_p_parity(engine, oracle, kind, seed):
+def test_general_p_parity(engine, oracle, kind, seed, n=400):
     """BASELINE.json config 4 shapes (10-level factor: p=10 MLE pass, 11-column expanded matrix with ridge) and a
     design with continuous covariates (> 32 distinct rows -> samplewise normal equations)."""
     from deseq2_b200 import synth
@@ -314,7 +314,7 @@ def test_general_p_parity(engine, oracle, kind, seed):
         lam = np.full(7, 1e-6) / np.log(2) ** 2
     p = x.shape[1]
     xgen = synth.design_factor(m, 10) if kind == "expanded11" else x
-    c = make_case(400, m, x=xgen, seed=seed, betaSD=0.5)
+    c = make_case(n, m, x=xgen, seed=seed, betaSD=0.5)
     c["x"] = x
     n = len(c["counts"])
     if kind == "expanded11":
