@@ -7,9 +7,11 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <sys/mman.h>
 
 #include <atomic>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200nb.h"
@@ -43,9 +45,34 @@ struct Workspace {
   void* p[S_NSLOTS] = {};
   size_t bytes[S_NSLOTS] = {};
   cudaStream_t stream = nullptr;
-  std::mutex mu;
 };
-Workspace g_ws;
+
+// ---------------------------------------------------------------- pinned staging for pageable host buffers
+// R hands over ordinary (pageable) memory.  cudaMemcpy from pageable memory runs at ~9 GB/s on the GPU box;
+// staging through a ring of pinned buffers filled by a few host threads while the previous chunk is in flight
+// reaches PCIe speed.  B200NB_STAGE_THREADS (default 8; 4..16 measure the same) OpenMP workers do the host-side memcpy.
+constexpr size_t kStageChunk = 16u << 20;
+constexpr int kStageRing = 3;
+struct Staging {
+  void* buf[kStageRing] = {};
+  cudaEvent_t ev[kStageRing] = {};
+  bool ready = false;
+};
+
+// Host-side context of the host entry points: device workspace, stream and pinned staging ring.  Context 0 belongs
+// to the calling thread; contexts 1.. are used by the extra worker threads of the gene-chunked path (opt-in, see
+// run_chunked below), each with its own stream so that one worker's copies overlap another worker's kernels.
+struct HostCtx {
+  Workspace ws;
+  Staging stage;
+};
+constexpr int kMaxWorkers = 4;
+HostCtx g_ctx[kMaxWorkers];
+thread_local HostCtx* t_ctx = &g_ctx[0];
+std::mutex g_call_mu;    // host entry points are serialised (one set of contexts per process)
+std::mutex g_arena_mu;   // guards the (re)allocation of the shared device arenas below
+#define g_ws (t_ctx->ws)
+#define g_stage (t_ctx->stage)
 
 int ws_get(Slot s, size_t bytes, void** out) {
   if (bytes == 0) bytes = 16;
@@ -73,17 +100,12 @@ constexpr int kRing = 1024;
 unsigned int* g_counters = nullptr;
 std::atomic<unsigned int> g_counter_next{0};
 int next_counter(unsigned int** out) {
+  std::lock_guard<std::mutex> lk(g_arena_mu);
   if (!g_counters) CU(cudaMalloc(&g_counters, sizeof(unsigned int) * kRing));
   *out = g_counters + (g_counter_next.fetch_add(1) % kRing);
   return 0;
 }
 
-// ---------------------------------------------------------------- pinned staging for pageable host buffers
-// R hands over ordinary (pageable) memory.  cudaMemcpy from pageable memory runs at ~9 GB/s on the GPU box;
-// staging through a ring of pinned buffers filled by a few host threads while the previous chunk is in flight
-// reaches PCIe speed.  B200NB_STAGE_THREADS (default 8; 4..16 measure the same) OpenMP workers do the host-side memcpy.
-constexpr size_t kStageChunk = 16u << 20;
-constexpr int kStageRing = 3;
 int stage_threads() {
   static int t = [] {
     const char* e = getenv("B200NB_STAGE_THREADS");
@@ -92,13 +114,6 @@ int stage_threads() {
   }();
   return t;
 }
-struct Staging {
-  void* buf[kStageRing] = {};
-  cudaEvent_t ev[kStageRing] = {};
-  bool ready = false;
-};
-Staging g_stage;
-
 int stage_init() {
   if (g_stage.ready) return 0;
   for (int i = 0; i < kStageRing; i++) {
@@ -109,12 +124,36 @@ int stage_init() {
   return 0;
 }
 
-void par_memcpy(void* dst, const void* src, size_t bytes) {
+// Large result matrices (hat_diagonals, mu) land in memory the caller has just allocated: every 4 KB page of it is
+// first touched by the D2H scatter, which was measured to run at ~6 GB/s for that reason.  Two opt-in knobs for the
+// next GPU session (both off by default: not timed yet): B200NB_D2H_HUGEPAGE=1 asks the kernel for transparent huge
+// pages on the destination range before it is touched (512x fewer faults); B200NB_D2H_THREADS=<T> uses a different
+// number of host threads for the device-to-host scatter than for the host-to-device gather.
+int d2h_threads() {
+  static int t = [] {
+    const char* e = getenv("B200NB_D2H_THREADS");
+    int v = e ? atoi(e) : 0;
+    return v < 1 ? stage_threads() : (v > 64 ? 64 : v);
+  }();
+  return t;
+}
+void advise_hugepages(void* p, size_t bytes) {
+  static const bool on = [] {
+    const char* e = getenv("B200NB_D2H_HUGEPAGE");
+    return e && atoi(e) != 0;
+  }();
+  if (!on || bytes < (8u << 20)) return;
+  const uintptr_t huge = (uintptr_t)2 << 20;
+  const uintptr_t lo = ((uintptr_t)p + huge - 1) & ~(huge - 1), hi = ((uintptr_t)p + bytes) & ~(huge - 1);
+  if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);   // a hint: failure is harmless
+}
+
+void par_memcpy(void* dst, const void* src, size_t bytes, int T = 0) {
   if (bytes < (1u << 20)) {
     memcpy(dst, src, bytes);
     return;
   }
-  const int T = stage_threads();
+  if (T <= 0) T = stage_threads();
 #pragma omp parallel for num_threads(T) schedule(static)
   for (int t = 0; t < T; t++) {
     const size_t lo = bytes * t / T, hi = bytes * (t + 1) / T;
@@ -168,7 +207,86 @@ int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     const size_t off = k * kStageChunk;
     const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
     CU(cudaEventSynchronize(g_stage.ev[b]));
-    par_memcpy(static_cast<char*>(dst) + off, g_stage.buf[b], len);
+    par_memcpy(static_cast<char*>(dst) + off, g_stage.buf[b], len, d2h_threads());
+  }
+  return 0;
+}
+
+// ---- row blocks of column-major host matrices (the gene-chunked path) ----------------------------------------
+// `host` is a column-major matrix with n_total rows (R layout); the block is rows [g0, g0 + gc) of its m columns and
+// lives on the device as a contiguous column-major gc x m matrix.  gc == n_total is the whole matrix: the contiguous
+// routines above.  Otherwise whole column segments are gathered into / scattered from the pinned ring.
+int h2d_block(void* dst, const void* host, size_t n_total, size_t g0, size_t gc, int m, int elem, cudaStream_t st) {
+  if (gc == n_total) return h2d_staged(dst, host, gc * m * elem, st);
+  const size_t col = gc * elem;
+  const char* src = static_cast<const char*>(host);
+  if (col * m <= (256u << 10) || col > kStageChunk) {
+    for (int j = 0; j < m; j++) {
+      const void* seg = src + ((size_t)j * n_total + g0) * elem;
+      if (col > kStageChunk) {
+        if (h2d_staged(static_cast<char*>(dst) + j * col, seg, col, st)) return 1;
+      } else {
+        CU(cudaMemcpyAsync(static_cast<char*>(dst) + j * col, seg, col, cudaMemcpyHostToDevice, st));
+      }
+    }
+    return 0;
+  }
+  if (stage_init()) return 1;
+  const int cpc = (int)(kStageChunk / col);   // whole columns per staging buffer (>= 1)
+  const int T = stage_threads();
+  int j = 0;
+  for (int k = 0; j < m; k++) {
+    const int b = k % kStageRing;
+    const int nc = (m - j < cpc) ? m - j : cpc;
+    if (k >= kStageRing) CU(cudaEventSynchronize(g_stage.ev[b]));
+    char* buf = static_cast<char*>(g_stage.buf[b]);
+#pragma omp parallel for num_threads(T) schedule(static) if (nc * col >= (1u << 20))
+    for (int c = 0; c < nc; c++) memcpy(buf + (size_t)c * col, src + ((size_t)(j + c) * n_total + g0) * elem, col);
+    CU(cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)j * col, buf, (size_t)nc * col, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(g_stage.ev[b], st));
+    j += nc;
+  }
+  for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(g_stage.ev[b]));
+  return 0;
+}
+
+// device (contiguous column-major gc x m) -> rows [g0, g0 + gc) of the column-major host matrix; synchronous on return
+int d2h_block(void* host, const void* src, size_t n_total, size_t g0, size_t gc, int m, int elem, cudaStream_t st) {
+  if (gc == n_total) return d2h_staged(host, src, gc * m * elem, st);
+  const size_t col = gc * elem;
+  char* dst = static_cast<char*>(host);
+  if (col * m <= (256u << 10) || col > kStageChunk) {
+    for (int j = 0; j < m; j++) {
+      void* seg = dst + ((size_t)j * n_total + g0) * elem;
+      if (col > kStageChunk) {
+        if (d2h_staged(seg, static_cast<const char*>(src) + j * col, col, st)) return 1;
+      } else {
+        CU(cudaMemcpyAsync(seg, static_cast<const char*>(src) + j * col, col, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    CU(cudaStreamSynchronize(st));
+    return 0;
+  }
+  if (stage_init()) return 1;
+  const int cpc = (int)(kStageChunk / col);
+  const int T = d2h_threads();
+  const int nbatch = (m + cpc - 1) / cpc;
+  auto issue = [&](int k) -> int {
+    const int b = k % kStageRing, j = k * cpc, nc = (m - j < cpc) ? m - j : cpc;
+    CU(cudaMemcpyAsync(g_stage.buf[b], static_cast<const char*>(src) + (size_t)j * col, (size_t)nc * col,
+                       cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(g_stage.ev[b], st));
+    return 0;
+  };
+  for (int k = 0; k < nbatch && k < kStageRing - 1; k++)
+    if (issue(k)) return 1;
+  for (int k = 0; k < nbatch; k++) {
+    if (k + kStageRing - 1 < nbatch && issue(k + kStageRing - 1)) return 1;
+    const int b = k % kStageRing, j = k * cpc, nc = (m - j < cpc) ? m - j : cpc;
+    CU(cudaEventSynchronize(g_stage.ev[b]));
+    const char* buf = static_cast<const char*>(g_stage.buf[b]);
+#pragma omp parallel for num_threads(T) schedule(static) if (nc * col >= (1u << 20))
+    for (int c = 0; c < nc; c++) memcpy(dst + ((size_t)(j + c) * n_total + g0) * elem, buf + (size_t)c * col, col);
   }
   return 0;
 }
@@ -183,6 +301,7 @@ void* g_scratch_arena = nullptr;
 size_t g_scratch_slot = 0;
 std::atomic<unsigned int> g_scratch_next{0};
 int next_scratch(size_t bytes, unsigned int** out) {
+  std::lock_guard<std::mutex> lk(g_arena_mu);
   bytes = (bytes + 255) & ~(size_t)255;
   if (g_scratch_slot < bytes) {
     if (g_scratch_arena) {
@@ -220,6 +339,7 @@ void* g_design_arena = nullptr;
 size_t g_design_slot = 0;
 std::atomic<unsigned int> g_design_next{0};
 int next_design_slot(size_t need, char** out) {
+  std::lock_guard<std::mutex> lk(g_arena_mu);
   need = (need + 255) & ~(size_t)255;
   if (g_design_slot < need) {
     if (g_design_arena) {
@@ -338,13 +458,14 @@ int check_dims(int n, int m, int p) {
 
 long long ld_for(int m) { return ((long long)m + 3) & ~3LL; }
 
-// copy a column-major host matrix to the device and convert to gene-major
-int upload_matrix(const void* host, int n, int m, int elem, Slot raw, Slot dst, cudaStream_t st, void** out) {
+// Rows [g0, g0 + n) of a column-major host matrix with n_total rows: copy to the device, convert to gene-major.
+int upload_matrix(const void* host, int n_total, int g0, int n, int m, int elem, Slot raw, Slot dst, cudaStream_t st,
+                  void** out) {
   void *d_raw, *d_dst;
   const long long ld = ld_for(m);
   if (ws_get(raw, (size_t)n * m * elem, &d_raw)) return 1;
   if (ws_get(dst, (size_t)n * ld * elem + 64, &d_dst)) return 1;
-  if (h2d_staged(d_raw, host, (size_t)n * m * elem, st)) return 1;
+  if (h2d_block(d_raw, host, (size_t)n_total, (size_t)g0, (size_t)n, m, elem, st)) return 1;
   CU(nb::launch_to_gene_major(d_raw, d_dst, n, m, ld, elem, st));
   g_launches++;
   *out = d_dst;
@@ -356,6 +477,68 @@ int upload_vec(const void* host, size_t bytes, Slot s, cudaStream_t st, void** o
   if (ws_get(s, bytes, &d)) return 1;
   CU(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st));
   *out = d;
+  return 0;
+}
+
+// ---------------------------------------------------------------- gene-chunked host path (opt-in)
+// B200NB_CHUNK_GENES=<genes per chunk> splits one host call into gene chunks that B200NB_CHUNK_WORKERS (default 2,
+// max 4) host threads process independently -- each with its own stream, device workspace and pinned ring -- so that
+// one chunk's H2D staging overlaps another chunk's kernels and D2H.  Genes are independent, so the results are those
+// of the unchunked call.  Off by default (0): it has not been timed on the GPU yet.
+int chunk_genes() {
+  static int v = [] {
+    const char* e = getenv("B200NB_CHUNK_GENES");
+    const int g = e ? atoi(e) : 0;
+    return g < 0 ? 0 : g;
+  }();
+  return v;
+}
+int chunk_workers() {
+  static int v = [] {
+    const char* e = getenv("B200NB_CHUNK_WORKERS");
+    const int w = e ? atoi(e) : 2;
+    return w < 1 ? 1 : (w > kMaxWorkers ? kMaxWorkers : w);
+  }();
+  return v;
+}
+
+// body(g0, count) handles genes [g0, g0 + count) through the current thread's context; returns non-zero on failure
+// with the message in the thread-local g_err.
+template <typename F>
+int run_chunked(int n, F&& body) {
+  const int want = chunk_genes();
+  if (want <= 0 || n < 2 * want) return body(0, n);
+  const int K = (n + want - 1) / want;
+  const int gc = (n + K - 1) / K;                       // balanced chunks
+  const int W = chunk_workers() < K ? chunk_workers() : K;
+  std::atomic<int> next{0}, failed{0};
+  char errs[kMaxWorkers][sizeof(g_err)];
+  for (int w = 0; w < kMaxWorkers; w++) errs[w][0] = 0;
+  auto work = [&](int w) {
+    t_ctx = &g_ctx[w];
+    if (w > 0 && g_bound_device >= 0) cudaSetDevice(g_bound_device);
+    for (;;) {
+      const int k = next.fetch_add(1);
+      if (k >= K || failed.load()) break;
+      const int g0 = k * gc, cnt = (n - g0 < gc) ? n - g0 : gc;
+      if (cnt <= 0) break;
+      if (body(g0, cnt)) {
+        memcpy(errs[w], g_err, sizeof(g_err));
+        failed.store(1);
+        break;
+      }
+    }
+    t_ctx = &g_ctx[0];
+  };
+  std::vector<std::thread> pool;
+  for (int w = 1; w < W; w++) pool.emplace_back(work, w);
+  work(0);
+  for (auto& t : pool) t.join();
+  if (failed.load()) {
+    for (int w = 0; w < kMaxWorkers; w++)
+      if (errs[w][0]) { memcpy(g_err, errs[w], sizeof(g_err)); break; }
+    return 1;
+  }
   return 0;
 }
 
@@ -377,19 +560,23 @@ int b200nb_device_count(void) {
 }
 
 void b200nb_release_workspace(void) {
-  std::lock_guard<std::mutex> lk(g_ws.mu);
-  for (int s = 0; s < S_NSLOTS; s++) {
-    if (g_ws.p[s]) cudaFree(g_ws.p[s]);
-    g_ws.p[s] = nullptr;
-    g_ws.bytes[s] = 0;
-  }
-  if (g_stage.ready) {
-    for (int i = 0; i < kStageRing; i++) {
-      cudaFreeHost(g_stage.buf[i]);
-      cudaEventDestroy(g_stage.ev[i]);
-      g_stage.buf[i] = nullptr;
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  for (int c = 0; c < kMaxWorkers; c++) {
+    Workspace& ws = g_ctx[c].ws;
+    Staging& sg = g_ctx[c].stage;
+    for (int s = 0; s < S_NSLOTS; s++) {
+      if (ws.p[s]) cudaFree(ws.p[s]);
+      ws.p[s] = nullptr;
+      ws.bytes[s] = 0;
     }
-    g_stage.ready = false;
+    if (sg.ready) {
+      for (int i = 0; i < kStageRing; i++) {
+        cudaFreeHost(sg.buf[i]);
+        cudaEventDestroy(sg.ev[i]);
+        sg.buf[i] = nullptr;
+      }
+      sg.ready = false;
+    }
   }
 }
 
@@ -547,28 +734,27 @@ int b200nb_cooks_dev(const void* y, int y_type, const double* mu, const double* 
 }
 
 /* ------------------------------------------------------------------ host entry points */
+/* Each entry point validates, takes the call lock and hands gene blocks [g0, g0 + n) of the caller's R-layout arrays
+ * (n_total rows) to a *_block routine; without B200NB_CHUNK_GENES there is one block, the whole call. */
 
-int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,
-                    const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
-                    double kappa_0, double tol, int maxit, int use_prior, const double* weights, int use_weights,
-                    double weight_threshold, int use_cr, int n, int m, int p,
-                    double* out_log_alpha, int32_t* out_iter, int32_t* out_iter_accept, double* out_last_change,
-                    double* out_initial_lp, double* out_initial_dlp, double* out_last_lp, double* out_last_dlp,
-                    double* out_last_d2lp) {
-  if (check_dims(n, m, p)) return 1;
-  if (n == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ws.mu);
+static int fit_disp_block(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,
+                          const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
+                          double kappa_0, double tol, int maxit, int use_prior, const double* weights,
+                          int use_weights, double weight_threshold, int use_cr, int n_total, int g0, int n, int m,
+                          int p, double* out_log_alpha, int32_t* out_iter, int32_t* out_iter_accept,
+                          double* out_last_change, double* out_initial_lp, double* out_initial_dlp,
+                          double* out_last_lp, double* out_last_dlp, double* out_last_d2lp) {
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
   const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
   const long long ld = ld_for(m);
   void *d_y, *d_mu, *d_w = nullptr, *d_x, *d_la, *d_pm, *d_outd, *d_outi;
-  if (upload_matrix(y, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
-  if (upload_matrix(mu_hat, n, m, 8, S_RAW1, S_MU, st, &d_mu)) return 1;
-  if (use_weights && upload_matrix(weights, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
+  if (upload_matrix(y, n_total, g0, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
+  if (upload_matrix(mu_hat, n_total, g0, n, m, 8, S_RAW1, S_MU, st, &d_mu)) return 1;
+  if (use_weights && upload_matrix(weights, n_total, g0, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
   if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
-  if (upload_vec(log_alpha, sizeof(double) * n, S_V0, st, &d_la)) return 1;
-  if (upload_vec(log_alpha_prior_mean, sizeof(double) * n, S_V1, st, &d_pm)) return 1;
+  if (upload_vec(log_alpha + g0, sizeof(double) * n, S_V0, st, &d_la)) return 1;
+  if (upload_vec(log_alpha_prior_mean + g0, sizeof(double) * n, S_V1, st, &d_pm)) return 1;
   if (ws_get(S_OUTD, sizeof(double) * 7 * n, &d_outd)) return 1;
   if (ws_get(S_OUTI, sizeof(int32_t) * 2 * n, &d_outi)) return 1;
   double* od = (double*)d_outd;
@@ -582,9 +768,58 @@ int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu
   double* outs[7] = {out_log_alpha, out_last_change, out_initial_lp, out_initial_dlp, out_last_lp, out_last_dlp,
                      out_last_d2lp};
   for (int k = 0; k < 7; k++)
-    CU(cudaMemcpyAsync(outs[k], od + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_iter, oi, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_iter_accept, oi + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(outs[k] + g0, od + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_iter + g0, oi, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_iter_accept + g0, oi + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,
+                    const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
+                    double kappa_0, double tol, int maxit, int use_prior, const double* weights, int use_weights,
+                    double weight_threshold, int use_cr, int n, int m, int p,
+                    double* out_log_alpha, int32_t* out_iter, int32_t* out_iter_accept, double* out_last_change,
+                    double* out_initial_lp, double* out_initial_dlp, double* out_last_lp, double* out_last_dlp,
+                    double* out_last_d2lp) {
+  if (check_dims(n, m, p)) return 1;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  auto block = [&](int g0, int cnt) {
+    return fit_disp_block(y, y_type, x, mu_hat, log_alpha, log_alpha_prior_mean, log_alpha_prior_sigmasq, min_log_alpha,
+                          kappa_0, tol, maxit, use_prior, weights, use_weights, weight_threshold, use_cr, n, g0, cnt, m,
+                          p, out_log_alpha, out_iter, out_iter_accept, out_last_change, out_initial_lp,
+                          out_initial_dlp, out_last_lp, out_last_dlp, out_last_d2lp);
+  };
+  if (use_generic(p)) return block(0, n);   // the general-p path analyses the design with a stream sync per launch
+  unsigned int* presize;
+  if (next_scratch(nb::disp_scratch_bytes(n), &presize)) return 1;   // size the shared arena before workers start
+  return run_chunked(n, block);
+}
+
+static int fit_disp_grid_block(const void* y, int y_type, const double* x, const double* mu_hat,
+                               const double* disp_grid, int disp_grid_n, const double* log_alpha_prior_mean,
+                               double log_alpha_prior_sigmasq, int use_prior, const double* weights, int use_weights,
+                               double weight_threshold, int use_cr, int n_total, int g0, int n, int m, int p,
+                               double* out_log_alpha) {
+  cudaStream_t st;
+  if (ws_stream(&st)) return 1;
+  const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
+  const long long ld = ld_for(m);
+  void *d_y, *d_mu, *d_w = nullptr, *d_x, *d_grid, *d_pm, *d_out;
+  if (upload_matrix(y, n_total, g0, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
+  if (upload_matrix(mu_hat, n_total, g0, n, m, 8, S_RAW1, S_MU, st, &d_mu)) return 1;
+  if (use_weights && upload_matrix(weights, n_total, g0, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
+  if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
+  if (upload_vec(disp_grid, sizeof(double) * disp_grid_n, S_V0, st, &d_grid)) return 1;
+  if (upload_vec(log_alpha_prior_mean + g0, sizeof(double) * n, S_V1, st, &d_pm)) return 1;
+  if (ws_get(S_OUTD, sizeof(double) * n, &d_out)) return 1;
+  if (b200nb_fit_disp_grid_dev(d_y, y_type, (const double*)d_x, (const double*)d_mu, (const double*)d_grid,
+                               disp_grid_n, (const double*)d_pm, log_alpha_prior_sigmasq, use_prior,
+                               (const double*)d_w, use_weights, weight_threshold, use_cr, n, m, p, ld, (double*)d_out,
+                               st))
+    return 1;
+  CU(cudaMemcpyAsync(out_log_alpha + g0, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return 0;
 }
@@ -595,51 +830,39 @@ int b200nb_fit_disp_grid(const void* y, int y_type, const double* x, const doubl
                          int n, int m, int p, double* out_log_alpha) {
   if (check_dims(n, m, p)) return 1;
   if (n == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ws.mu);
-  cudaStream_t st;
-  if (ws_stream(&st)) return 1;
-  const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
-  const long long ld = ld_for(m);
-  void *d_y, *d_mu, *d_w = nullptr, *d_x, *d_grid, *d_pm, *d_out;
-  if (upload_matrix(y, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
-  if (upload_matrix(mu_hat, n, m, 8, S_RAW1, S_MU, st, &d_mu)) return 1;
-  if (use_weights && upload_matrix(weights, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
-  if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
-  if (upload_vec(disp_grid, sizeof(double) * disp_grid_n, S_V0, st, &d_grid)) return 1;
-  if (upload_vec(log_alpha_prior_mean, sizeof(double) * n, S_V1, st, &d_pm)) return 1;
-  if (ws_get(S_OUTD, sizeof(double) * n, &d_out)) return 1;
-  if (b200nb_fit_disp_grid_dev(d_y, y_type, (const double*)d_x, (const double*)d_mu, (const double*)d_grid,
-                               disp_grid_n, (const double*)d_pm, log_alpha_prior_sigmasq, use_prior,
-                               (const double*)d_w, use_weights, weight_threshold, use_cr, n, m, p, ld, (double*)d_out,
-                               st))
-    return 1;
-  CU(cudaMemcpyAsync(out_log_alpha, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  return 0;
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  auto block = [&](int g0, int cnt) {
+    return fit_disp_grid_block(y, y_type, x, mu_hat, disp_grid, disp_grid_n, log_alpha_prior_mean,
+                               log_alpha_prior_sigmasq, use_prior, weights, use_weights, weight_threshold, use_cr, n,
+                               g0, cnt, m, p, out_log_alpha);
+  };
+  if (use_generic(p)) return block(0, n);
+  unsigned int* presize;
+  if (next_scratch(nb::disp_scratch_bytes(n), &presize)) return 1;
+  return run_chunked(n, block);
 }
 
-int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf, const double* alpha_hat,
-                    const double* contrast, const double* beta_mat, const double* lambda, const double* weights,
-                    int use_weights, double tol, int maxit, int use_qr, double minmu, int n, int m, int p,
-                    double* out_beta_mat, double* out_beta_var_mat, double* out_iter, double* out_hat_diagonals,
-                    double* out_contrast_num, double* out_contrast_denom, double* out_deviance, double* out_mu) {
-  if (check_dims(n, m, p)) return 1;
-  if (n == 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ws.mu);
+static int fit_beta_block(const void* y, int y_type, const double* x, const double* nf, const double* alpha_hat,
+                          const double* contrast, const double* beta_mat, const double* lambda,
+                          const double* weights, int use_weights, double tol, int maxit, int use_qr, double minmu,
+                          int n_total, int g0, int n, int m, int p, double* out_beta_mat, double* out_beta_var_mat,
+                          double* out_iter, double* out_hat_diagonals, double* out_contrast_num,
+                          double* out_contrast_denom, double* out_deviance, double* out_mu) {
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
   const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
   const long long ld = ld_for(m);
   void *d_y, *d_nf, *d_w = nullptr, *d_x, *d_alpha, *d_contrast, *d_lambda, *d_bin, *d_bout, *d_bvar, *d_outd;
   void *d_h = nullptr, *d_mu = nullptr, *d_hc = nullptr, *d_muc = nullptr;
-  if (upload_matrix(y, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
-  if (upload_matrix(nf, n, m, 8, S_RAW1, S_NF, st, &d_nf)) return 1;
-  if (use_weights && upload_matrix(weights, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
+  if (upload_matrix(y, n_total, g0, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
+  if (upload_matrix(nf, n_total, g0, n, m, 8, S_RAW1, S_NF, st, &d_nf)) return 1;
+  if (use_weights && upload_matrix(weights, n_total, g0, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
   if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
-  if (upload_vec(alpha_hat, sizeof(double) * n, S_V0, st, &d_alpha)) return 1;
+  if (upload_vec(alpha_hat + g0, sizeof(double) * n, S_V0, st, &d_alpha)) return 1;
   if (upload_vec(contrast, sizeof(double) * p, S_V1, st, &d_contrast)) return 1;
   if (upload_vec(lambda, sizeof(double) * p, S_V2, st, &d_lambda)) return 1;
-  if (upload_vec(beta_mat, sizeof(double) * n * p, S_BETA_IN, st, &d_bin)) return 1;
+  if (ws_get(S_BETA_IN, sizeof(double) * n * p, &d_bin)) return 1;
+  if (h2d_block(d_bin, beta_mat, (size_t)n_total, (size_t)g0, (size_t)n, p, 8, st)) return 1;
   if (ws_get(S_BETA_OUT, sizeof(double) * n * p, &d_bout)) return 1;
   if (ws_get(S_BETA_VAR, sizeof(double) * n * p, &d_bvar)) return 1;
   if (ws_get(S_OUTD, sizeof(double) * 4 * n, &d_outd)) return 1;
@@ -660,25 +883,49 @@ int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf
     return 1;
   if (out_hat_diagonals) {
     if (b200nb_to_col_major_dev((const double*)d_h, (double*)d_hc, n, m, ld, st)) return 1;
-    if (d2h_staged(out_hat_diagonals, d_hc, sizeof(double) * n * m, st)) return 1;
+    if (d2h_block(out_hat_diagonals, d_hc, (size_t)n_total, (size_t)g0, (size_t)n, m, 8, st)) return 1;
   }
   if (out_mu) {
     if (b200nb_to_col_major_dev((const double*)d_mu, (double*)d_muc, n, m, ld, st)) return 1;
-    if (d2h_staged(out_mu, d_muc, sizeof(double) * n * m, st)) return 1;
+    if (d2h_block(out_mu, d_muc, (size_t)n_total, (size_t)g0, (size_t)n, m, 8, st)) return 1;
   }
-  CU(cudaMemcpyAsync(out_beta_mat, d_bout, sizeof(double) * n * p, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_beta_var_mat, d_bvar, sizeof(double) * n * p, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_iter, od, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_contrast_num, od + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_contrast_denom, od + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_deviance, od + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (n == n_total) {
+    CU(cudaMemcpyAsync(out_beta_mat, d_bout, sizeof(double) * n * p, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_beta_var_mat, d_bvar, sizeof(double) * n * p, cudaMemcpyDeviceToHost, st));
+  } else {
+    if (d2h_block(out_beta_mat, d_bout, (size_t)n_total, (size_t)g0, (size_t)n, p, 8, st)) return 1;
+    if (d2h_block(out_beta_var_mat, d_bvar, (size_t)n_total, (size_t)g0, (size_t)n, p, 8, st)) return 1;
+  }
+  CU(cudaMemcpyAsync(out_iter + g0, od, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_contrast_num + g0, od + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_contrast_denom + g0, od + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_deviance + g0, od + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return 0;
 }
 
+int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf, const double* alpha_hat,
+                    const double* contrast, const double* beta_mat, const double* lambda, const double* weights,
+                    int use_weights, double tol, int maxit, int use_qr, double minmu, int n, int m, int p,
+                    double* out_beta_mat, double* out_beta_var_mat, double* out_iter, double* out_hat_diagonals,
+                    double* out_contrast_num, double* out_contrast_denom, double* out_deviance, double* out_mu) {
+  if (check_dims(n, m, p)) return 1;
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  if (out_hat_diagonals) advise_hugepages(out_hat_diagonals, sizeof(double) * (size_t)n * m);
+  if (out_mu) advise_hugepages(out_mu, sizeof(double) * (size_t)n * m);
+  auto block = [&](int g0, int cnt) {
+    return fit_beta_block(y, y_type, x, nf, alpha_hat, contrast, beta_mat, lambda, weights, use_weights, tol, maxit,
+                          use_qr, minmu, n, g0, cnt, m, p, out_beta_mat, out_beta_var_mat, out_iter, out_hat_diagonals,
+                          out_contrast_num, out_contrast_denom, out_deviance, out_mu);
+  };
+  if (use_generic(p)) return block(0, n);
+  return run_chunked(n, block);
+}
+
 int b200nb_test_special(const double* x, int n, double* out_lgamma, double* out_digamma, double* out_trigamma) {
   if (n <= 0) return 0;
-  std::lock_guard<std::mutex> lk(g_ws.mu);
+  std::lock_guard<std::mutex> lk(g_call_mu);
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
   void *d_x, *d_o;

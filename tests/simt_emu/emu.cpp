@@ -6,6 +6,7 @@
 #endif
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "cuda_runtime.h"
@@ -248,6 +249,9 @@ double rcp_approx_f64(double x) {
 }
 
 void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& kernel_body) {
+  // one grid at a time: host threads that launch concurrently (the chunk workers of capi.cu) are serialised here
+  static std::mutex launch_mu;
+  std::lock_guard<std::mutex> lk(launch_mu);
   if (cur >= 0) die("nested launch");
   const int nthreads = (int)(block.x * block.y * block.z);
   if (nthreads <= 0 || nthreads > 1024) die("bad block size");

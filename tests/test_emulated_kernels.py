@@ -11,7 +11,7 @@ bit-identity with the GPU's arithmetic (tolerances are those of the GPU tests).
 
 This is a CHECK of the product source, never a product path: the emulated library exists only under tests/, and
 only this module (or an explicit B200NB_LIB=... in the environment of a test run) loads it.
-The whole -m gpu parity suite can be run the same way on a machine without a GPU (about 8 minutes):
+The whole -m gpu parity suite can be run the same way on a machine without a GPU (about 90 seconds):
 
     B200NB_LIB=tests/simt_emu/_build/libb200nb_emu.so python -m pytest tests/test_parity_gpu.py tests/test_golden.py \\
         tests/test_r_shim.py -m gpu --deselect tests/test_parity_gpu.py::test_c2_full_size_properties
@@ -138,9 +138,54 @@ def test_emulated_engine_through_R_boundary(emu, oracle, tmp_path):
     named R list out -- the complete drop-in path of INTEGRATION.md, minus R and minus the GPU."""
     import build_emu
     import test_r_shim as TR
-    bdir = os.path.dirname(build_emu.build())
-    so = TR._build(str(tmp_path), "DESeq2_emu.so", [], ["-L" + bdir, "-lb200nb_emu", "-Wl,-rpath," + bdir])
+    path = build_emu.build()
+    so = TR._build(str(tmp_path), "DESeq2_emu.so", [], [path, "-Wl,-rpath," + os.path.dirname(path)])
     TR.test_engine_through_R_boundary(TR.MockR(so), oracle)
+
+
+_CHUNK_PROBE = r"""
+import sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from deseq2_b200 import wrappers as W
+from helpers import make_case, disp_args, beta_args
+c = make_case(500, 37, seed=5)
+g = W.fitDisp(**disp_args(c, c["mu"], np.log(c["alpha0"])))
+alpha = np.exp(g["log_alpha"])
+w = np.random.default_rng(1).uniform(0.3, 1, c["counts"].shape)
+b = W.fitBeta(**beta_args(c, alpha, weights=w, useWeights=True), return_mu=True)
+grid = np.linspace(np.log(1e-8), np.log(30), 20)
+gg = W.fitDispGrid(ySEXP=c["counts"].astype(np.float64), xSEXP=c["x"], mu_hatSEXP=c["mu"], disp_gridSEXP=grid,
+                   log_alpha_prior_meanSEXP=np.log(alpha), log_alpha_prior_sigmasqSEXP=0.5, usePriorSEXP=True,
+                   weightsSEXP=w, useWeightsSEXP=True, weightThresholdSEXP=1e-2, useCRSEXP=True)
+out = dict(grid=gg["log_alpha"])
+out.update(("d_" + k, v) for k, v in g.items())
+out.update(("b_" + k, v) for k, v in b.items())
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_chunked_host_path_is_bit_identical(emu, tmp_path):
+    """B200NB_CHUNK_GENES (capi.cu run_chunked: gene blocks of the R-layout arrays handled by worker threads with their
+    own streams / workspaces / pinned rings) must return exactly what the unchunked call returns: strided gather of
+    the column-major inputs, per-block launches, strided scatter of hat_diagonals / mu / beta matrices."""
+    import subprocess
+    import build_emu
+    script = tmp_path / "probe.py"
+    script.write_text(_CHUNK_PROBE.format(root=os.path.dirname(HERE), tests=HERE))
+    outs = {}
+    for tag, extra in (("whole", {}), ("w1", {"B200NB_CHUNK_GENES": "97", "B200NB_CHUNK_WORKERS": "1"}),
+                       ("w3", {"B200NB_CHUNK_GENES": "61", "B200NB_CHUNK_WORKERS": "3"})):
+        env = dict(os.environ, B200NB_LIB=build_emu.build(), **extra)
+        env.pop("B200NB_FORCE_GENERIC", None)
+        f = str(tmp_path / (tag + ".npz"))
+        r = subprocess.run([sys.executable, str(script), f], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = np.load(f)
+    assert len(outs["whole"].files) == 18
+    for tag in ("w1", "w3"):
+        for k in outs["whole"].files:
+            assert np.array_equal(outs["whole"][k], outs[tag][k], equal_nan=True), (tag, k)
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))), ids=os.path.basename)

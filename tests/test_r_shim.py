@@ -133,8 +133,9 @@ def r_oracle(oracle, tmp_path_factory):
 def r_engine(tmp_path_factory):
     import deseq2_b200
     tmp = str(tmp_path_factory.mktemp("shim_engine"))
-    ldir = os.path.dirname(deseq2_b200.lib_path())
-    so = _build(tmp, "DESeq2.so", [], ["-L" + ldir, "-lb200nb", "-Wl,-rpath," + ldir])
+    deseq2_b200.lib()                                    # fails loudly if the engine has not been built
+    path = deseq2_b200.lib_path()                        # = -L<dir> -lb200nb of INTEGRATION.md section 2
+    so = _build(tmp, "DESeq2.so", [], [path, "-Wl,-rpath," + os.path.dirname(path)])
     return MockR(so)
 
 
