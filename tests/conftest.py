@@ -27,3 +27,25 @@ def engine():
     from deseq2_b200 import wrappers
     deseq2_b200.lib()
     return wrappers
+
+
+@pytest.fixture(scope="module")
+def emu(oracle):
+    """deseq2_b200.wrappers bound, for the duration of one test module, to the EMULATED engine: the product's CUDA
+    sources compiled by g++ against tests/simt_emu/ and executed on CPU fibers (test infrastructure, see
+    tests/test_emulated_kernels.py).  The product itself never loads this library."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt_emu"))
+    import build_emu
+    from deseq2_b200 import _lib, wrappers
+    lib = C.CDLL(build_emu.build())
+    for name, argt in _lib.SIGNATURES.items():
+        f = getattr(lib, name)
+        f.argtypes = argt
+        f.restype = _lib._RESTYPE.get(name, C.c_int)
+    saved = _lib._lib
+    _lib._lib = lib
+    try:
+        yield wrappers
+    finally:
+        _lib._lib = saved

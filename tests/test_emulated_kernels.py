@@ -28,24 +28,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "simt_emu"))
 
 
-@pytest.fixture(scope="module")
-def emu(oracle):
-    """deseq2_b200.wrappers bound to the emulated library for the duration of this module."""
-    import build_emu
-    from deseq2_b200 import _lib, wrappers
-    lib = C.CDLL(build_emu.build())
-    for name, argt in _lib.SIGNATURES.items():
-        f = getattr(lib, name)
-        f.argtypes = argt
-        f.restype = _lib._RESTYPE.get(name, C.c_int)
-    saved = _lib._lib
-    _lib._lib = lib
-    try:
-        yield wrappers
-    finally:
-        _lib._lib = saved
-
-
 def test_emulated_library_exports_the_c_abi(emu):
     from deseq2_b200 import _lib
     lib = _lib.lib()
