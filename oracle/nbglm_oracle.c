@@ -452,6 +452,7 @@ int oracle_fit_disp(const double *y, const double *x, const double *mu_hat, cons
         double a_propose = a + kappa * dlp;
         if (a_propose < -30.0) kappa = (-30.0 - a) / dlp;
         if (a_propose > 10.0) kappa = (10.0 - a) / dlp;
+        const int clamped_hi = a_propose > 10.0;
         double theta_kappa = -1.0 * log_posterior(s, a + kappa * dlp, pm, log_alpha_prior_sigmasq, usePrior,
                                                   useWeights, weightThreshold, useCR);
         double theta_hat_kappa = -1.0 * lp - kappa * epsilon * dlp * dlp;
@@ -478,6 +479,11 @@ int oracle_fit_disp(const double *y, const double *x, const double *mu_hat, cons
           lp = lpnew;
           lp_abs = prop_abs;
           dlp = dlog_posterior(s, a, pm, log_alpha_prior_sigmasq, usePrior, useWeights, weightThreshold, useCR);
+          /* The search goes on from a point that was clamped to the upper bound: a + ((10 - a) / dlp) * dlp is 10 only up
+           * to rounding (it can land a few ulps above), and with dlp > 0 every later proposal is clamped again with
+           * kappa = (10 - a) / dlp of either sign or zero -- the reference itself then stops after one more step or
+           * spins to maxit depending on the last bits.  Not a decision any implementation can be held to. */
+          if (clamped_hi && dlp > 0.0) mg = 0.0;
           kappa = fmin(kappa * 1.1, kappa_0);
           if (acc % 5 == 0) kappa = kappa / 2.0;
         } else {

@@ -147,7 +147,12 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False) -> str:
+def build(force: bool = False, asan: bool = False) -> str:
+    """asan=True: a second library, libb200nb_emu_asan.so, instrumented with AddressSanitizer -- every out-of-bounds
+    access to "device" memory, dynamic shared memory or the pinned rings aborts with a report (the emulator's memcheck).
+    Load it in a Python started with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0."""
+    if asan:
+        return _build_variant("libb200nb_emu_asan.so", ["-fsanitize=address", "-fno-omit-frame-pointer"])
     stamp = os.path.join(BUILD, "fingerprint")
     fp = _fingerprint()
     if not force and os.path.exists(SO) and os.path.exists(stamp) and open(stamp).read() == fp:
@@ -175,6 +180,17 @@ def build(force: bool = False) -> str:
     with open(stamp, "w") as f:
         f.write(fp)
     return SO
+
+
+def _build_variant(name: str, extra: list[str]) -> str:
+    build()                                   # transformed sources live in _build/src
+    src = os.path.join(BUILD, "src")
+    so = os.path.join(BUILD, name)
+    cpps = [os.path.join(src, u + ".cpp") for u in UNITS] + [os.path.join(HERE, "emu.cpp")]
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=fast",
+                    "-fno-strict-aliasing", "-w", "-mfma", *extra, "-I", HERE, "-I", src, "-I",
+                    os.path.join(ROOT, "include"), "-o", so, *cpps], check=True)
+    return so
 
 
 if __name__ == "__main__":
