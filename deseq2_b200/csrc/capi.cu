@@ -733,6 +733,21 @@ int b200nb_cooks_dev(const void* y, int y_type, const double* mu, const double* 
   return 0;
 }
 
+int b200nb_size_factors_dev(const void* y, int y_type, int poscounts, int n, int m, long long ld,
+                            double* loggeomeans, double* scratch_gm, double* scratch_cm, double* size_factors,
+                            int32_t* n_finite, void* stream) {
+  if (check_dims(n, m, 1)) return 1;
+  if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
+  if (n < 1) return fail("size factors need at least one gene");
+  nb::SizeFactorArgs a{};
+  a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.poscounts = poscounts ? 1 : 0; a.n = n; a.m = m; a.ld = ld;
+  a.loggeomeans = loggeomeans; a.ratios = scratch_gm; a.ratios_colmajor = scratch_cm; a.size_factors = size_factors;
+  a.n_finite = n_finite;
+  CU(nb::launch_size_factors(a, (cudaStream_t)stream));
+  g_launches += 3;
+  return 0;
+}
+
 /* ------------------------------------------------------------------ host entry points */
 /* Each entry point validates, takes the call lock and hands gene blocks [g0, g0 + n) of the caller's R-layout arrays
  * (n_total rows) to a *_block routine; without B200NB_CHUNK_GENES there is one block, the whole call. */

@@ -111,6 +111,21 @@ struct PrepArgs {
 };
 cudaError_t launch_prep(const PrepArgs& a, cudaStream_t stream);
 
+// median-of-ratios size factors (size_factors.cu)
+struct SizeFactorArgs {
+  const void* y;
+  int y_is_f64;
+  int poscounts;               // 0: type "ratio", 1: type "poscounts" (R/core.R:541-549)
+  int n, m;
+  long long ld;
+  double* loggeomeans;         // n (out)
+  double* ratios;              // gene-major n x ld scratch
+  double* ratios_colmajor;     // n x m column-major scratch
+  double* size_factors;        // m (out)
+  int* n_finite;               // out: genes with a finite log geometric mean
+};
+cudaError_t launch_size_factors(const SizeFactorArgs& a, cudaStream_t stream);
+
 // Cook's distances (pipeline_kernels.cu)
 struct CooksArgs {
   const void* y;

@@ -49,6 +49,27 @@ def _ws(name, shape, dtype, dev):
     return t
 
 
+def size_factors(y, m, type="ratio"):
+    """b200nb_size_factors_dev: estimateSizeFactorsForMatrix (R/core.R:535-578, locfunc = median) on the device.
+    y: gene-major (n, ld) device tensor, m samples.  Returns {"sizeFactors": (m,) device tensor, "loggeomeans": (n,)}.
+    Raises like the reference when every gene contains a zero (the only host read: one int)."""
+    if type not in ("ratio", "poscounts"):
+        raise ValueError("type must be 'ratio' or 'poscounts'")
+    L = _lib.lib()
+    dev = y.device
+    n, ld = y.shape
+    out = {"sizeFactors": torch.empty(m, dtype=F64, device=dev), "loggeomeans": torch.empty(n, dtype=F64, device=dev)}
+    nfin = torch.zeros(1, dtype=torch.int32, device=dev)
+    gm = _ws("sf_ratios", (n, ld), F64, dev)
+    cm = _ws("sf_ratios_cm", (n * m,), F64, dev)
+    _lib.check(L.b200nb_size_factors_dev(_p(y), 1 if y.dtype == F64 else 0, int(type == "poscounts"), n, m, ld,
+                                         _p(out["loggeomeans"]), _p(gm), _p(cm), _p(out["sizeFactors"]), _p(nfin),
+                                         _stream()), "size_factors")
+    if int(nfin.item()) == 0:
+        raise ValueError("every gene contains at least one zero, cannot compute log geometric means")
+    return out
+
+
 def prep(y, x, sizeFactors, minDisp=1e-8, minmu=0.5, want_mu=True, want_beta0=True):
     """b200nb_prep_dev.  y: gene-major (n, ld) int32/float64 device tensor; x: (m, p) numpy; sizeFactors: (m,) numpy."""
     L = _lib.lib()
@@ -149,13 +170,18 @@ def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e
             "mu": res["full"]["mu"], "H": res["full"]["hat_diagonals"]}
 
 
-def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, maxit=100, betaTol=1e-8, minmu=0.5,
+def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, maxit=100, betaTol=1e-8, minmu=0.5,
                  outlierSD=2.0):
     """y: gene-major (N, ld) device tensor of counts (int32 or float64).  Returns a dict of device tensors over the
-    rows with a non-zero sum (`idx` maps them back to the N input rows) plus the trend / prior scalars."""
+    rows with a non-zero sum (`idx` maps them back to the N input rows) plus the trend / prior scalars.
+    sizeFactors=None estimates them on the device first (median of ratios, R/core.R:535-578; returned under
+    "sizeFactors")."""
     dev = y.device
     x = np.asarray(x, dtype=np.float64)
     m, p = x.shape
+    estimated = sizeFactors is None
+    if estimated:
+        sizeFactors = size_factors(y, m)["sizeFactors"].cpu().numpy()
     if m - p <= 3:
         raise NotImplementedError("residual df <= 3: the reference's Monte-Carlo prior-variance branch is not restated")
     import os
@@ -261,4 +287,4 @@ def DESeq_device(y, x, sizeFactors, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, max
             "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": fb["deviance"], "mu": fb["mu"],
             "H": fb["hat_diagonals"], "trendCoefs": tr[:2], "varLogDispEsts": varLogDispEsts,
             "dispPriorVar": dispPriorVar, "n_refit_geneest": n_refit_geneest, "n_refit_map": int(gi2.numel()),
-            "n_input_rows": y.shape[0]}
+            "n_input_rows": y.shape[0], "sizeFactors": np.asarray(sizeFactors, dtype=np.float64)}

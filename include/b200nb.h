@@ -119,6 +119,16 @@ int b200nb_cooks_dev(const void* y, int y_type, const double* mu, const double* 
                      const int32_t* cell_ptr, const int32_t* cell_samples, int ncell, int n, int m, int p,
                      long long ld, double* cooks, double* max_cooks, double* robust_disp, void* stream);
 
+/* b200nb_size_factors_dev: estimateSizeFactorsForMatrix (R/core.R:535-578; locfunc = median, no geoMeans /
+ * controlGenes).  poscounts = 0 is type "ratio", 1 is type "poscounts".  y gene-major (n x ld); loggeomeans[n] and
+ * size_factors[m] are outputs; scratch_gm (n x ld doubles) and scratch_cm (n x m doubles) are caller-provided device
+ * scratch; n_finite (device int) receives the number of genes with a finite log geometric mean -- R stops with
+ * "every gene contains at least one zero" when it is 0, the caller must do the same.  A sample with no usable
+ * ratio gets NaN (median of an empty set is NA in R). */
+int b200nb_size_factors_dev(const void* y, int y_type, int poscounts, int n, int m, long long ld,
+                            double* loggeomeans, double* scratch_gm, double* scratch_cm, double* size_factors,
+                            int32_t* n_finite, void* stream);
+
 /* ---- housekeeping */
 const char* b200nb_last_error(void);
 int b200nb_device_count(void);            /* number of visible CUDA devices (0 if none / no driver) */

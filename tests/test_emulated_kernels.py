@@ -92,6 +92,9 @@ def emu_device(emu, monkeypatch):
     monkeypatch.setattr(D, "_stream", null_stream)
     monkeypatch.setattr(DP, "_stream", null_stream)
     monkeypatch.setattr(TD, "DEV", "cpu")
+    import test_size_factors_gpu as TS
+    monkeypatch.setattr(TS, "DEV", "cpu")
+    TD.TS = TS
     DP._ws.clear() if hasattr(DP._ws, "clear") else None
     return TD
 
@@ -107,6 +110,12 @@ DEVICE_CASES = [
     ("DESeq on device ~condition", lambda T, e: T.test_device_pipeline_matches_host_pipeline(e, "condition", 240, 40)),
     ("DESeq on device ~batch+condition", lambda T, e: T.test_device_pipeline_matches_host_pipeline(e, "batch", 160, 36)),
     ("LRT on device", lambda T, e: T.test_lrt_device_matches_host(e, n=250)),
+    ("size factors 700x12", lambda T, e: T.TS.test_size_factors_match_numpy(e, 700, 12, 1, False)),
+    ("size factors 501x37 double", lambda T, e: T.TS.test_size_factors_match_numpy(e, 501, 37, 2, True)),
+    ("size factors 150x130", lambda T, e: T.TS.test_size_factors_match_numpy(e, 150, 130, 3, False)),
+    ("size factors 64x5", lambda T, e: T.TS.test_size_factors_match_numpy(e, 64, 5, 4, False)),
+    ("size factors degenerate", lambda T, e: T.TS.test_size_factors_degenerate_inputs(e)),
+    ("DESeq on device from raw counts", lambda T, e: T.TS.test_deseq_device_from_raw_counts(e, n=200)),
 ]
 
 
