@@ -170,12 +170,67 @@ def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e
             "mu": res["full"]["mu"], "H": res["full"]["hat_diagonals"]}
 
 
+def _refit_rows(ysub, x, sizeFactors, tr, varLogDispEsts, dispPriorVar, minDisp, kappa_0, dispTol, maxit, betaTol,
+                minmu, outlierSD):
+    """The per-gene chain of DESeq_device (GeneEst -> MAP -> Wald) on a subset of rows with the dispersion trend and
+    prior already known: what refitWithoutOutliers (R/core.R:2500-2528) does with objectSub.  Fresh tensors, no
+    shared workspace: the subset is small."""
+    dev = ysub.device
+    m, p = x.shape
+    maxDisp = float(max(10, m))
+    linearMu = modelMatrixGroups(x) == p
+    pr = prep(ysub, x, sizeFactors, minDisp=minDisp, minmu=minmu, want_mu=linearMu)
+    xd, sfd, bm, alpha0, beta0 = pr["xd"], pr["sfd"], pr["baseMean"], pr["alpha0"], pr["beta0"]
+    if linearMu:
+        mu = pr["mu_lin"].clone()
+    n = ysub.shape[0]
+    contrast = torch.zeros(p, dtype=F64, device=dev)
+    contrast[0] = 1.0
+    lam = torch.full((p,), 1e-6 / LN2 ** 2, dtype=F64, device=dev)
+    min_log_alpha = float(np.log(minDisp / 10))
+    if not linearMu:
+        mu = D.fit_beta(ysub, xd, sfd, alpha0, contrast, beta0, lam, betaTol, maxit, minmu=minmu, want_hat=False,
+                        want_mu=True)["mu"]
+    la0 = torch.log(alpha0)
+    r = D.fit_disp(ysub, xd, mu, la0, la0, 1.0, min_log_alpha, kappa_0, dispTol, maxit, False)
+    dge = torch.clamp(torch.exp(r["log_alpha"]), max=maxDisp)
+    dge = torch.where(r["last_lp"] < r["initial_lp"] + r["initial_lp"].abs() / 1e6, alpha0, dge)
+    conv = (r["iter"] < maxit) & (r["iter"] != 1)
+    gi, ga = _grid_refit(ysub, xd, mu, (~conv) & (dge > minDisp * 10), m, None, 1.0, False)
+    if ga is not None:
+        dge[gi] = ga
+    dge = torch.clamp(dge, minDisp, maxDisp)
+    dispFit = tr[0] + tr[1] / bm
+    logFit = torch.log(dispFit)
+    dispInit = torch.where(dge > 0.1 * dispFit, dge, dispFit)
+    rm = D.fit_disp(ysub, xd, mu, torch.log(dispInit), logFit, dispPriorVar, min_log_alpha, kappa_0, dispTol, maxit, True)
+    dispMAP = torch.exp(rm["log_alpha"])
+    gi2, ga2 = _grid_refit(ysub, xd, mu, rm["iter"] >= maxit, m, logFit, dispPriorVar, True)
+    if ga2 is not None:
+        dispMAP[gi2] = ga2
+    dispMAP = torch.clamp(dispMAP, minDisp, maxDisp)
+    dispOutlier = torch.log(dge) > logFit + outlierSD * torch.sqrt(varLogDispEsts)
+    dispersion = torch.where(dispOutlier, dge, dispMAP)
+    fb = D.fit_beta(ysub, xd, sfd, dispersion, contrast, beta0, lam, betaTol, maxit, minmu=minmu, want_hat=False,
+                    want_mu=False)
+    betaMatrix = fb["beta_mat"] / LN2
+    betaSE = torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0.0)) / LN2
+    stat = betaMatrix / betaSE
+    return {"baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP, "dispersion": dispersion,
+            "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"], "betaMatrix": betaMatrix.T,
+            "betaSE": betaSE.T, "WaldStatistic": stat.T, "WaldPvalue": (2.0 * torch.special.ndtr(-stat.abs())).T,
+            "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": fb["deviance"]}
+
+
 def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, maxit=100, betaTol=1e-8, minmu=0.5,
-                 outlierSD=2.0):
+                 outlierSD=2.0, minReplicatesForReplace=np.inf):
     """y: gene-major (N, ld) device tensor of counts (int32 or float64).  Returns a dict of device tensors over the
     rows with a non-zero sum (`idx` maps them back to the N input rows) plus the trend / prior scalars.
     sizeFactors=None estimates them on the device first (median of ratios, R/core.R:535-578; returned under
-    "sizeFactors")."""
+    "sizeFactors").  minReplicatesForReplace: the reference's default is 7 (replace count outliers by the trimmed mean
+    and refit those genes, R/core.R:419-426, 2069-2115, 2484-2565); the default here is Inf = off (what bench.py's
+    full_pipeline times).  With a finite value the per-gene results of the refitted rows are overwritten in place
+    and "replace" / "replaceable" / "n_replaced" are added."""
     dev = y.device
     x = np.asarray(x, dtype=np.float64)
     m, p = x.shape
@@ -279,12 +334,70 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
     betaSE = torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0.0)) / LN2
     stat = betaMatrix / betaSE
     pval = 2.0 * torch.special.ndtr(-stat.abs())
-    ck = cooks(ynz, fb["mu"], fb["hat_diagonals"], x, sizeFactors, want_matrix=False)   # R/core.R:1457-1460
+    from .pipeline import nOrMoreInCell
+    do_replace = bool(np.isfinite(minReplicatesForReplace)) and bool(nOrMoreInCell(x, minReplicatesForReplace).any())
+    ck = cooks(ynz, fb["mu"], fb["hat_diagonals"], x, sizeFactors, want_matrix=do_replace)   # R/core.R:1457-1460
     mark("wald_stats+cooks")
-    return {"stage_ms": stage_ms, "maxCooks": ck["maxCooks"], "idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
+    res = {"stage_ms": stage_ms, "maxCooks": ck["maxCooks"], "idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
             "dispersion": dispersion, "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"],
             "betaMatrix": betaMatrix.T, "betaSE": betaSE.T, "WaldStatistic": stat.T, "WaldPvalue": pval.T,
             "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": fb["deviance"], "mu": fb["mu"],
             "H": fb["hat_diagonals"], "trendCoefs": tr[:2], "varLogDispEsts": varLogDispEsts,
             "dispPriorVar": dispPriorVar, "n_refit_geneest": n_refit_geneest, "n_refit_map": int(gi2.numel()),
             "n_input_rows": y.shape[0], "sizeFactors": np.asarray(sizeFactors, dtype=np.float64)}
+    if do_replace and m > p:
+        _replace_and_refit(res, ynz, ck["cooks"], x, sizeFactors, sfd, tr, varLogDispEsts, dispPriorVar,
+                           minReplicatesForReplace, minDisp, kappa_0, dispTol, maxit, betaTol, minmu, outlierSD)
+    return res
+
+
+def _replace_and_refit(res, ynz, cooksm, x, sizeFactors, sfd, tr, varLogDispEsts, dispPriorVar, minReplicates, minDisp,
+                       kappa_0, dispTol, maxit, betaTol, minmu, outlierSD, trim=0.2):
+    """replaceOutliers + refitWithoutOutliers (R/core.R:2069-2115, 2484-2565) on the device results `res` (in place).
+    Only the flagged rows move: their counts are gathered, the outlying entries of replaceable samples become
+    as.integer(trimmed mean of the normalised counts * size factor), and the rows go through _refit_rows."""
+    from scipy import stats as _st
+    from .pipeline import nOrMoreInCell
+    dev = ynz.device
+    m, p = x.shape
+    cutoff = float(_st.f.ppf(0.99, p, m - p))
+    replaceable = torch.as_tensor(nOrMoreInCell(x, minReplicates), device=dev)
+    over = cooksm[:, :m] > cutoff                                   # NaN compares false, like NA in which()/any()
+    replace = over.any(dim=1)
+    rows = torch.nonzero(replace).squeeze(1)
+    res["replace"], res["replaceable"], res["n_replaced"] = replace, replaceable, int(rows.numel())
+    if rows.numel() == 0:
+        return
+    ys = ynz[rows][:, :m].to(F64)
+    srt, _ = torch.sort(ys / sfd[None, :], dim=1)
+    lo = int(np.floor(m * trim))
+    tbm = srt[:, lo:m - lo].mean(dim=1)
+    replacement = torch.trunc(tbm[:, None] * sfd[None, :])
+    new = torch.where(over[rows] & replaceable[None, :], replacement, ys)
+    res["baseMean"] = res["baseMean"].clone()
+    res["baseMean"][rows] = (new / sfd[None, :]).mean(dim=1)        # getBaseMeansAndVariances on the new counts
+    newAllZero = new.sum(dim=1) == 0
+    keep = ~newAllZero
+    rr = rows[keep]
+    if rr.numel() > 0:
+        ysub = torch.zeros((rr.numel(), ynz.shape[1]), dtype=F64, device=dev)
+        ysub[:, :m] = new[keep]
+        sub = _refit_rows(ysub, x, sizeFactors, tr, varLogDispEsts, dispPriorVar, minDisp, kappa_0, dispTol, maxit,
+                          betaTol, minmu, outlierSD)
+        for k, v in sub.items():
+            if k == "baseMean":
+                continue
+            res[k] = res[k].clone()
+            res[k][rr] = v.to(res[k].dtype)
+        for k in ("betaMatrix", "betaSE", "WaldStatistic", "WaldPvalue", "deviance"):
+            res[k][rows[newAllZero]] = float("nan")
+        if bool(replaceable.all()):
+            res["maxCooks"] = torch.full_like(res["maxCooks"], float("nan"))
+        else:                                   # replaceCooks[, replaceable] <- 0, then recordMaxCooks (:2537-2543)
+            from .pipeline import designCells
+            cells, sizes = designCells(x)
+            forCooks = torch.as_tensor(sizes[cells] >= 3, device=dev)
+            rc = cooksm[:, :m].clone()
+            rc[:, replaceable] = 0.0
+            res["maxCooks"] = (rc[:, forCooks].max(dim=1).values if bool(forCooks.any())
+                               else torch.full_like(res["maxCooks"], float("nan")))

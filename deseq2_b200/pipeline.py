@@ -22,7 +22,7 @@ numpy, one function per R function, same names, so the engine can be driven and 
 
 `engine` is any object with fitDisp / fitDispGrid / fitBeta taking the reference's argument names
 (deseq2_b200.wrappers is the product engine and the default; tests and the bench's CPU baseline pass the
-oracle).  Not restated (out of scope): outlier replacement / refit, local / mean trend fits,
+oracle).  Not restated (out of scope): local / mean trend fits,
 observation weights in the glue, results()/lfcShrink().
 """
 from __future__ import annotations
@@ -410,6 +410,39 @@ def recordMaxCooks(x, cooks):
     return np.full(cooks.shape[0], np.nan)
 
 
+def nOrMoreInCell(x, n):
+    """R/core.R:2366-2371: per sample, does its design cell (distinct design row) hold at least n samples?"""
+    cells, sizes = designCells(x)
+    return sizes[cells] >= n
+
+
+def replaceOutliers(counts, cooks, sizeFactors, x, trim=0.2, cooksCutoff=None, minReplicates=7):
+    """R/core.R:2069-2115 (size factors, no normalisation-factor matrix).  Returns (counts with the outlying entries of
+    replaceable samples set to as.integer(trimmed mean of the normalised counts * size factor), per-gene `replace`
+    flag, per-sample `replaceable` flag).  Like the reference, `replace` is raised by an outlier in ANY sample."""
+    from scipy import stats as _st
+    counts = np.asarray(counts)
+    n, m = counts.shape
+    p = x.shape[1]
+    if minReplicates < 3:
+        raise ValueError("at least 3 replicates are necessary in order to indentify a sample as a count outlier")
+    if m <= p:
+        return counts.copy(), np.zeros(n, bool), np.zeros(m, bool)
+    if cooksCutoff is None:
+        cooksCutoff = _st.f.ppf(0.99, p, m - p)
+    with np.errstate(invalid="ignore"):
+        over = cooks > cooksCutoff                      # NA > cutoff is NA in R and drops out of which()/any()
+    replace = over.any(axis=1)
+    trimBaseMean = _r_trimmed_mean(counts / sizeFactors[None, :], trim)
+    replacementCounts = np.trunc(trimBaseMean[:, None] * sizeFactors[None, :]).astype(counts.dtype)   # as.integer
+    newCounts = counts.copy()
+    newCounts[over] = replacementCounts[over]
+    whichSamples = nOrMoreInCell(x, minReplicates)
+    out = counts.copy()
+    out[:, whichSamples] = newCounts[:, whichSamples]
+    return out, replace, whichSamples
+
+
 def _fit_intercept_only(counts, nf, alpha_hat):
     """R/fitNbinomGLMs.R:99-137: reduced model ~1 with the default wide prior needs no IRLS (no native call)."""
     norm = counts / nf
@@ -549,8 +582,12 @@ def fitGLMsWithPrior(counts, nf, factors, dispersion, baseMean, dispFit, engine=
             "modelMatrix": x_exp, "mleBetaMatrix": mle["betaMatrix"], "names": enames, "mle": mle}
 
 
-def DESeq(counts, x, sizeFactors=None, engine=None):
-    """R/core.R:280-432 with test='Wald', fitType='parametric', betaPrior=FALSE, no outlier replacement.
+def DESeq(counts, x, sizeFactors=None, engine=None, minReplicatesForReplace=np.inf):
+    """R/core.R:280-432 with test='Wald', fitType='parametric', betaPrior=FALSE.
+    minReplicatesForReplace: the reference's default is 7 (outlier replacement + refit whenever a design cell has >= 7
+    samples, R/core.R:419-426, refitWithoutOutliers :2484-2565); the default here is Inf = off, which is what the
+    engine parity tests and bench.py's `full_pipeline` exercise.  With a finite value the result also carries
+    `replace` (genes refitted), `replaceable` (samples) and `replaceCounts`.
     Returns per-gene vectors over ALL rows; all-zero rows carry NaN (buildDataFrameWithNARows, R/core.R:2232)."""
     engine = engine or _default_engine
     counts = np.asarray(counts)
@@ -569,19 +606,63 @@ def DESeq(counts, x, sizeFactors=None, engine=None):
                                 tf["varLogDispEsts"], engine=engine)
     nf = np.broadcast_to(sizeFactors[None, :], cnz.shape)
     wt = nbinomWaldTest(cnz, nf, x, mp["dispersion"], engine=engine)
+    cooks = calculateCooksDistance(cnz, wt["mu"], wt["hat_diagonals"], sizeFactors, x)      # R/core.R:1457-1460
+    per_gene = {"baseMean": mv["baseMean"], "dispGeneEst": ge["dispGeneEst"], "dispFit": tf["dispFit"],
+                "dispMAP": mp["dispMAP"], "dispersion": mp["dispersion"], "dispOutlier": mp["dispOutlier"].astype(float),
+                "betaMatrix": wt["betaMatrix"], "betaSE": wt["betaSE"], "WaldStatistic": wt["WaldStatistic"],
+                "WaldPvalue": wt["WaldPvalue"], "betaConv": wt["betaConv"].astype(float), "betaIter": wt["betaIter"],
+                "deviance": wt["deviance"], "dispGeneIter": ge["dispGeneIter"].astype(float),
+                "dispIter": mp["dispIter"].astype(float), "maxCooks": recordMaxCooks(x, cooks)}
+    extra = {}
+    if np.isfinite(minReplicatesForReplace) and nOrMoreInCell(x, minReplicatesForReplace).any():
+        # ---- refitWithoutOutliers (R/core.R:2484-2565) on the rows that had a count replaced
+        newc, replace, replaceable = replaceOutliers(cnz, cooks, sizeFactors, x, minReplicates=minReplicatesForReplace)
+        nrefit = int(replace.sum())
+        newAllZero = replace & (newc.sum(axis=1) == 0)
+        if nrefit > 0:
+            mvNew = getBaseMeansAndVariances(newc, sizeFactors)
+            per_gene["baseMean"] = mvNew["baseMean"]
+        if nrefit > 0 and nrefit > int(newAllZero.sum()):
+            rr = replace & ~newAllZero
+            sub = newc[rr]
+            ge2 = estimateDispersionsGeneEst(sub, sizeFactors, x, engine=engine)
+            dispFit2 = tf["coefs"][0] + tf["coefs"][1] / ge2["baseMean"]       # dispersionFunction(object)(baseMean)
+            mp2 = estimateDispersionsMAP(sub, x, ge2["mu"], ge2["dispGeneEst"], dispFit2, dispPriorVar,
+                                         tf["varLogDispEsts"], engine=engine)
+            wt2 = nbinomWaldTest(sub, np.broadcast_to(sizeFactors[None, :], sub.shape), x, mp2["dispersion"],
+                                 engine=engine)
+            upd = {"dispGeneEst": ge2["dispGeneEst"], "dispFit": dispFit2, "dispMAP": mp2["dispMAP"],
+                   "dispersion": mp2["dispersion"], "dispOutlier": mp2["dispOutlier"].astype(float),
+                   "betaMatrix": wt2["betaMatrix"], "betaSE": wt2["betaSE"], "WaldStatistic": wt2["WaldStatistic"],
+                   "WaldPvalue": wt2["WaldPvalue"], "betaConv": wt2["betaConv"].astype(float),
+                   "betaIter": wt2["betaIter"], "deviance": wt2["deviance"],
+                   "dispGeneIter": ge2["dispGeneIter"].astype(float), "dispIter": mp2["dispIter"].astype(float)}
+            for k, v in upd.items():
+                per_gene[k] = per_gene[k].copy()
+                per_gene[k][rr] = v
+            for k in ("betaMatrix", "betaSE", "WaldStatistic", "WaldPvalue", "betaConv", "betaIter", "deviance"):
+                per_gene[k][newAllZero] = np.nan                                 # "results" columns (:2534)
+            if replaceable.all():
+                per_gene["maxCooks"] = np.full(len(cnz), np.nan)
+            else:
+                rc = cooks.copy()
+                rc[:, replaceable] = 0.0
+                per_gene["maxCooks"] = recordMaxCooks(x, rc)
+        full_counts = counts.copy()
+        full_counts[nz] = newc
+        rep_all = np.zeros(N, bool)
+        rep_all[nz] = replace
+        extra = {"replace": rep_all, "replaceable": replaceable, "replaceCounts": full_counts, "n_replaced": nrefit}
 
     def full(v):
         out = np.full((N,) + v.shape[1:], np.nan)
         out[nz] = v
         return out
 
-    return {"sizeFactors": sizeFactors, "baseMean": mvAll["baseMean"], "allZero": mvAll["allZero"],
-            "dispGeneEst": full(ge["dispGeneEst"]), "dispFit": full(tf["dispFit"]), "dispMAP": full(mp["dispMAP"]),
-            "dispersion": full(mp["dispersion"]), "dispOutlier": full(mp["dispOutlier"].astype(float)),
-            "dispPriorVar": dispPriorVar, "trendCoefs": tf["coefs"], "varLogDispEsts": tf["varLogDispEsts"],
-            "betaMatrix": full(wt["betaMatrix"]), "betaSE": full(wt["betaSE"]),
-            "WaldStatistic": full(wt["WaldStatistic"]), "WaldPvalue": full(wt["WaldPvalue"]),
-            "betaConv": full(wt["betaConv"].astype(float)), "betaIter": full(wt["betaIter"]),
-            "deviance": full(wt["deviance"]), "dispGeneIter": full(ge["dispGeneIter"].astype(float)),
-            "dispIter": full(mp["dispIter"].astype(float)),
-            "n_refit_geneest": ge["n_refit"], "n_refit_map": mp["n_refit"]}
+    res = {k: full(np.asarray(v, dtype=np.float64)) for k, v in per_gene.items()}
+    res.update({"sizeFactors": sizeFactors, "allZero": mvAll["allZero"], "dispPriorVar": dispPriorVar,
+                "trendCoefs": tf["coefs"], "varLogDispEsts": tf["varLogDispEsts"], "n_refit_geneest": ge["n_refit"],
+                "n_refit_map": mp["n_refit"]})
+    res["baseMean"] = np.where(nz, res["baseMean"], 0.0)
+    res.update(extra)
+    return res

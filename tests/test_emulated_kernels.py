@@ -116,6 +116,8 @@ DEVICE_CASES = [
     ("size factors 64x5", lambda T, e: T.TS.test_size_factors_match_numpy(e, 64, 5, 4, False)),
     ("size factors degenerate", lambda T, e: T.TS.test_size_factors_degenerate_inputs(e)),
     ("DESeq on device from raw counts", lambda T, e: T.TS.test_deseq_device_from_raw_counts(e, n=200)),
+    ("outlier replacement + refit ~condition", lambda T, e: T.TS.test_outlier_replacement_and_refit_device_vs_host(e, "condition", n=300)),
+    ("outlier replacement + refit, mixed cells", lambda T, e: T.TS.test_outlier_replacement_and_refit_device_vs_host(e, "mixed", n=300)),
 ]
 
 

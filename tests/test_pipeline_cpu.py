@@ -1,6 +1,7 @@
 """Host glue (deseq2_b200/pipeline.py, the numpy restatement of the R callers) driven by the oracle engine:
 BASELINE.json config 1 (makeExampleDESeqDataSet(n=1000, m=6), ~condition, Wald, CPU plumbing)."""
 import numpy as np
+import pytest
 
 from deseq2_b200 import pipeline, synth
 
@@ -134,3 +135,60 @@ def test_optim_fallback_matches_irls_and_rescues_divergence(oracle):
     assert r0["betaIter"][0] == 100 and not r0["betaConv"][0]
     assert np.all(np.isfinite(r1["betaMatrix"])) and np.all(np.abs(r1["betaMatrix"]) <= 30)
     assert r1["logLike"][0] >= r0["logLike"][0] - 1e-6
+
+
+def test_replace_outliers_semantics():
+    """R/core.R:2069-2115 (test_outlier.R:2-31 analogue): only entries above the Cook's cutoff in samples whose cell has
+    >= minReplicates samples are replaced, by as.integer(trimmed mean of normalised counts * size factor); the gene
+    is flagged even when its outlier sits in a non-replaceable sample."""
+    from scipy import stats
+    g = np.r_[np.zeros(8), np.ones(8), np.full(3, 2)].astype(int)
+    m = len(g)
+    x = np.zeros((m, 3))
+    x[:, 0] = 1
+    x[g == 1, 1] = 1
+    x[g == 2, 2] = 1
+    rng = np.random.default_rng(0)
+    counts = rng.poisson(50, (6, m)).astype(np.int32)
+    sf = np.exp(rng.normal(0, 0.2, m))
+    cooks = np.full((6, m), 0.1)
+    cut = stats.f.ppf(0.99, 3, m - 3)
+    cooks[1, 2] = cut * 1.5          # replaceable sample (cell of 8)
+    cooks[3, 17] = cut * 2.0         # sample in the cell of 3: flagged, not replaced
+    cooks[4, 5] = np.nan             # NA never counts
+    new, replace, replaceable = pipeline.replaceOutliers(counts, cooks, sf, x, minReplicates=7)
+    assert np.array_equal(replaceable, g < 2)
+    assert np.array_equal(replace, [False, True, False, True, False, False])
+    changed = np.argwhere(new != counts)
+    assert changed.tolist() == [[1, 2]]
+    norm = np.sort(counts[1] / sf)
+    lo = int(np.floor(m * 0.2))
+    assert new[1, 2] == int(norm[lo:m - lo].mean() * sf[2])
+    assert pipeline.nOrMoreInCell(x, 3).all() and not pipeline.nOrMoreInCell(x, 9).any()
+    with pytest.raises(ValueError):
+        pipeline.replaceOutliers(counts, cooks, sf, x, minReplicates=2)
+
+
+def test_refit_without_outliers_recovers_fold_changes(oracle):
+    """test_outlier.R:33-55 idea through the whole host pipeline: planted count outliers get Cook's distances above
+    qf(.99, p, m - p), are replaced, and the refit moves the fold changes back to the outlier-free estimates."""
+    m = 20
+    x = synth.design_condition(m)
+    d = synth.make_example_counts(400, m, x=x, seed=5, interceptMean=5.0)
+    counts = d["counts"].copy()
+    rng = np.random.default_rng(1)
+    planted = rng.choice(400, 16, replace=False)
+    counts[planted, rng.integers(0, m, 16)] += 100 + 12 * counts[planted].max(axis=1)
+    sf = d["sizeFactors"]
+    clean = pipeline.DESeq(d["counts"], x, sizeFactors=sf, engine=oracle)
+    raw = pipeline.DESeq(counts, x, sizeFactors=sf, engine=oracle)
+    fit = pipeline.DESeq(counts, x, sizeFactors=sf, engine=oracle, minReplicatesForReplace=7)
+    assert fit["replaceable"].all() and np.all(np.isnan(fit["maxCooks"]))
+    hit = np.intersect1d(planted, np.flatnonzero(fit["replace"]))
+    assert len(hit) >= 10 and fit["n_replaced"] < 40
+    untouched = ~fit["replace"] & ~fit["allZero"]
+    assert np.array_equal(fit["betaMatrix"][untouched], raw["betaMatrix"][untouched])
+    err_fit = np.abs(fit["betaMatrix"][hit, 1] - clean["betaMatrix"][hit, 1])
+    err_raw = np.abs(raw["betaMatrix"][hit, 1] - clean["betaMatrix"][hit, 1])
+    assert np.median(err_fit) < 0.25 * np.median(err_raw)
+    assert np.array_equal(fit["replaceCounts"][~fit["replace"]], counts[~fit["replace"]])

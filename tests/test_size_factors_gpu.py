@@ -86,3 +86,62 @@ def test_deseq_device_from_raw_counts(engine, n=3000):
     for k in ("dispGeneEst", "dispersion", "betaMatrix", "betaSE", "WaldPvalue", "maxCooks"):
         e = rel_err(a[k].cpu().numpy(), b[k].cpu().numpy(), floor=1e-9)
         assert np.mean(e < 1e-6) > 0.99, k
+
+
+@pytest.mark.parametrize("design", ["condition", "mixed"])
+def test_outlier_replacement_and_refit_device_vs_host(engine, design, n=2500):
+    """replaceOutliers + refitWithoutOutliers (R/core.R:2069-2115, 2484-2565; DESeq's default for cells with >= 7
+    replicates): the device-resident pipeline against the numpy restatement driving the same engine.  "mixed" has a
+    cell of 3 samples (used for Cook's, not replaceable) next to cells of 9, so maxCooks is recomputed, not NA."""
+    import torch
+    from deseq2_b200 import device as D, device_pipeline as DP, pipeline, synth
+    if design == "condition":
+        m = 20
+        x = synth.design_condition(m)
+    else:
+        g = np.r_[np.zeros(9), np.ones(9), np.full(3, 2)].astype(int)
+        m = len(g)
+        x = np.zeros((m, 3))
+        x[:, 0] = 1
+        x[g == 1, 1] = 1
+        x[g == 2, 2] = 1
+    d = synth.make_example_counts(n, m, x=x, seed=23, interceptMean=5.0)
+    counts = d["counts"].copy()
+    rng = np.random.default_rng(3)
+    planted = rng.choice(n, n // 25, replace=False)
+    counts[planted, rng.integers(0, m, len(planted))] += 100 + 12 * counts[planted].max(axis=1)    # count outliers
+    sf = d["sizeFactors"]
+    host = pipeline.DESeq(counts, x, sizeFactors=sf, engine=engine, minReplicatesForReplace=7)
+    dv = DP.DESeq_device(D.to_gene_major(counts, torch.device(DEV)), x, sf, minReplicatesForReplace=7)
+    idx = dv["idx"].cpu().numpy()
+    assert np.array_equal(idx, np.flatnonzero(~host["allZero"]))
+    raw = pipeline.DESeq(counts, x, sizeFactors=sf, engine=engine)
+    ok1 = raw["betaConv"][idx] == 1          # rows whose first-pass IRLS diverged go to optim in R: out of scope here
+    rep_h = host["replace"][idx]
+    rep_d = dv["replace"].cpu().numpy()
+    assert rep_h.sum() >= len(planted) * 0.5 and np.mean((rep_h == rep_d)[ok1]) > 0.995 and ok1.mean() > 0.97
+    assert np.array_equal(dv["replaceable"].cpu().numpy(), host["replaceable"])
+    both = rep_h & rep_d & ok1
+    assert np.max(rel_err(dv["baseMean"].cpu().numpy()[both], host["baseMean"][idx][both])) < 1e-12
+    for k in ("dispGeneEst", "dispersion"):
+        e = rel_err(dv[k].cpu().numpy()[both], host[k][idx][both])
+        assert np.mean(e < 1e-6) > 0.95, (k, np.mean(e < 1e-6))
+    conv = both & (host["betaConv"][idx] == 1)
+    e = rel_err(dv["betaMatrix"].cpu().numpy()[conv], host["betaMatrix"][idx][conv], floor=1e-6)
+    assert np.mean(e < 1e-5) > 0.95
+    mc_h, mc_d = host["maxCooks"][idx], dv["maxCooks"].cpu().numpy()
+    if design == "condition":
+        assert np.all(np.isnan(mc_h)) and np.all(np.isnan(mc_d))          # every sample replaceable: column set to NA
+    else:
+        # the device Cook's distances use the kernel's fused fitted mean, which is clamped at minmu = 0.5, the reference
+        # (and the numpy restatement) the unclamped nf * exp(x beta) of R/fitNbinomGLMs.R:180: compare where no fitted
+        # mean of the first pass sits below the clamp (DESIGN.md section 4.6)
+        mu1 = sf[None, :] * 2.0 ** (raw["betaMatrix"][idx] @ x.T)
+        ok2 = ok1 & (mu1 >= 0.5).all(axis=1)
+        assert ok2.mean() > 0.8 and np.max(rel_err(mc_d[ok2], mc_h[ok2], floor=1e-12)) < 1e-8
+    # the refit pulls the planted genes' fold changes back to what the data say without the outlier
+    clean = pipeline.DESeq(d["counts"], x, sizeFactors=sf, engine=engine)
+    pl = np.intersect1d(planted, np.flatnonzero(host["replace"]))
+    err_refit = np.abs(host["betaMatrix"][pl, 1] - clean["betaMatrix"][pl, 1])
+    err_raw = np.abs(raw["betaMatrix"][pl, 1] - clean["betaMatrix"][pl, 1])
+    assert np.median(err_refit) < 0.25 * np.median(err_raw)
