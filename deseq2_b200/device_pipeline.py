@@ -336,7 +336,14 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
     pval = 2.0 * torch.special.ndtr(-stat.abs())
     from .pipeline import nOrMoreInCell
     do_replace = bool(np.isfinite(minReplicatesForReplace)) and bool(nOrMoreInCell(x, minReplicatesForReplace).any())
-    ck = cooks(ynz, fb["mu"], fb["hat_diagonals"], x, sizeFactors, want_matrix=do_replace)   # R/core.R:1457-1460
+    # Cook's distances use the UNCLAMPED fitted mean nf * exp(x beta) that the reference recomputes in R
+    # (R/fitNbinomGLMs.R:180); the kernel's fused mean is clamped at minmu, so the entries on the clamp are redone here
+    # (elementwise torch glue; everything above the clamp keeps the kernel's value bit for bit).
+    mu_fit = fb["mu"]
+    mu_cooks = _ws("mu_cooks", (nn, ldd), F64, dev)
+    mu_cooks.copy_(mu_fit)
+    mu_cooks[:, :m] = torch.where(mu_fit[:, :m] <= minmu, sfd[None, :] * torch.exp(fb["beta_mat"].T @ xd), mu_fit[:, :m])
+    ck = cooks(ynz, mu_cooks, fb["hat_diagonals"], x, sizeFactors, want_matrix=do_replace)   # R/core.R:1457-1460
     mark("wald_stats+cooks")
     res = {"stage_ms": stage_ms, "maxCooks": ck["maxCooks"], "idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
             "dispersion": dispersion, "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"],
