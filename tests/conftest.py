@@ -49,3 +49,14 @@ def emu(oracle):
         yield wrappers
     finally:
         _lib._lib = saved
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _emulated_streams():
+    """With B200NB_LIB=<emulated engine> the whole `-m gpu` suite runs on the CPU: there is no CUDA stream to pass."""
+    from helpers import EMULATED
+    if EMULATED:
+        import ctypes as C
+        from deseq2_b200 import device, device_pipeline
+        device._stream = device_pipeline._stream = lambda: C.c_void_p(0)
+    yield

@@ -1,7 +1,15 @@
 """Shared helpers for the parity tests: realistic fitDisp / fitBeta inputs built with the host glue."""
+import os
+
 import numpy as np
 
 from deseq2_b200 import pipeline, synth
+
+# `-m gpu` tests run on "cuda"; when B200NB_LIB points at the emulated engine (tests/simt_emu/_build/libb200nb_emu*.so,
+# see tests/test_emulated_kernels.py) the same tests run with CPU tensors: in the emulator device pointers are host
+# pointers (tests/conftest.py then also replaces the CUDA stream getters of the torch wrappers by a null stream).
+EMULATED = "libb200nb_emu" in os.path.basename(os.environ.get("B200NB_LIB", ""))
+DEV = "cpu" if EMULATED else "cuda"
 
 DISP_KEYS = ("log_alpha", "last_change", "initial_lp", "initial_dlp", "last_lp", "last_dlp", "last_d2lp")
 

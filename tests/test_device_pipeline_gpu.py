@@ -3,11 +3,10 @@ DESeq() Wald path against the numpy restatement of the R callers (deseq2_b200/pi
 import numpy as np
 import pytest
 
-from helpers import rel_err
+from helpers import DEV, rel_err
 
 pytestmark = pytest.mark.gpu
 
-DEV = "cuda"      # tests/test_emulated_kernels.py re-runs these functions with DEV = "cpu" on the emulated engine
 
 
 def _setup(n, m, x=None, seed=1):

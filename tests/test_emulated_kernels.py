@@ -11,10 +11,12 @@ bit-identity with the GPU's arithmetic (tolerances are those of the GPU tests).
 
 This is a CHECK of the product source, never a product path: the emulated library exists only under tests/, and
 only this module (or an explicit B200NB_LIB=... in the environment of a test run) loads it.
-The whole -m gpu parity suite can be run the same way on a machine without a GPU (about 90 seconds):
+The whole -m gpu suite (parity, golden files, device-resident pipeline, R shim, size factors, outlier refit) runs the
+same way on a machine without a GPU, at the GPU tests' full sizes (a few minutes; tests/helpers.py switches the torch
+tensors to the CPU when B200NB_LIB names the emulated library):
 
-    B200NB_LIB=tests/simt_emu/_build/libb200nb_emu.so python -m pytest tests/test_parity_gpu.py tests/test_golden.py \\
-        tests/test_r_shim.py -m gpu --deselect tests/test_parity_gpu.py::test_c2_full_size_properties
+    B200NB_LIB=tests/simt_emu/_build/libb200nb_emu.so python -m pytest tests -m gpu \
+        --deselect tests/test_parity_gpu.py::test_c2_full_size_properties
 """
 import ctypes as C
 import glob

@@ -4,11 +4,10 @@ counts.  The same functions run on the emulated engine in tests/test_emulated_ke
 import numpy as np
 import pytest
 
-from helpers import rel_err
+from helpers import DEV, rel_err
 
 pytestmark = pytest.mark.gpu
 
-DEV = "cuda"
 
 
 def _poscounts_reference(counts):
