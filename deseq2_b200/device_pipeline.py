@@ -144,6 +144,27 @@ def _grid_refit(y, xd, mu, sel, m, prior_mean, prior_sigmasq, usePrior):
     return idx, torch.exp(la)
 
 
+def getContrast_device(ynz, x, sizeFactors, dispersion, betaMatrix, contrast, betaPriorVar=None, minmu=0.5):
+    """getContrast (R/results.R:760-827) on device tensors: fitBeta's maxit = 0 mode (covariance at the given betas).
+    ynz: gene-major counts the model was fitted to; betaMatrix: (n, p) log2-scale coefficients (DESeq_device's
+    "betaMatrix").  Returns log2FoldChange, lfcSE, stat, pvalue as device tensors."""
+    dev = ynz.device
+    x = np.asarray(x, dtype=np.float64)
+    m, p = x.shape
+    contrast = np.asarray(contrast, dtype=np.float64)
+    if contrast.shape != (p,):
+        raise ValueError("numeric contrast vector should have one element for every element of 'resultsNames(object)'")
+    pv = np.full(p, 1e6) if betaPriorVar is None else np.asarray(betaPriorVar, dtype=np.float64)
+    lam = torch.as_tensor(1.0 / (LN2 ** 2 * pv), device=dev)
+    sfd = torch.as_tensor(np.asarray(sizeFactors, dtype=np.float64), device=dev)
+    beta_nat = (betaMatrix.T * LN2).contiguous()                       # (p, n) = column-major n x p, natural log scale
+    r = D.fit_beta(ynz, D.x_to_device(x, dev), sfd, dispersion, torch.as_tensor(contrast, device=dev), beta_nat, lam,
+                   1e-8, 0, useQR=False, minmu=minmu, want_hat=False, want_mu=False)
+    est, se = r["contrast_num"] / LN2, r["contrast_denom"] / LN2
+    stat = est / se
+    return {"log2FoldChange": est, "lfcSE": se, "stat": stat, "pvalue": 2.0 * torch.special.ndtr(-stat.abs())}
+
+
 def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e-8, maxit=100, minmu=0.5):
     """nbinomLRT (R/core.R:1787-2012) on device tensors: two IRLS fits, LRT statistic 2 (l_full - l_reduced) and its
     chi-square p-value.  The kernel's deviance is -2 log-likelihood at the fitted (minmu-clamped) mean, i.e. what

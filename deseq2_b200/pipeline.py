@@ -15,6 +15,8 @@ numpy, one function per R function, same names, so the engine can be driven and 
   fitNbinomGLMs / fitNbinomGLMsOptim   R/fitNbinomGLMs.R:29-236, 340-407 (L-BFGS-B fallback opt-in: useOptim=True)
   nbinomWaldTest                 R/core.R:1332-1565  (betas, SEs, Wald statistic and p-value)
   nbinomLRT                      R/core.R:1787-2012  (full vs reduced fit, 2 (l_full - l_reduced), chi-square p-value)
+  getContrast                    R/results.R:760-827 (numeric contrasts through fitBeta's maxit = 0 mode)
+  replaceOutliers / refit        R/core.R:2069-2115, 2484-2565 (opt-in: DESeq(minReplicatesForReplace=7))
   robustMethodOfMomentsDisp / trimmedCellVariance / calculateCooksDistance / recordMaxCooks   R/core.R:2277-2359
   fitGLMsWithPrior / estimateBetaPriorVar / Hmisc.wtd.quantile / addAllContrasts / averagePriorsOverLevels /
   makeExpandedModelMatrix (additive factor designs)   R/fitNbinomGLMs.R:242-337, R/core.R:1601-1689, 2762-2803, R/expanded.R
@@ -441,6 +443,32 @@ def replaceOutliers(counts, cooks, sizeFactors, x, trim=0.2, cooksCutoff=None, m
     out = counts.copy()
     out[:, whichSamples] = newCounts[:, whichSamples]
     return out, replace, whichSamples
+
+
+def getContrast(counts, nf, x, dispersion, betaMatrix, contrast, betaPriorVar=None, engine=None, minmu=0.5):
+    """R/results.R:760-827: a numeric contrast c of the fitted coefficients, batched over genes through fitBeta's
+    maxit = 0 mode (no IRLS iteration: covariance at the given betas, c'beta and sqrt(c' Sigma c)).  `counts` are the
+    counts the model was fitted to (replaceCounts after an outlier refit), `betaMatrix` is on the log2 scale; rows are
+    the non-all-zero genes.  Returns log2FoldChange, lfcSE, stat, pvalue (useT = FALSE)."""
+    engine = engine or _default_engine
+    counts = np.asarray(counts)
+    n, m = counts.shape
+    p = x.shape[1]
+    contrast = np.asarray(contrast, dtype=np.float64)
+    if contrast.shape != (p,):
+        raise ValueError("numeric contrast vector should have one element for every element of 'resultsNames(object)'")
+    if betaPriorVar is None:
+        betaPriorVar = np.full(p, 1e6)                                    # betaPrior = FALSE (R/core.R:1421)
+    lam = 1.0 / (LN2 ** 2 * np.asarray(betaPriorVar, dtype=np.float64))
+    r = engine.fitBeta(ySEXP=counts, xSEXP=x, nfSEXP=np.broadcast_to(nf, counts.shape), alpha_hatSEXP=dispersion,
+                       contrastSEXP=contrast, beta_matSEXP=LN2 * np.asarray(betaMatrix, dtype=np.float64),
+                       lambdaSEXP=lam, weightsSEXP=None, useWeightsSEXP=False, tolSEXP=1e-8, maxitSEXP=0,
+                       useQRSEXP=False, minmuSEXP=minmu)
+    est = np.asarray(r["contrast_num"]).reshape(n) / LN2
+    se = np.asarray(r["contrast_denom"]).reshape(n) / LN2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        stat = est / se
+    return {"log2FoldChange": est, "lfcSE": se, "stat": stat, "pvalue": 2.0 * _sp.ndtr(-np.abs(stat))}
 
 
 def _fit_intercept_only(counts, nf, alpha_hat):

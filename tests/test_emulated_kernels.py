@@ -119,6 +119,7 @@ DEVICE_CASES = [
     ("size factors degenerate", lambda T, e: T.TS.test_size_factors_degenerate_inputs(e)),
     ("DESeq on device from raw counts", lambda T, e: T.TS.test_deseq_device_from_raw_counts(e, n=200)),
     ("outlier replacement + refit ~condition", lambda T, e: T.TS.test_outlier_replacement_and_refit_device_vs_host(e, "condition", n=300)),
+    ("getContrast on device", lambda T, e: T.TS.test_get_contrast_device_matches_host(e, n=200)),
     ("outlier replacement + refit, mixed cells", lambda T, e: T.TS.test_outlier_replacement_and_refit_device_vs_host(e, "mixed", n=300)),
 ]
 

@@ -192,3 +192,30 @@ def test_refit_without_outliers_recovers_fold_changes(oracle):
     err_raw = np.abs(raw["betaMatrix"][hit, 1] - clean["betaMatrix"][hit, 1])
     assert np.median(err_fit) < 0.25 * np.median(err_raw)
     assert np.array_equal(fit["replaceCounts"][~fit["replace"]], counts[~fit["replace"]])
+
+
+def test_get_contrast_equals_reparametrised_fit(oracle):
+    """R/results.R:760-827: contrast e_k reproduces the fitted coefficient and its SE; a level-vs-level contrast of a
+    3-level factor equals the coefficient of the model refitted with the other reference level."""
+    m = 18
+    g = np.arange(m) % 3
+    x = np.c_[np.ones(m), g == 1, g == 2].astype(float)               # reference level A: (Intercept, B_vs_A, C_vs_A)
+    d = synth.make_example_counts(300, m, x=x, seed=12, betaSD=0.8)
+    counts = d["counts"][d["counts"].sum(axis=1) > 0]
+    sf = d["sizeFactors"]
+    nf = np.broadcast_to(sf[None, :], counts.shape)
+    disp = np.clip(0.05 + 3.0 / (counts / sf).mean(axis=1), 1e-8, m)
+    fit = pipeline.nbinomWaldTest(counts, nf, x, disp, engine=oracle)
+    ok = fit["betaConv"] & ((counts / sf).min(axis=1) > 1)
+    c1 = pipeline.getContrast(counts, nf, x, disp, fit["betaMatrix"], [0, 1, 0], engine=oracle)
+    assert np.allclose(c1["log2FoldChange"][ok], fit["betaMatrix"][ok, 1], rtol=0, atol=1e-12)
+    assert np.allclose(c1["lfcSE"][ok], fit["betaSE"][ok, 1], rtol=1e-6)
+    assert np.allclose(c1["pvalue"][ok], fit["WaldPvalue"][ok, 1], rtol=1e-5, atol=1e-300)
+    x2 = np.c_[np.ones(m), g == 0, g == 1].astype(float)              # reference level C: (Intercept, A_vs_C, B_vs_C)
+    fit2 = pipeline.nbinomWaldTest(counts, nf, x2, disp, engine=oracle)
+    ok &= fit2["betaConv"]
+    c = pipeline.getContrast(counts, nf, x, disp, fit["betaMatrix"], [0, 1, -1], engine=oracle)   # B vs C
+    assert np.allclose(c["log2FoldChange"][ok], fit2["betaMatrix"][ok, 2], atol=2e-5)
+    assert np.allclose(c["lfcSE"][ok], fit2["betaSE"][ok, 2], rtol=1e-4)
+    with pytest.raises(ValueError):
+        pipeline.getContrast(counts, nf, x, disp, fit["betaMatrix"], [1, -1], engine=oracle)

@@ -141,3 +141,31 @@ def test_outlier_replacement_and_refit_device_vs_host(engine, design, n=2500):
     err_refit = np.abs(host["betaMatrix"][pl, 1] - clean["betaMatrix"][pl, 1])
     err_raw = np.abs(raw["betaMatrix"][pl, 1] - clean["betaMatrix"][pl, 1])
     assert np.median(err_refit) < 0.25 * np.median(err_raw)
+
+
+def test_get_contrast_device_matches_host(engine, n=1500):
+    """getContrast (R/results.R:760-827; the one direct R caller of fitBeta besides the wrappers) on device tensors
+    against the host glue: a level-vs-level contrast of a 3-level factor after a device-resident DESeq()."""
+    import torch
+    from deseq2_b200 import device as D, device_pipeline as DP, pipeline, synth
+    m = 18
+    g = np.arange(m) % 3
+    x = np.c_[np.ones(m), g == 1, g == 2].astype(float)
+    d = synth.make_example_counts(n, m, x=x, seed=31, betaSD=0.8)
+    sf = d["sizeFactors"]
+    y = D.to_gene_major(d["counts"], torch.device(DEV))
+    dv = DP.DESeq_device(y, x, sf)
+    idx = dv["idx"]
+    ynz = y[idx].contiguous()
+    cnz = d["counts"][idx.cpu().numpy()]
+    contrast = np.array([0.0, 1.0, -1.0])
+    got = DP.getContrast_device(ynz, x, sf, dv["dispersion"], dv["betaMatrix"], contrast)
+    ref = pipeline.getContrast(cnz, np.broadcast_to(sf[None, :], cnz.shape), x, dv["dispersion"].cpu().numpy(),
+                               dv["betaMatrix"].cpu().numpy(), contrast, engine=engine)
+    ok = dv["betaConv"].cpu().numpy()
+    for k in ("log2FoldChange", "lfcSE", "stat"):
+        assert np.max(rel_err(got[k].cpu().numpy()[ok], ref[k][ok], floor=1e-9)) < 1e-9, k
+    assert np.allclose(got["log2FoldChange"].cpu().numpy()[ok],
+                       (dv["betaMatrix"][:, 1] - dv["betaMatrix"][:, 2]).cpu().numpy()[ok], atol=1e-12)
+    pv = got["pvalue"].cpu().numpy()[ok]
+    assert np.all((pv >= 0) & (pv <= 1))
