@@ -12,11 +12,10 @@ bit-identity with the GPU's arithmetic (tolerances are those of the GPU tests).
 This is a CHECK of the product source, never a product path: the emulated library exists only under tests/, and
 only this module (or an explicit B200NB_LIB=... in the environment of a test run) loads it.
 The whole -m gpu suite (parity, golden files, device-resident pipeline, R shim, size factors, outlier refit) runs the
-same way on a machine without a GPU, at the GPU tests' full sizes, the 50 000 x 100 config-2 case included (about 7 minutes; tests/helpers.py switches the torch
-tensors to the CPU when B200NB_LIB names the emulated library):
+same way on a machine without a GPU, at the GPU tests' full sizes, the 50 000 x 100 config-2 case included (about
+7 minutes; tests/helpers.py switches the torch tensors to the CPU when B200NB_LIB names the emulated library):
 
-    B200NB_LIB=tests/simt_emu/_build/libb200nb_emu.so python -m pytest tests -m gpu \
-        --deselect tests/test_parity_gpu.py::test_c2_full_size_properties
+    B200NB_LIB=tests/simt_emu/_build/libb200nb_emu.so python -m pytest tests -m gpu
 """
 import ctypes as C
 import glob
