@@ -147,6 +147,12 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
+def build_experiment(tag: str, defines: list[str]) -> str:
+    """libb200nb_emu_<tag>.so: the emulated engine compiled with extra -D switches (the experiment builds of
+    csrc/Makefile's `exp` target), so that a kernel experiment can be checked for parity on the CPU first."""
+    return _build_variant(f"libb200nb_emu_{tag}.so", list(defines))
+
+
 def build(force: bool = False, asan: bool = False) -> str:
     """asan=True: a second library, libb200nb_emu_asan.so, instrumented with AddressSanitizer -- every out-of-bounds
     access to "device" memory, dynamic shared memory or the pinned rings aborts with a report (the emulator's memcheck).
