@@ -55,7 +55,12 @@ struct DispArgs {
   const int* mode_lists;
 };
 
-inline size_t disp_scratch_bytes(int n) { return (4 + 3 * (size_t)n) * sizeof(unsigned int); }
+#ifdef NB_EXP_SPLIT_MODES
+constexpr int kDispScratchHead = 8;   // experiment: [queue counter | 3 mode counters | second queue counter | pad]
+#else
+constexpr int kDispScratchHead = 4;   // [queue counter | 3 mode counters], then the three per-mode gene lists
+#endif
+inline size_t disp_scratch_bytes(int n) { return (kDispScratchHead + 3 * (size_t)n) * sizeof(unsigned int); }
 
 struct BetaArgs {
   const void* y;

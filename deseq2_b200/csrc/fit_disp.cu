@@ -479,6 +479,63 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(con
   }
 }
 
+#ifdef NB_EXP_SPLIT_MODES
+// EXPERIMENT (off by default, not yet timed): one kernel per evaluation-mode family instead of one kernel that walks
+// TAB | BIG | GEN.  ptxas needs 174 registers for the TAB-only body against 200 for all three; capped at 80 registers
+// (3 CTAs of 256 threads per SM = 24 warps instead of 16) the TAB-only kernel spills 40 bytes where the combined kernel
+// spills 416 -- 84 % of the evaluations of the C2 workload are TAB mode and 46 % of the issue slots are idle on
+// dependency / scoreboard stalls, which more resident warps should hide.  SPLIT = MODE_TAB: genes [0, n0) of the
+// queue on the first counter; SPLIT = MODE_GEN: BIG and GEN genes [n0, n) on the second counter.
+template <int P, bool USE_W, int SPLIT>
+__global__ void __launch_bounds__(256, SPLIT == MODE_TAB ? 3 : 2) fit_disp_split_kernel(const DispArgs A, int warps_per_cta,
+                                                                                      int mpad) {
+  extern __shared__ __align__(16) double smem[];
+  init_log_table();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int NROW = USE_W ? 3 : 2;
+  double* xs = smem;
+  double* rowbase = smem + (size_t)P * mpad + (size_t)warp * ((size_t)NROW * mpad + kTabMax);
+  DispWarpSmem S{rowbase, rowbase + mpad, USE_W ? rowbase + 2 * mpad : nullptr, rowbase + (size_t)NROW * mpad};
+  for (int idx = threadIdx.x; idx < P * A.m; idx += blockDim.x) {
+    const int k = idx / A.m, j = idx - k * A.m;
+    xs[k * mpad + j] = A.x[idx];
+  }
+  __syncthreads();
+  DispRow rv{S.ys, S.mus, S.wsm, xs, S.tab, A.m, mpad, 0};
+  const DispScal sc{A.prior_sigmasq, 1.0 / A.prior_sigmasq, A.weight_threshold, A.use_prior, A.use_cr};
+  const unsigned int n0 = A.mode_counts[MODE_TAB], n1 = A.mode_counts[MODE_BIG];
+  unsigned int* counter = (SPLIT == MODE_TAB) ? A.counter : A.counter + 4;
+  for (;;) {
+    unsigned int q = 0;
+    if (lane == 0) q = atomicAdd(counter, 1u);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    double sum_wy, ymax;
+    if (SPLIT == MODE_TAB) {
+      if (q >= n0) break;
+      const unsigned int g = A.mode_lists[q];
+      stage_row<USE_W>(A, g, mpad, lane, S, sum_wy, ymax);
+      build_table<USE_W>(S, A.m, lane);
+      rv.ntab = (int)ymax;
+      line_search_gene<P, USE_W, MODE_TAB>(A, rv, sc, g, sum_wy, lane);
+    } else {
+      q += n0;
+      if (q >= (unsigned int)A.n) break;
+      if (q < n0 + n1) {
+        const unsigned int g = A.mode_lists[(size_t)A.n + (q - n0)];
+        stage_row<USE_W>(A, g, mpad, lane, S, sum_wy, ymax);
+        line_search_gene<P, USE_W, MODE_BIG>(A, rv, sc, g, sum_wy, lane);
+      } else {
+        const unsigned int g = A.mode_lists[2 * (size_t)A.n + (q - n0 - n1)];
+        stage_row<USE_W>(A, g, mpad, lane, S, sum_wy, ymax);
+        line_search_gene<P, USE_W, MODE_GEN>(A, rv, sc, g, sum_wy, lane);
+      }
+    }
+    __syncwarp();
+  }
+}
+#endif
+
 // fitDispGrid (src/DESeq2.cpp:492-510): rare path (non-converged genes only); generic evaluation mode
 template <int P, bool USE_W>
 __global__ void __launch_bounds__(256, 2) fit_disp_grid_kernel(const DispArgs A, int warps_per_cta, int mpad) {
@@ -564,16 +621,45 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   // scratch: [queue counter | 3 mode counters | 3 n gene lists]
-  e = cudaMemsetAsync(a.scratch, 0, 4 * sizeof(unsigned int), stream);
+  e = cudaMemsetAsync(a.scratch, 0, kDispScratchHead * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
   a.counter = a.scratch;
   a.mode_counts = a.scratch + 1;
-  a.mode_lists = reinterpret_cast<int*>(a.scratch + 4);
+  a.mode_lists = reinterpret_cast<int*>(a.scratch + kDispScratchHead);
   if (!grid_mode) {
-    classify_kernel<<<(a.n + 7) / 8, 256, 0, stream>>>(a.y, a.y_is_f64, a.n, a.m, a.ld, reinterpret_cast<int*>(a.scratch + 4), a.scratch + 1);
+    classify_kernel<<<(a.n + 7) / 8, 256, 0, stream>>>(a.y, a.y_is_f64, a.n, a.m, a.ld, reinterpret_cast<int*>(a.scratch + kDispScratchHead), a.scratch + 1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
+#ifdef NB_EXP_SPLIT_MODES
+  if (!grid_mode && warps == 8) {
+    // per-family kernels, each sized to its own occupancy; an empty family costs one idle wave of CTAs
+    auto ktab = fit_disp_split_kernel<P, USE_W, MODE_TAB>;
+    auto kgen = fit_disp_split_kernel<P, USE_W, MODE_GEN>;
+    static size_t split_smem = 0;
+    static int split_ctas[2] = {0, 0};
+    if (split_smem != smem) {
+      e = cudaFuncSetAttribute(ktab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(kgen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split_ctas[0], ktab, 256, smem);
+      if (e != cudaSuccess) return e;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split_ctas[1], kgen, 256, smem);
+      if (e != cudaSuccess) return e;
+      if (split_ctas[0] < 1 || split_ctas[1] < 1) return cudaErrorLaunchOutOfResources;
+      split_smem = smem;
+    }
+    long long g0 = (long long)sms * split_ctas[0], g1 = (long long)sms * split_ctas[1];
+    if (g0 > want) g0 = want;
+    if (g1 > want) g1 = want;
+    ktab<<<(unsigned)(g0 < 1 ? 1 : g0), 256, smem, stream>>>(a, 8, mpad);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    kgen<<<(unsigned)(g1 < 1 ? 1 : g1), 256, smem, stream>>>(a, 8, mpad);
+    return cudaGetLastError();
+  }
+#endif
   kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, warps, mpad);
   return cudaGetLastError();
 }

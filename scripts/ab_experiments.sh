@@ -1,0 +1,33 @@
+#!/bin/bash
+# Round-2 A/B of the kernel experiments that were written (and parity-checked under the SIMT emulator) without GPU
+# access.  Step 1, on the build machine (no GPU needed):   scripts/ab_experiments.sh build
+# Step 2, on the GPU box (one gpurun call):                scripts/ab_experiments.sh run > gpurun_out/ab.txt
+# Each line of the output is the bench.py JSON line of one library; compare "value" and config.kernel_ms.
+set -e
+cd "$(dirname "$0")/.."
+declare -A EXP=(
+  [estrin_rcp3]="-DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC"
+  [estrin]="-DNB_EXP_LOG_ESTRIN"
+  [rcp3]="-DNB_EXP_RCP_CUBIC"
+  [split]="-DNB_EXP_SPLIT_MODES"
+  [split_estrin_rcp3]="-DNB_EXP_SPLIT_MODES -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC"
+  [lb3]="-DNB_LB_THREADS=256 -DNB_LB_CTAS=3"
+)
+if [ "$1" = build ]; then
+  make -C deseq2_b200/csrc -s
+  for name in "${!EXP[@]}"; do
+    make -C deseq2_b200/csrc exp EXPFLAGS="${EXP[$name]}" EXPNAME="$name" -s
+  done
+  ls -la deseq2_b200/libb200nb*.so
+elif [ "$1" = run ]; then
+  echo "default $(python bench.py --no-e2e --no-cpu-baseline --steps 30 | tail -1)"
+  for name in "${!EXP[@]}"; do
+    lib="$PWD/deseq2_b200/libb200nb_exp_$name.so"
+    [ -f "$lib" ] || continue
+    # correctness first: the parity suite must stay green with the experiment library
+    if B200NB_LIB="$lib" python -m pytest tests/test_parity_gpu.py -q -m gpu -x -k "mle_parity or map_parity or fit_beta_parity or big_and_mixed" > /dev/null 2>&1; then ok=parity-ok; else ok=PARITY-FAILED; fi
+    echo "$name $ok $(B200NB_LIB="$lib" python bench.py --no-e2e --no-cpu-baseline --steps 30 | tail -1)"
+  done
+else
+  echo "usage: $0 build|run"; exit 2
+fi
