@@ -109,7 +109,11 @@ __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta
 
 #ifndef NB_LB_THREADS
 #define NB_LB_THREADS 256
+#ifdef NB_EXP_BETA_CTAS3   // experiment (off by default): 3 CTAs/SM; ptxas then spills 84 bytes at 80 registers
+#define NB_LB_CTAS 3
+#else
 #define NB_LB_CTAS 2
+#endif
 #endif
 template <int P, bool USE_W>
 __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_beta_kernel(const BetaArgs A, int warps_per_cta, int mpad) {

@@ -67,7 +67,11 @@ __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal
 
   if (MODE == MODE_TAB) {
     // shared factor table: sum_k c_k log(r+k), sum_k c_k/(r+k)
+#ifdef NB_EXP_TAB_UNROLL4   // experiment (off by default): four independent log/rcp chains in flight instead of two
+#pragma unroll 4
+#else
 #pragma unroll 2
+#endif
     for (int k = lane; k < rv.ntab; k += 32) {
       const double ck = rv.tab[k];
       const double xk = r + (double)k;

@@ -12,6 +12,9 @@ declare -A EXP=(
   [split]="-DNB_EXP_SPLIT_MODES"
   [split_estrin_rcp3]="-DNB_EXP_SPLIT_MODES -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC"
   [lb3]="-DNB_LB_THREADS=256 -DNB_LB_CTAS=3"
+  [beta3]="-DNB_EXP_BETA_CTAS3"
+  [tab4]="-DNB_EXP_TAB_UNROLL4"
+  [all]="-DNB_EXP_SPLIT_MODES -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC -DNB_EXP_BETA_CTAS3 -DNB_EXP_TAB_UNROLL4"
 )
 if [ "$1" = build ]; then
   make -C deseq2_b200/csrc -s
