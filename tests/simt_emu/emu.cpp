@@ -160,13 +160,58 @@ bool try_release_warp(int w, int nthreads) {
   return true;
 }
 
+// Order in which the runnable lanes of a warp (and the warps of a CTA) get the CPU between barriers.  The hardware
+// gives no ordering guarantee between lanes that are not separated by a barrier, so a kernel must give the same
+// result under every order: SIMT_EMU_ORDER=reverse runs lanes and warps from the top down, SIMT_EMU_ORDER=random[:seed]
+// reshuffles them at every scheduling round (xorshift; deterministic for a given seed).  A shared-memory hand-off
+// that only works because lane i happens to run before lane j shows up as a wrong result under one of them.
+enum Order { FORWARD, REVERSE, RANDOM };
+Order sched_order() {
+  static Order o = [] {
+    const char* e = getenv("SIMT_EMU_ORDER");
+    if (!e) return FORWARD;
+    if (!strncmp(e, "reverse", 7)) return REVERSE;
+    if (!strncmp(e, "random", 6)) return RANDOM;
+    return FORWARD;
+  }();
+  return o;
+}
+uint64_t rng_state = [] {
+  const char* e = getenv("SIMT_EMU_ORDER");
+  const char* c = e ? strchr(e, ':') : nullptr;
+  return c ? strtoull(c + 1, nullptr, 10) * 2654435761ull + 88172645463325252ull : 88172645463325252ull;
+}();
+inline uint64_t rng_next() {
+  rng_state ^= rng_state << 13;
+  rng_state ^= rng_state >> 7;
+  rng_state ^= rng_state << 17;
+  return rng_state;
+}
+void make_order(int* idx, int n) {
+  for (int i = 0; i < n; i++) idx[i] = i;
+  const Order o = sched_order();
+  if (o == REVERSE) {
+    for (int i = 0; i < n; i++) idx[i] = n - 1 - i;
+  } else if (o == RANDOM) {
+    for (int i = n - 1; i > 0; i--) {
+      const int j = (int)(rng_next() % (uint64_t)(i + 1));
+      const int t = idx[i]; idx[i] = idx[j]; idx[j] = t;
+    }
+  }
+}
+
 void run_cta(int nthreads) {
   const int nwarps = (nthreads + 31) / 32;
+  int worder[32], lorder[32];
   for (;;) {
     bool progress = false, all_done = true;
-    for (int w = 0; w < nwarps; w++) {
+    make_order(worder, nwarps);
+    for (int wi = 0; wi < nwarps; wi++) {
+      const int w = worder[wi];
       const int lo = w * 32, hi = (lo + 32 < nthreads) ? lo + 32 : nthreads;
-      for (int i = lo; i < hi; i++) {
+      make_order(lorder, hi - lo);
+      for (int li = 0; li < hi - lo; li++) {
+        const int i = lo + lorder[li];
         if (fibers[i].state != RUNNABLE) continue;
         cur = i;
         threadIdx = fibers[i].tid;

@@ -119,3 +119,18 @@ def test_emulated_fuzz(emu, oracle, block):
         P = make_problem(s)
         if P is not None:
             check_problem(emu, oracle, P, ROBUST)
+
+
+@pytest.mark.parametrize("order", ["reverse", "random:11"])
+def test_emulated_fuzz_is_lane_order_independent(order):
+    """The emulator gives the CPU to the lanes of a warp in a configurable order between barriers (SIMT_EMU_ORDER,
+    fixed when the library is loaded, hence a subprocess).  The hardware promises no order, so the kernels must give
+    the same answers top-down and shuffled as bottom-up; a shared-memory hand-off without a barrier would not."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_emulated.py"), "9000", "30"],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, SIMT_EMU_ORDER=order))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().endswith("30 seeds, 0 failures"), r.stdout[-2000:]

@@ -89,3 +89,27 @@ def test_divergent_collective_is_reported_as_deadlock(st):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0
     assert "deadlock" in r.stderr and "warp collective" in r.stderr and "__syncthreads" in r.stderr
+
+
+@pytest.mark.parametrize("order", ["reverse", "random:7"])
+def test_lane_order_is_configurable(st, order):
+    """SIMT_EMU_ORDER changes which lane runs first between barriers: correct kernels do not care, the kernel with the
+    missing __syncwarp returns a different wrong answer (read in a fresh process: the order is fixed at load time)."""
+    code = ("import ctypes, numpy as np, json; l = ctypes.CDLL(%r); "
+            "g = np.zeros(32, dtype=np.int32); b = np.zeros(32, dtype=np.int32); "
+            "l.st_missing_syncwarp(ctypes.c_void_p(g.ctypes.data), 1); l.st_missing_syncwarp(ctypes.c_void_p(b.ctypes.data), 0); "
+            "s = np.zeros(9); m = np.zeros((288, 8), dtype=np.int32); "
+            "l.st_warp_collectives(ctypes.c_void_p(s.ctypes.data), ctypes.c_void_p(m.ctypes.data), 3, 96); "
+            "print(json.dumps([g.tolist(), b.tolist(), s.tolist()]))" % st._name)
+    import json
+    outs = {}
+    for o in ("forward", order):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60,
+                           env=dict(os.environ, SIMT_EMU_ORDER=o))
+        assert r.returncode == 0, r.stderr
+        outs[o] = json.loads(r.stdout)
+    good = [(i + 1) % 32 for i in range(32)]
+    assert outs["forward"][0] == good and outs[order][0] == good           # with the barrier: right under any order
+    assert outs["forward"][2] == outs[order][2]                            # collectives do not depend on the order
+    assert outs["forward"][1] != good and outs[order][1] != good           # without it: wrong under both ...
+    assert outs["forward"][1] != outs[order][1]                            # ... and differently wrong
