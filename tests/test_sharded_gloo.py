@@ -10,12 +10,17 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, emu_lib=None):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    if emu_lib:
+        os.environ["B200NB_LIB"] = emu_lib          # the product engine's own source, executed by the SIMT emulator
     import torch.distributed as dist
     from deseq2_b200 import sharded, synth
-    from oracle import oracle as O
+    if emu_lib:
+        from deseq2_b200 import wrappers as O
+    else:
+        from oracle import oracle as O
     dist.init_process_group("gloo", rank=rank, world_size=world)
     d = synth.make_example_counts(301, 8, seed=77)
     r = sharded.sharded_DESeq(d["counts"], d["x"], d["sizeFactors"], engine=O)
@@ -53,3 +58,26 @@ def test_sharded_equals_whole(oracle):
     for k in ("dispGeneEst", "dispFit", "dispMAP", "dispersion", "betaMatrix", "betaSE", "WaldStatistic", "deviance"):
         assert np.allclose(got[k], whole[k], rtol=1e-12, atol=0, equal_nan=True), k
     assert abs(got["dispPriorVar"] - whole["dispPriorVar"]) < 1e-14
+
+
+def test_sharded_equals_whole_with_the_emulated_engine(emu):
+    """The same two-rank run with the PRODUCT engine (wrappers -> C ABI -> the CUDA kernels' source on the SIMT emulator)
+    in every rank: what the multi-GPU deployment does, minus the GPUs.  Genes are independent, so the sharded result
+    equals the single-process result of the same engine exactly."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt_emu"))
+    import build_emu
+    from deseq2_b200 import pipeline, synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, build_emu.build())) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d = synth.make_example_counts(301, 8, seed=77)
+    whole = pipeline.DESeq(d["counts"], d["x"], sizeFactors=d["sizeFactors"], engine=emu)
+    for k in ("dispGeneEst", "dispFit", "dispMAP", "dispersion", "betaMatrix", "betaSE", "WaldStatistic", "deviance"):
+        assert np.allclose(got[k], whole[k], rtol=1e-12, atol=0, equal_nan=True), k
