@@ -464,9 +464,18 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(con
     if (q >= (unsigned int)A.n) break;
     int mode;
     unsigned int g;
+#ifdef NB_EXP_HEAVY_FIRST
+    // experiment (off by default): longest-processing-time-first order GEN | BIG | TAB, so that the persistent warps
+    // finish on the cheap table-mode genes instead of on the per-sample-lgamma ones (shorter tail of the launch)
+    const unsigned int n2 = (unsigned int)A.n - n0 - n1;
+    if (q < n2) { mode = MODE_GEN; g = A.mode_lists[2 * (size_t)A.n + q]; }
+    else if (q < n2 + n1) { mode = MODE_BIG; g = A.mode_lists[(size_t)A.n + (q - n2)]; }
+    else { mode = MODE_TAB; g = A.mode_lists[q - n2 - n1]; }
+#else
     if (q < n0) { mode = MODE_TAB; g = A.mode_lists[q]; }
     else if (q < n0 + n1) { mode = MODE_BIG; g = A.mode_lists[(size_t)A.n + (q - n0)]; }
     else { mode = MODE_GEN; g = A.mode_lists[2 * (size_t)A.n + (q - n0 - n1)]; }
+#endif
 
     double sum_wy, ymax;
     stage_row<USE_W>(A, g, mpad, lane, S, sum_wy, ymax);

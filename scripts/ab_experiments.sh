@@ -14,6 +14,7 @@ declare -A EXP=(
   [lb3]="-DNB_LB_THREADS=256 -DNB_LB_CTAS=3"
   [beta3]="-DNB_EXP_BETA_CTAS3"
   [tab4]="-DNB_EXP_TAB_UNROLL4"
+  [heavy_first]="-DNB_EXP_HEAVY_FIRST"
   [all]="-DNB_EXP_SPLIT_MODES -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC -DNB_EXP_BETA_CTAS3 -DNB_EXP_TAB_UNROLL4"
 )
 if [ "$1" = build ]; then
