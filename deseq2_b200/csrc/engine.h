@@ -55,7 +55,7 @@ struct DispArgs {
   const int* mode_lists;
 };
 
-#ifdef NB_EXP_SPLIT_MODES
+#if defined(NB_EXP_SPLIT_MODES) || defined(NB_EXP_HALF_WARP)
 constexpr int kDispScratchHead = 8;   // experiment: [queue counter | 3 mode counters | second queue counter | pad]
 #else
 constexpr int kDispScratchHead = 4;   // [queue counter | 3 mode counters], then the three per-mode gene lists

@@ -51,7 +51,18 @@ struct DispScal {
 constexpr int pow2_ceil(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // One fused pass: lp (and dlp when WANT_D) at log-alpha `a`.
-template <int P, bool USE_W, bool WANT_D, int MODE>
+// GL = lanes per gene: 32 (one warp per gene, the product path) or, in the NB_EXP_HALF_WARP experiment, 16 / 8 with
+// `lane` the lane index inside the group; reductions then stay inside the group.
+template <int N, int GL>
+__device__ __forceinline__ void group_allreduce_sum_n(double (&v)[N]) {
+#pragma unroll
+  for (int o = GL / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+}
+
+template <int P, bool USE_W, bool WANT_D, int MODE, int GL = 32>
 __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal& sc, double a, double pm,
                                                double sum_wy, int lane, double& lp, double& dlp) {
   constexpr int NS = SymP<P>::N;
@@ -72,7 +83,7 @@ __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal
 #else
 #pragma unroll 2
 #endif
-    for (int k = lane; k < rv.ntab; k += 32) {
+    for (int k = lane; k < rv.ntab; k += GL) {
       const double ck = rv.tab[k];
       const double xk = r + (double)k;
       acc[0] = fma(ck, log_pos(xk), acc[0]);
@@ -81,10 +92,10 @@ __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal
   }
 
   const int mlast = rv.m - 1;
-  for (int j0 = lane; j0 < rv.m; j0 += 128) {
+  for (int j0 = lane; j0 < rv.m; j0 += 4 * GL) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int jr = j0 + 32 * u;
+      const int jr = j0 + GL * u;
       const int j = min(jr, mlast);
       double vw = (jr < rv.m) ? 1.0 : 0.0;
       const double y = rv.y[j], mu = rv.mu[j];
@@ -130,7 +141,8 @@ __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal
       }
     }
   }
-  warp_allreduce_sum_rs<NA>(acc, lane);
+  if (GL == 32) warp_allreduce_sum_rs<NA>(acc, lane);
+  else group_allreduce_sum_n<NA, GL>(acc);
 
   double cr = 0.0, dcr = 0.0;
   if (sc.use_cr) {
@@ -164,7 +176,7 @@ __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal
 
 // second derivative at `a` (once per gene): src/DESeq2.cpp:111-158.  In TAB mode the digamma / trigamma
 // differences come from the factor table: psi(y+r)-psi(r) = sum_{k<y} 1/(r+k), psi'(y+r)-psi'(r) = -sum 1/(r+k)^2.
-template <int P, bool USE_W>
+template <int P, bool USE_W, int GL = 32>
 __device__ __forceinline__ double disp_d2(const DispRow& rv, const DispScal& sc, int mode, double a, int lane) {
   constexpr int NS = SymP<P>::N;
   const double alpha = exp_fast(a);   // a is confined to [-30, 10] by the line search / grid
@@ -179,14 +191,14 @@ __device__ __forceinline__ double disp_d2(const DispRow& rv, const DispScal& sc,
 #pragma unroll
   for (int i = 0; i < 2 + 3 * NS; i++) acc[i] = 0.0;
   if (mode == MODE_TAB) {
-    for (int k = lane; k < rv.ntab; k += 32) {
+    for (int k = lane; k < rv.ntab; k += GL) {
       const double ck = rv.tab[k];
       const double ik = rcp_fast(r + (double)k);
       acc[0] = fma(-ck, ik, acc[0]);
       acc[1] = fma(-ck * r2, ik * ik, acc[1]);
     }
   }
-  for (int j = lane; j < rv.m; j += 32) {
+  for (int j = lane; j < rv.m; j += GL) {
     const double y = rv.y[j], mu = rv.mu[j];
     const double onema = fma(mu, alpha, 1.0);
     const double wi = rcp_fast(onema);
@@ -228,7 +240,8 @@ __device__ __forceinline__ double disp_d2(const DispRow& rv, const DispScal& sc,
         }
     }
   }
-  warp_allreduce_sum_n(acc);
+  if (GL == 32) warp_allreduce_sum_n(acc);
+  else group_allreduce_sum_n<2 + 3 * NS, GL>(acc);
   double cr2 = 0.0, dcr = 0.0;
   if (sc.use_cr) {
     SymP<P> B, dB, d2B, Bi;
@@ -492,6 +505,10 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(con
   }
 }
 
+#ifdef NB_EXP_HALF_WARP
+#include "fit_disp_grp.cuh"
+#endif
+
 #ifdef NB_EXP_SPLIT_MODES
 // EXPERIMENT (off by default, not yet timed): one kernel per evaluation-mode family instead of one kernel that walks
 // TAB | BIG | GEN.  ptxas needs 174 registers for the TAB-only body against 200 for all three; capped at 80 registers
@@ -644,6 +661,30 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
+#ifdef NB_EXP_HALF_WARP
+  {
+    constexpr int GL = 16, NG = 32 / GL;
+    const size_t gsmem = xbytes + (size_t)8 * NG * rowbytes;
+    if (!grid_mode && gsmem <= smem_cap / 2) {
+      auto kg = fit_disp_grp_kernel<P, USE_W, GL>;
+      static size_t g_smem = 0;
+      static int g_ctas = 0;
+      if (g_smem != gsmem || g_ctas < 1) {
+        e = cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas, kg, 256, gsmem);
+        if (e != cudaSuccess) return e;
+        if (g_ctas < 1) return cudaErrorLaunchOutOfResources;
+        g_smem = gsmem;
+      }
+      long long gg = (long long)sms * g_ctas;
+      const long long gwant = ((long long)a.n + 8 * NG - 1) / (8 * NG);
+      if (gg > gwant) gg = gwant;
+      kg<<<(unsigned)(gg < 1 ? 1 : gg), 256, gsmem, stream>>>(a, mpad);
+      return cudaGetLastError();
+    }
+  }
+#endif
 #ifdef NB_EXP_SPLIT_MODES
   if (!grid_mode && warps == 8) {
     // per-family kernels, each sized to its own occupancy; an empty family costs one idle wave of CTAs
