@@ -46,7 +46,9 @@ constexpr int pow2_ceil_b(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // One fused IRLS pass: mu (stored to shared memory), mu-dependent part of the deviance, X'WX and X'Wz.
 // Four samples per lane per trip (clamped index + validity factor) for instruction-level parallelism.
-template <int P, bool USE_W>
+// GL = lanes per gene: 32 in the product kernel; 16 in the NB_EXP_HALF_WARP experiment (`lane` is then the lane index
+// inside the group and the reduction stays inside the group).
+template <int P, bool USE_W, int GL = 32>
 __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta)[P], double alpha, double r,
                                           double log_alpha, double minmu, double log_minmu, int lane, double& dev_var,
                                           SymP<P>& XtWX, double (&XtWz)[P]) {
@@ -56,10 +58,10 @@ __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta
 #pragma unroll
   for (int i = 0; i < NA; i++) acc[i] = 0.0;
   const int mlast = rv.m - 1;
-  for (int j0 = lane; j0 < rv.m; j0 += 128) {
+  for (int j0 = lane; j0 < rv.m; j0 += 4 * GL) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int jr = j0 + 32 * u;
+      const int jr = j0 + GL * u;
       const int j = min(jr, mlast);
       double vw = (jr < rv.m) ? 1.0 : 0.0;
       double xv[P];
@@ -99,7 +101,15 @@ __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta
       }
     }
   }
-  warp_allreduce_sum_rs<NA>(acc, lane);
+  if (GL == 32) {
+    warp_allreduce_sum_rs<NA>(acc, lane);
+  } else {
+#pragma unroll
+    for (int o = GL / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NA; i++) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+  }
   dev_var = acc[0];
 #pragma unroll
   for (int i = 0; i < NS; i++) XtWX.v[i] = acc[1 + i];
@@ -310,6 +320,10 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_beta_kernel(con
   }
 }
 
+#ifdef NB_EXP_HALF_WARP
+#include "fit_beta_grp.cuh"
+#endif
+
 template <int P, bool USE_W>
 cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
   const int mpad = (a.m + 3) & ~3;
@@ -345,6 +359,30 @@ cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
   if (grid < 1) grid = 1;
   e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
+#ifdef NB_EXP_HALF_WARP
+  {
+    constexpr int GL = 16, NG = 32 / GL;
+    const size_t gsmem = fixed + (size_t)8 * NG * rowbytes;
+    if (gsmem <= smem_cap / 2) {
+      auto kg = fit_beta_grp_kernel<P, USE_W, GL>;
+      static size_t g_smem = 0;
+      static int g_ctas = 0;
+      if (g_smem != gsmem || g_ctas < 1) {
+        e = cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas, kg, 256, gsmem);
+        if (e != cudaSuccess) return e;
+        if (g_ctas < 1) return cudaErrorLaunchOutOfResources;
+        g_smem = gsmem;
+      }
+      long long gg = (long long)sms * g_ctas;
+      const long long gwant = ((long long)a.n + 8 * NG - 1) / (8 * NG);
+      if (gg > gwant) gg = gwant;
+      kg<<<(unsigned)(gg < 1 ? 1 : gg), 256, gsmem, stream>>>(a, mpad);
+      return cudaGetLastError();
+    }
+  }
+#endif
   kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, warps, mpad);
   return cudaGetLastError();
 }
