@@ -61,6 +61,7 @@ __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta
   for (int j0 = lane; j0 < rv.m; j0 += 4 * GL) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
+      if (GL != 32 && (j0 - lane) + GL * u >= rv.m) break;   // narrow groups: skip sweeps with no sample at all
       const int jr = j0 + GL * u;
       const int j = min(jr, mlast);
       double vw = (jr < rv.m) ? 1.0 : 0.0;
