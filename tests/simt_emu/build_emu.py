@@ -192,10 +192,30 @@ def _build_variant(name: str, extra: list[str]) -> str:
     build()                                   # transformed sources live in _build/src
     src = os.path.join(BUILD, "src")
     so = os.path.join(BUILD, name)
-    cpps = [os.path.join(src, u + ".cpp") for u in UNITS] + [os.path.join(HERE, "emu.cpp")]
-    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=fast",
-                    "-fno-strict-aliasing", "-w", "-mfma", *extra, "-I", HERE, "-I", src, "-I",
-                    os.path.join(ROOT, "include"), "-o", so, *cpps], check=True)
+    stamp = so + ".stamp"
+    key = _fingerprint() + " " + " ".join(extra)
+    if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == key:
+        return so
+    odir = os.path.join(BUILD, "obj_" + name)
+    os.makedirs(odir, exist_ok=True)
+    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-fopenmp", "-ffp-contract=fast", "-fno-strict-aliasing", "-w", "-mfma",
+             *extra, "-I", HERE, "-I", src, "-I", os.path.join(ROOT, "include")]
+    procs, objs = [], []
+    for u in UNITS + ["emu"]:
+        cpp = os.path.join(HERE, "emu.cpp") if u == "emu" else os.path.join(src, u + ".cpp")
+        obj = os.path.join(odir, u + ".o")
+        objs.append(obj)
+        procs.append((u, subprocess.Popen(["/usr/bin/g++", *flags, "-c", cpp, "-o", obj], stderr=subprocess.PIPE,
+                                          text=True)))
+    for u, p in procs:
+        err = p.communicate()[1]
+        if p.returncode:
+            raise RuntimeError(f"simt_emu variant {name}: {u} failed\n{err[-6000:]}")
+    link = [f for f in extra if f.startswith("-fsanitize")]
+    subprocess.run(["/usr/bin/g++", "-shared", "-fopenmp", *link, "-o", so, *objs], check=True)
+    shutil.rmtree(odir, ignore_errors=True)
+    with open(stamp, "w") as f:
+        f.write(key)
     return so
 
 

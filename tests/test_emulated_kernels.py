@@ -186,3 +186,23 @@ def test_chunked_host_path_is_bit_identical(emu, tmp_path):
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))), ids=os.path.basename)
 def test_emulated_engine_matches_golden(emu, path):
     TG.test_engine_matches_golden(emu, path)
+
+
+EXPERIMENT_FLAGS = ["-DNB_EXP_HALF_WARP", "-DNB_EXP_SPLIT_MODES", "-DNB_EXP_LOG_ESTRIN", "-DNB_EXP_RCP_CUBIC",
+                    "-DNB_EXP_TAB_UNROLL4", "-DNB_EXP_HEAVY_FIRST"]
+
+
+def test_kernel_experiments_keep_parity(tmp_path):
+    """The kernel experiments of DESIGN.md section 8 (compile-time switches, all off in the product build) must stay
+    correct while they wait for GPU time: build the emulated engine with every switch on -- two genes per warp for
+    m up to ~330, per-mode-family kernels above that, Estrin log, cubic reciprocal step, 4-way table loop, heaviest mode
+    first -- and run a slice of the parity suite against it in a fresh process."""
+    import subprocess
+    import build_emu
+    lib = build_emu.build_experiment("ci_all", EXPERIMENT_FLAGS)
+    sel = "800-37 or 1500-6 or big_and_mixed or maxit0 or condition-51 or batch-61 or edge_shapes or divergence or C3"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_parity_gpu.py"), "-q", "-m", "gpu", "-x",
+                        "-p", "no:cacheprovider", "-k", sel], env=dict(os.environ, B200NB_LIB=lib), capture_output=True,
+                       text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
