@@ -51,7 +51,18 @@ struct Workspace {
 // R hands over ordinary (pageable) memory.  cudaMemcpy from pageable memory runs at ~9 GB/s on the GPU box;
 // staging through a ring of pinned buffers filled by a few host threads while the previous chunk is in flight
 // reaches PCIe speed.  B200NB_STAGE_THREADS (default 8; 4..16 measure the same) OpenMP workers do the host-side memcpy.
-constexpr size_t kStageChunk = 16u << 20;
+// bytes per pinned staging buffer: 16 MB as measured in round 1; B200NB_STAGE_CHUNK_MB (1..256) is a knob for the next
+// GPU session (smaller chunks start the first DMA sooner, larger ones pay fewer event round trips)
+size_t stage_chunk_bytes() {
+  static const size_t v = [] {
+    const char* e = getenv("B200NB_STAGE_CHUNK_MB");
+    long mb = e ? atol(e) : 16;
+    if (mb < 1 || mb > 256) mb = 16;
+    return (size_t)mb << 20;
+  }();
+  return v;
+}
+#define kStageChunk (stage_chunk_bytes())
 constexpr int kStageRing = 3;
 struct Staging {
   void* buf[kStageRing] = {};
