@@ -75,6 +75,10 @@ def lib():
             l = C.CDLL(_SO)
         except OSError as e:  # pragma: no cover
             raise EngineError(f"cannot load {_SO}: {e}") from e
+        if hasattr(l, "simt_emu_launches") and os.environ.get("B200NB_TEST_EMULATOR") != "1":
+            # tests/simt_emu builds the CUDA sources into a CPU library to CHECK them; it is never a way to run
+            raise EngineError(f"{_SO} is the SIMT-emulated test build of the engine; the product only runs on a CUDA "
+                              "device (set B200NB_TEST_EMULATOR=1 only inside the test-suite)")
         for name, argt in SIGNATURES.items():
             f = getattr(l, name)
             f.argtypes = argt

@@ -7,6 +7,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "simt_emu")]
 import build_emu                      # noqa: E402
+os.environ["B200NB_TEST_EMULATOR"] = "1"
 os.environ.setdefault("B200NB_LIB", build_emu.build())      # an experiment build can be named from outside
 from deseq2_b200 import wrappers      # noqa: E402
 from oracle import oracle as O        # noqa: E402

@@ -4,6 +4,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the product refuses to load the SIMT-emulated test build of the engine unless the test-suite says so (inherited by
+# the subprocesses some tests start)
+os.environ["B200NB_TEST_EMULATOR"] = "1"
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

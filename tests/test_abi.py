@@ -82,3 +82,16 @@ def test_na_screening_mirrors_r_wrappers():
     with pytest.raises(ValueError, match="alpha_hatSEXP"):
         wrappers.fitBetaWrapper(y, x, np.ones((3, 4)), np.array([1.0, np.nan, 1.0]), np.zeros((3, 2)), [1e-6, 1e-6], None,
                                 False, 1e-8, 10, True, 0.5)
+
+
+def test_product_refuses_the_emulated_engine():
+    """The SIMT-emulated build of the engine (tests/simt_emu) is a checker, not a way to run: without the test-suite's
+    B200NB_TEST_EMULATOR=1 the loader refuses it, so no configuration of the product computes on the CPU."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt_emu"))
+    import build_emu
+    env = {k: v for k, v in os.environ.items() if k != "B200NB_TEST_EMULATOR"}
+    env["B200NB_LIB"] = build_emu.build()
+    r = subprocess.run([sys.executable, "-c", "import deseq2_b200; deseq2_b200.lib()"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "SIMT-emulated test build" in r.stderr
