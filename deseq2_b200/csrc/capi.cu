@@ -159,7 +159,21 @@ void advise_hugepages(void* p, size_t bytes) {
   if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);   // a hint: failure is harmless
 }
 
-void par_memcpy(void* dst, const void* src, size_t bytes, int T = 0) {
+// B200NB_D2H_POPULATE=1 (opt-in, not yet timed on the GPU box): each copying thread first asks the kernel to populate
+// the page tables of its destination slice in one call (MADV_POPULATE_WRITE, Linux >= 5.14) instead of taking one page
+// fault per 4 KB while it copies; on the build container that took a 40 MB first-touch scatter from 3.7 to 2.7 ms.
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+bool d2h_populate() {
+  static const bool on = [] {
+    const char* e = getenv("B200NB_D2H_POPULATE");
+    return e && atoi(e) != 0;
+  }();
+  return on;
+}
+
+void par_memcpy(void* dst, const void* src, size_t bytes, int T = 0, bool populate_dst = false) {
   if (bytes < (1u << 20)) {
     memcpy(dst, src, bytes);
     return;
@@ -168,6 +182,10 @@ void par_memcpy(void* dst, const void* src, size_t bytes, int T = 0) {
 #pragma omp parallel for num_threads(T) schedule(static)
   for (int t = 0; t < T; t++) {
     const size_t lo = bytes * t / T, hi = bytes * (t + 1) / T;
+    if (populate_dst) {
+      const uintptr_t a = ((uintptr_t)dst + lo + 4095) & ~(uintptr_t)4095, b = ((uintptr_t)dst + hi) & ~(uintptr_t)4095;
+      if (b > a) madvise(reinterpret_cast<void*>(a), b - a, MADV_POPULATE_WRITE);   // a hint: failure is harmless
+    }
     memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
   }
 }
@@ -218,7 +236,7 @@ int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     const size_t off = k * kStageChunk;
     const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
     CU(cudaEventSynchronize(g_stage.ev[b]));
-    par_memcpy(static_cast<char*>(dst) + off, g_stage.buf[b], len, d2h_threads());
+    par_memcpy(static_cast<char*>(dst) + off, g_stage.buf[b], len, d2h_threads(), d2h_populate());
   }
   return 0;
 }

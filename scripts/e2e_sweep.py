@@ -12,7 +12,8 @@ SETTINGS = [{}]
 for genes, workers in itertools.product(("6250", "12500", "25000"), ("2", "3")):
     SETTINGS.append({"B200NB_CHUNK_GENES": genes, "B200NB_CHUNK_WORKERS": workers})
 SETTINGS += [{"B200NB_STAGE_CHUNK_MB": "4"}, {"B200NB_STAGE_CHUNK_MB": "8"}, {"B200NB_STAGE_CHUNK_MB": "32"},
-             {"B200NB_D2H_HUGEPAGE": "1"}, {"B200NB_D2H_THREADS": "16"}, {"B200NB_D2H_THREADS": "32"},
+             {"B200NB_D2H_HUGEPAGE": "1"}, {"B200NB_D2H_POPULATE": "1"},
+             {"B200NB_D2H_POPULATE": "1", "B200NB_D2H_THREADS": "16"}, {"B200NB_D2H_THREADS": "16"}, {"B200NB_D2H_THREADS": "32"},
              {"B200NB_STAGE_THREADS": "16", "B200NB_D2H_THREADS": "32"},
              {"B200NB_D2H_HUGEPAGE": "1", "B200NB_D2H_THREADS": "16"},
              {"B200NB_CHUNK_GENES": "12500", "B200NB_CHUNK_WORKERS": "2", "B200NB_D2H_HUGEPAGE": "1"},
