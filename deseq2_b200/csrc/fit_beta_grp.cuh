@@ -9,8 +9,23 @@
 // (beta_pass with GL lanes); decisions: the reference's (src/DESeq2.cpp:334-383 / :388-425, post-loop :429-455).
 #pragma once
 
+// Group width and CTA shape of the experiment: NB_EXP_GROUP_LANES = 16 (default: 2 genes per warp, 256-thread CTAs, 2 per
+// SM) or 8 (4 genes per warp; 128-thread CTAs, 3 per SM, so that 12 warps x 4 gene slices still fit in shared memory).
+#ifndef NB_EXP_GROUP_LANES
+#define NB_EXP_GROUP_LANES 16
+#endif
+#if NB_EXP_GROUP_LANES == 16
+#define NB_GRP_THREADS 256
+#define NB_GRP_CTAS 2
+#elif NB_EXP_GROUP_LANES == 8
+#define NB_GRP_THREADS 128
+#define NB_GRP_CTAS 3
+#else
+#error "NB_EXP_GROUP_LANES must be 16 or 8"
+#endif
+
 template <int P, bool USE_W, int GL>
-__global__ void __launch_bounds__(256, 2) fit_beta_grp_kernel(const BetaArgs A, int mpad) {
+__global__ void __launch_bounds__(NB_GRP_THREADS, NB_GRP_CTAS) fit_beta_grp_kernel(const BetaArgs A, int mpad) {
   extern __shared__ __align__(16) double smem[];
   init_log_table();
   constexpr int NG = 32 / GL;

@@ -664,24 +664,24 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
   }
 #ifdef NB_EXP_HALF_WARP
   {
-    constexpr int GL = 16, NG = 32 / GL;
-    const size_t gsmem = xbytes + (size_t)8 * NG * rowbytes;
-    if (!grid_mode && gsmem <= smem_cap / 2) {
+    constexpr int GL = NB_EXP_GROUP_LANES, NG = 32 / GL, GW = NB_GRP_THREADS / 32;
+    const size_t gsmem = xbytes + (size_t)GW * NG * rowbytes;
+    if (!grid_mode && gsmem <= smem_cap / NB_GRP_CTAS) {
       auto kg = fit_disp_grp_kernel<P, USE_W, GL>;
       static size_t g_smem = 0;
       static int g_ctas = 0;
       if (g_smem != gsmem || g_ctas < 1) {
         e = cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas, kg, 256, gsmem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas, kg, NB_GRP_THREADS, gsmem);
         if (e != cudaSuccess) return e;
         if (g_ctas < 1) return cudaErrorLaunchOutOfResources;
         g_smem = gsmem;
       }
       long long gg = (long long)sms * g_ctas;
-      const long long gwant = ((long long)a.n + 8 * NG - 1) / (8 * NG);
+      const long long gwant = ((long long)a.n + GW * NG - 1) / (GW * NG);
       if (gg > gwant) gg = gwant;
-      kg<<<(unsigned)(gg < 1 ? 1 : gg), 256, gsmem, stream>>>(a, mpad);
+      kg<<<(unsigned)(gg < 1 ? 1 : gg), NB_GRP_THREADS, gsmem, stream>>>(a, mpad);
       return cudaGetLastError();
     }
   }

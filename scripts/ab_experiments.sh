@@ -16,6 +16,7 @@ declare -A EXP=(
   [tab4]="-DNB_EXP_TAB_UNROLL4"
   [heavy_first]="-DNB_EXP_HEAVY_FIRST"
   [half_warp]="-DNB_EXP_HALF_WARP"
+  [quarter_warp]="-DNB_EXP_HALF_WARP -DNB_EXP_GROUP_LANES=8"
   [half_warp_estrin_rcp3]="-DNB_EXP_HALF_WARP -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC"
   [all]="-DNB_EXP_SPLIT_MODES -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC -DNB_EXP_BETA_CTAS3 -DNB_EXP_TAB_UNROLL4"
 )
