@@ -10,6 +10,7 @@
 #include <sys/mman.h>
 
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -509,6 +510,38 @@ int upload_vec(const void* host, size_t bytes, Slot s, cudaStream_t st, void** o
   return 0;
 }
 
+// B200NB_HOST_TIMING=1: the host entry points print where their wall time goes (upload incl. layout conversion /
+// kernels / download) to stderr; it adds a stream synchronisation between the phases, so it is a diagnosis aid, not
+// something to leave on while measuring.
+bool host_timing() {
+  static const bool on = [] {
+    const char* e = getenv("B200NB_HOST_TIMING");
+    return e && atoi(e) != 0;
+  }();
+  return on;
+}
+struct PhaseClock {
+  std::chrono::steady_clock::time_point t0;
+  double ms[3] = {0.0, 0.0, 0.0};
+  int phase = 0;
+  bool on;
+  cudaStream_t st;
+  explicit PhaseClock(cudaStream_t s) : on(host_timing()), st(s) {
+    if (on) t0 = std::chrono::steady_clock::now();
+  }
+  void next() {   // close the current phase
+    if (!on || phase > 2) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    ms[phase++] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+  void report(const char* what, int g0, int n) {
+    if (on) fprintf(stderr, "b200nb timing %s genes [%d, %d): upload %.3f ms, kernels %.3f ms, download %.3f ms\n", what, g0,
+                    g0 + n, ms[0], ms[1], ms[2]);
+  }
+};
+
 // ---------------------------------------------------------------- gene-chunked host path (opt-in)
 // B200NB_CHUNK_GENES=<genes per chunk> splits one host call into gene chunks that B200NB_CHUNK_WORKERS (default 2,
 // max 4) host threads process independently -- each with its own stream, device workspace and pinned ring -- so that
@@ -790,6 +823,7 @@ static int fit_disp_block(const void* y, int y_type, const double* x, const doub
                           double* out_last_lp, double* out_last_dlp, double* out_last_d2lp) {
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
+  PhaseClock clk(st);
   const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
   const long long ld = ld_for(m);
   void *d_y, *d_mu, *d_w = nullptr, *d_x, *d_la, *d_pm, *d_outd, *d_outi;
@@ -803,12 +837,14 @@ static int fit_disp_block(const void* y, int y_type, const double* x, const doub
   if (ws_get(S_OUTI, sizeof(int32_t) * 2 * n, &d_outi)) return 1;
   double* od = (double*)d_outd;
   int32_t* oi = (int32_t*)d_outi;
+  clk.next();
   if (b200nb_fit_disp_dev(d_y, y_type, (const double*)d_x, (const double*)d_mu, (const double*)d_la,
                           (const double*)d_pm, log_alpha_prior_sigmasq, min_log_alpha, kappa_0, tol, maxit, use_prior,
                           (const double*)d_w, use_weights, weight_threshold, use_cr, n, m, p, ld, od, oi, oi + n,
                           od + n, od + 2 * (size_t)n, od + 3 * (size_t)n, od + 4 * (size_t)n, od + 5 * (size_t)n,
                           od + 6 * (size_t)n, st))
     return 1;
+  clk.next();
   double* outs[7] = {out_log_alpha, out_last_change, out_initial_lp, out_initial_dlp, out_last_lp, out_last_dlp,
                      out_last_d2lp};
   for (int k = 0; k < 7; k++)
@@ -816,6 +852,8 @@ static int fit_disp_block(const void* y, int y_type, const double* x, const doub
   CU(cudaMemcpyAsync(out_iter + g0, oi, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(out_iter_accept + g0, oi + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  clk.next();
+  clk.report("fitDisp", g0, n);
   return 0;
 }
 
@@ -894,6 +932,7 @@ static int fit_beta_block(const void* y, int y_type, const double* x, const doub
                           double* out_contrast_denom, double* out_deviance, double* out_mu) {
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
+  PhaseClock clk(st);
   const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
   const long long ld = ld_for(m);
   void *d_y, *d_nf, *d_w = nullptr, *d_x, *d_alpha, *d_contrast, *d_lambda, *d_bin, *d_bout, *d_bvar, *d_outd;
@@ -919,12 +958,14 @@ static int fit_beta_block(const void* y, int y_type, const double* x, const doub
     if (ws_get(S_MUC, sizeof(double) * n * m, &d_muc)) return 1;
   }
   double* od = (double*)d_outd;
+  clk.next();
   if (b200nb_fit_beta_dev(d_y, y_type, (const double*)d_x, (const double*)d_nf, 0, (const double*)d_alpha,
                           (const double*)d_contrast, (const double*)d_bin, (const double*)d_lambda,
                           (const double*)d_w, use_weights, tol, maxit, use_qr, minmu, n, m, p, ld, (double*)d_bout,
                           (double*)d_bvar, od, (double*)d_h, od + n, od + 2 * (size_t)n, od + 3 * (size_t)n,
                           (double*)d_mu, st))
     return 1;
+  clk.next();
   if (out_hat_diagonals) {
     if (b200nb_to_col_major_dev((const double*)d_h, (double*)d_hc, n, m, ld, st)) return 1;
     if (d2h_block(out_hat_diagonals, d_hc, (size_t)n_total, (size_t)g0, (size_t)n, m, 8, st)) return 1;
@@ -945,6 +986,8 @@ static int fit_beta_block(const void* y, int y_type, const double* x, const doub
   CU(cudaMemcpyAsync(out_contrast_denom + g0, od + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(out_deviance + g0, od + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  clk.next();
+  clk.report("fitBeta", g0, n);
   return 0;
 }
 

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SETTINGS = [{}]
+SETTINGS = [{}, {"B200NB_HOST_TIMING": "1"}]     # the second run prints the per-phase breakdown to stderr (shown below)
 for genes, workers in itertools.product(("6250", "12500", "25000"), ("2", "3")):
     SETTINGS.append({"B200NB_CHUNK_GENES": genes, "B200NB_CHUNK_WORKERS": workers})
 SETTINGS += [{"B200NB_STAGE_CHUNK_MB": "4"}, {"B200NB_STAGE_CHUNK_MB": "8"}, {"B200NB_STAGE_CHUNK_MB": "32"},
@@ -24,4 +24,6 @@ for s in SETTINGS:
     r = subprocess.run([sys.executable, os.path.join(HERE, "e2e_probe.py")], env=env, capture_output=True, text=True,
                        timeout=600)
     line = (r.stdout.strip().splitlines() or [r.stderr.strip()[-300:]])[-1]
+    if "B200NB_HOST_TIMING" in s:
+        print("\n".join(l for l in r.stderr.splitlines() if l.startswith("b200nb timing"))[-1500:], flush=True)
     print(" ".join(f"{k[7:]}={v}" for k, v in s.items()) or "default", "|", line, flush=True)
