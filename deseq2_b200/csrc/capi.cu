@@ -924,7 +924,39 @@ int b200nb_fit_disp_grid(const void* y, int y_type, const double* x, const doubl
   return run_chunked(n, block);
 }
 
-static int fit_beta_block(const void* y, int y_type, const double* x, const double* nf, const double* alpha_hat,
+// B200NB_DETECT_SF=1 (opt-in, not yet timed): R always hands fitBeta an n x m matrix of normalisation factors, which for
+// the usual size-factor analysis is the same row n times (R/core.R:2221-2228).  One parallel read of the matrix tells;
+// if so, only the m factors cross PCIe and the kernel takes its size-factor-vector path (log nf once per CTA instead
+// of once per gene and sample).  Same values in, same results out; any NaN or differing entry keeps the matrix path.
+static bool detect_sf() {
+  static const bool on = [] {
+    const char* e = getenv("B200NB_DETECT_SF");
+    return e && atoi(e) != 0;
+  }();
+  return on;
+}
+static bool rows_identical(const double* a, size_t n, int m) {
+  std::atomic<int> differs{0};
+  const int T = stage_threads();
+#pragma omp parallel for num_threads(T) schedule(dynamic, 1)
+  for (int j = 0; j < m; j++) {
+    if (differs.load(std::memory_order_relaxed)) continue;
+    const double* c = a + (size_t)j * n;
+    const double v = c[0];
+    bool same = (v == v);
+    for (size_t i0 = 0; i0 < n && same; i0 += 4096) {
+      const size_t i1 = (i0 + 4096 < n) ? i0 + 4096 : n;
+      int bad = 0;
+      for (size_t i = i0; i < i1; i++) bad |= (c[i] != v);
+      same = !bad;
+    }
+    if (!same) differs.store(1, std::memory_order_relaxed);
+  }
+  return differs.load() == 0;
+}
+
+static int fit_beta_block(const void* y, int y_type, const double* x, const double* nf, const double* sf_vector,
+                          const double* alpha_hat,
                           const double* contrast, const double* beta_mat, const double* lambda,
                           const double* weights, int use_weights, double tol, int maxit, int use_qr, double minmu,
                           int n_total, int g0, int n, int m, int p, double* out_beta_mat, double* out_beta_var_mat,
@@ -938,7 +970,11 @@ static int fit_beta_block(const void* y, int y_type, const double* x, const doub
   void *d_y, *d_nf, *d_w = nullptr, *d_x, *d_alpha, *d_contrast, *d_lambda, *d_bin, *d_bout, *d_bvar, *d_outd;
   void *d_h = nullptr, *d_mu = nullptr, *d_hc = nullptr, *d_muc = nullptr;
   if (upload_matrix(y, n_total, g0, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
-  if (upload_matrix(nf, n_total, g0, n, m, 8, S_RAW1, S_NF, st, &d_nf)) return 1;
+  if (sf_vector) {
+    if (upload_vec(sf_vector, sizeof(double) * m, S_NF, st, &d_nf)) return 1;
+  } else {
+    if (upload_matrix(nf, n_total, g0, n, m, 8, S_RAW1, S_NF, st, &d_nf)) return 1;
+  }
   if (use_weights && upload_matrix(weights, n_total, g0, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
   if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
   if (upload_vec(alpha_hat + g0, sizeof(double) * n, S_V0, st, &d_alpha)) return 1;
@@ -959,7 +995,7 @@ static int fit_beta_block(const void* y, int y_type, const double* x, const doub
   }
   double* od = (double*)d_outd;
   clk.next();
-  if (b200nb_fit_beta_dev(d_y, y_type, (const double*)d_x, (const double*)d_nf, 0, (const double*)d_alpha,
+  if (b200nb_fit_beta_dev(d_y, y_type, (const double*)d_x, (const double*)d_nf, sf_vector ? 1 : 0, (const double*)d_alpha,
                           (const double*)d_contrast, (const double*)d_bin, (const double*)d_lambda,
                           (const double*)d_w, use_weights, tol, maxit, use_qr, minmu, n, m, p, ld, (double*)d_bout,
                           (double*)d_bvar, od, (double*)d_h, od + n, od + 2 * (size_t)n, od + 3 * (size_t)n,
@@ -1001,8 +1037,14 @@ int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf
   std::lock_guard<std::mutex> lk(g_call_mu);
   if (out_hat_diagonals) advise_hugepages(out_hat_diagonals, sizeof(double) * (size_t)n * m);
   if (out_mu) advise_hugepages(out_mu, sizeof(double) * (size_t)n * m);
+  std::vector<double> sfv;
+  if (detect_sf() && rows_identical(nf, (size_t)n, m)) {
+    sfv.resize(m);
+    for (int j = 0; j < m; j++) sfv[j] = nf[(size_t)j * n];
+  }
+  const double* sf_vector = sfv.empty() ? nullptr : sfv.data();
   auto block = [&](int g0, int cnt) {
-    return fit_beta_block(y, y_type, x, nf, alpha_hat, contrast, beta_mat, lambda, weights, use_weights, tol, maxit,
+    return fit_beta_block(y, y_type, x, nf, sf_vector, alpha_hat, contrast, beta_mat, lambda, weights, use_weights, tol, maxit,
                           use_qr, minmu, n, g0, cnt, m, p, out_beta_mat, out_beta_var_mat, out_iter, out_hat_diagonals,
                           out_contrast_num, out_contrast_denom, out_deviance, out_mu);
   };

@@ -12,6 +12,7 @@ SETTINGS = [{}, {"B200NB_HOST_TIMING": "1"}]     # the second run prints the per
 for genes, workers in itertools.product(("6250", "12500", "25000"), ("2", "3")):
     SETTINGS.append({"B200NB_CHUNK_GENES": genes, "B200NB_CHUNK_WORKERS": workers})
 SETTINGS += [{"B200NB_STAGE_CHUNK_MB": "4"}, {"B200NB_STAGE_CHUNK_MB": "8"}, {"B200NB_STAGE_CHUNK_MB": "32"},
+             {"B200NB_DETECT_SF": "1"}, {"B200NB_DETECT_SF": "1", "B200NB_D2H_POPULATE": "1"},
              {"B200NB_D2H_HUGEPAGE": "1"}, {"B200NB_D2H_POPULATE": "1"},
              {"B200NB_D2H_POPULATE": "1", "B200NB_D2H_THREADS": "16"}, {"B200NB_D2H_THREADS": "16"}, {"B200NB_D2H_THREADS": "32"},
              {"B200NB_STAGE_THREADS": "16", "B200NB_D2H_THREADS": "32"},
