@@ -247,6 +247,7 @@ def main():
                                 timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local_rank)
     L = deseq2_b200.lib()
+    cfg["engine_library"] = os.path.basename(deseq2_b200.lib_path())   # experiment builds are named libb200nb_exp_*.so
 
     w = build_workload(n, m, 20260923 + 2 + 1000 * rank, W)
     ng = len(w["counts"])           # genes with a non-zero row sum: the ones that count for `value`
