@@ -1,7 +1,7 @@
 """Randomised shapes and options through the emulated engine (the CUDA kernels' source on CPU fibers, tests/simt_emu/)
 against the oracle.  Fixed seeds, so the test is deterministic; the generator covers what hand-written cases tend to
 miss: m around the 4- / 32- / 128-sample unroll boundaries, m barely above p, 1-gene and 1-sample problems, p from 1
-to 8 (register-resident p <= 4 kernels and the shared-memory general-p kernels), factor and continuous designs,
+to 32 (register-resident p <= 4 kernels and the shared-memory general-p kernels up to B200NB_MAX_P), factor and continuous designs,
 integer / double / non-integer counts, all-zero genes, observation weights with entries below the Cox-Reid threshold,
 prior and CR switches, tiny maxit, ridge penalties, size-factor vs gene-wise normalisation, both QR flags.
 A 400-seed run of the same generator (scripts/fuzz_emulated.py) found no discrepancy on valid inputs."""
@@ -17,7 +17,7 @@ def make_problem(s):
     rng = np.random.default_rng(s)
     n = int(rng.integers(1, 30))
     m = int(rng.choice(M_CHOICES))
-    p = int(rng.choice([1, 2, 3, 4, 5, 6, 8]))
+    p = int(rng.choice([1, 2, 3, 4, 5, 6, 8, 12, 32]))
     if m <= p:
         p = max(1, m - 1)
     kind = str(rng.choice(["factor", "cov"]))
