@@ -244,14 +244,18 @@ def _refit_rows(ysub, x, sizeFactors, tr, varLogDispEsts, dispPriorVar, minDisp,
 
 
 def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, maxit=100, betaTol=1e-8, minmu=0.5,
-                 outlierSD=2.0, minReplicatesForReplace=np.inf):
+                 outlierSD=2.0, minReplicatesForReplace=np.inf, allgather=None):
     """y: gene-major (N, ld) device tensor of counts (int32 or float64).  Returns a dict of device tensors over the
     rows with a non-zero sum (`idx` maps them back to the N input rows) plus the trend / prior scalars.
     sizeFactors=None estimates them on the device first (median of ratios, R/core.R:535-578; returned under
     "sizeFactors").  minReplicatesForReplace: the reference's default is 7 (replace count outliers by the trimmed mean
     and refit those genes, R/core.R:419-426, 2069-2115, 2484-2565); the default here is Inf = off (what bench.py's
     full_pipeline times).  With a finite value the per-gene results of the refitted rows are overwritten in place
-    and "replace" / "replaceable" / "n_replaced" are added."""
+    and "replace" / "replaceable" / "n_replaced" are added.
+    allgather: for the gene-sharded multi-GPU run (deseq2_b200/sharded.py::sharded_DESeq_device): a callable that
+    concatenates a per-gene 1-D device tensor over the ranks, in rank order.  It is used at the one point where the
+    reference needs every gene (R/parallel.R:25-28): the dispersion trend and the prior variance are then fitted,
+    identically on every rank, to all genes' baseMean / dispGeneEst instead of the shard's."""
     dev = y.device
     x = np.asarray(x, dtype=np.float64)
     m, p = x.shape
@@ -316,10 +320,11 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
     mark("rules+grid_mle")
 
     # ---- estimateDispersionsFit + dispersionFunction<- + PriorVar (R/core.R:864-940, R/methods.R:142-190, R/core.R:1135-1208)
-    tr = trend_fit(bm, dge, minDisp)
+    bm_all, dge_all = (allgather(bm), allgather(dge)) if allgather is not None else (bm, dge)
+    tr = trend_fit(bm_all, dge_all, minDisp)
     dispFit = tr[0] + tr[1] / bm
-    above = dge >= minDisp * 100
-    resid = (torch.log(dge) - torch.log(dispFit))[above]
+    above = dge_all >= minDisp * 100
+    resid = (torch.log(dge_all) - torch.log(tr[0] + tr[1] / bm_all))[above]
     med = _median(resid)
     varLogDispEsts = (1.4826 * _median((resid - med).abs())) ** 2
     expVar = torch.special.polygamma(1, torch.tensor((m - p) / 2.0, dtype=F64, device=dev))

@@ -90,3 +90,37 @@ def sharded_DESeq(counts, x, sizeFactors, engine=None):
             "betaIter": allp[:, 4], "deviance": allp[:, 5], "betaMatrix": allp[:, k:k + p],
             "betaSE": allp[:, k + p:k + 2 * p], "WaldStatistic": allp[:, k + 2 * p:k + 3 * p],
             "WaldPvalue": allp[:, k + 3 * p:k + 4 * p], "dispPriorVar": dispPriorVar, "trendCoefs": tf["coefs"]}
+
+
+def allgather_1d(t: torch.Tensor) -> torch.Tensor:
+    """Concatenate a 1-D tensor of rank-dependent length over the ranks (rank order), on the tensor's device: sizes
+    first, then one all_gather_into_tensor of shards padded to the largest."""
+    world = dist.get_world_size()
+    n_local = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    sizes = torch.empty(world, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(sizes, n_local)
+    sizes = [int(v) for v in sizes.tolist()]
+    cap = max(max(sizes), 1)
+    buf = torch.zeros(cap, dtype=t.dtype, device=t.device)
+    buf[: t.numel()] = t
+    out = torch.empty(world * cap, dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, buf)
+    return torch.cat([out[r * cap: r * cap + sizes[r]] for r in range(world)])
+
+
+def sharded_DESeq_device(y_local, x, sizeFactors, **kw):
+    """Device-resident DESeq() on this rank's gene shard (y_local: gene-major counts of the shard, on the rank's GPU)
+    with the reference's global step on all genes (dispersion trend + prior variance, R/parallel.R:25-28) done through
+    one all-gather of two per-gene vectors; everything else -- and in particular the n x m matrices -- stays on the
+    shard.  Returns the shard's result dict (device tensors) plus "gathered": betaMatrix, betaSE, dispersion and
+    WaldPvalue of ALL genes on every rank (R/parallel.R:54-66's rbind), in rank order."""
+    from . import device_pipeline as DP
+    res = DP.DESeq_device(y_local, x, sizeFactors, allgather=allgather_1d, **kw)
+    p = res["betaMatrix"].shape[1]
+    cols = [res["dispersion"]] + [res["betaMatrix"][:, k].contiguous() for k in range(p)] \
+        + [res["betaSE"][:, k].contiguous() for k in range(p)] + [res["WaldPvalue"][:, k].contiguous() for k in range(p)]
+    g = [allgather_1d(c) for c in cols]
+    res["gathered"] = {"dispersion": g[0], "betaMatrix": torch.stack(g[1:1 + p], dim=1),
+                       "betaSE": torch.stack(g[1 + p:1 + 2 * p], dim=1),
+                       "WaldPvalue": torch.stack(g[1 + 2 * p:1 + 3 * p], dim=1)}
+    return res
