@@ -323,6 +323,33 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_beta_kernel(con
 
 #ifdef NB_EXP_HALF_WARP
 #include "fit_beta_grp.cuh"
+
+template <int P, bool USE_W, int GL>
+cudaError_t launch_beta_grp(const BetaArgs& a, int mpad, size_t fixed, size_t rowbytes, int sms, cudaStream_t stream,
+                            bool& launched) {
+  constexpr int NG = 32 / GL, GW = GrpShape<GL>::threads / 32;
+  const size_t gsmem = fixed + (size_t)GW * NG * rowbytes;
+  launched = false;
+  if (gsmem > (size_t)227 * 1024 / GrpShape<GL>::ctas) return cudaSuccess;
+  auto kg = fit_beta_grp_kernel<P, USE_W, GL>;
+  static size_t g_smem = 0;
+  static int g_ctas = 0;
+  cudaError_t e = cudaSuccess;
+  if (g_smem != gsmem || g_ctas < 1) {
+    e = cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas, kg, GrpShape<GL>::threads, gsmem);
+    if (e != cudaSuccess) return e;
+    if (g_ctas < 1) return cudaErrorLaunchOutOfResources;
+    g_smem = gsmem;
+  }
+  long long gg = (long long)sms * g_ctas;
+  const long long gwant = ((long long)a.n + GW * NG - 1) / (GW * NG);
+  if (gg > gwant) gg = gwant;
+  kg<<<(unsigned)(gg < 1 ? 1 : gg), GrpShape<GL>::threads, gsmem, stream>>>(a, mpad);
+  launched = true;
+  return cudaGetLastError();
+}
 #endif
 
 template <int P, bool USE_W>
@@ -362,26 +389,11 @@ cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
   if (e != cudaSuccess) return e;
 #ifdef NB_EXP_HALF_WARP
   {
-    constexpr int GL = NB_EXP_GROUP_LANES, NG = 32 / GL, GW = NB_GRP_THREADS / 32;
-    const size_t gsmem = fixed + (size_t)GW * NG * rowbytes;
-    if (gsmem <= smem_cap / NB_GRP_CTAS) {
-      auto kg = fit_beta_grp_kernel<P, USE_W, GL>;
-      static size_t g_smem = 0;
-      static int g_ctas = 0;
-      if (g_smem != gsmem || g_ctas < 1) {
-        e = cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas, kg, NB_GRP_THREADS, gsmem);
-        if (e != cudaSuccess) return e;
-        if (g_ctas < 1) return cudaErrorLaunchOutOfResources;
-        g_smem = gsmem;
-      }
-      long long gg = (long long)sms * g_ctas;
-      const long long gwant = ((long long)a.n + GW * NG - 1) / (GW * NG);
-      if (gg > gwant) gg = gwant;
-      kg<<<(unsigned)(gg < 1 ? 1 : gg), NB_GRP_THREADS, gsmem, stream>>>(a, mpad);
-      return cudaGetLastError();
-    }
+    const int gl = group_lanes_for(a.m);
+    bool launched = false;
+    if (gl == 8) e = launch_beta_grp<P, USE_W, 8>(a, mpad, fixed, rowbytes, sms, stream, launched);
+    else if (gl == 16) e = launch_beta_grp<P, USE_W, 16>(a, mpad, fixed, rowbytes, sms, stream, launched);
+    if (e != cudaSuccess || launched) return e;
   }
 #endif
   kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, warps, mpad);

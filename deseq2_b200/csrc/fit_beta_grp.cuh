@@ -9,23 +9,31 @@
 // (beta_pass with GL lanes); decisions: the reference's (src/DESeq2.cpp:334-383 / :388-425, post-loop :429-455).
 #pragma once
 
-// Group width and CTA shape of the experiment: NB_EXP_GROUP_LANES = 16 (default: 2 genes per warp, 256-thread CTAs, 2 per
-// SM) or 8 (4 genes per warp; 128-thread CTAs, 3 per SM, so that 12 warps x 4 gene slices still fit in shared memory).
-#ifndef NB_EXP_GROUP_LANES
-#define NB_EXP_GROUP_LANES 16
-#endif
-#if NB_EXP_GROUP_LANES == 16
-#define NB_GRP_THREADS 256
-#define NB_GRP_CTAS 2
-#elif NB_EXP_GROUP_LANES == 8
-#define NB_GRP_THREADS 128
-#define NB_GRP_CTAS 3
-#else
-#error "NB_EXP_GROUP_LANES must be 16 or 8"
+// CTA shape per group width: 16 lanes (2 genes per warp): 256 threads, 2 CTAs per SM; 8 lanes (4 genes per warp): 128
+// threads, 3 CTAs per SM, so that 12 warps x 4 gene slices still fit in shared memory.
+#ifndef NB_GRP_SHAPE_DEFINED
+#define NB_GRP_SHAPE_DEFINED
+template <int GL>
+struct GrpShape {
+  static_assert(GL == 16 || GL == 8, "group width must be 16 or 8 lanes");
+  static constexpr int threads = (GL == 8) ? 128 : 256;
+  static constexpr int ctas = (GL == 8) ? 3 : 2;
+};
+// Which width to use for m samples: B200NB_GROUP_LANES = 8 | 16 | 32 forces one (32 = the product kernel); otherwise
+// 8 lanes up to 40 samples, 16 above (the launcher falls back to the product kernel when the slices do not fit).
+inline int group_lanes_for(int m) {
+  static const int forced = [] {
+    const char* e = getenv("B200NB_GROUP_LANES");
+    const int v = e ? atoi(e) : 0;
+    return (v == 8 || v == 16 || v == 32) ? v : 0;
+  }();
+  if (forced) return forced;
+  return m <= 40 ? 8 : 16;
+}
 #endif
 
 template <int P, bool USE_W, int GL>
-__global__ void __launch_bounds__(NB_GRP_THREADS, NB_GRP_CTAS) fit_beta_grp_kernel(const BetaArgs A, int mpad) {
+__global__ void __launch_bounds__(GrpShape<GL>::threads, GrpShape<GL>::ctas) fit_beta_grp_kernel(const BetaArgs A, int mpad) {
   extern __shared__ __align__(16) double smem[];
   init_log_table();
   constexpr int NG = 32 / GL;

@@ -16,7 +16,6 @@ declare -A EXP=(
   [tab4]="-DNB_EXP_TAB_UNROLL4"
   [heavy_first]="-DNB_EXP_HEAVY_FIRST"
   [half_warp]="-DNB_EXP_HALF_WARP"
-  [quarter_warp]="-DNB_EXP_HALF_WARP -DNB_EXP_GROUP_LANES=8"
   [half_warp_estrin_rcp3]="-DNB_EXP_HALF_WARP -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC"
   [all]="-DNB_EXP_SPLIT_MODES -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC -DNB_EXP_BETA_CTAS3 -DNB_EXP_TAB_UNROLL4"
 )
@@ -34,6 +33,11 @@ elif [ "$1" = run ]; then
     # correctness first: the parity suite must stay green with the experiment library
     if B200NB_LIB="$lib" python -m pytest tests/test_parity_gpu.py -q -m gpu -x -k "mle_parity or map_parity or fit_beta_parity or big_and_mixed" > /dev/null 2>&1; then ok=parity-ok; else ok=PARITY-FAILED; fi
     echo "$name $ok $(B200NB_LIB="$lib" python bench.py --no-e2e --no-cpu-baseline --steps 30 | tail -1)"
+    if [[ "$name" == half_warp* ]]; then   # the grouped kernels pick 8 lanes for m <= 40 and 16 above; force each width
+      for gl in 8 16; do
+        echo "$name lanes=$gl $(B200NB_GROUP_LANES=$gl B200NB_LIB="$lib" python bench.py --no-e2e --no-cpu-baseline --steps 30 | tail -1)"
+      done
+    fi
   done
 else
   echo "usage: $0 build|run"; exit 2
