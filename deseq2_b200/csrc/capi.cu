@@ -63,7 +63,7 @@ size_t stage_chunk_bytes() {
   }();
   return v;
 }
-#define kStageChunk (stage_chunk_bytes())
+#define kStageChunk (stage_chunk_bytes())   // kept as a name: the copy routines below read like the fixed-size originals
 constexpr int kStageRing = 3;
 struct Staging {
   void* buf[kStageRing] = {};
@@ -83,26 +83,26 @@ HostCtx g_ctx[kMaxWorkers];
 thread_local HostCtx* t_ctx = &g_ctx[0];
 std::mutex g_call_mu;    // host entry points are serialised (one set of contexts per process)
 std::mutex g_arena_mu;   // guards the (re)allocation of the shared device arenas below
-#define g_ws (t_ctx->ws)
-#define g_stage (t_ctx->stage)
+inline Workspace& cur_ws() { return t_ctx->ws; }        // the calling thread's context
+inline Staging& cur_stage() { return t_ctx->stage; }
 
 int ws_get(Slot s, size_t bytes, void** out) {
   if (bytes == 0) bytes = 16;
-  if (g_ws.bytes[s] < bytes) {
-    if (g_ws.p[s]) cudaFree(g_ws.p[s]);
-    g_ws.p[s] = nullptr;
-    g_ws.bytes[s] = 0;
+  if (cur_ws().bytes[s] < bytes) {
+    if (cur_ws().p[s]) cudaFree(cur_ws().p[s]);
+    cur_ws().p[s] = nullptr;
+    cur_ws().bytes[s] = 0;
     size_t want = bytes + bytes / 8;
-    CU(cudaMalloc(&g_ws.p[s], want));
-    g_ws.bytes[s] = want;
+    CU(cudaMalloc(&cur_ws().p[s], want));
+    cur_ws().bytes[s] = want;
   }
-  *out = g_ws.p[s];
+  *out = cur_ws().p[s];
   return 0;
 }
 
 int ws_stream(cudaStream_t* st) {
-  if (!g_ws.stream) CU(cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking));
-  *st = g_ws.stream;
+  if (!cur_ws().stream) CU(cudaStreamCreateWithFlags(&cur_ws().stream, cudaStreamNonBlocking));
+  *st = cur_ws().stream;
   return 0;
 }
 
@@ -127,12 +127,12 @@ int stage_threads() {
   return t;
 }
 int stage_init() {
-  if (g_stage.ready) return 0;
+  if (cur_stage().ready) return 0;
   for (int i = 0; i < kStageRing; i++) {
-    CU(cudaHostAlloc(&g_stage.buf[i], kStageChunk, cudaHostAllocDefault));
-    CU(cudaEventCreateWithFlags(&g_stage.ev[i], cudaEventDisableTiming));
+    CU(cudaHostAlloc(&cur_stage().buf[i], kStageChunk, cudaHostAllocDefault));
+    CU(cudaEventCreateWithFlags(&cur_stage().ev[i], cudaEventDisableTiming));
   }
-  g_stage.ready = true;
+  cur_stage().ready = true;
   return 0;
 }
 
@@ -201,14 +201,14 @@ int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   for (int k = 0; off < bytes; k++) {
     const int b = k % kStageRing;
     const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
-    if (k >= kStageRing) CU(cudaEventSynchronize(g_stage.ev[b]));
-    par_memcpy(g_stage.buf[b], static_cast<const char*>(src) + off, len);
-    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, g_stage.buf[b], len, cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(g_stage.ev[b], st));
+    if (k >= kStageRing) CU(cudaEventSynchronize(cur_stage().ev[b]));
+    par_memcpy(cur_stage().buf[b], static_cast<const char*>(src) + off, len);
+    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, cur_stage().buf[b], len, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(cur_stage().ev[b], st));
     off += len;
   }
   // the ring is reused by the next transfer: drain it
-  for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(g_stage.ev[b]));
+  for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(cur_stage().ev[b]));
   return 0;
 }
 
@@ -225,8 +225,8 @@ int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     const int b = (int)(k % kStageRing);
     const size_t off = k * kStageChunk;
     const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
-    CU(cudaMemcpyAsync(g_stage.buf[b], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(g_stage.ev[b], st));
+    CU(cudaMemcpyAsync(cur_stage().buf[b], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(cur_stage().ev[b], st));
     return 0;
   };
   for (size_t k = 0; k < nchunk && k < (size_t)kStageRing - 1; k++)
@@ -236,8 +236,8 @@ int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     const int b = (int)(k % kStageRing);
     const size_t off = k * kStageChunk;
     const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
-    CU(cudaEventSynchronize(g_stage.ev[b]));
-    par_memcpy(static_cast<char*>(dst) + off, g_stage.buf[b], len, d2h_threads(), d2h_populate());
+    CU(cudaEventSynchronize(cur_stage().ev[b]));
+    par_memcpy(static_cast<char*>(dst) + off, cur_stage().buf[b], len, d2h_threads(), d2h_populate());
   }
   return 0;
 }
@@ -268,15 +268,15 @@ int h2d_block(void* dst, const void* host, size_t n_total, size_t g0, size_t gc,
   for (int k = 0; j < m; k++) {
     const int b = k % kStageRing;
     const int nc = (m - j < cpc) ? m - j : cpc;
-    if (k >= kStageRing) CU(cudaEventSynchronize(g_stage.ev[b]));
-    char* buf = static_cast<char*>(g_stage.buf[b]);
+    if (k >= kStageRing) CU(cudaEventSynchronize(cur_stage().ev[b]));
+    char* buf = static_cast<char*>(cur_stage().buf[b]);
 #pragma omp parallel for num_threads(T) schedule(static) if (nc * col >= (1u << 20))
     for (int c = 0; c < nc; c++) memcpy(buf + (size_t)c * col, src + ((size_t)(j + c) * n_total + g0) * elem, col);
     CU(cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)j * col, buf, (size_t)nc * col, cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(g_stage.ev[b], st));
+    CU(cudaEventRecord(cur_stage().ev[b], st));
     j += nc;
   }
-  for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(g_stage.ev[b]));
+  for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(cur_stage().ev[b]));
   return 0;
 }
 
@@ -303,9 +303,9 @@ int d2h_block(void* host, const void* src, size_t n_total, size_t g0, size_t gc,
   const int nbatch = (m + cpc - 1) / cpc;
   auto issue = [&](int k) -> int {
     const int b = k % kStageRing, j = k * cpc, nc = (m - j < cpc) ? m - j : cpc;
-    CU(cudaMemcpyAsync(g_stage.buf[b], static_cast<const char*>(src) + (size_t)j * col, (size_t)nc * col,
+    CU(cudaMemcpyAsync(cur_stage().buf[b], static_cast<const char*>(src) + (size_t)j * col, (size_t)nc * col,
                        cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(g_stage.ev[b], st));
+    CU(cudaEventRecord(cur_stage().ev[b], st));
     return 0;
   };
   for (int k = 0; k < nbatch && k < kStageRing - 1; k++)
@@ -313,8 +313,8 @@ int d2h_block(void* host, const void* src, size_t n_total, size_t g0, size_t gc,
   for (int k = 0; k < nbatch; k++) {
     if (k + kStageRing - 1 < nbatch && issue(k + kStageRing - 1)) return 1;
     const int b = k % kStageRing, j = k * cpc, nc = (m - j < cpc) ? m - j : cpc;
-    CU(cudaEventSynchronize(g_stage.ev[b]));
-    const char* buf = static_cast<const char*>(g_stage.buf[b]);
+    CU(cudaEventSynchronize(cur_stage().ev[b]));
+    const char* buf = static_cast<const char*>(cur_stage().buf[b]);
 #pragma omp parallel for num_threads(T) schedule(static) if (nc * col >= (1u << 20))
     for (int c = 0; c < nc; c++) memcpy(dst + ((size_t)(j + c) * n_total + g0) * elem, buf + (size_t)c * col, col);
   }
