@@ -42,6 +42,23 @@ __device__ __forceinline__ double lgamma_diff(double y, double r, double lg_r) {
   return lgamma_pos(y + r) - lg_r;
 }
 
+// lgamma(y + 1) for the mu-independent part of the deviance.  NB_EXP_LFACT_TABLE (experiment, off by default): counts
+// below 256 read log(y!) from a per-CTA shared table filled once with the very same lgamma_pos(k + 1), so the value --
+// and every result -- is bit-identical while one Stirling evaluation per sample and gene is saved.
+#ifdef NB_EXP_LFACT_TABLE
+__shared__ double s_lfact[256];
+__device__ __forceinline__ void init_lfact_table() {   // call before the first log_factorial; contains a __syncthreads
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lfact[i] = lgamma_pos((double)i + 1.0);
+  __syncthreads();
+}
+__device__ __forceinline__ double log_factorial(double y) {
+  return (y < 256.0 && y == floor(y)) ? s_lfact[(int)y] : lgamma_pos(y + 1.0);
+}
+#else
+__device__ __forceinline__ void init_lfact_table() {}
+__device__ __forceinline__ double log_factorial(double y) { return lgamma_pos(y + 1.0); }
+#endif
+
 constexpr int pow2_ceil_b(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // One fused IRLS pass: mu (stored to shared memory), mu-dependent part of the deviance, X'WX and X'Wz.
@@ -130,6 +147,7 @@ template <int P, bool USE_W>
 __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_beta_kernel(const BetaArgs A, int warps_per_cta, int mpad) {
   extern __shared__ __align__(16) double smem[];
   init_log_table();
+  init_lfact_table();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   // per-warp rows: y, mu, [lnf if nf is a matrix], [w]
@@ -207,7 +225,7 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_beta_kernel(con
       double c = 0.0;
       for (int j = lane; j < A.m; j += 32) {
         const double y = ys[j];
-        double t = lgamma_diff(y, r, lg_r) - lgamma_pos(y + 1.0);
+        double t = lgamma_diff(y, r, lg_r) - log_factorial(y);
         if (USE_W) t *= wsm[j];
         c += t;
       }

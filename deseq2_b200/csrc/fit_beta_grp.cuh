@@ -36,6 +36,7 @@ template <int P, bool USE_W, int GL>
 __global__ void __launch_bounds__(GrpShape<GL>::threads, GrpShape<GL>::ctas) fit_beta_grp_kernel(const BetaArgs A, int mpad) {
   extern __shared__ __align__(16) double smem[];
   init_log_table();
+  init_lfact_table();
   constexpr int NG = 32 / GL;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(GrpShape<GL>::threads, GrpShape<GL>::ctas) fit
       double c = 0.0;
       for (int j = lg; j < A.m; j += GL) {
         const double y = ys[j];
-        double t = lgamma_diff(y, r, lg_r) - lgamma_pos(y + 1.0);
+        double t = lgamma_diff(y, r, lg_r) - log_factorial(y);
         if (USE_W) t *= wsm[j];
         c += t;
       }

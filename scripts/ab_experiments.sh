@@ -15,9 +15,10 @@ declare -A EXP=(
   [beta3]="-DNB_EXP_BETA_CTAS3"
   [tab4]="-DNB_EXP_TAB_UNROLL4"
   [heavy_first]="-DNB_EXP_HEAVY_FIRST"
+  [lfact]="-DNB_EXP_LFACT_TABLE"
   [half_warp]="-DNB_EXP_HALF_WARP"
   [half_warp_estrin_rcp3]="-DNB_EXP_HALF_WARP -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC"
-  [all]="-DNB_EXP_SPLIT_MODES -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC -DNB_EXP_BETA_CTAS3 -DNB_EXP_TAB_UNROLL4"
+  [all]="-DNB_EXP_SPLIT_MODES -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC -DNB_EXP_BETA_CTAS3 -DNB_EXP_TAB_UNROLL4 -DNB_EXP_LFACT_TABLE"
 )
 if [ "$1" = build ]; then
   make -C deseq2_b200/csrc -s

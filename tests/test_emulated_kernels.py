@@ -189,7 +189,7 @@ def test_emulated_engine_matches_golden(emu, path):
 
 
 EXPERIMENT_FLAGS = ["-DNB_EXP_HALF_WARP", "-DNB_EXP_SPLIT_MODES", "-DNB_EXP_LOG_ESTRIN", "-DNB_EXP_RCP_CUBIC",
-                    "-DNB_EXP_TAB_UNROLL4", "-DNB_EXP_HEAVY_FIRST"]
+                    "-DNB_EXP_TAB_UNROLL4", "-DNB_EXP_HEAVY_FIRST", "-DNB_EXP_LFACT_TABLE"]
 
 
 def test_kernel_experiments_keep_parity(tmp_path):
