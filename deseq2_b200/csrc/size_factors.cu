@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(512) sf_median_kernel(const double* __restrict
     __syncthreads();
     if (tid == 0) {
       unsigned int k = s_k, b = 0;
-      while (k >= hist[b]) { k -= hist[b]; b++; }            // terminates: k < number of keys under this prefix
+      while (b < 255u && k >= hist[b]) { k -= hist[b]; b++; }   // k < number of keys under this prefix; b is bounded anyway
       s_k = k;
       s_prefix = prefix | ((unsigned long long)b << (8 * pass));
     }
