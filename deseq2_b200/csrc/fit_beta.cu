@@ -407,7 +407,7 @@ cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
   if (e != cudaSuccess) return e;
 #ifdef NB_EXP_HALF_WARP
   {
-    const int gl = group_lanes_for(a.m);
+    const int gl = group_lanes_beta(a.m);
     bool launched = false;
     if (gl == 8) e = launch_beta_grp<P, USE_W, 8>(a, mpad, fixed, rowbytes, sms, stream, launched);
     else if (gl == 16) e = launch_beta_grp<P, USE_W, 16>(a, mpad, fixed, rowbytes, sms, stream, launched);

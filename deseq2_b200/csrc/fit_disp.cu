@@ -694,7 +694,7 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
   }
 #ifdef NB_EXP_HALF_WARP
   if (!grid_mode) {
-    const int gl = group_lanes_for(a.m);
+    const int gl = group_lanes_disp(a.m);
     bool launched = false;
     if (gl == 8) e = launch_disp_grp<P, USE_W, 8>(a, mpad, xbytes, rowbytes, sms, stream, launched);
     else if (gl == 16) e = launch_disp_grp<P, USE_W, 16>(a, mpad, xbytes, rowbytes, sms, stream, launched);

@@ -25,18 +25,21 @@ struct GrpShape {
   static constexpr int threads = (GL == 8) ? 128 : 256;
   static constexpr int ctas = (GL == 8) ? 3 : 2;
 };
-// Which width to use for m samples: B200NB_GROUP_LANES = 8 | 16 | 32 forces one (32 = the product kernel); otherwise
-// 8 lanes up to 40 samples, 16 above (the launcher falls back to the product kernel when the slices do not fit).
-inline int group_lanes_for(int m) {
+#endif
+
+// Which width this kernel uses for m samples: B200NB_GROUP_LANES_DISP, else B200NB_GROUP_LANES, = 8 | 16 | 32 forces one
+// (32 = the product kernel); otherwise 8 lanes up to 40 samples, 16 above (the launcher falls back to the product
+// kernel when the slices do not fit in shared memory).
+inline int group_lanes_disp(int m) {
   static const int forced = [] {
-    const char* e = getenv("B200NB_GROUP_LANES");
+    const char* e = getenv("B200NB_GROUP_LANES_DISP");
+    if (!e) e = getenv("B200NB_GROUP_LANES");
     const int v = e ? atoi(e) : 0;
     return (v == 8 || v == 16 || v == 32) ? v : 0;
   }();
   if (forced) return forced;
   return m <= 40 ? 8 : 16;
 }
-#endif
 
 template <int GL>
 __device__ __forceinline__ double group_allreduce_sum(double v) {

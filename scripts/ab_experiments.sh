@@ -38,6 +38,9 @@ elif [ "$1" = run ]; then
       for gl in 8 16; do
         echo "$name lanes=$gl $(B200NB_GROUP_LANES=$gl B200NB_LIB="$lib" python bench.py --no-e2e --no-cpu-baseline --steps 30 | tail -1)"
       done
+      # one kernel grouped, the other as in the product (config.kernel_ms tells the two apart anyway)
+      echo "$name disp-only $(B200NB_GROUP_LANES_BETA=32 B200NB_LIB="$lib" python bench.py --no-e2e --no-cpu-baseline --steps 30 | tail -1)"
+      echo "$name beta-only $(B200NB_GROUP_LANES_DISP=32 B200NB_LIB="$lib" python bench.py --no-e2e --no-cpu-baseline --steps 30 | tail -1)"
     fi
   done
 else
