@@ -55,12 +55,21 @@ struct DispArgs {
   const int* mode_lists;
 };
 
-#if defined(NB_EXP_SPLIT_MODES) || defined(NB_EXP_HALF_WARP)
+#if defined(NB_EXP_TAB_BUCKETS)
+// experiment: [queue counter | 3 mode counters | 2 more queue counters | pad to 8 | 8 bucket counts | 8 bucket fills | pad],
+// then the three gene lists, one bucket code per gene and a scratch list for the bucket sort
+constexpr int kDispScratchHead = 32;
+constexpr int kDispScratchLists = 5;
+#elif defined(NB_EXP_SPLIT_MODES) || defined(NB_EXP_HALF_WARP)
 constexpr int kDispScratchHead = 8;   // experiment: [queue counter | 3 mode counters | second queue counter | pad]
+constexpr int kDispScratchLists = 3;
 #else
 constexpr int kDispScratchHead = 4;   // [queue counter | 3 mode counters], then the three per-mode gene lists
+constexpr int kDispScratchLists = 3;
 #endif
-inline size_t disp_scratch_bytes(int n) { return (kDispScratchHead + 3 * (size_t)n) * sizeof(unsigned int); }
+inline size_t disp_scratch_bytes(int n) {
+  return (kDispScratchHead + kDispScratchLists * (size_t)n) * sizeof(unsigned int);
+}
 
 struct BetaArgs {
   const void* y;

@@ -283,8 +283,42 @@ __device__ __forceinline__ double disp_d2(const DispRow& rv, const DispScal& sc,
 // one list per mode so the persistent kernel can work through one mode at a time (keeps the instruction
 // working set of an SM inside the instruction cache: the first fused version stalled 70% on instruction fetch,
 // profiles/r01b_*).  lists[mode * n + i], counts[mode].
+#ifdef NB_EXP_TAB_BUCKETS
+// EXPERIMENT (off by default): TAB genes ordered by the length of their count table, longest first (8 buckets of 32),
+// so that genes which share a warp in the narrow-group kernels wait for tables of similar length, and the launch ends
+// on the cheap genes.  classify_kernel records a bucket per TAB gene and counts the buckets; bucket_sort_kernel places
+// the TAB list into a scratch list in bucket order (counting sort); the launcher copies it back over the TAB list.
+constexpr int kTabBuckets = 8;
+__global__ void __launch_bounds__(256) bucket_sort_kernel(const int* __restrict__ tab_list, const int* __restrict__ code,
+                                                          const unsigned int* __restrict__ n_tab,
+                                                          const unsigned int* __restrict__ bcount,
+                                                          unsigned int* __restrict__ bfill, int* __restrict__ sorted) {
+  const unsigned int n0 = *n_tab;
+  unsigned int start[kTabBuckets];      // longest tables (highest bucket) first
+  unsigned int run = 0;
+#pragma unroll
+  for (int b = kTabBuckets - 1; b >= 0; b--) {
+    start[b] = run;
+    run += bcount[b];
+  }
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += gridDim.x * blockDim.x) {
+    const int g = tab_list[i];
+    const int b = code[g];
+    unsigned int base = 0;
+#pragma unroll
+    for (int k = 0; k < kTabBuckets; k++)
+      if (k == b) base = start[k];
+    sorted[base + atomicAdd(&bfill[b], 1u)] = g;
+  }
+}
+#endif
+
 __global__ void __launch_bounds__(256) classify_kernel(const void* y, int y_is_f64, int n, int m, long long ld,
-                                                       int* lists, unsigned int* counts) {
+                                                       int* lists, unsigned int* counts
+#ifdef NB_EXP_TAB_BUCKETS
+                                                       , int* code, unsigned int* bcount
+#endif
+) {
   const int lane = threadIdx.x & 31;
   const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (g >= n) return;
@@ -306,6 +340,13 @@ __global__ void __launch_bounds__(256) classify_kernel(const void* y, int y_is_f
   if (lane == 0) {
     const unsigned int pos = atomicAdd(&counts[mode], 1u);
     lists[(size_t)mode * n + pos] = g;
+#ifdef NB_EXP_TAB_BUCKETS
+    if (mode == MODE_TAB) {
+      const int b = min(kTabBuckets - 1, (int)ymax / (kTabMax / kTabBuckets));
+      code[g] = b;
+      atomicAdd(&bcount[b], 1u);
+    }
+#endif
   }
 }
 
@@ -688,9 +729,24 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
   a.mode_counts = a.scratch + 1;
   a.mode_lists = reinterpret_cast<int*>(a.scratch + kDispScratchHead);
   if (!grid_mode) {
+#ifdef NB_EXP_TAB_BUCKETS
+    int* lists = reinterpret_cast<int*>(a.scratch + kDispScratchHead);
+    int* code = lists + 3 * (size_t)a.n;
+    int* sorted = lists + 4 * (size_t)a.n;
+    classify_kernel<<<(a.n + 7) / 8, 256, 0, stream>>>(a.y, a.y_is_f64, a.n, a.m, a.ld, lists, a.scratch + 1, code, a.scratch + 8);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    bucket_sort_kernel<<<(a.n + 255) / 256 > 1184 ? 1184 : (a.n + 255) / 256, 256, 0, stream>>>(lists, code, a.scratch + 1 + MODE_TAB, a.scratch + 8, a.scratch + 16, sorted);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // entries beyond the TAB count are never read by the kernels, so copying the whole n-entry region is harmless
+    e = cudaMemcpyAsync(lists, sorted, sizeof(int) * (size_t)a.n, cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return e;
+#else
     classify_kernel<<<(a.n + 7) / 8, 256, 0, stream>>>(a.y, a.y_is_f64, a.n, a.m, a.ld, reinterpret_cast<int*>(a.scratch + kDispScratchHead), a.scratch + 1);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+#endif
   }
 #ifdef NB_EXP_HALF_WARP
   if (!grid_mode) {

@@ -17,7 +17,9 @@ declare -A EXP=(
   [heavy_first]="-DNB_EXP_HEAVY_FIRST"
   [lfact]="-DNB_EXP_LFACT_TABLE"
   [half_warp]="-DNB_EXP_HALF_WARP"
-  [half_warp_estrin_rcp3]="-DNB_EXP_HALF_WARP -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC"
+  [half_warp_buckets]="-DNB_EXP_HALF_WARP -DNB_EXP_TAB_BUCKETS"
+  [buckets]="-DNB_EXP_TAB_BUCKETS"
+  [half_warp_buckets_estrin_rcp3]="-DNB_EXP_HALF_WARP -DNB_EXP_TAB_BUCKETS -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC"
   [all]="-DNB_EXP_SPLIT_MODES -DNB_EXP_LOG_ESTRIN -DNB_EXP_RCP_CUBIC -DNB_EXP_BETA_CTAS3 -DNB_EXP_TAB_UNROLL4 -DNB_EXP_LFACT_TABLE"
 )
 if [ "$1" = build ]; then

@@ -188,7 +188,7 @@ def test_emulated_engine_matches_golden(emu, path):
     TG.test_engine_matches_golden(emu, path)
 
 
-EXPERIMENT_FLAGS = ["-DNB_EXP_HALF_WARP", "-DNB_EXP_SPLIT_MODES", "-DNB_EXP_LOG_ESTRIN", "-DNB_EXP_RCP_CUBIC",
+EXPERIMENT_FLAGS = ["-DNB_EXP_HALF_WARP", "-DNB_EXP_TAB_BUCKETS", "-DNB_EXP_SPLIT_MODES", "-DNB_EXP_LOG_ESTRIN", "-DNB_EXP_RCP_CUBIC",
                     "-DNB_EXP_TAB_UNROLL4", "-DNB_EXP_HEAVY_FIRST", "-DNB_EXP_LFACT_TABLE"]
 
 
