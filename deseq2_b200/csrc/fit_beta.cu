@@ -119,8 +119,10 @@ __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta
       }
     }
   }
-  if (GL == 32) {
+  if constexpr (GL == 32) {
     warp_allreduce_sum_rs<NA>(acc, lane);
+  } else if constexpr (NA <= GL) {
+    group_allreduce_sum_rs<NA, GL>(acc, lane);
   } else {
 #pragma unroll
     for (int o = GL / 2; o > 0; o >>= 1) {

@@ -142,7 +142,8 @@ __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal
       }
     }
   }
-  if (GL == 32) warp_allreduce_sum_rs<NA>(acc, lane);
+  if constexpr (GL == 32) warp_allreduce_sum_rs<NA>(acc, lane);
+  else if constexpr (NA <= GL) group_allreduce_sum_rs<NA, GL>(acc, lane);
   else group_allreduce_sum_n<NA, GL>(acc);
 
   double cr = 0.0, dcr = 0.0;

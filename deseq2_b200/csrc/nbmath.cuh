@@ -333,4 +333,39 @@ __device__ __forceinline__ void warp_allreduce_sum_rs(double (&v)[N], int lane) 
   }
 }
 
+// The same reduce-scatter + all-gather inside lane groups of GL lanes (GL = 16 or 8; lg = lane index inside the group,
+// N <= GL): used by the several-genes-per-warp experiment kernels, never instantiated by the product kernels.
+template <int N, int GL>
+__device__ __forceinline__ void group_allreduce_sum_rs(double (&v)[N], int lg) {
+  static_assert(N >= 1 && N <= GL && (N & (N - 1)) == 0 && (GL == 16 || GL == 8), "N must be a power of two <= GL");
+  int width = N;
+  int o = GL / 2;
+#pragma unroll
+  for (; o > 0 && width > 1; o >>= 1) {
+    const bool upper = (lg & o) != 0;
+    const int half = width / 2;
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+      if (i < half) {
+        const double keep = upper ? v[i + half] : v[i];
+        const double send = upper ? v[i] : v[i + half];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    width = half;
+  }
+#pragma unroll
+  for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+  const double mine = v[0];
+  constexpr int LOGN = (N == 1) ? 0 : (N == 2) ? 1 : (N == 4) ? 2 : (N == 8) ? 3 : 4;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    int src = 0;
+#pragma unroll
+    for (int s = 0; s < LOGN; s++)
+      if ((i >> (LOGN - 1 - s)) & 1) src |= ((GL / 2) >> s);
+    v[i] = __shfl_sync(0xffffffffu, mine, src, GL);   // width GL: the source lane is taken inside the caller's group
+  }
+}
+
 }  // namespace nb
