@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round-2 A/B of the kernel experiments that were written (and parity-checked under the SIMT emulator) without GPU
 # access.  Step 1, on the build machine (no GPU needed):   scripts/ab_experiments.sh build
-# Step 2, on the GPU box (one gpurun call):                scripts/ab_experiments.sh run > gpurun_out/ab.txt
+# Step 2, on the GPU box (one gpurun call):                scripts/ab_experiments.sh quick > gpurun_out/ab_quick.txt
+#                                                          scripts/ab_experiments.sh run > gpurun_out/ab.txt
 # Each line of the output is the bench.py JSON line of one library; compare "value" and config.kernel_ms.
 set -e
 cd "$(dirname "$0")/.."
@@ -27,7 +28,17 @@ if [ "$1" = build ]; then
   for name in "${!EXP[@]}"; do
     make -C deseq2_b200/csrc exp EXPFLAGS="${EXP[$name]}" EXPNAME="$name" -s
   done
-  ls -la deseq2_b200/libb200nb*.so
+  nvcc -O2 -std=c++17 -Wno-deprecated-gpu-targets -o scripts/microbench scripts/microbench.cu -ldl
+  ls -la deseq2_b200/libb200nb*.so scripts/microbench
+elif [ "$1" = quick ]; then
+  # seconds instead of minutes: kernel times of every library on one resident workload, no Python (scripts/microbench.cu)
+  scripts/microbench --genes 50000 --samples 100 deseq2_b200/libb200nb.so deseq2_b200/libb200nb_exp_*.so
+  for gl in 8 16; do
+    echo "== B200NB_GROUP_LANES=$gl (libraries built with NB_EXP_HALF_WARP)"
+    B200NB_GROUP_LANES=$gl scripts/microbench --genes 50000 --samples 100 deseq2_b200/libb200nb.so deseq2_b200/libb200nb_exp_half_warp*.so
+  done
+  echo "== 20 000 genes x 12 samples (a typical small experiment)"
+  scripts/microbench --genes 20000 --samples 12 deseq2_b200/libb200nb.so deseq2_b200/libb200nb_exp_half_warp*.so
 elif [ "$1" = run ]; then
   echo "default $(python bench.py --no-e2e --no-cpu-baseline --steps 30 | tail -1)"
   for name in "${!EXP[@]}"; do
@@ -46,5 +57,5 @@ elif [ "$1" = run ]; then
     fi
   done
 else
-  echo "usage: $0 build|run"; exit 2
+  echo "usage: $0 build|quick|run"; exit 2
 fi
