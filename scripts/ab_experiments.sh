@@ -39,6 +39,20 @@ elif [ "$1" = quick ]; then
   done
   echo "== 20 000 genes x 12 samples (a typical small experiment)"
   scripts/microbench --genes 20000 --samples 12 deseq2_b200/libb200nb.so deseq2_b200/libb200nb_exp_half_warp*.so
+elif [ "$1" = host ]; then
+  # the end-to-end path (R-layout pageable buffers through the host entry points) under the run-time knobs of capi.cu;
+  # one process per setting because the knobs are read once; `B200NB_HOST_TIMING=1` adds the per-phase breakdown
+  mb="scripts/microbench --host --genes 50000 --samples 100 --reps 9 deseq2_b200/libb200nb.so"
+  $mb
+  B200NB_HOST_TIMING=1 scripts/microbench --host --genes 50000 --samples 100 --reps 1 deseq2_b200/libb200nb.so 2>&1 | tail -4
+  for s in "B200NB_DETECT_SF=1" "B200NB_D2H_POPULATE=1" "B200NB_D2H_HUGEPAGE=1" "B200NB_D2H_THREADS=16" "B200NB_D2H_THREADS=32" \
+           "B200NB_STAGE_THREADS=16" "B200NB_STAGE_CHUNK_MB=4" "B200NB_STAGE_CHUNK_MB=32" \
+           "B200NB_CHUNK_GENES=12500 B200NB_CHUNK_WORKERS=2" "B200NB_CHUNK_GENES=12500 B200NB_CHUNK_WORKERS=3" \
+           "B200NB_CHUNK_GENES=6250 B200NB_CHUNK_WORKERS=3" "B200NB_CHUNK_GENES=25000 B200NB_CHUNK_WORKERS=2" \
+           "B200NB_CHUNK_GENES=12500 B200NB_CHUNK_WORKERS=3 B200NB_DETECT_SF=1 B200NB_D2H_POPULATE=1" \
+           "B200NB_CHUNK_GENES=12500 B200NB_CHUNK_WORKERS=3 B200NB_DETECT_SF=1 B200NB_D2H_POPULATE=1 B200NB_D2H_THREADS=16"; do
+    echo "$s | $(env $s $mb | tail -1)"
+  done
 elif [ "$1" = run ]; then
   echo "default $(python bench.py --no-e2e --no-cpu-baseline --steps 30 | tail -1)"
   for name in "${!EXP[@]}"; do
@@ -57,5 +71,5 @@ elif [ "$1" = run ]; then
     fi
   done
 else
-  echo "usage: $0 build|quick|run"; exit 2
+  echo "usage: $0 build|quick|host|run"; exit 2
 fi

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <random>
 #include <string>
 #include <vector>
@@ -38,6 +39,12 @@ typedef int (*fit_beta_dev_t)(const void*, int, const double*, const double*, in
                               const double*, const double*, const double*, int, double, int, int, double, int, int, int,
                               long long, double*, double*, double*, double*, double*, double*, double*, double*, void*);
 typedef const char* (*last_error_t)(void);
+typedef int (*fit_disp_host_t)(const void*, int, const double*, const double*, const double*, const double*, double, double,
+                               double, double, int, int, const double*, int, double, int, int, int, int, double*, int32_t*,
+                               int32_t*, double*, double*, double*, double*, double*, double*);
+typedef int (*fit_beta_host_t)(const void*, int, const double*, const double*, const double*, const double*, const double*,
+                               const double*, const double*, int, double, int, int, double, int, int, int, double*, double*,
+                               double*, double*, double*, double*, double*, double*);
 
 template <typename T>
 static T* to_device(const std::vector<T>& h) {
@@ -54,8 +61,10 @@ static double median(std::vector<float> v) {
 
 int main(int argc, char** argv) {
   int n = 50000, m = 100, reps = 20;
+  bool host_mode = false;   // --host: time the HOST entry points (R-layout pageable buffers, fresh result buffers each call)
   std::vector<std::string> libs;
   for (int i = 1; i < argc; i++) {
+    if (!strcmp(argv[i], "--host")) { host_mode = true; continue; }
     if (!strcmp(argv[i], "--genes") && i + 1 < argc) n = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--samples") && i + 1 < argc) m = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--reps") && i + 1 < argc) reps = atoi(argv[++i]);
@@ -136,6 +145,61 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
+
+  if (host_mode) {
+    // R layout: column-major n x m; the host entry points of ONE library (knobs are read from the environment once per
+    // process, so run the binary once per setting); a step = fitDisp + fitDisp + fitBeta like bench.py's e2e
+    std::vector<int32_t> yc((size_t)n * m);
+    std::vector<double> muc((size_t)n * m), nfc((size_t)n * m), b0c((size_t)n * p, 0.0);
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < m; j++) {
+        yc[(size_t)j * n + i] = y[(size_t)i * ld + j];
+        muc[(size_t)j * n + i] = mu[(size_t)i * ld + j];
+        nfc[(size_t)j * n + i] = sf[j];
+      }
+    for (int i = 0; i < n; i++) b0c[i] = beta0[i];
+    void* h = dlopen(libs[0].c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) { printf("%s: dlopen failed: %s\n", libs[0].c_str(), dlerror()); return 1; }
+    auto fdh = (fit_disp_host_t)dlsym(h, "b200nb_fit_disp");
+    auto fbh = (fit_beta_host_t)dlsym(h, "b200nb_fit_beta");
+    auto le = (last_error_t)dlsym(h, "b200nb_last_error");
+    std::vector<double> tstep, t1, t3;
+    for (int r = 0; r < reps + 2; r++) {
+      // fresh result buffers every call, like R's allocVector: their pages are first touched by the library
+      double* o[14];
+      for (auto& q : o) q = (double*)malloc(sizeof(double) * n);
+      int32_t* it = (int32_t*)malloc(sizeof(int32_t) * n);
+      int32_t* ita = (int32_t*)malloc(sizeof(int32_t) * n);
+      double* H = (double*)malloc(sizeof(double) * (size_t)n * m);
+      double* bo = (double*)malloc(sizeof(double) * (size_t)n * p);
+      double* bv = (double*)malloc(sizeof(double) * (size_t)n * p);
+      double* sc4[4];
+      for (auto& q : sc4) q = (double*)malloc(sizeof(double) * n);
+      const auto c0 = std::chrono::steady_clock::now();
+      int rc = fdh(yc.data(), 0, x.data(), muc.data(), la0.data(), la0.data(), 1.0, log(1e-8 / 10), 1.0, 1e-6, 100, 0, nullptr, 0,
+                   1e-2, 1, n, m, p, o[0], it, ita, o[1], o[2], o[3], o[4], o[5], o[6]);
+      const auto c1 = std::chrono::steady_clock::now();
+      rc |= fdh(yc.data(), 0, x.data(), muc.data(), o[0], la0.data(), 1.0, log(1e-8 / 10), 1.0, 1e-6, 100, 1, nullptr, 0, 1e-2, 1,
+                n, m, p, o[7], it, ita, o[8], o[9], o[10], o[11], o[12], o[13]);
+      const auto c2 = std::chrono::steady_clock::now();
+      rc |= fbh(yc.data(), 0, x.data(), nfc.data(), alpha.data(), contrast.data(), b0c.data(), lam.data(), nullptr, 0, 1e-8, 100, 1,
+                0.5, n, m, p, bo, bv, sc4[0], H, sc4[1], sc4[2], sc4[3], nullptr);
+      const auto c3 = std::chrono::steady_clock::now();
+      if (rc) { printf("host call failed: %s\n", le()); return 1; }
+      if (r >= 2) {
+        t1.push_back(std::chrono::duration<double, std::milli>(c1 - c0).count());
+        t3.push_back(std::chrono::duration<double, std::milli>(c3 - c2).count());
+        tstep.push_back(std::chrono::duration<double, std::milli>(c3 - c0).count());
+      }
+      for (auto q : o) free(q);
+      for (auto q : sc4) free(q);
+      free(it); free(ita); free(H); free(bo); free(bv);
+    }
+    std::sort(tstep.begin(), tstep.end()); std::sort(t1.begin(), t1.end()); std::sort(t3.begin(), t3.end());
+    printf("host path %s: step %.2f ms (fitDisp %.2f, fitBeta %.2f; medians of %d) = %.2f M genes/s end to end\n", libs[0].c_str(),
+           tstep[tstep.size() / 2], t1[t1.size() / 2], t3[t3.size() / 2], reps, n / tstep[tstep.size() / 2] / 1e3);
+    return 0;
+  }
 
   std::vector<double> ref_la, ref_beta;
   printf("workload: %d genes x %d samples, p = %d (gene-major, resident); %d timed repetitions per kernel\n", n, m, p, reps);
