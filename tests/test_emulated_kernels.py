@@ -206,3 +206,26 @@ def test_kernel_experiments_keep_parity(tmp_path):
                        text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+def test_microbench_program_runs_against_the_emulated_engine(emu, tmp_path):
+    """scripts/microbench.cu (the Python-free A/B timer for the GPU box) compiled against the emulator's runtime header:
+    device mode on two libraries (the second must reproduce the first to rounding) and host mode with the chunked path."""
+    import subprocess
+    import build_emu
+    exe = str(tmp_path / "microbench_emu")
+    sim = os.path.join(HERE, "simt_emu")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-x", "c++", "-w", "-I", sim, "-o", exe,
+                    os.path.join(os.path.dirname(HERE), "scripts", "microbench.cu"), os.path.join(sim, "emu.cpp"), "-ldl"],
+                   check=True, capture_output=True, text=True)
+    lib = build_emu.build()
+    env = dict(os.environ, B200NB_TEST_EMULATOR="1")
+    r = subprocess.run([exe, "--genes", "150", "--samples", "24", "--reps", "1", lib, lib], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = [l for l in r.stdout.splitlines() if "fitDisp" in l and "fitBeta" in l]
+    assert len(lines) == 2 and "max|dlog_alpha| 0.00e+00" in lines[1] and "max|dbeta| 0.00e+00" in lines[1]
+    r = subprocess.run([exe, "--host", "--genes", "150", "--samples", "24", "--reps", "1", lib],
+                       env=dict(env, B200NB_CHUNK_GENES="40", B200NB_DETECT_SF="1"), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "end to end" in r.stdout, r.stdout + r.stderr
