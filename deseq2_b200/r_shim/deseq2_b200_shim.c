@@ -20,6 +20,7 @@
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
+#include <R_ext/Utils.h>
 
 #include "../../include/b200nb.h"
 
@@ -43,6 +44,7 @@ SEXP _DESeq2_fitDisp(SEXP ySEXP, SEXP xSEXP, SEXP mu_hatSEXP, SEXP log_alphaSEXP
                      SEXP log_alpha_prior_sigmasqSEXP, SEXP min_log_alphaSEXP, SEXP kappa_0SEXP, SEXP tolSEXP,
                      SEXP maxitSEXP, SEXP usePriorSEXP, SEXP weightsSEXP, SEXP useWeightsSEXP,
                      SEXP weightThresholdSEXP, SEXP useCRSEXP) {
+  R_CheckUserInterrupt();   /* the reference polls every 100 genes (src/DESeq2.cpp:195,320,493); a call here takes milliseconds */
   const int n = Rf_nrows(ySEXP), m = Rf_ncols(ySEXP), p = Rf_ncols(xSEXP);
   int yt;
   const void *y = y_ptr(ySEXP, &yt);
@@ -72,6 +74,7 @@ SEXP _DESeq2_fitDisp(SEXP ySEXP, SEXP xSEXP, SEXP mu_hatSEXP, SEXP log_alphaSEXP
 SEXP _DESeq2_fitDispGrid(SEXP ySEXP, SEXP xSEXP, SEXP mu_hatSEXP, SEXP disp_gridSEXP,
                          SEXP log_alpha_prior_meanSEXP, SEXP log_alpha_prior_sigmasqSEXP, SEXP usePriorSEXP,
                          SEXP weightsSEXP, SEXP useWeightsSEXP, SEXP weightThresholdSEXP, SEXP useCRSEXP) {
+  R_CheckUserInterrupt();   /* the reference polls every 100 genes (src/DESeq2.cpp:195,320,493); a call here takes milliseconds */
   const int n = Rf_nrows(ySEXP), m = Rf_ncols(ySEXP), p = Rf_ncols(xSEXP);
   int yt;
   const void *y = y_ptr(ySEXP, &yt);
@@ -96,6 +99,7 @@ SEXP _DESeq2_fitDispGrid(SEXP ySEXP, SEXP xSEXP, SEXP mu_hatSEXP, SEXP disp_grid
 SEXP _DESeq2_fitBeta(SEXP ySEXP, SEXP xSEXP, SEXP nfSEXP, SEXP alpha_hatSEXP, SEXP contrastSEXP, SEXP beta_matSEXP,
                      SEXP lambdaSEXP, SEXP weightsSEXP, SEXP useWeightsSEXP, SEXP tolSEXP, SEXP maxitSEXP,
                      SEXP useQRSEXP, SEXP minmuSEXP) {
+  R_CheckUserInterrupt();   /* the reference polls every 100 genes (src/DESeq2.cpp:195,320,493); a call here takes milliseconds */
   const int n = Rf_nrows(ySEXP), m = Rf_ncols(ySEXP), p = Rf_ncols(xSEXP);
   int yt;
   const void *y = y_ptr(ySEXP, &yt);

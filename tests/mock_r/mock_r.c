@@ -51,6 +51,9 @@ void mock_reset(void) {
   protect_underflow = 0;
   err_msg[0] = 0;
 }
+static int n_interrupt_checks = 0;
+void R_CheckUserInterrupt(void) { n_interrupt_checks++; }
+int mock_interrupt_checks(void) { return n_interrupt_checks; }
 int mock_protect_depth(void) { return protect_depth; }
 int mock_protect_underflow(void) { return protect_underflow; }
 const char *mock_last_error(void) { return err_msg; }

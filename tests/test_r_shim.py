@@ -161,7 +161,9 @@ def test_registration_table(r_oracle):
 def test_fitDisp_marshalling(r_oracle, oracle):
     c, ones, la = _case()
     a = disp_args(c, c["mu"], la, weights=ones)
+    before = r_oracle.lib.mock_interrupt_checks()
     got, types = r_oracle.dot_call("_DESeq2_fitDisp", *_ordered(a))
+    assert r_oracle.lib.mock_interrupt_checks() == before + 1          # user interrupts are polled, as in the reference
     assert list(got) == DISP_NAMES
     assert [types[k] for k in DISP_NAMES] == [REALSXP, INTSXP, INTSXP] + [REALSXP] * 6     # src/DESeq2.cpp:181-190
     ref = oracle.fitDisp(**a)
