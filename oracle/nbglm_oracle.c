@@ -5,9 +5,14 @@
  * deseq2_b200/csrc.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it.  The product (deseq2_b200/) never links or calls it.
  *
- * PARITY UNPINNED w.r.t. a live reference: R, Rcpp, RcppArmadillo and libRmath are absent from
- * this image, so /root/reference/src/DESeq2.cpp cannot be compiled.  This
- * is an independent restatement of the algorithm, function by function:
+ * PARITY PIN: R, Rcpp, RcppArmadillo and libRmath are absent from this image, but the reference's
+ * translation unit /root/reference/src/DESeq2.cpp IS compiled here, unchanged, against stand-in
+ * headers for the closed subset of Rcpp / Armadillo / Rmath it uses (oracle/ref_standin/, recipe
+ * oracle/Makefile `ref` -> oracle/_ref/libdeseq2_ref.so), and tests/test_oracle_vs_reference.py holds
+ * this restatement to it: identical line-search control flow on every non-knife-edge gene, 1e-9 on
+ * every fitBeta output, identical grid points.  What stays unpinned is only what the reference itself
+ * does not vendor: R's nmath (restated from the published algorithms, checked against mpmath) and
+ * LAPACK (any backward-stable p x p solve).  This file is the restatement, function by function:
  *
  *   oracle_fit_beta       <- src/DESeq2.cpp:283-465  (fitBeta: QR branch :334-383, normal-eq :388-425,
  *                                                     post-loop hat diagonal / sandwich covariance :429-455)
