@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200nb_fit_disp_grid_dev": [vp, _I, vp, vp, vp, _I, vp, _D, _I, vp, _I, _D, _I, _I, _I, _I, _LL, vp, vp],
     "b200nb_fit_beta_dev": [vp, _I, vp, vp, _I, vp, vp, vp, vp, vp, _I, _D, _I, _I, _D, _I, _I, _I, _LL]
     + [vp] * 8 + [vp],
+    "b200nb_nb_loglik_dev": [vp, _I, vp, vp, _I, vp, vp, vp, _I, _I, _I, _I, _LL, vp, vp, vp],
     "b200nb_to_gene_major_dev": [vp, vp, _I, _I, _LL, _I, vp],
     "b200nb_to_col_major_dev": [vp, vp, _I, _I, _LL, vp],
     "b200nb_prep_dev": [vp, _I, vp, vp, vp, _D, _D, _D, _D, _I, _I, _I, _LL, vp, vp, vp, vp, vp, vp, vp],

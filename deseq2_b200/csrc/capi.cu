@@ -743,6 +743,22 @@ int b200nb_fit_beta_dev(const void* y, int y_type, const double* x, const double
   return 0;
 }
 
+int b200nb_nb_loglik_dev(const void* y, int y_type, const double* x, const double* nf, int nf_is_vector,
+                         const double* alpha_hat, const double* beta_mat, const double* weights, int use_weights, int n,
+                         int m, int p, long long ld, double* out_loglik, double* out_mu, void* stream) {
+  if (check_dims(n, m, p)) return 1;
+  if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
+  if (use_weights && !weights) return fail("use_weights set but weights == NULL");
+  if (!out_loglik) return fail("out_loglik == NULL");
+  nb::LogLikArgs a{};
+  a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.x = x; a.nf = nf; a.nf_is_vector = nf_is_vector;
+  a.alpha = alpha_hat; a.beta = beta_mat; a.w = use_weights ? weights : nullptr; a.n = n; a.m = m; a.p = p; a.ld = ld;
+  a.loglik = out_loglik; a.mu_out = out_mu;
+  CU(nb::launch_nb_loglik(a, (cudaStream_t)stream));
+  if (n > 0) g_launches++;
+  return 0;
+}
+
 int b200nb_to_gene_major_dev(const void* src, void* dst, int n, int m, long long ld, int elem_size, void* stream) {
   CU(nb::launch_to_gene_major(src, dst, n, m, ld, elem_size, (cudaStream_t)stream));
   g_launches++;

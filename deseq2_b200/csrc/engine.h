@@ -105,6 +105,23 @@ struct BetaArgs {
   int G, grouped;
 };
 
+// nbinomLogLike at the unclamped fitted mean (fit_beta.cu::nb_loglik_kernel)
+struct LogLikArgs {
+  const void* y;
+  int y_is_f64;
+  const double* x;        // m x p column-major
+  const double* nf;       // gene-major n x ld, or length-m size-factor vector
+  int nf_is_vector;
+  const double* alpha;    // n
+  const double* beta;     // n x p column-major, natural log scale
+  const double* w;        // gene-major weights or nullptr
+  int n, m, p;
+  long long ld;
+  double* loglik;         // n
+  double* mu_out;         // gene-major n x ld or nullptr: nf * exp(x beta), not clamped
+};
+cudaError_t launch_nb_loglik(const LogLikArgs& a, cudaStream_t stream);
+
 // per-gene pre-steps (pipeline_kernels.cu)
 struct PrepArgs {
   const void* y;

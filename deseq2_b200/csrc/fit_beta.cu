@@ -431,7 +431,53 @@ cudaError_t launch_beta_p(const BetaArgs& a, cudaStream_t stream) {
   }
 }
 
+// ---------------------------------------------------------------- nbinomLogLike at the UNCLAMPED fitted mean
+// What R recomputes right after the native call (R/fitNbinomGLMs.R:180-182): mu = nf * exp(x beta) -- no minmu clamp --
+// and logLike = rowSums([w *] dnbinom(y, mu = mu, size = 1/alpha, log = TRUE)) (nbinomLogLike, R/core.R:2208-2217).
+// nbinomLRT's statistic is 2 (logLike_full - logLike_reduced) (R/core.R:1877) and Cook's distances use this mean
+// (R/core.R:1457): both differ from the IRLS kernel's clamped deviance / mean whenever a fitted mean sits below minmu
+// (a design cell of zeros).  One warp per gene, any p <= kMaxP, same direct-form log NB as beta_pass.
+__global__ void __launch_bounds__(256) nb_loglik_kernel(const LogLikArgs A) {
+  init_log_table();
+  init_lfact_table();
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= A.n) return;
+  const size_t off = (size_t)g * A.ld;
+  const double alpha = A.alpha[g];
+  const double r = 1.0 / alpha, log_alpha = log(alpha), lg_r = lgamma_pos(r);
+  double acc = 0.0;
+  for (int j = lane; j < A.m; j += 32) {
+    double eta = 0.0;
+    for (int k = 0; k < A.p; k++) eta = fma(__ldg(A.x + (size_t)k * A.m + j), A.beta[(size_t)g + (size_t)A.n * k], eta);
+    const double nf = A.nf_is_vector ? __ldg(A.nf + j) : A.nf[off + j];
+    const double le = eta + log(nf);
+    const double mu = (fabs(le) < 700.0) ? exp_fast(le) : exp(le);
+    if (A.mu_out != nullptr) A.mu_out[off + j] = mu;
+    const double y = A.y_is_f64 ? static_cast<const double*>(A.y)[off + j]
+                                : (double)static_cast<const int32_t*>(A.y)[off + j];
+    double t;
+    if (mu == 0.0) {
+      t = (y == 0.0) ? 0.0 : -INFINITY;            // dnbinom_mu: point mass at zero
+    } else {
+      const double am = mu * alpha, u1 = 1.0 + am;
+      const double l1p = log_pos(u1) + (am - (u1 - 1.0)) * rcp_fast(u1);
+      t = lgamma_diff(y, r, lg_r) - log_factorial(y) + fma(y, le + log_alpha, -(y + r) * l1p);
+    }
+    if (A.w != nullptr) t *= A.w[off + j];
+    acc += t;
+  }
+  acc = warp_allreduce_sum(acc);
+  if (lane == 0) A.loglik[g] = acc;
+}
+
 }  // namespace
+
+cudaError_t launch_nb_loglik(const LogLikArgs& a, cudaStream_t stream) {
+  if (a.n == 0) return cudaSuccess;
+  nb_loglik_kernel<<<(a.n + 7) / 8, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_fit_beta(const BetaArgs& a, cudaStream_t stream) {
   if (a.n == 0) return cudaSuccess;

@@ -144,6 +144,22 @@ def fit_beta(y, x, nf, alpha_hat, contrast, beta_mat, lambda_, tol, maxit, useQR
     return out
 
 
+def nb_loglik(y, x, nf, alpha_hat, beta_mat, weights=None, want_mu=True, out_mu=None):
+    """b200nb_nb_loglik_dev: the unclamped fitted mean nf * exp(x beta) and nbinomLogLike at it -- what R recomputes
+    right after fitBeta (R/fitNbinomGLMs.R:180-182).  beta_mat: (p, n) contiguous, natural-log scale.
+    Returns {"logLike": (n,), "mu": (n, ld) or None}."""
+    L = _lib.lib()
+    n, ld = y.shape
+    xd = _x_dev(x, y.device)
+    p, m = xd.shape
+    ll = torch.empty(n, dtype=F64, device=y.device)
+    mu = out_mu if out_mu is not None else (torch.empty((n, ld), dtype=F64, device=y.device) if want_mu else None)
+    rc = L.b200nb_nb_loglik_dev(_p(y), _ytype(y), _p(xd), _p(nf), int(nf.dim() == 1), _p(alpha_hat), _p(beta_mat),
+                                _p(weights), int(weights is not None), n, m, p, ld, _p(ll), _p(mu), _stream())
+    _lib.check(rc, "nb_loglik_dev")
+    return {"logLike": ll, "mu": mu}
+
+
 def x_to_device(x, device="cuda"):
     """design matrix (m, p) numpy -> device tensor of shape (p, m) contiguous == R's column-major m x p."""
     return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64).T), device=device)

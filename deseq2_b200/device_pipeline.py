@@ -166,9 +166,10 @@ def getContrast_device(ynz, x, sizeFactors, dispersion, betaMatrix, contrast, be
 
 
 def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e-8, maxit=100, minmu=0.5):
-    """nbinomLRT (R/core.R:1787-2012) on device tensors: two IRLS fits, LRT statistic 2 (l_full - l_reduced) and its
-    chi-square p-value.  The kernel's deviance is -2 log-likelihood at the fitted (minmu-clamped) mean, i.e. what
-    R/fitNbinomGLMs.R:180-182 recomputes in R whenever no fitted mean sits on the clamp."""
+    """nbinomLRT (R/core.R:1787-2012) on device tensors: two IRLS fits, LRT statistic 2 (logLike_full - logLike_reduced)
+    (R/core.R:1877) and its chi-square p-value.  The log-likelihoods are evaluated at the UNCLAMPED fitted means
+    nf * exp(x beta) as the reference does (R/fitNbinomGLMs.R:180-182) by b200nb_nb_loglik_dev -- NOT taken from the IRLS
+    kernel's deviance, which is at the minmu-clamped mean and differs by several units when a design cell is all zeros."""
     dev = ynz.device
     sfd = torch.as_tensor(np.asarray(sizeFactors, dtype=np.float64), device=dev)
     res = {}
@@ -180,11 +181,13 @@ def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e
         contrast[0] = 1.0
         lam = torch.full((p,), 1e-6 / LN2 ** 2, dtype=F64, device=dev)
         res[name] = D.fit_beta(ynz, pr["xd"], sfd, dispersion, contrast, pr["beta0"], lam, betaTol, maxit, minmu=minmu,
-                               want_hat=(name == "full"), want_mu=(name == "full"))
+                               want_hat=(name == "full"), want_mu=False)
+        ll = D.nb_loglik(ynz, pr["xd"], sfd, dispersion, res[name]["beta_mat"], want_mu=(name == "full"))
+        res[name]["logLike"], res[name]["mu"] = ll["logLike"], ll["mu"]
     df = x_full.shape[1] - x_reduced.shape[1]
-    stat = res["reduced"]["deviance"] - res["full"]["deviance"]
+    stat = 2.0 * (res["full"]["logLike"] - res["reduced"]["logLike"])
     pval = torch.special.gammaincc(torch.tensor(df / 2.0, dtype=F64, device=dev), torch.clamp(stat, min=0.0) / 2.0)
-    return {"LRTStatistic": stat, "LRTPvalue": pval, "deviance": res["full"]["deviance"], "df": df,
+    return {"LRTStatistic": stat, "LRTPvalue": pval, "deviance": -2.0 * res["full"]["logLike"], "df": df,
             "betaMatrix": (res["full"]["beta_mat"] / LN2).T,
             "betaSE": (torch.sqrt(torch.clamp(res["full"]["beta_var_mat"], min=0.0)) / LN2).T,
             "fullBetaConv": res["full"]["iter"] < maxit, "reducedBetaConv": res["reduced"]["iter"] < maxit,
@@ -237,6 +240,7 @@ def _refit_rows(ysub, x, sizeFactors, tr, varLogDispEsts, dispPriorVar, minDisp,
     betaMatrix = fb["beta_mat"] / LN2
     betaSE = torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0.0)) / LN2
     stat = betaMatrix / betaSE
+    fb["deviance"] = -2.0 * D.nb_loglik(ysub, xd, sfd, dispersion, fb["beta_mat"], want_mu=False)["logLike"]
     return {"baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP, "dispersion": dispersion,
             "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"], "betaMatrix": betaMatrix.T,
             "betaSE": betaSE.T, "WaldStatistic": stat.T, "WaldPvalue": (2.0 * torch.special.ndtr(-stat.abs())).T,
@@ -353,7 +357,7 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
     outb = {"beta_mat": torch.empty((p, nn), dtype=F64, device=dev), "beta_var_mat": torch.empty((p, nn), dtype=F64, device=dev),
             "iter": torch.empty(nn, dtype=F64, device=dev), "contrast_num": torch.empty(nn, dtype=F64, device=dev),
             "contrast_denom": torch.empty(nn, dtype=F64, device=dev), "deviance": torch.empty(nn, dtype=F64, device=dev),
-            "hat_diagonals": _ws("H", (nn, ldd), F64, dev), "mu": _ws("mu_fit", (nn, ldd), F64, dev)}
+            "hat_diagonals": _ws("H", (nn, ldd), F64, dev), "mu": None}
     fb = D.fit_beta(ynz, xd, sfd, dispersion, contrast, beta0, lam, betaTol, maxit, minmu=minmu, out=outb)
     mark("fit_beta")
     betaMatrix = fb["beta_mat"] / LN2                      # (p, n)
@@ -362,19 +366,17 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
     pval = 2.0 * torch.special.ndtr(-stat.abs())
     from .pipeline import nOrMoreInCell
     do_replace = bool(np.isfinite(minReplicatesForReplace)) and bool(nOrMoreInCell(x, minReplicatesForReplace).any())
-    # Cook's distances use the UNCLAMPED fitted mean nf * exp(x beta) that the reference recomputes in R
-    # (R/fitNbinomGLMs.R:180); the kernel's fused mean is clamped at minmu, so the entries on the clamp are redone here
-    # (elementwise torch glue; everything above the clamp keeps the kernel's value bit for bit).
-    mu_fit = fb["mu"]
-    mu_cooks = _ws("mu_cooks", (nn, ldd), F64, dev)
-    mu_cooks.copy_(mu_fit)
-    mu_cooks[:, :m] = torch.where(mu_fit[:, :m] <= minmu, sfd[None, :] * torch.exp(fb["beta_mat"].T @ xd), mu_fit[:, :m])
+    # Cook's distances and the reported deviance use the UNCLAMPED fitted mean nf * exp(x beta) and the log-likelihood
+    # at it, which the reference recomputes in R right after the native call (R/fitNbinomGLMs.R:180-182): one small
+    # kernel (b200nb_nb_loglik_dev); the IRLS kernel's fused mean / deviance are at the minmu clamp.
+    ll = D.nb_loglik(ynz, xd, sfd, dispersion, fb["beta_mat"], out_mu=_ws("mu_cooks", (nn, ldd), F64, dev))
+    mu_cooks = ll["mu"]
     ck = cooks(ynz, mu_cooks, fb["hat_diagonals"], x, sizeFactors, want_matrix=do_replace)   # R/core.R:1457-1460
     mark("wald_stats+cooks")
     res = {"stage_ms": stage_ms, "maxCooks": ck["maxCooks"], "idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
             "dispersion": dispersion, "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"],
             "betaMatrix": betaMatrix.T, "betaSE": betaSE.T, "WaldStatistic": stat.T, "WaldPvalue": pval.T,
-            "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": fb["deviance"], "mu": fb["mu"],
+            "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": -2.0 * ll["logLike"], "mu": mu_cooks,
             "H": fb["hat_diagonals"], "trendCoefs": tr[:2], "varLogDispEsts": varLogDispEsts,
             "dispPriorVar": dispPriorVar, "n_refit_geneest": n_refit_geneest, "n_refit_map": int(gi2.numel()),
             "n_input_rows": y.shape[0], "sizeFactors": np.asarray(sizeFactors, dtype=np.float64)}

@@ -87,12 +87,35 @@ def modelMatrixGroups(x):
     return len({tuple(r) for r in np.asarray(x)})
 
 
+def _stirling_tail(x):
+    xi = 1.0 / x
+    x2 = xi * xi
+    return xi * (1.0 / 12 - x2 * (1.0 / 360 - x2 * (1.0 / 1260 - x2 * (1.0 / 1680 - x2 * (1.0 / 1188)))))
+
+
+def _lgamma_diff(y, r):
+    """lgamma(y + r) - lgamma(r) without the cancellation of two ~r log r numbers (r = 1/alpha reaches 1e8, where the
+    direct difference loses ~1e-7 per sample): for r >= 10 the Stirling forms are subtracted analytically."""
+    r = np.broadcast_to(r, y.shape)
+    big = r >= 10.0
+    out = np.empty(y.shape)
+    rb, yb = r[big], y[big]
+    out[big] = yb * np.log(yb + rb) + (rb - 0.5) * np.log1p(yb / rb) - yb + _stirling_tail(yb + rb) - _stirling_tail(rb)
+    out[~big] = _sp.gammaln(y[~big] + r[~big]) - _sp.gammaln(r[~big])
+    return out
+
+
 def nbinomLogLike(counts, mu, disp):
-    """R/core.R:2208-2217 without weights (direct lgamma form; the mu-free part is included)."""
-    size = 1.0 / disp[:, None]
+    """R/core.R:2208-2217 without weights: rowSums(dnbinom(counts, mu = mu, size = 1/disp, log = TRUE)).  Evaluated in
+    the cancellation-free direct form (the same as the device kernels), with dnbinom_mu's point mass at mu = 0."""
     y = np.asarray(counts, dtype=np.float64)
-    return (_sp.gammaln(y + size) - _sp.gammaln(size) - _sp.gammaln(y + 1) + size * np.log(size / (size + mu))
-            + y * np.log(mu / (size + mu))).sum(axis=1)
+    mu = np.asarray(mu, dtype=np.float64)
+    alpha = np.asarray(disp, dtype=np.float64)[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = (_lgamma_diff(y, 1.0 / alpha) - _sp.gammaln(y + 1) + _sp.xlogy(y, mu * alpha)
+             - (y + 1.0 / alpha) * np.log1p(mu * alpha))
+    t = np.where(mu == 0, np.where(y == 0, 0.0, -np.inf), t)
+    return t.sum(axis=1)
 
 
 def estimateDispersionsGeneEst(counts, sizeFactors, x, engine=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6,

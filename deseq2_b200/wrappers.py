@@ -26,11 +26,27 @@ def _ptr(a):
 
 def _ymat(y):
     y = np.asarray(y)
+    if y.ndim != 2:
+        raise ValueError("the count matrix must be two-dimensional (genes x samples)")
     if y.dtype == np.int32:
         return np.asfortranarray(y), _Y_INT32
     if np.issubdtype(y.dtype, np.integer):
+        # R's INTSXP is 32 bit; a wider integer that does not fit is an error, never a silent wrap
+        if y.size and (y.max() > np.iinfo(np.int32).max or y.min() < np.iinfo(np.int32).min):
+            raise ValueError("integer counts exceed the int32 range of R's integer type; pass them as float64")
         return np.asfortranarray(y.astype(np.int32)), _Y_INT32
     return np.asfortranarray(y, dtype=np.float64), _Y_F64
+
+
+def _vec_n(a, n, name, fname, broadcast=False):
+    """A length-n double vector; the C ABI reads exactly n doubles, so a wrong length would be an out-of-bounds read.
+    broadcast=True accepts a scalar and repeats it (R recycles a length-1 lambda)."""
+    v = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+    if broadcast and v.size == 1 and n != 1:
+        v = np.full(n, v[0])
+    if v.size != n:
+        raise ValueError(f"{fname}: {name} has length {v.size}, expected {n}")
+    return v
 
 
 def _fmat(a):
@@ -41,10 +57,13 @@ def _vec(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def _weights(weightsSEXP, useWeightsSEXP):
+def _weights(weightsSEXP, useWeightsSEXP, shape=None, fname=""):
     if not useWeightsSEXP or weightsSEXP is None:
         return None
-    return _fmat(weightsSEXP)
+    w = _fmat(weightsSEXP)
+    if shape is not None and w.shape != shape:
+        raise ValueError(f"{fname}: weights have shape {w.shape}, expected {shape}")
+    return w
 
 
 def fitDisp(ySEXP, xSEXP, mu_hatSEXP, log_alphaSEXP, log_alpha_prior_meanSEXP, log_alpha_prior_sigmasqSEXP,
@@ -60,9 +79,9 @@ def fitDisp(ySEXP, xSEXP, mu_hatSEXP, log_alphaSEXP, log_alpha_prior_meanSEXP, l
     p = x.shape[1]
     if x.shape[0] != m or mu.shape != (n, m):
         raise ValueError("fitDisp: non-conformable arguments")
-    la = _vec(log_alphaSEXP)
-    pm = _vec(log_alpha_prior_meanSEXP)
-    w = _weights(weightsSEXP, useWeightsSEXP)
+    la = _vec_n(log_alphaSEXP, n, "log_alpha", "fitDisp")
+    pm = _vec_n(log_alpha_prior_meanSEXP, n, "log_alpha_prior_mean", "fitDisp")
+    w = _weights(weightsSEXP, useWeightsSEXP, (n, m), "fitDisp")
     out = {k: np.empty(n) for k in ("log_alpha", "last_change", "initial_lp", "initial_dlp", "last_lp", "last_dlp",
                                     "last_d2lp")}
     out["iter"] = np.empty(n, dtype=np.int32)
@@ -88,9 +107,11 @@ def fitDispGrid(ySEXP, xSEXP, mu_hatSEXP, disp_gridSEXP, log_alpha_prior_meanSEX
     mu = _fmat(mu_hatSEXP)
     n, m = y.shape
     p = x.shape[1]
+    if x.shape[0] != m or mu.shape != (n, m):
+        raise ValueError("fitDispGrid: non-conformable arguments")
     grid = _vec(disp_gridSEXP)
-    pm = _vec(log_alpha_prior_meanSEXP)
-    w = _weights(weightsSEXP, useWeightsSEXP)
+    pm = _vec_n(log_alpha_prior_meanSEXP, n, "log_alpha_prior_mean", "fitDispGrid")
+    w = _weights(weightsSEXP, useWeightsSEXP, (n, m), "fitDispGrid")
     la = np.empty(n)
     rc = L.b200nb_fit_disp_grid(_ptr(y), yt, _ptr(x), _ptr(mu), _ptr(grid), len(grid), _ptr(pm),
                                 float(log_alpha_prior_sigmasqSEXP), int(bool(usePriorSEXP)), _ptr(w),
@@ -113,11 +134,14 @@ def fitBeta(ySEXP, xSEXP, nfSEXP, alpha_hatSEXP, contrastSEXP, beta_matSEXP, lam
     p = x.shape[1]
     if x.shape[0] != m or nf.shape != (n, m):
         raise ValueError("fitBeta: non-conformable arguments")
-    alpha = _vec(alpha_hatSEXP)
-    contrast = _vec(contrastSEXP)
-    beta0 = _fmat(np.asarray(beta_matSEXP, dtype=np.float64).reshape(n, p))
-    lam = _vec(lambdaSEXP)
-    w = _weights(weightsSEXP, useWeightsSEXP)
+    alpha = _vec_n(alpha_hatSEXP, n, "alpha_hat", "fitBeta")
+    contrast = _vec_n(contrastSEXP, p, "contrast", "fitBeta")
+    beta0 = np.asarray(beta_matSEXP, dtype=np.float64)
+    if beta0.size != n * p:
+        raise ValueError(f"fitBeta: beta_mat has {beta0.size} elements, expected {n} x {p}")
+    beta0 = _fmat(beta0.reshape(n, p))
+    lam = _vec_n(lambdaSEXP, p, "lambda", "fitBeta", broadcast=True)
+    w = _weights(weightsSEXP, useWeightsSEXP, (n, m), "fitBeta")
     beta = np.empty((n, p), order="F")
     var = np.empty((n, p), order="F")
     it = np.empty(n)

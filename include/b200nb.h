@@ -91,6 +91,15 @@ int b200nb_fit_beta_dev(const void* y, int y_type, const double* x, const double
                         double* out_contrast_num, double* out_contrast_denom, double* out_deviance, double* out_mu,
                         void* stream);
 
+/* b200nb_nb_loglik_dev: what R recomputes right after fitBeta (R/fitNbinomGLMs.R:180-182): the fitted mean
+ * mu = nf * exp(x beta) WITHOUT the minmu clamp (out_mu, gene-major n x ld, may be NULL) and
+ * logLike = rowSums([w *] dnbinom(y, mu, size = 1/alpha, log = TRUE)) (nbinomLogLike, R/core.R:2208-2217; out_loglik[n]).
+ * nbinomLRT's statistic (R/core.R:1877) and Cook's distances (R/core.R:1457) are built from these, not from the
+ * clamped quantities inside the IRLS.  beta_mat: n x p column-major, natural-log scale (fitBeta's out_beta_mat). */
+int b200nb_nb_loglik_dev(const void* y, int y_type, const double* x, const double* nf, int nf_is_vector,
+                         const double* alpha_hat, const double* beta_mat, const double* weights, int use_weights, int n,
+                         int m, int p, long long ld, double* out_loglik, double* out_mu, void* stream);
+
 /* layout helpers on device buffers: R column-major n x m <-> gene-major n x ld.  elem_size 4 (int32) or 8. */
 int b200nb_to_gene_major_dev(const void* src_colmajor, void* dst, int n, int m, long long ld, int elem_size,
                              void* stream);
