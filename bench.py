@@ -61,7 +61,7 @@ def build_workload(n, m, seed, engine):
     x, sf = d["x"], d["sizeFactors"]
     ge = pipeline.estimateDispersionsGeneEst(counts, sf, x, engine=engine)
     tf = pipeline.estimateDispersionsFit(ge["dispGeneEst"], ge["baseMean"])
-    pv = pipeline.estimateDispersionsPriorVar(tf["varLogDispEsts"], m, x.shape[1])
+    pv = pipeline.estimateDispersionsPriorVar(tf["varLogDispEsts"], m, x.shape[1], ge["dispGeneEst"], tf["dispFit"])
     mp = pipeline.estimateDispersionsMAP(counts, x, ge["mu"], ge["dispGeneEst"], tf["dispFit"], pv,
                                          tf["varLogDispEsts"], engine=engine)
     norm = counts / sf[None, :]

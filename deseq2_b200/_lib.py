@@ -42,7 +42,8 @@ SIGNATURES = {
     "b200nb_fit_disp_grid_dev": [vp, _I, vp, vp, vp, _I, vp, _D, _I, vp, _I, _D, _I, _I, _I, _I, _LL, vp, vp],
     "b200nb_fit_beta_dev": [vp, _I, vp, vp, _I, vp, vp, vp, vp, vp, _I, _D, _I, _I, _D, _I, _I, _I, _LL]
     + [vp] * 8 + [vp],
-    "b200nb_nb_loglik_dev": [vp, _I, vp, vp, _I, vp, vp, vp, _I, _I, _I, _I, _LL, vp, vp, vp],
+    "b200nb_nb_loglik_dev": [vp, _I, vp, vp, _I, vp, vp, vp, _I, _D, _I, _I, _I, _LL, vp, vp, vp],
+    "b200nb_beta_optim_dev": [vp, _I, vp, vp, _I, vp, vp, vp, vp, _I, _I, _I, _I, _I, _LL, vp, vp, vp, vp],
     "b200nb_to_gene_major_dev": [vp, vp, _I, _I, _LL, _I, vp],
     "b200nb_to_col_major_dev": [vp, vp, _I, _I, _LL, vp],
     "b200nb_prep_dev": [vp, _I, vp, vp, vp, _D, _D, _D, _D, _I, _I, _I, _LL, vp, vp, vp, vp, vp, vp, vp],
@@ -53,6 +54,8 @@ SIGNATURES = {
     "b200nb_device_count": [],
     "b200nb_kernel_launches": [],
     "b200nb_release_workspace": [],
+    "b200nb_cache_clear": [],
+    "b200nb_host_stats": [vp, _I],
     "b200nb_version": [],
     "b200nb_test_special": [vp, _I, vp, vp, vp],
 }
@@ -61,6 +64,7 @@ _RESTYPE = {
     "b200nb_version": C.c_char_p,
     "b200nb_kernel_launches": C.c_longlong,
     "b200nb_release_workspace": None,
+    "b200nb_cache_clear": None,
 }
 
 

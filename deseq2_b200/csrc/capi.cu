@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of libb200nb.so (declared in include/b200nb.h).
-// Host entry points: H2D copy of R-layout buffers -> device transpose to gene-major -> kernels ->
-// (transpose back) -> D2H.  Device entry points: enqueue only.  No CPU fallback anywhere.
+// Host entry points: R-layout pageable buffers -> (content-addressed device cache | pinned staging -> H2D -> device
+// transpose to gene-major) -> kernels -> (transpose back) -> D2H through the pinned ring into the caller's result
+// buffers.  Device entry points: enqueue only.  No CPU fallback anywhere.
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -11,12 +12,14 @@
 
 #include <atomic>
 #include <chrono>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
 
 #include "../../include/b200nb.h"
 #include "engine.h"
+#include "hostrt.h"
 
 namespace {
 
@@ -37,74 +40,392 @@ int fail(const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-// grow-only device workspace of the host entry points (one set per process; calls are serialised)
+std::mutex g_call_mu;    // host entry points are serialised (one workspace / cache / pinned ring per process)
+std::mutex g_arena_mu;   // guards the (re)allocation of the shared device arenas below
+
+// ---------------------------------------------------------------- device workspace of the host entry points
+// grow-only slots (one set per process; calls are serialised)
 enum Slot {
-  S_RAW0, S_RAW1, S_RAW2, S_Y, S_MU, S_W, S_NF, S_X, S_V0, S_V1, S_V2, S_OUTD, S_OUTI, S_H, S_MUO, S_HC, S_MUC,
-  S_BETA_IN, S_BETA_OUT, S_BETA_VAR, S_NSLOTS
+  S_RAW, S_SMALL_IN, S_SMALL_OUT, S_NF, S_H, S_MUO, S_HC, S_NSLOTS
 };
 struct Workspace {
   void* p[S_NSLOTS] = {};
   size_t bytes[S_NSLOTS] = {};
   cudaStream_t stream = nullptr;
 };
-
-// ---------------------------------------------------------------- pinned staging for pageable host buffers
-// R hands over ordinary (pageable) memory.  cudaMemcpy from pageable memory runs at ~9 GB/s on the GPU box;
-// staging through a ring of pinned buffers filled by a few host threads while the previous chunk is in flight
-// reaches PCIe speed.  B200NB_STAGE_THREADS (default 8; 4..16 measure the same) OpenMP workers do the host-side memcpy.
-// bytes per pinned staging buffer: 16 MB as measured in round 1; B200NB_STAGE_CHUNK_MB (1..256) is a knob for the next
-// GPU session (smaller chunks start the first DMA sooner, larger ones pay fewer event round trips)
-size_t stage_chunk_bytes() {
-  static const size_t v = [] {
-    const char* e = getenv("B200NB_STAGE_CHUNK_MB");
-    long mb = e ? atol(e) : 16;
-    if (mb < 1 || mb > 256) mb = 16;
-    return (size_t)mb << 20;
-  }();
-  return v;
-}
-#define kStageChunk (stage_chunk_bytes())   // kept as a name: the copy routines below read like the fixed-size originals
-constexpr int kStageRing = 3;
-struct Staging {
-  void* buf[kStageRing] = {};
-  cudaEvent_t ev[kStageRing] = {};
-  bool ready = false;
-};
-
-// Host-side context of the host entry points: device workspace, stream and pinned staging ring.  Context 0 belongs
-// to the calling thread; contexts 1.. are used by the extra worker threads of the gene-chunked path (opt-in, see
-// run_chunked below), each with its own stream so that one worker's copies overlap another worker's kernels.
-struct HostCtx {
-  Workspace ws;
-  Staging stage;
-};
-constexpr int kMaxWorkers = 4;
-HostCtx g_ctx[kMaxWorkers];
-thread_local HostCtx* t_ctx = &g_ctx[0];
-std::mutex g_call_mu;    // host entry points are serialised (one set of contexts per process)
-std::mutex g_arena_mu;   // guards the (re)allocation of the shared device arenas below
-inline Workspace& cur_ws() { return t_ctx->ws; }        // the calling thread's context
-inline Staging& cur_stage() { return t_ctx->stage; }
+Workspace g_ws;
 
 int ws_get(Slot s, size_t bytes, void** out) {
   if (bytes == 0) bytes = 16;
-  if (cur_ws().bytes[s] < bytes) {
-    if (cur_ws().p[s]) cudaFree(cur_ws().p[s]);
-    cur_ws().p[s] = nullptr;
-    cur_ws().bytes[s] = 0;
+  if (g_ws.bytes[s] < bytes) {
+    if (g_ws.p[s]) cudaFree(g_ws.p[s]);
+    g_ws.p[s] = nullptr;
+    g_ws.bytes[s] = 0;
     size_t want = bytes + bytes / 8;
-    CU(cudaMalloc(&cur_ws().p[s], want));
-    cur_ws().bytes[s] = want;
+    CU(cudaMalloc(&g_ws.p[s], want));
+    g_ws.bytes[s] = want;
   }
-  *out = cur_ws().p[s];
+  *out = g_ws.p[s];
   return 0;
 }
 
 int ws_stream(cudaStream_t* st) {
-  if (!cur_ws().stream) CU(cudaStreamCreateWithFlags(&cur_ws().stream, cudaStreamNonBlocking));
-  *st = cur_ws().stream;
+  if (!g_ws.stream) CU(cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking));
+  *st = g_ws.stream;
   return 0;
 }
+
+// ---------------------------------------------------------------- host worker pool (hostrt.h)
+// B200NB_HOST_THREADS (default min(16, CPUs of the GPU's NUMA node that the process may use)); B200NB_NUMA_BIND=0
+// keeps the workers on the caller's affinity mask instead of the GPU's node.
+std::unique_ptr<hostrt::Pool> g_pool;
+hostrt::Pool& pool() {
+  if (!g_pool || g_pool->pid() != getpid()) {
+    if (g_pool) (void)g_pool.release();   // forked child: the parent's threads are not ours to join
+    std::vector<int> cpus;
+    if (hostrt::env_int("B200NB_NUMA_BIND", 1, 0, 1)) {
+      int dev = 0;
+      char bus[64] = "";
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) == cudaSuccess)
+        cpus = hostrt::node_cpus(hostrt::pci_numa_node(bus));
+    }
+    const int avail = cpus.empty() ? hostrt::affinity_count() : (int)cpus.size();
+    int dflt = avail < 16 ? avail : 16;
+    if (dflt < 1) dflt = 1;
+    g_pool.reset(new hostrt::Pool(hostrt::env_int("B200NB_HOST_THREADS", dflt, 1, 128), cpus));
+  }
+  return *g_pool;
+}
+
+// traffic / cache statistics of the host entry points (b200nb_host_stats)
+std::atomic<long long> g_h2d_bytes{0}, g_d2h_bytes{0}, g_cache_hits{0}, g_cache_misses{0}, g_cache_hit_bytes{0},
+    g_hashed_bytes{0};
+
+// ---------------------------------------------------------------- pinned staging ring
+// R hands over ordinary (pageable) memory; cudaMemcpy from pageable memory runs at ~9 GB/s on the GPU box.  A ring of
+// pinned buffers filled by the pool while the previous buffer is in flight reaches PCIe speed.
+constexpr size_t kStageChunk = (size_t)8 << 20;
+constexpr int kStageRing = 4;
+constexpr size_t kBlock = (size_t)512 << 10;   // unit of work of one pool task
+struct Staging {
+  void* buf[kStageRing] = {};
+  cudaEvent_t ev[kStageRing] = {};
+  void* small = nullptr;        // pinned scratch for the packed small vectors (grow-only)
+  size_t small_bytes = 0;
+  bool ready = false;
+};
+Staging g_stage;
+int stage_init() {
+  if (g_stage.ready) return 0;
+  for (int i = 0; i < kStageRing; i++) {
+    CU(cudaHostAlloc(&g_stage.buf[i], kStageChunk, cudaHostAllocDefault));
+    CU(cudaEventCreateWithFlags(&g_stage.ev[i], cudaEventDisableTiming));
+  }
+  g_stage.ready = true;
+  return 0;
+}
+int stage_small(size_t bytes, void** out) {
+  if (g_stage.small_bytes < bytes) {
+    if (g_stage.small) cudaFreeHost(g_stage.small);
+    g_stage.small = nullptr;
+    g_stage.small_bytes = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    CU(cudaHostAlloc(&g_stage.small, want, cudaHostAllocDefault));
+    g_stage.small_bytes = want;
+  }
+  *out = g_stage.small;
+  return 0;
+}
+
+void par_memcpy(void* dst, const void* src, size_t bytes) {
+  if (bytes < (1u << 20)) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t nb = (bytes + kBlock - 1) / kBlock;
+  pool().parallel_for(nb, [&](size_t b) {
+    const size_t lo = b * kBlock, hi = (lo + kBlock < bytes) ? lo + kBlock : bytes;
+    memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
+  });
+}
+
+hostrt::Hash128 par_hash(const void* src, size_t bytes) {
+  const size_t nb = (bytes + kBlock - 1) / kBlock;
+  std::vector<hostrt::Hash128> part(nb);
+  pool().parallel_for(nb, [&](size_t b) {
+    const size_t lo = b * kBlock, hi = (lo + kBlock < bytes) ? lo + kBlock : bytes;
+    part[b] = hostrt::hash_range(static_cast<const char*>(src) + lo, hi - lo, lo / 8);
+  });
+  hostrt::Hash128 h;
+  for (const auto& q : part) h.add(q);
+  g_hashed_bytes += (long long)bytes;
+  return h;
+}
+
+// pageable host -> device through the pinned ring; when `hash` is given the content hash is computed on the way (each
+// task hashes the block it has just copied, from the pinned copy, while it is still in its cache)
+int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st, hostrt::Hash128* hash) {
+  if (hash) *hash = hostrt::Hash128();
+  if (bytes == 0) return 0;
+  if (stage_init()) return 1;
+  size_t off = 0;
+  for (int k = 0; off < bytes; k++) {
+    const int b = k % kStageRing;
+    const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
+    if (k >= kStageRing) CU(cudaEventSynchronize(g_stage.ev[b]));
+    char* pin = static_cast<char*>(g_stage.buf[b]);
+    const char* s = static_cast<const char*>(src) + off;
+    const size_t nb = (len + kBlock - 1) / kBlock;
+    std::vector<hostrt::Hash128> part(hash ? nb : 0);
+    pool().parallel_for(nb, [&](size_t t) {
+      const size_t lo = t * kBlock, hi = (lo + kBlock < len) ? lo + kBlock : len;
+      memcpy(pin + lo, s + lo, hi - lo);
+      if (hash) part[t] = hostrt::hash_range(pin + lo, hi - lo, (off + lo) / 8);
+    });
+    if (hash)
+      for (const auto& q : part) hash->add(q);
+    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, pin, len, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(g_stage.ev[b], st));
+    off += len;
+  }
+  // the ring is reused by the next transfer: drain it
+  for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(g_stage.ev[b]));
+  g_h2d_bytes += (long long)bytes;
+  return 0;
+}
+
+// device -> pageable host through the pinned ring; synchronous on return
+int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if (stage_init()) return 1;
+  const size_t nchunk = (bytes + kStageChunk - 1) / kStageChunk;
+  auto issue = [&](size_t k) -> int {
+    const int b = (int)(k % kStageRing);
+    const size_t off = k * kStageChunk;
+    const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
+    CU(cudaMemcpyAsync(g_stage.buf[b], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(g_stage.ev[b], st));
+    return 0;
+  };
+  for (size_t k = 0; k < nchunk && k < (size_t)kStageRing - 1; k++)
+    if (issue(k)) return 1;
+  for (size_t k = 0; k < nchunk; k++) {
+    if (k + kStageRing - 1 < nchunk && issue(k + kStageRing - 1)) return 1;
+    const int b = (int)(k % kStageRing);
+    const size_t off = k * kStageChunk;
+    const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
+    CU(cudaEventSynchronize(g_stage.ev[b]));
+    par_memcpy(static_cast<char*>(dst) + off, g_stage.buf[b], len);
+  }
+  g_d2h_bytes += (long long)bytes;
+  return 0;
+}
+
+// ---------------------------------------------------------------- content-addressed device cache of input matrices
+// One DESeq() run hands the SAME count matrix to fitDisp (MLE), fitDisp (MAP) and fitBeta, and the same fitted means to
+// both fitDisp calls -- but as fresh R copies (objectNZ <- object[!allZero, ], R/core.R:706, 1016, 1405), so neither
+// the pointer nor the SEXP identifies them.  Their CONTENT does: every large input matrix is hashed (128 bit, all
+// bytes, by the pool -- a pure read at memory bandwidth, cheaper than staging it through pinned memory and PCIe), and
+// a matrix whose (rows, columns, element size, hash) is already resident on the device in gene-major form is not
+// uploaded again.  On a miss the hash is computed while the matrix is staged, so it costs no extra pass.  LRU, bounded
+// by B200NB_CACHE_MB (default 8192; 0 disables the cache) and kCacheEntries.
+constexpr int kCacheEntries = 8;
+struct CacheEntry {
+  bool valid = false;
+  size_t n = 0;
+  int m = 0, elem = 0;
+  hostrt::Hash128 hash;
+  void* dev = nullptr;     // gene-major n x ld
+  size_t cap = 0;          // bytes allocated at dev
+  uint64_t last_use = 0;
+};
+CacheEntry g_cache[kCacheEntries];
+uint64_t g_cache_clock = 0;
+size_t cache_limit_bytes() {
+  static const size_t v = (size_t)hostrt::env_int("B200NB_CACHE_MB", 8192, 0, 1 << 20) << 20;
+  return v;
+}
+void cache_clear(bool free_memory) {
+  for (auto& e : g_cache) {
+    e.valid = false;
+    if (free_memory && e.dev) {
+      cudaFree(e.dev);
+      e.dev = nullptr;
+      e.cap = 0;
+    }
+  }
+}
+
+long long ld_for(int m) { return ((long long)m + 3) & ~3LL; }
+
+// Column-major host matrix (n x m, elem 4 or 8) -> gene-major device matrix, through the cache.
+int upload_matrix(const void* host, int n, int m, int elem, cudaStream_t st, void** out) {
+  const long long ld = ld_for(m);
+  const size_t bytes = (size_t)n * m * elem, dbytes = (size_t)n * ld * elem + 64;
+  const bool use_cache = cache_limit_bytes() >= dbytes;
+  hostrt::Hash128 h;
+  bool have_hash = false;
+  if (use_cache) {
+    bool candidate = false;
+    for (const auto& e : g_cache) candidate = candidate || (e.valid && e.n == (size_t)n && e.m == m && e.elem == elem);
+    if (candidate) {
+      h = par_hash(host, bytes);
+      have_hash = true;
+      for (auto& e : g_cache)
+        if (e.valid && e.n == (size_t)n && e.m == m && e.elem == elem && e.hash == h) {
+          e.last_use = ++g_cache_clock;
+          g_cache_hits++;
+          g_cache_hit_bytes += (long long)bytes;
+          *out = e.dev;
+          return 0;
+        }
+    }
+  }
+  // miss: pick the destination (an invalid or the least recently used entry; evict while over the byte limit)
+  CacheEntry* dst = nullptr;
+  if (use_cache) {
+    g_cache_misses++;
+    for (auto& e : g_cache)
+      if (!e.valid && (!dst || e.cap >= dbytes)) dst = &e;
+    if (!dst) {
+      for (auto& e : g_cache)
+        if (!dst || e.last_use < dst->last_use) dst = &e;
+    }
+    dst->valid = false;
+    size_t total = 0;
+    for (const auto& e : g_cache) total += (&e == dst) ? 0 : e.cap;
+    while (total + dbytes > cache_limit_bytes()) {
+      CacheEntry* victim = nullptr;
+      for (auto& e : g_cache)
+        if (&e != dst && e.cap > 0 && (!victim || e.last_use < victim->last_use)) victim = &e;
+      if (!victim) break;
+      total -= victim->cap;
+      cudaFree(victim->dev);
+      victim->dev = nullptr;
+      victim->cap = 0;
+      victim->valid = false;
+    }
+    if (dst->cap < dbytes) {
+      if (dst->dev) cudaFree(dst->dev);
+      dst->dev = nullptr;
+      dst->cap = 0;
+      CU(cudaMalloc(&dst->dev, dbytes + dbytes / 16));
+      dst->cap = dbytes + dbytes / 16;
+    }
+  }
+  void *d_raw, *d_dst;
+  if (ws_get(S_RAW, bytes, &d_raw)) return 1;
+  if (dst) {
+    d_dst = dst->dev;
+  } else {
+    // cache disabled / matrix larger than the cache: a plain workspace slot per role would alias two uploads of one
+    // call, so such matrices get their own allocation, freed by the caller's epilogue (see UploadGuard)
+    CU(cudaMalloc(&d_dst, dbytes));
+  }
+  if (h2d_staged(d_raw, host, bytes, st, (use_cache && !have_hash) ? &h : nullptr)) return 1;
+  CU(nb::launch_to_gene_major(d_raw, d_dst, n, m, ld, elem, st));
+  g_launches++;
+  if (dst) {
+    dst->valid = true;
+    dst->n = (size_t)n;
+    dst->m = m;
+    dst->elem = elem;
+    dst->hash = h;
+    dst->last_use = ++g_cache_clock;
+  }
+  *out = d_dst;
+  return 0;
+}
+
+// owns the uncached uploads of one call (freed when the call ends, after its final stream synchronisation)
+struct UploadGuard {
+  std::vector<void*> owned;
+  int get(const void* host, int n, int m, int elem, cudaStream_t st, void** out) {
+    const size_t dbytes = (size_t)n * ld_for(m) * elem + 64;
+    const bool cached = cache_limit_bytes() >= dbytes;
+    if (upload_matrix(host, n, m, elem, st, out)) return 1;
+    if (!cached) owned.push_back(*out);
+    return 0;
+  }
+  ~UploadGuard() {
+    for (void* p : owned) cudaFree(p);
+  }
+};
+
+// Packs small host vectors into one pinned buffer -> one H2D copy; add() returns the device address the piece will have.
+struct SmallIn {
+  std::vector<std::pair<const void*, size_t>> parts;
+  size_t total = 0;
+  size_t add(const void* p, size_t bytes) {
+    const size_t off = total;
+    parts.emplace_back(p, bytes);
+    total += (bytes + 15) & ~(size_t)15;
+    return off;
+  }
+  int upload(cudaStream_t st, char** dev_base) {
+    void *pin, *dev;
+    if (stage_small(total, &pin)) return 1;
+    if (ws_get(S_SMALL_IN, total, &dev)) return 1;
+    size_t off = 0;
+    for (const auto& q : parts) {
+      memcpy(static_cast<char*>(pin) + off, q.first, q.second);
+      off += (q.second + 15) & ~(size_t)15;
+    }
+    CU(cudaMemcpyAsync(dev, pin, total, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // the pinned scratch is reused by the packed download of the same call
+    g_h2d_bytes += (long long)total;
+    *dev_base = static_cast<char*>(dev);
+    return 0;
+  }
+};
+
+// One D2H copy of a packed device region into pinned memory, then scattered to the caller's vectors.
+struct SmallOut {
+  struct Part { void* host; size_t off, bytes; };
+  std::vector<Part> parts;
+  size_t total = 0;
+  size_t add(void* host, size_t bytes) {
+    const size_t off = total;
+    parts.push_back({host, off, bytes});
+    total += (bytes + 15) & ~(size_t)15;
+    return off;
+  }
+  int device(char** dev_base) {
+    void* dev;
+    if (ws_get(S_SMALL_OUT, total, &dev)) return 1;
+    *dev_base = static_cast<char*>(dev);
+    return 0;
+  }
+  int download(const char* dev_base, cudaStream_t st) {
+    void* pin;
+    if (stage_small(total, &pin)) return 1;
+    CU(cudaMemcpyAsync(pin, dev_base, total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (const auto& q : parts)
+      if (q.host) memcpy(q.host, static_cast<const char*>(pin) + q.off, q.bytes);
+    g_d2h_bytes += (long long)total;
+    return 0;
+  }
+};
+
+// Background population of a freshly allocated result matrix (see hostrt.h); joined before the scatter.
+struct Populate {
+  std::vector<std::thread> th;
+  void start(void* p, size_t bytes) {
+    if (!p || bytes < ((size_t)4 << 20) || !hostrt::env_int("B200NB_POPULATE", 1, 0, 1)) return;
+    const int T = 4;
+    for (int t = 0; t < T; t++) {
+      char* lo = static_cast<char*>(p) + bytes * t / T;
+      char* hi = static_cast<char*>(p) + bytes * (t + 1) / T;
+      th.emplace_back([lo, hi] { hostrt::populate_write(lo, (size_t)(hi - lo)); });
+    }
+  }
+  void join() {
+    for (auto& t : th) t.join();
+    th.clear();
+  }
+  ~Populate() { join(); }
+};
 
 // device-side work-queue counters: a ring of slots, one per launch, so launches in flight on different
 // streams never share a counter (a slot is reused only after kRing further launches).
@@ -118,208 +439,6 @@ int next_counter(unsigned int** out) {
   return 0;
 }
 
-int stage_threads() {
-  static int t = [] {
-    const char* e = getenv("B200NB_STAGE_THREADS");
-    int v = e ? atoi(e) : 8;
-    return v < 1 ? 1 : (v > 64 ? 64 : v);
-  }();
-  return t;
-}
-int stage_init() {
-  if (cur_stage().ready) return 0;
-  for (int i = 0; i < kStageRing; i++) {
-    CU(cudaHostAlloc(&cur_stage().buf[i], kStageChunk, cudaHostAllocDefault));
-    CU(cudaEventCreateWithFlags(&cur_stage().ev[i], cudaEventDisableTiming));
-  }
-  cur_stage().ready = true;
-  return 0;
-}
-
-// Large result matrices (hat_diagonals, mu) land in memory the caller has just allocated: every 4 KB page of it is
-// first touched by the D2H scatter, which was measured to run at ~6 GB/s for that reason.  Two opt-in knobs for the
-// next GPU session (both off by default: not timed yet): B200NB_D2H_HUGEPAGE=1 asks the kernel for transparent huge
-// pages on the destination range before it is touched (512x fewer faults); B200NB_D2H_THREADS=<T> uses a different
-// number of host threads for the device-to-host scatter than for the host-to-device gather.
-int d2h_threads() {
-  static int t = [] {
-    const char* e = getenv("B200NB_D2H_THREADS");
-    int v = e ? atoi(e) : 0;
-    return v < 1 ? stage_threads() : (v > 64 ? 64 : v);
-  }();
-  return t;
-}
-void advise_hugepages(void* p, size_t bytes) {
-  static const bool on = [] {
-    const char* e = getenv("B200NB_D2H_HUGEPAGE");
-    return e && atoi(e) != 0;
-  }();
-  if (!on || bytes < (8u << 20)) return;
-  const uintptr_t huge = (uintptr_t)2 << 20;
-  const uintptr_t lo = ((uintptr_t)p + huge - 1) & ~(huge - 1), hi = ((uintptr_t)p + bytes) & ~(huge - 1);
-  if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);   // a hint: failure is harmless
-}
-
-// B200NB_D2H_POPULATE=1 (opt-in, not yet timed on the GPU box): each copying thread first asks the kernel to populate
-// the page tables of its destination slice in one call (MADV_POPULATE_WRITE, Linux >= 5.14) instead of taking one page
-// fault per 4 KB while it copies; on the build container that took a 40 MB first-touch scatter from 3.7 to 2.7 ms.
-#ifndef MADV_POPULATE_WRITE
-#define MADV_POPULATE_WRITE 23
-#endif
-bool d2h_populate() {
-  static const bool on = [] {
-    const char* e = getenv("B200NB_D2H_POPULATE");
-    return e && atoi(e) != 0;
-  }();
-  return on;
-}
-
-void par_memcpy(void* dst, const void* src, size_t bytes, int T = 0, bool populate_dst = false) {
-  if (bytes < (1u << 20)) {
-    memcpy(dst, src, bytes);
-    return;
-  }
-  if (T <= 0) T = stage_threads();
-#pragma omp parallel for num_threads(T) schedule(static)
-  for (int t = 0; t < T; t++) {
-    const size_t lo = bytes * t / T, hi = bytes * (t + 1) / T;
-    if (populate_dst) {
-      const uintptr_t a = ((uintptr_t)dst + lo + 4095) & ~(uintptr_t)4095, b = ((uintptr_t)dst + hi) & ~(uintptr_t)4095;
-      if (b > a) madvise(reinterpret_cast<void*>(a), b - a, MADV_POPULATE_WRITE);   // a hint: failure is harmless
-    }
-    memcpy(static_cast<char*>(dst) + lo, static_cast<const char*>(src) + lo, hi - lo);
-  }
-}
-
-int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
-  if (bytes <= (256u << 10)) {
-    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
-    return 0;
-  }
-  if (stage_init()) return 1;
-  size_t off = 0;
-  for (int k = 0; off < bytes; k++) {
-    const int b = k % kStageRing;
-    const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
-    if (k >= kStageRing) CU(cudaEventSynchronize(cur_stage().ev[b]));
-    par_memcpy(cur_stage().buf[b], static_cast<const char*>(src) + off, len);
-    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, cur_stage().buf[b], len, cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(cur_stage().ev[b], st));
-    off += len;
-  }
-  // the ring is reused by the next transfer: drain it
-  for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(cur_stage().ev[b]));
-  return 0;
-}
-
-// device -> pageable host through the pinned ring; synchronous on return
-int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
-  if (bytes <= (256u << 10)) {
-    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return 0;
-  }
-  if (stage_init()) return 1;
-  const size_t nchunk = (bytes + kStageChunk - 1) / kStageChunk;
-  auto issue = [&](size_t k) -> int {
-    const int b = (int)(k % kStageRing);
-    const size_t off = k * kStageChunk;
-    const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
-    CU(cudaMemcpyAsync(cur_stage().buf[b], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(cur_stage().ev[b], st));
-    return 0;
-  };
-  for (size_t k = 0; k < nchunk && k < (size_t)kStageRing - 1; k++)
-    if (issue(k)) return 1;
-  for (size_t k = 0; k < nchunk; k++) {
-    if (k + kStageRing - 1 < nchunk && issue(k + kStageRing - 1)) return 1;
-    const int b = (int)(k % kStageRing);
-    const size_t off = k * kStageChunk;
-    const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
-    CU(cudaEventSynchronize(cur_stage().ev[b]));
-    par_memcpy(static_cast<char*>(dst) + off, cur_stage().buf[b], len, d2h_threads(), d2h_populate());
-  }
-  return 0;
-}
-
-// ---- row blocks of column-major host matrices (the gene-chunked path) ----------------------------------------
-// `host` is a column-major matrix with n_total rows (R layout); the block is rows [g0, g0 + gc) of its m columns and
-// lives on the device as a contiguous column-major gc x m matrix.  gc == n_total is the whole matrix: the contiguous
-// routines above.  Otherwise whole column segments are gathered into / scattered from the pinned ring.
-int h2d_block(void* dst, const void* host, size_t n_total, size_t g0, size_t gc, int m, int elem, cudaStream_t st) {
-  if (gc == n_total) return h2d_staged(dst, host, gc * m * elem, st);
-  const size_t col = gc * elem;
-  const char* src = static_cast<const char*>(host);
-  if (col * m <= (256u << 10) || col > kStageChunk) {
-    for (int j = 0; j < m; j++) {
-      const void* seg = src + ((size_t)j * n_total + g0) * elem;
-      if (col > kStageChunk) {
-        if (h2d_staged(static_cast<char*>(dst) + j * col, seg, col, st)) return 1;
-      } else {
-        CU(cudaMemcpyAsync(static_cast<char*>(dst) + j * col, seg, col, cudaMemcpyHostToDevice, st));
-      }
-    }
-    return 0;
-  }
-  if (stage_init()) return 1;
-  const int cpc = (int)(kStageChunk / col);   // whole columns per staging buffer (>= 1)
-  const int T = stage_threads();
-  int j = 0;
-  for (int k = 0; j < m; k++) {
-    const int b = k % kStageRing;
-    const int nc = (m - j < cpc) ? m - j : cpc;
-    if (k >= kStageRing) CU(cudaEventSynchronize(cur_stage().ev[b]));
-    char* buf = static_cast<char*>(cur_stage().buf[b]);
-#pragma omp parallel for num_threads(T) schedule(static) if (nc * col >= (1u << 20))
-    for (int c = 0; c < nc; c++) memcpy(buf + (size_t)c * col, src + ((size_t)(j + c) * n_total + g0) * elem, col);
-    CU(cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)j * col, buf, (size_t)nc * col, cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(cur_stage().ev[b], st));
-    j += nc;
-  }
-  for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(cur_stage().ev[b]));
-  return 0;
-}
-
-// device (contiguous column-major gc x m) -> rows [g0, g0 + gc) of the column-major host matrix; synchronous on return
-int d2h_block(void* host, const void* src, size_t n_total, size_t g0, size_t gc, int m, int elem, cudaStream_t st) {
-  if (gc == n_total) return d2h_staged(host, src, gc * m * elem, st);
-  const size_t col = gc * elem;
-  char* dst = static_cast<char*>(host);
-  if (col * m <= (256u << 10) || col > kStageChunk) {
-    for (int j = 0; j < m; j++) {
-      void* seg = dst + ((size_t)j * n_total + g0) * elem;
-      if (col > kStageChunk) {
-        if (d2h_staged(seg, static_cast<const char*>(src) + j * col, col, st)) return 1;
-      } else {
-        CU(cudaMemcpyAsync(seg, static_cast<const char*>(src) + j * col, col, cudaMemcpyDeviceToHost, st));
-      }
-    }
-    CU(cudaStreamSynchronize(st));
-    return 0;
-  }
-  if (stage_init()) return 1;
-  const int cpc = (int)(kStageChunk / col);
-  const int T = d2h_threads();
-  const int nbatch = (m + cpc - 1) / cpc;
-  auto issue = [&](int k) -> int {
-    const int b = k % kStageRing, j = k * cpc, nc = (m - j < cpc) ? m - j : cpc;
-    CU(cudaMemcpyAsync(cur_stage().buf[b], static_cast<const char*>(src) + (size_t)j * col, (size_t)nc * col,
-                       cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(cur_stage().ev[b], st));
-    return 0;
-  };
-  for (int k = 0; k < nbatch && k < kStageRing - 1; k++)
-    if (issue(k)) return 1;
-  for (int k = 0; k < nbatch; k++) {
-    if (k + kStageRing - 1 < nbatch && issue(k + kStageRing - 1)) return 1;
-    const int b = k % kStageRing, j = k * cpc, nc = (m - j < cpc) ? m - j : cpc;
-    CU(cudaEventSynchronize(cur_stage().ev[b]));
-    const char* buf = static_cast<const char*>(cur_stage().buf[b]);
-#pragma omp parallel for num_threads(T) schedule(static) if (nc * col >= (1u << 20))
-    for (int c = 0; c < nc; c++) memcpy(dst + ((size_t)(j + c) * n_total + g0) * elem, buf + (size_t)c * col, col);
-  }
-  return 0;
-}
 
 // scratch buffers for fit_disp launches (work queue + per-mode gene lists): ONE device arena cut into a ring of
 // equal slots, one slot per launch in flight (slot reuse after kScratchRing further launches; launches on one stream
@@ -486,38 +605,11 @@ int check_dims(int n, int m, int p) {
   return 0;
 }
 
-long long ld_for(int m) { return ((long long)m + 3) & ~3LL; }
-
-// Rows [g0, g0 + n) of a column-major host matrix with n_total rows: copy to the device, convert to gene-major.
-int upload_matrix(const void* host, int n_total, int g0, int n, int m, int elem, Slot raw, Slot dst, cudaStream_t st,
-                  void** out) {
-  void *d_raw, *d_dst;
-  const long long ld = ld_for(m);
-  if (ws_get(raw, (size_t)n * m * elem, &d_raw)) return 1;
-  if (ws_get(dst, (size_t)n * ld * elem + 64, &d_dst)) return 1;
-  if (h2d_block(d_raw, host, (size_t)n_total, (size_t)g0, (size_t)n, m, elem, st)) return 1;
-  CU(nb::launch_to_gene_major(d_raw, d_dst, n, m, ld, elem, st));
-  g_launches++;
-  *out = d_dst;
-  return 0;
-}
-
-int upload_vec(const void* host, size_t bytes, Slot s, cudaStream_t st, void** out) {
-  void* d;
-  if (ws_get(s, bytes, &d)) return 1;
-  CU(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st));
-  *out = d;
-  return 0;
-}
-
-// B200NB_HOST_TIMING=1: the host entry points print where their wall time goes (upload incl. layout conversion /
-// kernels / download) to stderr; it adds a stream synchronisation between the phases, so it is a diagnosis aid, not
-// something to leave on while measuring.
+// B200NB_HOST_TIMING=1: the host entry points print where their wall time goes (hashing + upload incl. layout
+// conversion / kernels / download) to stderr; it adds a stream synchronisation between the phases, so it is a
+// diagnosis aid, not something to leave on while measuring.
 bool host_timing() {
-  static const bool on = [] {
-    const char* e = getenv("B200NB_HOST_TIMING");
-    return e && atoi(e) != 0;
-  }();
+  static const bool on = hostrt::env_int("B200NB_HOST_TIMING", 0, 0, 1) != 0;
   return on;
 }
 struct PhaseClock {
@@ -526,8 +618,12 @@ struct PhaseClock {
   int phase = 0;
   bool on;
   cudaStream_t st;
+  long long h2d0, d2h0, hit0, hashed0;
   explicit PhaseClock(cudaStream_t s) : on(host_timing()), st(s) {
-    if (on) t0 = std::chrono::steady_clock::now();
+    if (on) {
+      t0 = std::chrono::steady_clock::now();
+      h2d0 = g_h2d_bytes; d2h0 = g_d2h_bytes; hit0 = g_cache_hit_bytes; hashed0 = g_hashed_bytes;
+    }
   }
   void next() {   // close the current phase
     if (!on || phase > 2) return;
@@ -536,80 +632,21 @@ struct PhaseClock {
     ms[phase++] = std::chrono::duration<double, std::milli>(t1 - t0).count();
     t0 = t1;
   }
-  void report(const char* what, int g0, int n) {
-    if (on) fprintf(stderr, "b200nb timing %s genes [%d, %d): upload %.3f ms, kernels %.3f ms, download %.3f ms\n", what, g0,
-                    g0 + n, ms[0], ms[1], ms[2]);
+  void report(const char* what, int n) {
+    if (on)
+      fprintf(stderr, "b200nb timing %s %d genes: hash+upload %.3f ms, kernels %.3f ms, download %.3f ms | H2D %.1f MB, "
+                      "D2H %.1f MB, hashed %.1f MB, served from the device cache %.1f MB\n", what, n, ms[0], ms[1], ms[2],
+              (g_h2d_bytes - h2d0) / 1e6, (g_d2h_bytes - d2h0) / 1e6, (g_hashed_bytes - hashed0) / 1e6,
+              (g_cache_hit_bytes - hit0) / 1e6);
   }
 };
-
-// ---------------------------------------------------------------- gene-chunked host path (opt-in)
-// B200NB_CHUNK_GENES=<genes per chunk> splits one host call into gene chunks that B200NB_CHUNK_WORKERS (default 2,
-// max 4) host threads process independently -- each with its own stream, device workspace and pinned ring -- so that
-// one chunk's H2D staging overlaps another chunk's kernels and D2H.  Genes are independent, so the results are those
-// of the unchunked call.  Off by default (0): it has not been timed on the GPU yet.
-int chunk_genes() {
-  static int v = [] {
-    const char* e = getenv("B200NB_CHUNK_GENES");
-    const int g = e ? atoi(e) : 0;
-    return g < 0 ? 0 : g;
-  }();
-  return v;
-}
-int chunk_workers() {
-  static int v = [] {
-    const char* e = getenv("B200NB_CHUNK_WORKERS");
-    const int w = e ? atoi(e) : 2;
-    return w < 1 ? 1 : (w > kMaxWorkers ? kMaxWorkers : w);
-  }();
-  return v;
-}
-
-// body(g0, count) handles genes [g0, g0 + count) through the current thread's context; returns non-zero on failure
-// with the message in the thread-local g_err.
-template <typename F>
-int run_chunked(int n, F&& body) {
-  const int want = chunk_genes();
-  if (want <= 0 || n < 2 * want) return body(0, n);
-  const int K = (n + want - 1) / want;
-  const int gc = (n + K - 1) / K;                       // balanced chunks
-  const int W = chunk_workers() < K ? chunk_workers() : K;
-  std::atomic<int> next{0}, failed{0};
-  char errs[kMaxWorkers][sizeof(g_err)];
-  for (int w = 0; w < kMaxWorkers; w++) errs[w][0] = 0;
-  auto work = [&](int w) {
-    t_ctx = &g_ctx[w];
-    if (w > 0 && g_bound_device >= 0) cudaSetDevice(g_bound_device);
-    for (;;) {
-      const int k = next.fetch_add(1);
-      if (k >= K || failed.load()) break;
-      const int g0 = k * gc, cnt = (n - g0 < gc) ? n - g0 : gc;
-      if (cnt <= 0) break;
-      if (body(g0, cnt)) {
-        memcpy(errs[w], g_err, sizeof(g_err));
-        failed.store(1);
-        break;
-      }
-    }
-    t_ctx = &g_ctx[0];
-  };
-  std::vector<std::thread> pool;
-  for (int w = 1; w < W; w++) pool.emplace_back(work, w);
-  work(0);
-  for (auto& t : pool) t.join();
-  if (failed.load()) {
-    for (int w = 0; w < kMaxWorkers; w++)
-      if (errs[w][0]) { memcpy(g_err, errs[w], sizeof(g_err)); break; }
-    return 1;
-  }
-  return 0;
-}
 
 }  // namespace
 
 extern "C" {
 
 const char* b200nb_last_error(void) { return g_err; }
-const char* b200nb_version(void) { return "b200nb 0.1 (sm_100a)"; }
+const char* b200nb_version(void) { return "b200nb 0.2 (sm_100a)"; }
 long long b200nb_kernel_launches(void) { return g_launches.load(); }
 
 int b200nb_device_count(void) {
@@ -621,25 +658,37 @@ int b200nb_device_count(void) {
   return c;
 }
 
+void b200nb_cache_clear(void) {
+  std::lock_guard<std::mutex> lk(g_call_mu);
+  cache_clear(false);
+}
+
+int b200nb_host_stats(long long* out, int n) {
+  const long long v[6] = {g_h2d_bytes.load(), g_d2h_bytes.load(), g_cache_hits.load(), g_cache_misses.load(),
+                          g_cache_hit_bytes.load(), g_hashed_bytes.load()};
+  for (int i = 0; i < n && i < 6; i++) out[i] = v[i];
+  return 6;
+}
+
 void b200nb_release_workspace(void) {
   std::lock_guard<std::mutex> lk(g_call_mu);
-  for (int c = 0; c < kMaxWorkers; c++) {
-    Workspace& ws = g_ctx[c].ws;
-    Staging& sg = g_ctx[c].stage;
-    for (int s = 0; s < S_NSLOTS; s++) {
-      if (ws.p[s]) cudaFree(ws.p[s]);
-      ws.p[s] = nullptr;
-      ws.bytes[s] = 0;
-    }
-    if (sg.ready) {
-      for (int i = 0; i < kStageRing; i++) {
-        cudaFreeHost(sg.buf[i]);
-        cudaEventDestroy(sg.ev[i]);
-        sg.buf[i] = nullptr;
-      }
-      sg.ready = false;
-    }
+  cache_clear(true);
+  for (int s = 0; s < S_NSLOTS; s++) {
+    if (g_ws.p[s]) cudaFree(g_ws.p[s]);
+    g_ws.p[s] = nullptr;
+    g_ws.bytes[s] = 0;
   }
+  if (g_stage.ready) {
+    for (int i = 0; i < kStageRing; i++) {
+      cudaFreeHost(g_stage.buf[i]);
+      cudaEventDestroy(g_stage.ev[i]);
+      g_stage.buf[i] = nullptr;
+    }
+    g_stage.ready = false;
+  }
+  if (g_stage.small) cudaFreeHost(g_stage.small);
+  g_stage.small = nullptr;
+  g_stage.small_bytes = 0;
 }
 
 /* ------------------------------------------------------------------ device entry points */
@@ -744,8 +793,9 @@ int b200nb_fit_beta_dev(const void* y, int y_type, const double* x, const double
 }
 
 int b200nb_nb_loglik_dev(const void* y, int y_type, const double* x, const double* nf, int nf_is_vector,
-                         const double* alpha_hat, const double* beta_mat, const double* weights, int use_weights, int n,
-                         int m, int p, long long ld, double* out_loglik, double* out_mu, void* stream) {
+                         const double* alpha_hat, const double* beta_mat, const double* weights, int use_weights,
+                         double minmu, int n, int m, int p, long long ld, double* out_loglik, double* out_mu,
+                         void* stream) {
   if (check_dims(n, m, p)) return 1;
   if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
   if (use_weights && !weights) return fail("use_weights set but weights == NULL");
@@ -753,8 +803,26 @@ int b200nb_nb_loglik_dev(const void* y, int y_type, const double* x, const doubl
   nb::LogLikArgs a{};
   a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.x = x; a.nf = nf; a.nf_is_vector = nf_is_vector;
   a.alpha = alpha_hat; a.beta = beta_mat; a.w = use_weights ? weights : nullptr; a.n = n; a.m = m; a.p = p; a.ld = ld;
-  a.loglik = out_loglik; a.mu_out = out_mu;
+  a.minmu = minmu > 0.0 ? minmu : 0.0; a.loglik = out_loglik; a.mu_out = out_mu;
   CU(nb::launch_nb_loglik(a, (cudaStream_t)stream));
+  if (n > 0) g_launches++;
+  return 0;
+}
+
+int b200nb_beta_optim_dev(const void* y, int y_type, const double* x, const double* nf, int nf_is_vector,
+                          const double* alpha_hat, const double* lambda, const double* beta_start,
+                          const double* weights, int use_weights, int maxit, int n, int m, int p, long long ld,
+                          double* out_beta_mat, int32_t* out_converged, int32_t* out_iter, void* stream) {
+  if (check_dims(n, m, p)) return 1;
+  if (ld < m || (ld & 3)) return fail("ld=%lld must be >= m and a multiple of 4", ld);
+  if (use_weights && !weights) return fail("use_weights set but weights == NULL");
+  if (maxit < 1) return fail("maxit must be >= 1");
+  nb::OptimArgs a{};
+  a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.x = x; a.nf = nf; a.nf_is_vector = nf_is_vector;
+  a.alpha = alpha_hat; a.lambda = lambda; a.beta_in = beta_start; a.w = use_weights ? weights : nullptr;
+  a.bound = 30.0 * 0.693147180559945309417232121458; a.maxit = maxit; a.n = n; a.m = m; a.p = p; a.ld = ld;
+  a.beta_out = out_beta_mat; a.converged = out_converged; a.iter = out_iter;
+  CU(nb::launch_beta_optim(a, (cudaStream_t)stream));
   if (n > 0) g_launches++;
   return 0;
 }
@@ -827,51 +895,6 @@ int b200nb_size_factors_dev(const void* y, int y_type, int poscounts, int n, int
 }
 
 /* ------------------------------------------------------------------ host entry points */
-/* Each entry point validates, takes the call lock and hands gene blocks [g0, g0 + n) of the caller's R-layout arrays
- * (n_total rows) to a *_block routine; without B200NB_CHUNK_GENES there is one block, the whole call. */
-
-static int fit_disp_block(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,
-                          const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
-                          double kappa_0, double tol, int maxit, int use_prior, const double* weights,
-                          int use_weights, double weight_threshold, int use_cr, int n_total, int g0, int n, int m,
-                          int p, double* out_log_alpha, int32_t* out_iter, int32_t* out_iter_accept,
-                          double* out_last_change, double* out_initial_lp, double* out_initial_dlp,
-                          double* out_last_lp, double* out_last_dlp, double* out_last_d2lp) {
-  cudaStream_t st;
-  if (ws_stream(&st)) return 1;
-  PhaseClock clk(st);
-  const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
-  const long long ld = ld_for(m);
-  void *d_y, *d_mu, *d_w = nullptr, *d_x, *d_la, *d_pm, *d_outd, *d_outi;
-  if (upload_matrix(y, n_total, g0, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
-  if (upload_matrix(mu_hat, n_total, g0, n, m, 8, S_RAW1, S_MU, st, &d_mu)) return 1;
-  if (use_weights && upload_matrix(weights, n_total, g0, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
-  if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
-  if (upload_vec(log_alpha + g0, sizeof(double) * n, S_V0, st, &d_la)) return 1;
-  if (upload_vec(log_alpha_prior_mean + g0, sizeof(double) * n, S_V1, st, &d_pm)) return 1;
-  if (ws_get(S_OUTD, sizeof(double) * 7 * n, &d_outd)) return 1;
-  if (ws_get(S_OUTI, sizeof(int32_t) * 2 * n, &d_outi)) return 1;
-  double* od = (double*)d_outd;
-  int32_t* oi = (int32_t*)d_outi;
-  clk.next();
-  if (b200nb_fit_disp_dev(d_y, y_type, (const double*)d_x, (const double*)d_mu, (const double*)d_la,
-                          (const double*)d_pm, log_alpha_prior_sigmasq, min_log_alpha, kappa_0, tol, maxit, use_prior,
-                          (const double*)d_w, use_weights, weight_threshold, use_cr, n, m, p, ld, od, oi, oi + n,
-                          od + n, od + 2 * (size_t)n, od + 3 * (size_t)n, od + 4 * (size_t)n, od + 5 * (size_t)n,
-                          od + 6 * (size_t)n, st))
-    return 1;
-  clk.next();
-  double* outs[7] = {out_log_alpha, out_last_change, out_initial_lp, out_initial_dlp, out_last_lp, out_last_dlp,
-                     out_last_d2lp};
-  for (int k = 0; k < 7; k++)
-    CU(cudaMemcpyAsync(outs[k] + g0, od + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_iter + g0, oi, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_iter_accept + g0, oi + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  clk.next();
-  clk.report("fitDisp", g0, n);
-  return 0;
-}
 
 int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu_hat, const double* log_alpha,
                     const double* log_alpha_prior_mean, double log_alpha_prior_sigmasq, double min_log_alpha,
@@ -882,43 +905,44 @@ int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu
                     double* out_last_d2lp) {
   if (check_dims(n, m, p)) return 1;
   if (n == 0) return 0;
+  if (use_weights && !weights) return fail("use_weights set but weights == NULL");
   std::lock_guard<std::mutex> lk(g_call_mu);
-  auto block = [&](int g0, int cnt) {
-    return fit_disp_block(y, y_type, x, mu_hat, log_alpha, log_alpha_prior_mean, log_alpha_prior_sigmasq, min_log_alpha,
-                          kappa_0, tol, maxit, use_prior, weights, use_weights, weight_threshold, use_cr, n, g0, cnt, m,
-                          p, out_log_alpha, out_iter, out_iter_accept, out_last_change, out_initial_lp,
-                          out_initial_dlp, out_last_lp, out_last_dlp, out_last_d2lp);
-  };
-  if (use_generic(p)) return block(0, n);   // the general-p path analyses the design with a stream sync per launch
-  unsigned int* presize;
-  if (next_scratch(nb::disp_scratch_bytes(n), &presize)) return 1;   // size the shared arena before workers start
-  return run_chunked(n, block);
-}
-
-static int fit_disp_grid_block(const void* y, int y_type, const double* x, const double* mu_hat,
-                               const double* disp_grid, int disp_grid_n, const double* log_alpha_prior_mean,
-                               double log_alpha_prior_sigmasq, int use_prior, const double* weights, int use_weights,
-                               double weight_threshold, int use_cr, int n_total, int g0, int n, int m, int p,
-                               double* out_log_alpha) {
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
+  PhaseClock clk(st);
   const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
   const long long ld = ld_for(m);
-  void *d_y, *d_mu, *d_w = nullptr, *d_x, *d_grid, *d_pm, *d_out;
-  if (upload_matrix(y, n_total, g0, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
-  if (upload_matrix(mu_hat, n_total, g0, n, m, 8, S_RAW1, S_MU, st, &d_mu)) return 1;
-  if (use_weights && upload_matrix(weights, n_total, g0, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
-  if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
-  if (upload_vec(disp_grid, sizeof(double) * disp_grid_n, S_V0, st, &d_grid)) return 1;
-  if (upload_vec(log_alpha_prior_mean + g0, sizeof(double) * n, S_V1, st, &d_pm)) return 1;
-  if (ws_get(S_OUTD, sizeof(double) * n, &d_out)) return 1;
-  if (b200nb_fit_disp_grid_dev(d_y, y_type, (const double*)d_x, (const double*)d_mu, (const double*)d_grid,
-                               disp_grid_n, (const double*)d_pm, log_alpha_prior_sigmasq, use_prior,
-                               (const double*)d_w, use_weights, weight_threshold, use_cr, n, m, p, ld, (double*)d_out,
-                               st))
+  UploadGuard up;
+  void *d_y, *d_mu, *d_w = nullptr;
+  if (up.get(y, n, m, ye, st, &d_y)) return 1;
+  if (up.get(mu_hat, n, m, 8, st, &d_mu)) return 1;
+  if (use_weights && up.get(weights, n, m, 8, st, &d_w)) return 1;
+  SmallIn in;
+  const size_t o_x = in.add(x, sizeof(double) * m * p), o_la = in.add(log_alpha, sizeof(double) * n),
+               o_pm = in.add(log_alpha_prior_mean, sizeof(double) * n);
+  char* din;
+  if (in.upload(st, &din)) return 1;
+  SmallOut out;
+  double* hd[7] = {out_log_alpha, out_last_change, out_initial_lp, out_initial_dlp, out_last_lp, out_last_dlp,
+                   out_last_d2lp};
+  size_t od[7];
+  for (int k = 0; k < 7; k++) od[k] = out.add(hd[k], sizeof(double) * n);
+  const size_t oi = out.add(out_iter, sizeof(int32_t) * n), oia = out.add(out_iter_accept, sizeof(int32_t) * n);
+  char* dout;
+  if (out.device(&dout)) return 1;
+  clk.next();
+  auto D = [&](size_t off) { return reinterpret_cast<double*>(dout + off); };
+  if (b200nb_fit_disp_dev(d_y, y_type, reinterpret_cast<const double*>(din + o_x), (const double*)d_mu,
+                          reinterpret_cast<const double*>(din + o_la), reinterpret_cast<const double*>(din + o_pm),
+                          log_alpha_prior_sigmasq, min_log_alpha, kappa_0, tol, maxit, use_prior, (const double*)d_w,
+                          use_weights, weight_threshold, use_cr, n, m, p, ld, D(od[0]),
+                          reinterpret_cast<int32_t*>(dout + oi), reinterpret_cast<int32_t*>(dout + oia), D(od[1]),
+                          D(od[2]), D(od[3]), D(od[4]), D(od[5]), D(od[6]), st))
     return 1;
-  CU(cudaMemcpyAsync(out_log_alpha + g0, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  clk.next();
+  if (out.download(dout, st)) return 1;
+  clk.next();
+  clk.report("fitDisp", n);
   return 0;
 }
 
@@ -928,36 +952,46 @@ int b200nb_fit_disp_grid(const void* y, int y_type, const double* x, const doubl
                          int n, int m, int p, double* out_log_alpha) {
   if (check_dims(n, m, p)) return 1;
   if (n == 0) return 0;
+  if (use_weights && !weights) return fail("use_weights set but weights == NULL");
+  if (disp_grid_n < 2) return fail("disp_grid needs at least 2 points");
   std::lock_guard<std::mutex> lk(g_call_mu);
-  auto block = [&](int g0, int cnt) {
-    return fit_disp_grid_block(y, y_type, x, mu_hat, disp_grid, disp_grid_n, log_alpha_prior_mean,
-                               log_alpha_prior_sigmasq, use_prior, weights, use_weights, weight_threshold, use_cr, n,
-                               g0, cnt, m, p, out_log_alpha);
-  };
-  if (use_generic(p)) return block(0, n);
-  unsigned int* presize;
-  if (next_scratch(nb::disp_scratch_bytes(n), &presize)) return 1;
-  return run_chunked(n, block);
+  cudaStream_t st;
+  if (ws_stream(&st)) return 1;
+  const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
+  const long long ld = ld_for(m);
+  UploadGuard up;
+  void *d_y, *d_mu, *d_w = nullptr;
+  if (up.get(y, n, m, ye, st, &d_y)) return 1;
+  if (up.get(mu_hat, n, m, 8, st, &d_mu)) return 1;
+  if (use_weights && up.get(weights, n, m, 8, st, &d_w)) return 1;
+  SmallIn in;
+  const size_t o_x = in.add(x, sizeof(double) * m * p), o_grid = in.add(disp_grid, sizeof(double) * disp_grid_n),
+               o_pm = in.add(log_alpha_prior_mean, sizeof(double) * n);
+  char* din;
+  if (in.upload(st, &din)) return 1;
+  SmallOut out;
+  const size_t o_la = out.add(out_log_alpha, sizeof(double) * n);
+  char* dout;
+  if (out.device(&dout)) return 1;
+  if (b200nb_fit_disp_grid_dev(d_y, y_type, reinterpret_cast<const double*>(din + o_x), (const double*)d_mu,
+                               reinterpret_cast<const double*>(din + o_grid), disp_grid_n,
+                               reinterpret_cast<const double*>(din + o_pm), log_alpha_prior_sigmasq, use_prior,
+                               (const double*)d_w, use_weights, weight_threshold, use_cr, n, m, p, ld,
+                               reinterpret_cast<double*>(dout + o_la), st))
+    return 1;
+  return out.download(dout, st);
 }
 
-// B200NB_DETECT_SF=1 (opt-in, not yet timed): R always hands fitBeta an n x m matrix of normalisation factors, which for
-// the usual size-factor analysis is the same row n times (R/core.R:2221-2228).  One parallel read of the matrix tells;
-// if so, only the m factors cross PCIe and the kernel takes its size-factor-vector path (log nf once per CTA instead
-// of once per gene and sample).  Same values in, same results out; any NaN or differing entry keeps the matrix path.
-static bool detect_sf() {
-  static const bool on = [] {
-    const char* e = getenv("B200NB_DETECT_SF");
-    return e && atoi(e) != 0;
-  }();
-  return on;
-}
+// R always hands fitBeta an n x m matrix of normalisation factors, which for the usual size-factor analysis is the same
+// row n times (R/core.R:2221-2228).  One parallel read of the matrix tells (it stops at the first differing entry); if
+// so, only the m factors cross PCIe and the kernel takes its size-factor-vector path (log nf once per CTA instead of
+// once per gene and sample).  Same values in, same results out; any NaN or differing entry keeps the matrix path.
+// B200NB_SF_DETECT=0 switches the check off.
 static bool rows_identical(const double* a, size_t n, int m) {
   std::atomic<int> differs{0};
-  const int T = stage_threads();
-#pragma omp parallel for num_threads(T) schedule(dynamic, 1)
-  for (int j = 0; j < m; j++) {
-    if (differs.load(std::memory_order_relaxed)) continue;
-    const double* c = a + (size_t)j * n;
+  pool().parallel_for((size_t)m, [&](size_t j) {
+    if (differs.load(std::memory_order_relaxed)) return;
+    const double* c = a + j * n;
     const double v = c[0];
     bool same = (v == v);
     for (size_t i0 = 0; i0 < n && same; i0 += 4096) {
@@ -967,80 +1001,8 @@ static bool rows_identical(const double* a, size_t n, int m) {
       same = !bad;
     }
     if (!same) differs.store(1, std::memory_order_relaxed);
-  }
+  });
   return differs.load() == 0;
-}
-
-static int fit_beta_block(const void* y, int y_type, const double* x, const double* nf, const double* sf_vector,
-                          const double* alpha_hat,
-                          const double* contrast, const double* beta_mat, const double* lambda,
-                          const double* weights, int use_weights, double tol, int maxit, int use_qr, double minmu,
-                          int n_total, int g0, int n, int m, int p, double* out_beta_mat, double* out_beta_var_mat,
-                          double* out_iter, double* out_hat_diagonals, double* out_contrast_num,
-                          double* out_contrast_denom, double* out_deviance, double* out_mu) {
-  cudaStream_t st;
-  if (ws_stream(&st)) return 1;
-  PhaseClock clk(st);
-  const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
-  const long long ld = ld_for(m);
-  void *d_y, *d_nf, *d_w = nullptr, *d_x, *d_alpha, *d_contrast, *d_lambda, *d_bin, *d_bout, *d_bvar, *d_outd;
-  void *d_h = nullptr, *d_mu = nullptr, *d_hc = nullptr, *d_muc = nullptr;
-  if (upload_matrix(y, n_total, g0, n, m, ye, S_RAW0, S_Y, st, &d_y)) return 1;
-  if (sf_vector) {
-    if (upload_vec(sf_vector, sizeof(double) * m, S_NF, st, &d_nf)) return 1;
-  } else {
-    if (upload_matrix(nf, n_total, g0, n, m, 8, S_RAW1, S_NF, st, &d_nf)) return 1;
-  }
-  if (use_weights && upload_matrix(weights, n_total, g0, n, m, 8, S_RAW2, S_W, st, &d_w)) return 1;
-  if (upload_vec(x, sizeof(double) * m * p, S_X, st, &d_x)) return 1;
-  if (upload_vec(alpha_hat + g0, sizeof(double) * n, S_V0, st, &d_alpha)) return 1;
-  if (upload_vec(contrast, sizeof(double) * p, S_V1, st, &d_contrast)) return 1;
-  if (upload_vec(lambda, sizeof(double) * p, S_V2, st, &d_lambda)) return 1;
-  if (ws_get(S_BETA_IN, sizeof(double) * n * p, &d_bin)) return 1;
-  if (h2d_block(d_bin, beta_mat, (size_t)n_total, (size_t)g0, (size_t)n, p, 8, st)) return 1;
-  if (ws_get(S_BETA_OUT, sizeof(double) * n * p, &d_bout)) return 1;
-  if (ws_get(S_BETA_VAR, sizeof(double) * n * p, &d_bvar)) return 1;
-  if (ws_get(S_OUTD, sizeof(double) * 4 * n, &d_outd)) return 1;
-  if (out_hat_diagonals) {
-    if (ws_get(S_H, sizeof(double) * n * ld, &d_h)) return 1;
-    if (ws_get(S_HC, sizeof(double) * n * m, &d_hc)) return 1;
-  }
-  if (out_mu) {
-    if (ws_get(S_MUO, sizeof(double) * n * ld, &d_mu)) return 1;
-    if (ws_get(S_MUC, sizeof(double) * n * m, &d_muc)) return 1;
-  }
-  double* od = (double*)d_outd;
-  clk.next();
-  if (b200nb_fit_beta_dev(d_y, y_type, (const double*)d_x, (const double*)d_nf, sf_vector ? 1 : 0, (const double*)d_alpha,
-                          (const double*)d_contrast, (const double*)d_bin, (const double*)d_lambda,
-                          (const double*)d_w, use_weights, tol, maxit, use_qr, minmu, n, m, p, ld, (double*)d_bout,
-                          (double*)d_bvar, od, (double*)d_h, od + n, od + 2 * (size_t)n, od + 3 * (size_t)n,
-                          (double*)d_mu, st))
-    return 1;
-  clk.next();
-  if (out_hat_diagonals) {
-    if (b200nb_to_col_major_dev((const double*)d_h, (double*)d_hc, n, m, ld, st)) return 1;
-    if (d2h_block(out_hat_diagonals, d_hc, (size_t)n_total, (size_t)g0, (size_t)n, m, 8, st)) return 1;
-  }
-  if (out_mu) {
-    if (b200nb_to_col_major_dev((const double*)d_mu, (double*)d_muc, n, m, ld, st)) return 1;
-    if (d2h_block(out_mu, d_muc, (size_t)n_total, (size_t)g0, (size_t)n, m, 8, st)) return 1;
-  }
-  if (n == n_total) {
-    CU(cudaMemcpyAsync(out_beta_mat, d_bout, sizeof(double) * n * p, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out_beta_var_mat, d_bvar, sizeof(double) * n * p, cudaMemcpyDeviceToHost, st));
-  } else {
-    if (d2h_block(out_beta_mat, d_bout, (size_t)n_total, (size_t)g0, (size_t)n, p, 8, st)) return 1;
-    if (d2h_block(out_beta_var_mat, d_bvar, (size_t)n_total, (size_t)g0, (size_t)n, p, 8, st)) return 1;
-  }
-  CU(cudaMemcpyAsync(out_iter + g0, od, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_contrast_num + g0, od + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_contrast_denom + g0, od + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_deviance + g0, od + 3 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  clk.next();
-  clk.report("fitBeta", g0, n);
-  return 0;
 }
 
 int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf, const double* alpha_hat,
@@ -1050,22 +1012,68 @@ int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf
                     double* out_contrast_num, double* out_contrast_denom, double* out_deviance, double* out_mu) {
   if (check_dims(n, m, p)) return 1;
   if (n == 0) return 0;
+  if (use_weights && !weights) return fail("use_weights set but weights == NULL");
   std::lock_guard<std::mutex> lk(g_call_mu);
-  if (out_hat_diagonals) advise_hugepages(out_hat_diagonals, sizeof(double) * (size_t)n * m);
-  if (out_mu) advise_hugepages(out_mu, sizeof(double) * (size_t)n * m);
+  cudaStream_t st;
+  if (ws_stream(&st)) return 1;
+  PhaseClock clk(st);
+  // the result matrices are fresh allocations of the caller: fault their pages in while the GPU works
+  Populate pop_h, pop_mu;
+  pop_h.start(out_hat_diagonals, sizeof(double) * (size_t)n * m);
+  pop_mu.start(out_mu, sizeof(double) * (size_t)n * m);
+  const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
+  const long long ld = ld_for(m);
+  UploadGuard up;
+  void *d_y, *d_nf = nullptr, *d_w = nullptr;
   std::vector<double> sfv;
-  if (detect_sf() && rows_identical(nf, (size_t)n, m)) {
+  if (hostrt::env_int("B200NB_SF_DETECT", 1, 0, 1) && rows_identical(nf, (size_t)n, m)) {
     sfv.resize(m);
     for (int j = 0; j < m; j++) sfv[j] = nf[(size_t)j * n];
+    g_hashed_bytes += (long long)sizeof(double) * n * m;   // bytes read on the host instead of being uploaded
   }
-  const double* sf_vector = sfv.empty() ? nullptr : sfv.data();
-  auto block = [&](int g0, int cnt) {
-    return fit_beta_block(y, y_type, x, nf, sf_vector, alpha_hat, contrast, beta_mat, lambda, weights, use_weights, tol, maxit,
-                          use_qr, minmu, n, g0, cnt, m, p, out_beta_mat, out_beta_var_mat, out_iter, out_hat_diagonals,
-                          out_contrast_num, out_contrast_denom, out_deviance, out_mu);
-  };
-  if (use_generic(p)) return block(0, n);
-  return run_chunked(n, block);
+  if (up.get(y, n, m, ye, st, &d_y)) return 1;
+  if (sfv.empty() && up.get(nf, n, m, 8, st, &d_nf)) return 1;
+  if (use_weights && up.get(weights, n, m, 8, st, &d_w)) return 1;
+  SmallIn in;
+  const size_t o_x = in.add(x, sizeof(double) * m * p), o_alpha = in.add(alpha_hat, sizeof(double) * n),
+               o_c = in.add(contrast, sizeof(double) * p), o_lam = in.add(lambda, sizeof(double) * p),
+               o_b = in.add(beta_mat, sizeof(double) * n * p),
+               o_sf = sfv.empty() ? 0 : in.add(sfv.data(), sizeof(double) * m);
+  char* din;
+  if (in.upload(st, &din)) return 1;
+  SmallOut out;
+  const size_t o_bo = out.add(out_beta_mat, sizeof(double) * n * p), o_bv = out.add(out_beta_var_mat, sizeof(double) * n * p),
+               o_it = out.add(out_iter, sizeof(double) * n), o_cn = out.add(out_contrast_num, sizeof(double) * n),
+               o_cd = out.add(out_contrast_denom, sizeof(double) * n), o_dev = out.add(out_deviance, sizeof(double) * n);
+  char* dout;
+  if (out.device(&dout)) return 1;
+  void *d_h = nullptr, *d_mu = nullptr, *d_hc = nullptr;
+  if (out_hat_diagonals && ws_get(S_H, sizeof(double) * n * ld, &d_h)) return 1;
+  if (out_mu && ws_get(S_MUO, sizeof(double) * n * ld, &d_mu)) return 1;
+  if ((out_hat_diagonals || out_mu) && ws_get(S_HC, sizeof(double) * n * m, &d_hc)) return 1;
+  clk.next();
+  auto Din = [&](size_t off) { return reinterpret_cast<const double*>(din + off); };
+  auto Dout = [&](size_t off) { return reinterpret_cast<double*>(dout + off); };
+  if (b200nb_fit_beta_dev(d_y, y_type, Din(o_x), sfv.empty() ? (const double*)d_nf : Din(o_sf), sfv.empty() ? 0 : 1,
+                          Din(o_alpha), Din(o_c), Din(o_b), Din(o_lam), (const double*)d_w, use_weights, tol, maxit,
+                          use_qr, minmu, n, m, p, ld, Dout(o_bo), Dout(o_bv), Dout(o_it), (double*)d_h, Dout(o_cn),
+                          Dout(o_cd), Dout(o_dev), (double*)d_mu, st))
+    return 1;
+  clk.next();
+  if (out_hat_diagonals) {
+    if (b200nb_to_col_major_dev((const double*)d_h, (double*)d_hc, n, m, ld, st)) return 1;
+    pop_h.join();
+    if (d2h_staged(out_hat_diagonals, d_hc, sizeof(double) * (size_t)n * m, st)) return 1;
+  }
+  if (out_mu) {
+    if (b200nb_to_col_major_dev((const double*)d_mu, (double*)d_hc, n, m, ld, st)) return 1;
+    pop_mu.join();
+    if (d2h_staged(out_mu, d_hc, sizeof(double) * (size_t)n * m, st)) return 1;
+  }
+  if (out.download(dout, st)) return 1;
+  clk.next();
+  clk.report("fitBeta", n);
+  return 0;
 }
 
 int b200nb_test_special(const double* x, int n, double* out_lgamma, double* out_digamma, double* out_trigamma) {
@@ -1073,17 +1081,19 @@ int b200nb_test_special(const double* x, int n, double* out_lgamma, double* out_
   std::lock_guard<std::mutex> lk(g_call_mu);
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
-  void *d_x, *d_o;
-  if (upload_vec(x, sizeof(double) * n, S_V0, st, &d_x)) return 1;
-  if (ws_get(S_OUTD, sizeof(double) * 3 * n, &d_o)) return 1;
-  double* o = (double*)d_o;
-  CU(nb::launch_special_test((const double*)d_x, n, o, o + n, o + 2 * (size_t)n, st));
+  SmallIn in;
+  const size_t o_x = in.add(x, sizeof(double) * n);
+  char* din;
+  if (in.upload(st, &din)) return 1;
+  SmallOut out;
+  const size_t o_l = out.add(out_lgamma, sizeof(double) * n), o_d = out.add(out_digamma, sizeof(double) * n),
+               o_t = out.add(out_trigamma, sizeof(double) * n);
+  char* dout;
+  if (out.device(&dout)) return 1;
+  CU(nb::launch_special_test(reinterpret_cast<const double*>(din + o_x), n, reinterpret_cast<double*>(dout + o_l),
+                             reinterpret_cast<double*>(dout + o_d), reinterpret_cast<double*>(dout + o_t), st));
   g_launches++;
-  CU(cudaMemcpyAsync(out_lgamma, o, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_digamma, o + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(out_trigamma, o + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  return 0;
+  return out.download(dout, st);
 }
 
 }  // extern "C"

@@ -117,10 +117,33 @@ struct LogLikArgs {
   const double* w;        // gene-major weights or nullptr
   int n, m, p;
   long long ld;
+  double minmu;           // > 0: the log-likelihood (not mu_out) is evaluated at max(mu, minmu) -- what
+                          // fitNbinomGLMsOptim stores for the rows it refits (R/fitNbinomGLMs.R:386-398); 0: no clamp
   double* loglik;         // n
   double* mu_out;         // gene-major n x ld or nullptr: nf * exp(x beta), not clamped
 };
 cudaError_t launch_nb_loglik(const LogLikArgs& a, cudaStream_t stream);
+
+// box-constrained maximisation of the penalised NB log-likelihood for rows the IRLS left unfitted (fit_optim.cu)
+struct OptimArgs {
+  const void* y;
+  int y_is_f64;
+  const double* x;        // m x p column-major
+  const double* nf;       // gene-major n x ld, or length-m size-factor vector
+  int nf_is_vector;
+  const double* alpha;    // n
+  const double* lambda;   // p, natural-log scale (lambda_log2 / ln(2)^2)
+  const double* beta_in;  // n x p column-major start values, natural-log scale (NaN -> 0, clipped into the box)
+  const double* w;        // gene-major weights or nullptr
+  double bound;           // box half-width on the natural-log scale (30 ln 2)
+  int maxit;
+  int n, m, p;
+  long long ld;
+  double* beta_out;       // n x p column-major
+  int32_t* converged;     // n: 1 = stationary point reached (optim's convergence == 0)
+  int32_t* iter;          // n: Newton iterations used
+};
+cudaError_t launch_beta_optim(const OptimArgs& a, cudaStream_t stream);
 
 // per-gene pre-steps (pipeline_kernels.cu)
 struct PrepArgs {

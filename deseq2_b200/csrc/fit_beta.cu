@@ -452,8 +452,13 @@ __global__ void __launch_bounds__(256) nb_loglik_kernel(const LogLikArgs A) {
     for (int k = 0; k < A.p; k++) eta = fma(__ldg(A.x + (size_t)k * A.m + j), A.beta[(size_t)g + (size_t)A.n * k], eta);
     const double nf = A.nf_is_vector ? __ldg(A.nf + j) : A.nf[off + j];
     const double le = eta + log(nf);
-    const double mu = (fabs(le) < 700.0) ? exp_fast(le) : exp(le);
+    double mu = (fabs(le) < 700.0) ? exp_fast(le) : exp(le);
     if (A.mu_out != nullptr) A.mu_out[off + j] = mu;
+    double lmu = le;
+    if (A.minmu > 0.0 && !(mu >= A.minmu)) {
+      mu = A.minmu;
+      lmu = log(A.minmu);
+    }
     const double y = A.y_is_f64 ? static_cast<const double*>(A.y)[off + j]
                                 : (double)static_cast<const int32_t*>(A.y)[off + j];
     double t;
@@ -462,7 +467,7 @@ __global__ void __launch_bounds__(256) nb_loglik_kernel(const LogLikArgs A) {
     } else {
       const double am = mu * alpha, u1 = 1.0 + am;
       const double l1p = log_pos(u1) + (am - (u1 - 1.0)) * rcp_fast(u1);
-      t = lgamma_diff(y, r, lg_r) - log_factorial(y) + fma(y, le + log_alpha, -(y + r) * l1p);
+      t = lgamma_diff(y, r, lg_r) - log_factorial(y) + fma(y, lmu + log_alpha, -(y + r) * l1p);
     }
     if (A.w != nullptr) t *= A.w[off + j];
     acc += t;

@@ -144,7 +144,26 @@ def fit_beta(y, x, nf, alpha_hat, contrast, beta_mat, lambda_, tol, maxit, useQR
     return out
 
 
-def nb_loglik(y, x, nf, alpha_hat, beta_mat, weights=None, want_mu=True, out_mu=None):
+def beta_optim(y, x, nf, alpha_hat, lambda_nat, beta_start, weights=None, maxit=200):
+    """b200nb_beta_optim_dev: fitNbinomGLMsOptim (R/fitNbinomGLMs.R:340-407) on the (few) rows passed in.
+    beta_start: (p, n) contiguous, natural-log scale.  Returns {"beta_mat": (p, n), "converged": (n,) int32, "iter"}."""
+    L = _lib.lib()
+    n, ld = y.shape
+    xd = _x_dev(x, y.device)
+    p, m = xd.shape
+    lam = lambda_nat if isinstance(lambda_nat, torch.Tensor) else torch.as_tensor(
+        np.asarray(lambda_nat, dtype=np.float64), device=y.device)
+    out = {"beta_mat": torch.empty((p, n), dtype=F64, device=y.device),
+           "converged": torch.zeros(n, dtype=torch.int32, device=y.device),
+           "iter": torch.zeros(n, dtype=torch.int32, device=y.device)}
+    rc = L.b200nb_beta_optim_dev(_p(y), _ytype(y), _p(xd), _p(nf), int(nf.dim() == 1), _p(alpha_hat), _p(lam),
+                                 _p(beta_start), _p(weights), int(weights is not None), int(maxit), n, m, p, ld,
+                                 _p(out["beta_mat"]), _p(out["converged"]), _p(out["iter"]), _stream())
+    _lib.check(rc, "beta_optim_dev")
+    return out
+
+
+def nb_loglik(y, x, nf, alpha_hat, beta_mat, weights=None, want_mu=True, out_mu=None, minmu=0.0):
     """b200nb_nb_loglik_dev: the unclamped fitted mean nf * exp(x beta) and nbinomLogLike at it -- what R recomputes
     right after fitBeta (R/fitNbinomGLMs.R:180-182).  beta_mat: (p, n) contiguous, natural-log scale.
     Returns {"logLike": (n,), "mu": (n, ld) or None}."""
@@ -155,7 +174,8 @@ def nb_loglik(y, x, nf, alpha_hat, beta_mat, weights=None, want_mu=True, out_mu=
     ll = torch.empty(n, dtype=F64, device=y.device)
     mu = out_mu if out_mu is not None else (torch.empty((n, ld), dtype=F64, device=y.device) if want_mu else None)
     rc = L.b200nb_nb_loglik_dev(_p(y), _ytype(y), _p(xd), _p(nf), int(nf.dim() == 1), _p(alpha_hat), _p(beta_mat),
-                                _p(weights), int(weights is not None), n, m, p, ld, _p(ll), _p(mu), _stream())
+                                _p(weights), int(weights is not None), float(minmu), n, m, p, ld, _p(ll), _p(mu),
+                                _stream())
     _lib.check(rc, "nb_loglik_dev")
     return {"logLike": ll, "mu": mu}
 

@@ -165,7 +165,45 @@ def getContrast_device(ynz, x, sizeFactors, dispersion, betaMatrix, contrast, be
     return {"log2FoldChange": est, "lfcSE": se, "stat": stat, "pvalue": 2.0 * torch.special.ndtr(-stat.abs())}
 
 
-def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e-8, maxit=100, minmu=0.5):
+def _optim_fallback(ysrc, xd, sfd, dispersion, fb, beta0, lam, contrast, maxit, minmu, ll, useOptim=True):
+    """R/fitNbinomGLMs.R:186-227 on device results: rows with NA coefficients or non-positive variances -- and, with
+    useOptim (the reference's default), rows whose IRLS did not converge -- are refitted by b200nb_beta_optim_dev
+    (fitNbinomGLMsOptim, :340-407); their coefficients, standard errors (sandwich at the clamped mean, :386-396),
+    fitted means and log-likelihoods are overwritten in `fb` / `ll` in place.  The hat diagonals keep the IRLS values,
+    as in the reference (:234).  Returns betaConv (n,) bool.  Costs one host sync (the number of such rows)."""
+    beta = fb["beta_mat"]                                             # (p, n), natural-log scale
+    betaConv = fb["iter"] < maxit
+    rowStable = ~torch.isnan(beta).any(dim=0)
+    rowVarPositive = ~(fb["beta_var_mat"] <= 0).any(dim=0)
+    need = (~rowStable) | (~rowVarPositive)
+    if useOptim:
+        need = need | (~betaConv)
+    rows = torch.nonzero(need).squeeze(1)
+    if rows.numel() == 0:
+        return betaConv, 0
+    usable = rowStable[rows] & ((beta[:, rows] / LN2).abs() < 30.0).all(dim=0)
+    start = torch.where(usable[None, :], beta[:, rows], beta0[:, rows]).contiguous()
+    start = torch.nan_to_num(start, nan=0.0)
+    ysub = ysrc[rows].contiguous()
+    asub = dispersion[rows].contiguous()
+    o = D.beta_optim(ysub, xd, sfd, asub, lam, start)
+    cov = D.fit_beta(ysub, xd, sfd, asub, contrast, o["beta_mat"], lam, 1e-8, 0, minmu=minmu, want_hat=False,
+                     want_mu=False)
+    l2 = D.nb_loglik(ysub, xd, sfd, asub, o["beta_mat"], want_mu=ll.get("mu") is not None, minmu=minmu)
+    fb["beta_mat"][:, rows] = o["beta_mat"]
+    fb["beta_var_mat"][:, rows] = cov["beta_var_mat"]
+    fb["contrast_num"][rows] = cov["contrast_num"]
+    fb["contrast_denom"][rows] = cov["contrast_denom"]
+    ll["logLike"][rows] = l2["logLike"]
+    if ll.get("mu") is not None:
+        ll["mu"][rows] = l2["mu"]
+    betaConv = betaConv.clone()
+    betaConv[rows] = betaConv[rows] | (o["converged"] != 0)
+    return betaConv, int(rows.numel())
+
+
+def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e-8, maxit=100, minmu=0.5,
+                     useOptim=True):
     """nbinomLRT (R/core.R:1787-2012) on device tensors: two IRLS fits, LRT statistic 2 (logLike_full - logLike_reduced)
     (R/core.R:1877) and its chi-square p-value.  The log-likelihoods are evaluated at the UNCLAMPED fitted means
     nf * exp(x beta) as the reference does (R/fitNbinomGLMs.R:180-182) by b200nb_nb_loglik_dev -- NOT taken from the IRLS
@@ -183,6 +221,8 @@ def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e
         res[name] = D.fit_beta(ynz, pr["xd"], sfd, dispersion, contrast, pr["beta0"], lam, betaTol, maxit, minmu=minmu,
                                want_hat=(name == "full"), want_mu=False)
         ll = D.nb_loglik(ynz, pr["xd"], sfd, dispersion, res[name]["beta_mat"], want_mu=(name == "full"))
+        res[name]["conv"], _ = _optim_fallback(ynz, pr["xd"], sfd, dispersion, res[name], pr["beta0"], lam, contrast,
+                                               maxit, minmu, ll, useOptim=useOptim)
         res[name]["logLike"], res[name]["mu"] = ll["logLike"], ll["mu"]
     df = x_full.shape[1] - x_reduced.shape[1]
     stat = 2.0 * (res["full"]["logLike"] - res["reduced"]["logLike"])
@@ -190,12 +230,12 @@ def nbinomLRT_device(ynz, x_full, x_reduced, sizeFactors, dispersion, betaTol=1e
     return {"LRTStatistic": stat, "LRTPvalue": pval, "deviance": -2.0 * res["full"]["logLike"], "df": df,
             "betaMatrix": (res["full"]["beta_mat"] / LN2).T,
             "betaSE": (torch.sqrt(torch.clamp(res["full"]["beta_var_mat"], min=0.0)) / LN2).T,
-            "fullBetaConv": res["full"]["iter"] < maxit, "reducedBetaConv": res["reduced"]["iter"] < maxit,
+            "fullBetaConv": res["full"]["conv"], "reducedBetaConv": res["reduced"]["conv"],
             "mu": res["full"]["mu"], "H": res["full"]["hat_diagonals"]}
 
 
 def _refit_rows(ysub, x, sizeFactors, tr, varLogDispEsts, dispPriorVar, minDisp, kappa_0, dispTol, maxit, betaTol,
-                minmu, outlierSD):
+                minmu, outlierSD, useOptim=True):
     """The per-gene chain of DESeq_device (GeneEst -> MAP -> Wald) on a subset of rows with the dispersion trend and
     prior already known: what refitWithoutOutliers (R/core.R:2500-2528) does with objectSub.  Fresh tensors, no
     shared workspace: the subset is small."""
@@ -237,18 +277,20 @@ def _refit_rows(ysub, x, sizeFactors, tr, varLogDispEsts, dispPriorVar, minDisp,
     dispersion = torch.where(dispOutlier, dge, dispMAP)
     fb = D.fit_beta(ysub, xd, sfd, dispersion, contrast, beta0, lam, betaTol, maxit, minmu=minmu, want_hat=False,
                     want_mu=False)
+    ll = D.nb_loglik(ysub, xd, sfd, dispersion, fb["beta_mat"], want_mu=False)
+    betaConv, _ = _optim_fallback(ysub, xd, sfd, dispersion, fb, beta0, lam, contrast, maxit, minmu, ll, useOptim=useOptim)
     betaMatrix = fb["beta_mat"] / LN2
     betaSE = torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0.0)) / LN2
     stat = betaMatrix / betaSE
-    fb["deviance"] = -2.0 * D.nb_loglik(ysub, xd, sfd, dispersion, fb["beta_mat"], want_mu=False)["logLike"]
+    fb["deviance"] = -2.0 * ll["logLike"]
     return {"baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP, "dispersion": dispersion,
             "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"], "betaMatrix": betaMatrix.T,
             "betaSE": betaSE.T, "WaldStatistic": stat.T, "WaldPvalue": (2.0 * torch.special.ndtr(-stat.abs())).T,
-            "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": fb["deviance"]}
+            "betaIter": fb["iter"], "betaConv": betaConv, "deviance": fb["deviance"]}
 
 
 def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6, maxit=100, betaTol=1e-8, minmu=0.5,
-                 outlierSD=2.0, minReplicatesForReplace=np.inf, allgather=None):
+                 outlierSD=2.0, minReplicatesForReplace=np.inf, allgather=None, useOptim=True):
     """y: gene-major (N, ld) device tensor of counts (int32 or float64).  Returns a dict of device tensors over the
     rows with a non-zero sum (`idx` maps them back to the N input rows) plus the trend / prior scalars.
     sizeFactors=None estimates them on the device first (median of ratios, R/core.R:535-578; returned under
@@ -266,8 +308,6 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
     estimated = sizeFactors is None
     if estimated:
         sizeFactors = size_factors(y, m)["sizeFactors"].cpu().numpy()
-    if m - p <= 3:
-        raise NotImplementedError("residual df <= 3: the reference's Monte-Carlo prior-variance branch is not restated")
     import os
     import time
     stage_ms = {}
@@ -331,8 +371,17 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
     resid = (torch.log(dge_all) - torch.log(tr[0] + tr[1] / bm_all))[above]
     med = _median(resid)
     varLogDispEsts = (1.4826 * _median((resid - med).abs())) ** 2
-    expVar = torch.special.polygamma(1, torch.tensor((m - p) / 2.0, dtype=F64, device=dev))
-    dispPriorVar = float(torch.clamp(varLogDispEsts - expVar, min=0.25).item())
+    if m - p <= 3 and m > p:
+        # 2-vs-2 / 3-vs-2 experiments: the reference's Monte-Carlo KL match (R/core.R:1157-1193) is host glue (numpy);
+        # it needs the log-dispersion residuals of all genes: one D2H of two doubles per gene
+        from .pipeline import estimateDispersionsPriorVar
+        dispPriorVar = estimateDispersionsPriorVar(float(varLogDispEsts.item()), m, p, dge_all.cpu().numpy(),
+                                                   (tr[0] + tr[1] / bm_all).cpu().numpy(), minDisp)
+    elif m > p:
+        expVar = torch.special.polygamma(1, torch.tensor((m - p) / 2.0, dtype=F64, device=dev))
+        dispPriorVar = float(torch.clamp(varLogDispEsts - expVar, min=0.25).item())
+    else:
+        dispPriorVar = float(varLogDispEsts.item())
     status = tr[2].item()
     if status != 0:
         raise FloatingPointError(f"parametric dispersion fit failed on device (status {int(status)})")
@@ -360,34 +409,39 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
             "hat_diagonals": _ws("H", (nn, ldd), F64, dev), "mu": None}
     fb = D.fit_beta(ynz, xd, sfd, dispersion, contrast, beta0, lam, betaTol, maxit, minmu=minmu, out=outb)
     mark("fit_beta")
+    # Cook's distances and the reported deviance use the UNCLAMPED fitted mean nf * exp(x beta) and the log-likelihood
+    # at it, which the reference recomputes in R right after the native call (R/fitNbinomGLMs.R:180-182): one small
+    # kernel (b200nb_nb_loglik_dev); the IRLS kernel's fused mean / deviance are at the minmu clamp.
+    ll = D.nb_loglik(ynz, xd, sfd, dispersion, fb["beta_mat"], out_mu=_ws("mu_cooks", (nn, ldd), F64, dev))
+    # rows the IRLS could not fit go to the box-constrained maximiser (R/fitNbinomGLMs.R:203-227, useOptim = TRUE)
+    betaConv, n_optim = _optim_fallback(ynz, xd, sfd, dispersion, fb, beta0, lam, contrast, maxit, minmu, ll,
+                                        useOptim=useOptim)
+    mark("loglik+optim")
     betaMatrix = fb["beta_mat"] / LN2                      # (p, n)
     betaSE = torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0.0)) / LN2
     stat = betaMatrix / betaSE
     pval = 2.0 * torch.special.ndtr(-stat.abs())
     from .pipeline import nOrMoreInCell
     do_replace = bool(np.isfinite(minReplicatesForReplace)) and bool(nOrMoreInCell(x, minReplicatesForReplace).any())
-    # Cook's distances and the reported deviance use the UNCLAMPED fitted mean nf * exp(x beta) and the log-likelihood
-    # at it, which the reference recomputes in R right after the native call (R/fitNbinomGLMs.R:180-182): one small
-    # kernel (b200nb_nb_loglik_dev); the IRLS kernel's fused mean / deviance are at the minmu clamp.
-    ll = D.nb_loglik(ynz, xd, sfd, dispersion, fb["beta_mat"], out_mu=_ws("mu_cooks", (nn, ldd), F64, dev))
     mu_cooks = ll["mu"]
     ck = cooks(ynz, mu_cooks, fb["hat_diagonals"], x, sizeFactors, want_matrix=do_replace)   # R/core.R:1457-1460
     mark("wald_stats+cooks")
     res = {"stage_ms": stage_ms, "maxCooks": ck["maxCooks"], "idx": idx, "baseMean": bm, "dispGeneEst": dge, "dispFit": dispFit, "dispMAP": dispMAP,
             "dispersion": dispersion, "dispOutlier": dispOutlier, "dispGeneIter": r["iter"], "dispIter": rm["iter"],
             "betaMatrix": betaMatrix.T, "betaSE": betaSE.T, "WaldStatistic": stat.T, "WaldPvalue": pval.T,
-            "betaIter": fb["iter"], "betaConv": fb["iter"] < maxit, "deviance": -2.0 * ll["logLike"], "mu": mu_cooks,
+            "betaIter": fb["iter"], "betaConv": betaConv, "n_optim": n_optim, "deviance": -2.0 * ll["logLike"], "mu": mu_cooks,
             "H": fb["hat_diagonals"], "trendCoefs": tr[:2], "varLogDispEsts": varLogDispEsts,
             "dispPriorVar": dispPriorVar, "n_refit_geneest": n_refit_geneest, "n_refit_map": int(gi2.numel()),
             "n_input_rows": y.shape[0], "sizeFactors": np.asarray(sizeFactors, dtype=np.float64)}
     if do_replace and m > p:
         _replace_and_refit(res, ynz, ck["cooks"], x, sizeFactors, sfd, tr, varLogDispEsts, dispPriorVar,
-                           minReplicatesForReplace, minDisp, kappa_0, dispTol, maxit, betaTol, minmu, outlierSD)
+                           minReplicatesForReplace, minDisp, kappa_0, dispTol, maxit, betaTol, minmu, outlierSD,
+                           useOptim=useOptim)
     return res
 
 
 def _replace_and_refit(res, ynz, cooksm, x, sizeFactors, sfd, tr, varLogDispEsts, dispPriorVar, minReplicates, minDisp,
-                       kappa_0, dispTol, maxit, betaTol, minmu, outlierSD, trim=0.2):
+                       kappa_0, dispTol, maxit, betaTol, minmu, outlierSD, trim=0.2, useOptim=True):
     """replaceOutliers + refitWithoutOutliers (R/core.R:2069-2115, 2484-2565) on the device results `res` (in place).
     Only the flagged rows move: their counts are gathered, the outlying entries of replaceable samples become
     as.integer(trimmed mean of the normalised counts * size factor), and the rows go through _refit_rows."""
@@ -418,7 +472,7 @@ def _replace_and_refit(res, ynz, cooksm, x, sizeFactors, sfd, tr, varLogDispEsts
         ysub = torch.zeros((rr.numel(), ynz.shape[1]), dtype=F64, device=dev)
         ysub[:, :m] = new[keep]
         sub = _refit_rows(ysub, x, sizeFactors, tr, varLogDispEsts, dispPriorVar, minDisp, kappa_0, dispTol, maxit,
-                          betaTol, minmu, outlierSD)
+                          betaTol, minmu, outlierSD, useOptim=useOptim)
         for k, v in sub.items():
             if k == "baseMean":
                 continue

@@ -10,9 +10,9 @@ numpy, one function per R function, same names, so the engine can be driven and 
   estimateDispersionsGeneEst     R/core.R:657-860
   parametricDispersionFit        R/core.R:2166-2189  (Gamma GLM, identity link, glm.fit IRLS restated)
   dispersionFunction<-           R/methods.R:142-190 (dispFit, varLogDispEsts = mad^2)
-  estimateDispersionsPriorVar    R/core.R:1135-1208  (m - p > 3 branch)
+  estimateDispersionsPriorVar    R/core.R:1135-1208  (incl. the Monte-Carlo branch for 1..3 residual df, own RNG)
   estimateDispersionsMAP         R/core.R:943-1131
-  fitNbinomGLMs / fitNbinomGLMsOptim   R/fitNbinomGLMs.R:29-236, 340-407 (L-BFGS-B fallback opt-in: useOptim=True)
+  fitNbinomGLMs / fitNbinomGLMsOptim   R/fitNbinomGLMs.R:29-236, 340-407 (L-BFGS-B fallback, useOptim=TRUE by default as in the reference)
   nbinomWaldTest                 R/core.R:1332-1565  (betas, SEs, Wald statistic and p-value)
   nbinomLRT                      R/core.R:1787-2012  (full vs reduced fit, 2 (l_full - l_reduced), chi-square p-value)
   getContrast                    R/results.R:760-827 (numeric contrasts through fitBeta's maxit = 0 mode)
@@ -223,12 +223,66 @@ def estimateDispersionsFit(dispGeneEst, baseMean, minDisp=1e-8):
     return {"dispFit": dispFit, "coefs": coefs, "varLogDispEsts": varLogDispEsts}
 
 
-def estimateDispersionsPriorVar(varLogDispEsts, m, p):
-    """R/core.R:1135-1208, the m - p > 3 branch (the Monte-Carlo branch for 1..3 residual df is not restated)."""
-    if m - p <= 3:
-        raise NotImplementedError("residual df <= 3: the reference uses a Monte-Carlo KL match (R/core.R:1161-1193)")
-    expVarLogDisp = _sp.polygamma(1, (m - p) / 2.0)
-    return max(varLogDispEsts - expVarLogDisp, 0.25)
+def _loess_quadratic(xg, yg, xnew, span):
+    """stats::loess(y ~ x, span = span) with its defaults degree = 2, family = "gaussian", evaluated directly at xnew
+    (R's default surface = "interpolate" evaluates the same local fits at kd-tree vertices and blends them; on a smooth
+    200-point curve the two agree far inside the Monte-Carlo noise of the curve itself): local quadratic least squares
+    over the q = floor(n * span + 1e-5) nearest points with tricube weights."""
+    n = len(xg)
+    q = max(int(np.floor(n * span + 1e-5)), 3)
+    out = np.empty(len(xnew))
+    for i, x0 in enumerate(xnew):
+        d = np.abs(xg - x0)
+        idx = np.argpartition(d, q - 1)[:q]
+        h = d[idx].max()
+        w = (1.0 - (d[idx] / h) ** 3) ** 3 if h > 0 else np.ones(q)
+        w = np.maximum(w, 0.0)
+        X = np.c_[np.ones(q), xg[idx] - x0, (xg[idx] - x0) ** 2]
+        sw = np.sqrt(w)
+        coef, *_ = np.linalg.lstsq(X * sw[:, None], yg[idx] * sw, rcond=None)
+        out[i] = coef[0]
+    return out
+
+
+def estimateDispersionsPriorVar(varLogDispEsts, m, p, dispGeneEst=None, dispFit=None, minDisp=1e-8):
+    """R/core.R:1135-1208.  m - p > 3: MAD-based variance minus the sampling variance trigamma((m-p)/2), floor 0.25.
+    1 <= m - p <= 3 (2-vs-2, 3-vs-2 experiments, :1157-1193): the reference matches the histogram of the log
+    dispersion residuals against simulated log(chisq_{m-p}/(m-p)) + N(0, v) on a grid of v by KL divergence, smooths
+    the curve with loess(span = .2) and takes the argmin; needs dispGeneEst and dispFit.  The reference fixes R's RNG
+    (set.seed(2): Mersenne-Twister + inversion) for reproducibility; R's generator is not restated here, numpy's
+    PCG64(2) plays its role, so the value agrees with R's within the Monte-Carlo noise of 1e4 draws per grid point
+    (a few grid steps of 0.008), not bit for bit -- host glue that stays R in a real drop-in.
+    m == p: no sampling variance is subtracted."""
+    if m - p <= 3 and m > p:
+        if dispGeneEst is None or dispFit is None:
+            raise ValueError("residual df <= 3: the Monte-Carlo branch needs dispGeneEst and dispFit")
+        dispGeneEst = np.asarray(dispGeneEst, dtype=np.float64)
+        resid = np.log(dispGeneEst) - np.log(np.asarray(dispFit, dtype=np.float64))
+        above = dispGeneEst >= minDisp * 100
+        if above.sum() == 0:
+            raise ValueError("no data found which is greater than minDisp")
+        rng = np.random.Generator(np.random.PCG64(2))
+        brks = np.arange(-20, 21) / 2.0
+        obs = resid[above]
+        obs = obs[(obs > brks[0]) & (obs < brks[-1])]
+        obsDens = np.histogram(obs, bins=brks)[0] / (max(len(obs), 1) * 0.5)
+        grid = np.linspace(0.0, 8.0, 200)
+        kl = np.empty(len(grid))
+        df = m - p
+        for i, v in enumerate(grid):
+            r = np.log(rng.chisquare(df, 10000)) + rng.normal(0.0, np.sqrt(v), 10000) - np.log(df)
+            r = r[(r > brks[0]) & (r < brks[-1])]
+            rDens = np.histogram(r, bins=brks)[0] / (max(len(r), 1) * 0.5)
+            z = np.r_[obsDens, rDens]
+            small = z[z > 0].min()
+            kl[i] = np.sum(obsDens * (np.log(obsDens + small) - np.log(rDens + small)))
+        fine = np.linspace(0.0, 8.0, 1000)
+        fitted = _loess_quadratic(grid, kl, fine, 0.2)
+        return float(max(fine[int(np.argmin(fitted))], 0.25))
+    if m > p:
+        expVarLogDisp = _sp.polygamma(1, (m - p) / 2.0)
+        return float(max(varLogDispEsts - expVarLogDisp, 0.25))
+    return float(varLogDispEsts)
 
 
 def estimateDispersionsMAP(counts, x, mu, dispGeneEst, dispFit, dispPriorVar, varLogDispEsts, engine=None,
@@ -302,10 +356,11 @@ def fitNbinomGLMsOptim(counts, nf, x, lambda_, rowsForOptim, rowStable, alpha_ha
 
 
 def fitNbinomGLMs(counts, nf, x, alpha_hat, lambda_=None, engine=None, betaTol=1e-8, maxit=100, useQR=True,
-                  minmu=0.5, useOptim=False, forceOptim=False):
-    """R/fitNbinomGLMs.R:29-236 without weights.  useOptim=True adds the reference's L-BFGS-B fallback for rows that
-    did not converge / are unstable / have non-positive variance (:203-227; the reference's default is TRUE, the
-    default here is FALSE so that the engine's raw output is what the parity tests and the bench see)."""
+                  minmu=0.5, useOptim=True, forceOptim=False):
+    """R/fitNbinomGLMs.R:29-236 without weights.  As in the reference (:203-227) rows with NA coefficients or
+    non-positive variances ALWAYS go to the L-BFGS-B fallback, and with useOptim=TRUE (the reference's default, :30)
+    so do the rows whose IRLS did not converge (iter == maxit, which includes the |beta| > 30 sentinel).  Parity tests
+    that need the engine's raw output pass useOptim=False."""
     engine = engine or _default_engine
     counts = np.asarray(counts)
     n, m = counts.shape
@@ -329,10 +384,12 @@ def fitNbinomGLMs(counts, nf, x, alpha_hat, lambda_=None, engine=None, betaTol=1
     betaConv = betaRes["iter"] < maxit
     betaMatrix = betaRes["beta_mat"] / LN2
     betaSE = np.sqrt(np.maximum(betaRes["beta_var_mat"], 0.0)) / LN2
-    if useOptim or forceOptim:
-        rowStable = ~np.isnan(betaRes["beta_mat"]).any(axis=1)
-        rowVarPositive = ~(betaRes["beta_var_mat"] <= 0).any(axis=1)
-        rows = np.arange(n) if forceOptim else np.flatnonzero(~betaConv | ~rowStable | ~rowVarPositive)
+    rowStable = ~np.isnan(betaRes["beta_mat"]).any(axis=1)
+    rowVarPositive = ~(betaRes["beta_var_mat"] <= 0).any(axis=1)
+    rows = np.flatnonzero((~betaConv | ~rowStable | ~rowVarPositive) if useOptim else (~rowStable | ~rowVarPositive))
+    if forceOptim:
+        rows = np.arange(n)
+    if True:
         if rows.size:
             o = fitNbinomGLMsOptim(counts, np.broadcast_to(nf, counts.shape), x, lambda_, rows, rowStable, alpha_hat,
                                    betaMatrix, betaSE, betaConv, beta_mat / LN2, mu, logLike, minmu=minmu)
@@ -342,10 +399,11 @@ def fitNbinomGLMs(counts, nf, x, alpha_hat, lambda_=None, engine=None, betaTol=1
             "betaIter": betaRes["iter"], "hat_diagonals": betaRes["hat_diagonals"], "betaRes": betaRes}
 
 
-def nbinomWaldTest(counts, nf, x, dispersion, engine=None, betaTol=1e-8, maxit=100, useQR=True, minmu=0.5):
+def nbinomWaldTest(counts, nf, x, dispersion, engine=None, betaTol=1e-8, maxit=100, useQR=True, minmu=0.5,
+                   useOptim=True):
     """R/core.R:1332-1565, betaPrior=FALSE, useT=FALSE; Cook's distances are not restated."""
     fit = fitNbinomGLMs(counts, nf, x, dispersion, engine=engine, betaTol=betaTol, maxit=maxit, useQR=useQR,
-                        minmu=minmu)
+                        minmu=minmu, useOptim=useOptim)
     with np.errstate(divide="ignore", invalid="ignore"):
         WaldStatistic = fit["betaMatrix"] / fit["betaSE"]
     WaldPvalue = 2.0 * _sp.ndtr(-np.abs(WaldStatistic))
@@ -507,7 +565,8 @@ def _fit_intercept_only(counts, nf, alpha_hat):
             "hat_diagonals": w / xtwx[:, None]}
 
 
-def nbinomLRT(counts, nf, full, reduced, dispersion, engine=None, betaTol=1e-8, maxit=100, useQR=True, minmu=0.5):
+def nbinomLRT(counts, nf, full, reduced, dispersion, engine=None, betaTol=1e-8, maxit=100, useQR=True, minmu=0.5,
+              useOptim=True):
     """R/core.R:1787-2012 with user-supplied model matrices, betaPrior=FALSE; Cook's distances are not restated.
     `full` / `reduced` are m x p model matrices (reduced nested in full)."""
     from scipy import stats as _st
@@ -515,12 +574,12 @@ def nbinomLRT(counts, nf, full, reduced, dispersion, engine=None, betaTol=1e-8, 
     if reduced.shape[1] >= full.shape[1]:
         raise ValueError("less than one degree of freedom, perhaps full and reduced models are not in the correct order")
     fullModel = fitNbinomGLMs(counts, nf, full, dispersion, engine=engine, betaTol=betaTol, maxit=maxit, useQR=useQR,
-                              minmu=minmu)
+                              minmu=minmu, useOptim=useOptim)
     if reduced.shape[1] == 1 and np.all(reduced == 1):
         reducedModel = _fit_intercept_only(counts, nf, dispersion)
     else:
         reducedModel = fitNbinomGLMs(counts, nf, reduced, dispersion, engine=engine, betaTol=betaTol, maxit=maxit,
-                                     useQR=useQR, minmu=minmu)
+                                     useQR=useQR, minmu=minmu, useOptim=useOptim)
     df = full.shape[1] - reduced.shape[1]
     LRTStatistic = 2.0 * (fullModel["logLike"] - reducedModel["logLike"])
     LRTPvalue = _st.chi2.sf(LRTStatistic, df)
@@ -633,7 +692,7 @@ def fitGLMsWithPrior(counts, nf, factors, dispersion, baseMean, dispFit, engine=
             "modelMatrix": x_exp, "mleBetaMatrix": mle["betaMatrix"], "names": enames, "mle": mle}
 
 
-def DESeq(counts, x, sizeFactors=None, engine=None, minReplicatesForReplace=np.inf):
+def DESeq(counts, x, sizeFactors=None, engine=None, minReplicatesForReplace=np.inf, useOptim=True):
     """R/core.R:280-432 with test='Wald', fitType='parametric', betaPrior=FALSE.
     minReplicatesForReplace: the reference's default is 7 (outlier replacement + refit whenever a design cell has >= 7
     samples, R/core.R:419-426, refitWithoutOutliers :2484-2565); the default here is Inf = off, which is what the
@@ -652,11 +711,11 @@ def DESeq(counts, x, sizeFactors=None, engine=None, minReplicatesForReplace=np.i
     mv = {k: v[nz] for k, v in mvAll.items()}
     ge = estimateDispersionsGeneEst(cnz, sizeFactors, x, engine=engine, mv=mv)
     tf = estimateDispersionsFit(ge["dispGeneEst"], ge["baseMean"])
-    dispPriorVar = estimateDispersionsPriorVar(tf["varLogDispEsts"], m, p)
+    dispPriorVar = estimateDispersionsPriorVar(tf["varLogDispEsts"], m, p, ge["dispGeneEst"], tf["dispFit"])
     mp = estimateDispersionsMAP(cnz, x, ge["mu"], ge["dispGeneEst"], tf["dispFit"], dispPriorVar,
                                 tf["varLogDispEsts"], engine=engine)
     nf = np.broadcast_to(sizeFactors[None, :], cnz.shape)
-    wt = nbinomWaldTest(cnz, nf, x, mp["dispersion"], engine=engine)
+    wt = nbinomWaldTest(cnz, nf, x, mp["dispersion"], engine=engine, useOptim=useOptim)
     cooks = calculateCooksDistance(cnz, wt["mu"], wt["hat_diagonals"], sizeFactors, x)      # R/core.R:1457-1460
     per_gene = {"baseMean": mv["baseMean"], "dispGeneEst": ge["dispGeneEst"], "dispFit": tf["dispFit"],
                 "dispMAP": mp["dispMAP"], "dispersion": mp["dispersion"], "dispOutlier": mp["dispOutlier"].astype(float),
@@ -681,7 +740,7 @@ def DESeq(counts, x, sizeFactors=None, engine=None, minReplicatesForReplace=np.i
             mp2 = estimateDispersionsMAP(sub, x, ge2["mu"], ge2["dispGeneEst"], dispFit2, dispPriorVar,
                                          tf["varLogDispEsts"], engine=engine)
             wt2 = nbinomWaldTest(sub, np.broadcast_to(sizeFactors[None, :], sub.shape), x, mp2["dispersion"],
-                                 engine=engine)
+                                 engine=engine, useOptim=useOptim)
             upd = {"dispGeneEst": ge2["dispGeneEst"], "dispFit": dispFit2, "dispMAP": mp2["dispMAP"],
                    "dispersion": mp2["dispersion"], "dispOutlier": mp2["dispOutlier"].astype(float),
                    "betaMatrix": wt2["betaMatrix"], "betaSE": wt2["betaSE"], "WaldStatistic": wt2["WaldStatistic"],

@@ -73,7 +73,7 @@ def sharded_DESeq(counts, x, sizeFactors, engine=None):
     g1 = all_gather_rows(np.stack([full_local(ge["dispGeneEst"]), full_local(ge["baseMean"])], axis=1), N)
     ok = ~np.isnan(g1[:, 0])
     tf = pipeline.estimateDispersionsFit(g1[ok, 0], g1[ok, 1])
-    dispPriorVar = pipeline.estimateDispersionsPriorVar(tf["varLogDispEsts"], m, p)
+    dispPriorVar = pipeline.estimateDispersionsPriorVar(tf["varLogDispEsts"], m, p, g1[ok, 0], tf["dispFit"])
     dispFit_mine = tf["coefs"][0] + tf["coefs"][1] / ge["baseMean"]
     mp = pipeline.estimateDispersionsMAP(cnz, x, ge["mu"], ge["dispGeneEst"], dispFit_mine, dispPriorVar,
                                          tf["varLogDispEsts"], engine=engine)

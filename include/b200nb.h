@@ -95,10 +95,25 @@ int b200nb_fit_beta_dev(const void* y, int y_type, const double* x, const double
  * mu = nf * exp(x beta) WITHOUT the minmu clamp (out_mu, gene-major n x ld, may be NULL) and
  * logLike = rowSums([w *] dnbinom(y, mu, size = 1/alpha, log = TRUE)) (nbinomLogLike, R/core.R:2208-2217; out_loglik[n]).
  * nbinomLRT's statistic (R/core.R:1877) and Cook's distances (R/core.R:1457) are built from these, not from the
- * clamped quantities inside the IRLS.  beta_mat: n x p column-major, natural-log scale (fitBeta's out_beta_mat). */
+ * clamped quantities inside the IRLS.  beta_mat: n x p column-major, natural-log scale (fitBeta's out_beta_mat).
+ * minmu > 0 evaluates the log-likelihood (not out_mu) at max(mu, minmu): what fitNbinomGLMsOptim stores for the rows
+ * it refits (R/fitNbinomGLMs.R:386-398); 0 = no clamp. */
 int b200nb_nb_loglik_dev(const void* y, int y_type, const double* x, const double* nf, int nf_is_vector,
-                         const double* alpha_hat, const double* beta_mat, const double* weights, int use_weights, int n,
-                         int m, int p, long long ld, double* out_loglik, double* out_mu, void* stream);
+                         const double* alpha_hat, const double* beta_mat, const double* weights, int use_weights,
+                         double minmu, int n, int m, int p, long long ld, double* out_loglik, double* out_mu,
+                         void* stream);
+
+/* b200nb_beta_optim_dev: fitNbinomGLMsOptim (R/fitNbinomGLMs.R:340-407) for the rows whose IRLS did not converge /
+ * diverged / gave NA: box-constrained maximisation of logLike + log prior (ridge lambda, natural-log scale here:
+ * lambda_log2 / ln(2)^2; box |beta| <= 30 ln 2 = |beta_log2| <= 30).  The objective is strictly concave, so the unique
+ * maximiser is what optim(method = "L-BFGS-B") converges to; a projected Newton iteration finds it (maxit iterations
+ * at most; out_converged = 1 plays optim's convergence == 0).  Pass ONLY the rows to refit (gathered gene-major rows).
+ * beta_start / out_beta_mat: n x p column-major, natural-log scale.  Standard errors, fitted means and the
+ * log-likelihood at the optimum come from b200nb_fit_beta_dev(maxit = 0) and b200nb_nb_loglik_dev. */
+int b200nb_beta_optim_dev(const void* y, int y_type, const double* x, const double* nf, int nf_is_vector,
+                          const double* alpha_hat, const double* lambda, const double* beta_start,
+                          const double* weights, int use_weights, int maxit, int n, int m, int p, long long ld,
+                          double* out_beta_mat, int32_t* out_converged, int32_t* out_iter, void* stream);
 
 /* layout helpers on device buffers: R column-major n x m <-> gene-major n x ld.  elem_size 4 (int32) or 8. */
 int b200nb_to_gene_major_dev(const void* src_colmajor, void* dst, int n, int m, long long ld, int elem_size,
@@ -143,6 +158,15 @@ const char* b200nb_last_error(void);
 int b200nb_device_count(void);            /* number of visible CUDA devices (0 if none / no driver) */
 long long b200nb_kernel_launches(void);   /* kernels this library has launched in this process */
 void b200nb_release_workspace(void);      /* frees cached device / pinned buffers of the host entry points */
+/* The host entry points keep the gene-major device copies of the large input matrices of recent calls, addressed by
+ * CONTENT (dimensions + a 128-bit hash of every byte, recomputed from the caller's buffer on each call), so the count
+ * matrix and the fitted means that one DESeq() run passes to fitDisp, fitDisp and fitBeta cross PCIe once.
+ * b200nb_cache_clear() forgets them (the memory stays allocated for reuse); B200NB_CACHE_MB=0 disables the cache. */
+void b200nb_cache_clear(void);
+/* cumulative counters of the host entry points: out[0] bytes copied host->device, [1] device->host, [2] cache hits,
+ * [3] cache misses, [4] bytes served from the cache instead of being uploaded, [5] bytes hashed / scanned on the host.
+ * Writes min(n, 6) values, returns 6. */
+int b200nb_host_stats(long long* out, int n);
 const char* b200nb_version(void);
 
 /* test hook: lgamma / digamma / trigamma of the device math on host arrays x[0..n) (x > 0) */

@@ -243,6 +243,10 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetPCIBusId(char* s, int len, int) {   // no such device: the host pool then stays unbound
+  if (len > 0) s[0] = 0;
+  return cudaSuccess;
+}
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 /* two "SMs", one resident CTA each: persistent kernels get a grid of 2, the second CTA finds the queue drained */
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 2; return cudaSuccess; }

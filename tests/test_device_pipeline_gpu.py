@@ -58,31 +58,58 @@ def test_trend_kernel_matches_numpy(engine, n=20000):
     assert np.max(rel_err(out[:2], ref)) < 1e-8
 
 
-@pytest.mark.parametrize("design,n,m", [("condition", 6000, 40), ("batch", 3000, 36), ("factor10", 1500, 120)])
-def test_device_pipeline_matches_host_pipeline(engine, design, n, m):
+class _MarginOracle:
+    """The CPU oracle as a pipeline engine that also records, per fitDisp call, every gene's decision margin."""
+
+    def __init__(self, oracle):
+        self.o, self.margins = oracle, []
+        self.fitDispGrid, self.fitBeta = oracle.fitDispGrid, oracle.fitBeta
+
+    def fitDisp(self, **kw):
+        r = self.o.fitDisp(**kw, with_margin=True)
+        self.margins.append(r["margin"])
+        return r
+
+
+@pytest.mark.parametrize("design,n,m", [("condition", 6000, 40), ("condition", 4000, 6), ("condition", 3000, 12),
+                                        ("batch", 3000, 36), ("factor10", 1500, 120)])
+def test_device_pipeline_matches_host_pipeline(engine, oracle, design, n, m):
+    """The device-resident DESeq() against the numpy restatement of the R glue driving the same engine through the C ABI:
+    EVERY gene within 1e-6 on dispGeneEst / dispMAP / dispersion / beta / SE, unless its line search took a different
+    number of steps -- which is only accepted for genes the oracle marks as knife-edge (decision margin below 4096
+    rounding bounds: the two sides' pre-steps differ by rounding, numpy vs prep_kernel), and must be rare."""
     from deseq2_b200 import device_pipeline as DP, pipeline, synth
     x = {"condition": synth.design_condition(m), "batch": synth.design_batch_condition(m, 3),
          "factor10": synth.design_factor(m, 10)}[design]
     d, y = _setup(n, m, x=x, seed=11)
-    host = pipeline.DESeq(d["counts"], x, sizeFactors=d["sizeFactors"], engine=engine)
-    dv = DP.DESeq_device(y, x, d["sizeFactors"])
+    host = pipeline.DESeq(d["counts"], x, sizeFactors=d["sizeFactors"], engine=engine, useOptim=False)
+    dv = DP.DESeq_device(y, x, d["sizeFactors"], useOptim=False)
     idx = dv["idx"].cpu().numpy()
     assert np.array_equal(idx, np.flatnonzero(~host["allZero"]))
     assert np.max(rel_err(dv["trendCoefs"].cpu().numpy(), host["trendCoefs"])) < 1e-6
     assert abs(dv["dispPriorVar"] - host["dispPriorVar"]) < 1e-6 * max(1.0, host["dispPriorVar"])
-    # per-gene results: inputs of the line searches differ by rounding between numpy and the device pre-steps, so a
-    # few knife-edge genes may stop one step apart; everything else must agree to 1e-6
+    same = ((dv["dispGeneIter"].cpu().numpy() == host["dispGeneIter"][idx])
+            & (dv["dispIter"].cpu().numpy() == host["dispIter"][idx]))
+    print(f"\n{design} {n}x{m}: line-search step counts differ on {np.sum(~same)} of {len(same)} genes")
     for k in ("dispGeneEst", "dispMAP", "dispersion"):
         e = rel_err(dv[k].cpu().numpy(), host[k][idx])
-        assert np.mean(e < 1e-6) > 0.97, (k, np.mean(e < 1e-6))
-        assert np.quantile(e, 0.999) < 5e-2, (k, np.quantile(e, 0.999))
-    conv = host["betaConv"][idx] == 1
+        assert np.max(e[same]) < 1e-6, (k, np.max(e[same]), int(np.sum(e[same] >= 1e-6)))
+    conv = (host["betaConv"][idx] == 1) & same
+    assert np.array_equal(dv["betaIter"].cpu().numpy()[same], host["betaIter"][idx][same])
     e = rel_err(dv["betaMatrix"].cpu().numpy()[conv], host["betaMatrix"][idx][conv], floor=1e-6)
-    assert np.mean(e < 1e-5) > 0.97
+    assert np.max(e) < 1e-6, np.max(e)
+    se = rel_err(dv["betaSE"].cpu().numpy()[conv], host["betaSE"][idx][conv])
+    assert np.max(se) < 1e-6, np.max(se)
     pv = dv["WaldPvalue"].cpu().numpy()
     assert np.all((pv[conv] >= 0) & (pv[conv] <= 1))
-    se = rel_err(dv["betaSE"].cpu().numpy()[conv], host["betaSE"][idx][conv])
-    assert np.mean(se < 1e-5) > 0.97
+    if np.any(~same):
+        assert np.mean(~same) < 0.005
+        mo = _MarginOracle(oracle)
+        pipeline.DESeq(d["counts"], x, sizeFactors=d["sizeFactors"], engine=mo, useOptim=False)
+        margin = np.minimum(mo.margins[-2], mo.margins[-1])          # the MLE and the MAP line search of the same genes
+        assert np.all(margin[~same] < 4096), (np.flatnonzero(~same)[:8], margin[~same][:8])
+        e = rel_err(dv["dispersion"].cpu().numpy(), host["dispersion"][idx])
+        assert np.max(e[~same]) < 5e-2
 
 
 @pytest.mark.parametrize("design,m", [("condition", 12), ("condition", 60), ("batch", 36), ("covariate", 20),
@@ -147,3 +174,60 @@ def test_lrt_device_matches_host(engine, n=3000):
     big = ok & (host["LRTPvalue"] > 1e-12)
     assert np.max(rel_err(pv[big], host["LRTPvalue"][big])) < 1e-6
     assert np.max(rel_err(got["betaMatrix"].cpu().numpy()[ok], host["betaMatrix"][ok], floor=1e-6)) < 1e-6
+
+
+def test_optim_fallback_device_vs_host(engine, n=240):
+    """R/fitNbinomGLMs.R:203-227, 340-407 (test_optim.R:29-39): rows whose IRLS does not converge are refitted by the
+    box-constrained maximiser -- on the device (b200nb_beta_optim_dev) vs the host glue (scipy L-BFGS-B = R's optim).
+    Both maximise the same strictly concave objective, so they meet at its unique maximiser; L-BFGS-B stops at
+    factr = 1e7 (about 1e-5 in beta), the device Newton iteration goes on to ~1e-10, hence the tolerances."""
+    import torch
+    from deseq2_b200 import device as D, device_pipeline as DP, pipeline, synth
+    m = 10
+    x = synth.design_condition(m)
+    d = synth.make_example_counts(n, m, x=x, seed=91)
+    counts = d["counts"][d["counts"].sum(axis=1) > 0].copy()
+    bad = np.arange(0, len(counts), 12)
+    counts[bad] = np.array([0, 0, 0, 0, 0, 1000, 1000, 0, 0, 0])            # the reference's own divergent row
+    counts[bad[::2], 5] = 3000                                             # ... and variations of it
+    sf = d["sizeFactors"]
+    nf = np.broadcast_to(sf[None, :], counts.shape)
+    alpha = np.clip(0.1 + 4 / (counts / sf).mean(axis=1), 1e-8, m)
+    raw = pipeline.fitNbinomGLMs(counts, nf, x, alpha, engine=engine, useOptim=False)
+    assert (~raw["betaConv"][bad]).all(), "the planted rows must defeat the IRLS"
+    host = pipeline.fitNbinomGLMs(counts, nf, x, alpha, engine=engine)       # useOptim = TRUE, the reference default
+    dev = torch.device(DEV)
+    y = D.to_gene_major(counts, dev)
+    pr = DP.prep(y, x, sf, want_mu=False)
+    LN2 = np.log(2.0)
+    lam = torch.full((2,), 1e-6 / LN2 ** 2, dtype=torch.float64, device=dev)
+    contrast = torch.tensor([1.0, 0.0], dtype=torch.float64, device=dev)
+    ad = torch.as_tensor(alpha, device=dev)
+    fb = D.fit_beta(y, pr["xd"], pr["sfd"], ad, contrast, pr["beta0"], lam, 1e-8, 100, want_mu=False)
+    ll = D.nb_loglik(y, pr["xd"], pr["sfd"], ad, fb["beta_mat"], want_mu=True)
+    conv, nopt = DP._optim_fallback(y, pr["xd"], pr["sfd"], ad, fb, pr["beta0"], lam, contrast, 100, 0.5, ll)
+    rows = np.flatnonzero(~raw["betaConv"])
+    assert nopt == len(rows) and set(bad) <= set(rows)
+    conv = conv.cpu().numpy()
+    assert conv[rows].all() and np.array_equal(conv, host["betaConv"] | conv)
+    got_beta = (fb["beta_mat"] / LN2).T.cpu().numpy()
+    got_se = (torch.sqrt(torch.clamp(fb["beta_var_mat"], min=0)) / LN2).T.cpu().numpy()
+    got_ll = ll["logLike"].cpu().numpy()
+    # the device optimum is at least as good as L-BFGS-B's, and the two agree to L-BFGS-B's own stopping accuracy
+    assert np.all(got_ll[rows] >= host["logLike"][rows] - 1e-7 * (1 + np.abs(host["logLike"][rows])))
+    assert np.max(np.abs(got_ll[rows] - host["logLike"][rows]) / (1 + np.abs(host["logLike"][rows]))) < 1e-6
+    # The planted rows have a design cell of zeros: the likelihood is flat in that cell's coefficient beyond
+    # mu ~ 1e-4 and only the 1e-6 ridge fixes it, so L-BFGS-B stops (factr = 1e7) a unit or two short of the maximiser the
+    # Newton iteration reaches.  What is identifiable must agree: the fitted means of the samples that carry counts.
+    got_mu = ll["mu"].cpu().numpy()[:, :m]
+    for r_ in rows:
+        sel = host["mu"][r_] > 0.5
+        assert sel.any()
+        assert np.max(rel_err(got_mu[r_, sel], host["mu"][r_, sel])) < 1e-3, r_
+        assert np.all(got_mu[r_, ~sel] < 1e-2)
+        if np.max(np.abs(got_beta[r_] - host["betaMatrix"][r_])) < 1e-3:       # a fully identified row: SEs agree too
+            assert np.max(rel_err(got_se[r_], host["betaSE"][r_])) < 5e-3
+    assert np.all(np.abs(got_beta[rows]) <= 30.0 + 1e-9) and np.all(np.isfinite(got_se[rows]))
+    # rows the IRLS did fit are untouched
+    ok = raw["betaConv"]
+    assert np.max(rel_err(got_beta[ok], raw["betaMatrix"][ok], floor=1e-9)) < 1e-6

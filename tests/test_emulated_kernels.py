@@ -75,6 +75,9 @@ CASES = [
     ("edge 7x33", lambda e, o: TP.test_edge_shapes(e, o, 7, 33)),
     ("edge 2x3000", lambda e, o: TP.test_edge_shapes(e, o, 2, 3000)),
     ("empty input", lambda e, o: TP.test_empty_input_is_a_no_op(e)),
+    ("post-rule parity m=4 (Monte-Carlo prior variance)", lambda e, o: TP.test_post_rule_parity_every_gene(e, o, 4, 250, 0.3)),
+    ("post-rule parity m=6", lambda e, o: TP.test_post_rule_parity_every_gene(e, o, 6, 300, 0.25)),
+    ("post-rule parity m=12", lambda e, o: TP.test_post_rule_parity_every_gene(e, o, 12, 250, 0.12)),
 ]
 
 
@@ -108,9 +111,11 @@ DEVICE_CASES = [
     ("cooks ~batch+condition", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "batch", 36, n=150)),
     ("cooks covariate (one cell per sample)", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "covariate", 20, n=150)),
     ("cooks 10-level factor", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "factor10", 200, n=60)),
-    ("DESeq on device ~condition", lambda T, e: T.test_device_pipeline_matches_host_pipeline(e, "condition", 240, 40)),
-    ("DESeq on device ~batch+condition", lambda T, e: T.test_device_pipeline_matches_host_pipeline(e, "batch", 160, 36)),
+    ("DESeq on device ~condition", lambda T, e, o: T.test_device_pipeline_matches_host_pipeline(e, o, "condition", 240, 40)),
+    ("DESeq on device ~condition m=6", lambda T, e, o: T.test_device_pipeline_matches_host_pipeline(e, o, "condition", 300, 6)),
+    ("DESeq on device ~batch+condition", lambda T, e, o: T.test_device_pipeline_matches_host_pipeline(e, o, "batch", 160, 36)),
     ("LRT on device", lambda T, e: T.test_lrt_device_matches_host(e, n=250)),
+    ("optim fallback on device", lambda T, e: T.test_optim_fallback_device_vs_host(e, n=120)),
     ("size factors 700x12", lambda T, e: T.TS.test_size_factors_match_numpy(e, 700, 12, 1, False)),
     ("size factors 501x37 double", lambda T, e: T.TS.test_size_factors_match_numpy(e, 501, 37, 2, True)),
     ("size factors 150x130", lambda T, e: T.TS.test_size_factors_match_numpy(e, 150, 130, 3, False)),
@@ -124,8 +129,12 @@ DEVICE_CASES = [
 
 
 @pytest.mark.parametrize("name,run", DEVICE_CASES, ids=[c[0] for c in DEVICE_CASES])
-def test_emulated_device_pipeline(emu, emu_device, name, run):
-    run(emu_device, emu)
+def test_emulated_device_pipeline(emu, emu_device, oracle, name, run):
+    import inspect
+    if len(inspect.signature(run).parameters) == 3:
+        run(emu_device, emu, oracle)
+    else:
+        run(emu_device, emu)
 
 
 def test_emulated_engine_through_R_boundary(emu, oracle, tmp_path):

@@ -121,7 +121,7 @@ def test_optim_fallback_matches_irls_and_rescues_divergence(oracle):
     counts = d["counts"][d["counts"].min(axis=1) > 3]
     nf = np.ones(counts.shape)
     alpha = np.full(len(counts), 0.1)
-    a = pipeline.fitNbinomGLMs(counts, nf, x, alpha, engine=oracle)
+    a = pipeline.fitNbinomGLMs(counts, nf, x, alpha, engine=oracle, useOptim=False)
     b = pipeline.fitNbinomGLMs(counts, nf, x, alpha, engine=oracle, forceOptim=True)
     conv = a["betaConv"]
     assert conv.mean() > 0.8
@@ -130,8 +130,8 @@ def test_optim_fallback_matches_irls_and_rescues_divergence(oracle):
     assert np.allclose(a["betaSE"][conv], b["betaSE"][conv], rtol=1e-2)
     y = np.array([[0, 0, 0, 0, 0, 1000, 1000, 0, 0, 0]], dtype=np.int32)
     x2 = np.c_[np.ones(10), np.r_[np.zeros(5), np.ones(5)]]
-    r0 = pipeline.fitNbinomGLMs(y, np.ones((1, 10)), x2, np.array([0.1]), engine=oracle)
-    r1 = pipeline.fitNbinomGLMs(y, np.ones((1, 10)), x2, np.array([0.1]), engine=oracle, useOptim=True)
+    r0 = pipeline.fitNbinomGLMs(y, np.ones((1, 10)), x2, np.array([0.1]), engine=oracle, useOptim=False)
+    r1 = pipeline.fitNbinomGLMs(y, np.ones((1, 10)), x2, np.array([0.1]), engine=oracle)   # reference default: useOptim
     assert r0["betaIter"][0] == 100 and not r0["betaConv"][0]
     assert np.all(np.isfinite(r1["betaMatrix"])) and np.all(np.abs(r1["betaMatrix"]) <= 30)
     assert r1["logLike"][0] >= r0["logLike"][0] - 1e-6

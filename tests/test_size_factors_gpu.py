@@ -114,8 +114,11 @@ def test_outlier_replacement_and_refit_device_vs_host(engine, design, n=2500):
     dv = DP.DESeq_device(D.to_gene_major(counts, torch.device(DEV)), x, sf, minReplicatesForReplace=7)
     idx = dv["idx"].cpu().numpy()
     assert np.array_equal(idx, np.flatnonzero(~host["allZero"]))
-    raw = pipeline.DESeq(counts, x, sizeFactors=sf, engine=engine)
-    ok1 = raw["betaConv"][idx] == 1          # rows whose first-pass IRLS diverged go to optim in R: out of scope here
+    raw = pipeline.DESeq(counts, x, sizeFactors=sf, engine=engine, useOptim=False)
+    # rows whose first-pass IRLS diverged go to the box-constrained maximiser on both sides (L-BFGS-B on the host, projected
+    # Newton on the device: tests/test_device_pipeline_gpu.py::test_optim_fallback_device_vs_host); they stop at different
+    # distances from the optimum along flat directions, so they are compared there, not here
+    ok1 = raw["betaConv"][idx] == 1
     rep_h = host["replace"][idx]
     rep_d = dv["replace"].cpu().numpy()
     assert rep_h.sum() >= len(planted) * 0.5 and np.mean((rep_h == rep_d)[ok1]) > 0.995 and ok1.mean() > 0.97
