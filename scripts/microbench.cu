@@ -163,6 +163,7 @@ int main(int argc, char** argv) {
     auto fdh = (fit_disp_host_t)dlsym(h, "b200nb_fit_disp");
     auto fbh = (fit_beta_host_t)dlsym(h, "b200nb_fit_beta");
     auto le = (last_error_t)dlsym(h, "b200nb_last_error");
+    auto cache_clear = (void (*)(void))dlsym(h, "b200nb_cache_clear");   // a step = a new DESeq() run: nothing may be reused
     std::vector<double> tstep, t1, t3;
     for (int r = 0; r < reps + 2; r++) {
       // fresh result buffers every call, like R's allocVector: their pages are first touched by the library
@@ -175,6 +176,7 @@ int main(int argc, char** argv) {
       double* bv = (double*)malloc(sizeof(double) * (size_t)n * p);
       double* sc4[4];
       for (auto& q : sc4) q = (double*)malloc(sizeof(double) * n);
+      if (cache_clear) cache_clear();
       const auto c0 = std::chrono::steady_clock::now();
       int rc = fdh(yc.data(), 0, x.data(), muc.data(), la0.data(), la0.data(), 1.0, log(1e-8 / 10), 1.0, 1e-6, 100, 0, nullptr, 0,
                    1e-2, 1, n, m, p, o[0], it, ita, o[1], o[2], o[3], o[4], o[5], o[6]);

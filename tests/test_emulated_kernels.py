@@ -75,6 +75,7 @@ CASES = [
     ("edge 7x33", lambda e, o: TP.test_edge_shapes(e, o, 7, 33)),
     ("edge 2x3000", lambda e, o: TP.test_edge_shapes(e, o, 2, 3000)),
     ("empty input", lambda e, o: TP.test_empty_input_is_a_no_op(e)),
+    ("host input cache: content-addressed, never stale", lambda e, o: TP.test_host_cache_is_content_addressed_and_never_stale(e, o)),
     ("post-rule parity m=4 (Monte-Carlo prior variance)", lambda e, o: TP.test_post_rule_parity_every_gene(e, o, 4, 250, 0.3)),
     ("post-rule parity m=6", lambda e, o: TP.test_post_rule_parity_every_gene(e, o, 6, 300, 0.25)),
     ("post-rule parity m=12", lambda e, o: TP.test_post_rule_parity_every_gene(e, o, 12, 250, 0.12)),

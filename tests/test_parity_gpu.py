@@ -513,3 +513,68 @@ def test_post_rule_parity_every_gene(engine, oracle, m, n, max_raw_mismatch):
     assert np.max(rel_err(fe["betaMatrix"][conv], fo["betaMatrix"][conv], floor=1e-6)) < TOL
     assert np.max(rel_err(fe["betaSE"][conv], fo["betaSE"][conv])) < TOL
     assert np.max(rel_err(fe["logLike"][conv], fo["logLike"][conv])) < TOL
+
+
+# ---------------------------------------------------------------- host-path input cache (content-addressed) and speculation
+
+def _host_stats():
+    import ctypes as C
+    import deseq2_b200
+    st = (C.c_longlong * 6)()
+    deseq2_b200.lib().b200nb_host_stats(st, 6)
+    return dict(h2d=st[0], d2h=st[1], hits=st[2], misses=st[3], hit_bytes=st[4], hashed=st[5])
+
+
+def test_host_cache_is_content_addressed_and_never_stale(engine, oracle):
+    """The host entry points keep device copies of their input matrices keyed by CONTENT.  (1) a fresh copy of the same
+    matrix at another address is a hit (no upload) with identical results; (2) the same buffer modified IN PLACE in a
+    few entries far from the sampled fingerprint blocks must NOT be served from the cache -- the speculative launch is
+    discarded and the results are those of the modified data; (3) a normalisation-factor matrix that is a replicated
+    size-factor vector except for one entry deep inside takes the matrix path; (4) b200nb_cache_clear forgets."""
+    import deseq2_b200
+    L = deseq2_b200.lib()
+    c = make_case(3000, 40, seed=77)
+    a = disp_args(c, c["mu"], np.log(c["alpha0"]))
+    L.b200nb_cache_clear()
+    s0 = _host_stats()
+    g1 = engine.fitDisp(**a)
+    s1 = _host_stats()
+    assert s1["misses"] - s0["misses"] == 2 and s1["h2d"] - s0["h2d"] > c["counts"].size * 12
+    a2 = dict(a, ySEXP=np.array(c["counts"], copy=True), mu_hatSEXP=np.array(c["mu"], copy=True))   # new addresses
+    g2 = engine.fitDisp(**a2)
+    s2 = _host_stats()
+    assert s2["hits"] - s1["hits"] == 2 and s2["h2d"] - s1["h2d"] < 0.2 * c["counts"].size * 12
+    for k in DISP_KEYS + ("iter", "iter_accept"):
+        assert np.array_equal(g1[k], g2[k], equal_nan=True), k
+    # (2) in-place change of two entries in the middle of the buffers
+    y3 = np.asfortranarray(a2["ySEXP"])
+    mu3 = np.asfortranarray(a2["mu_hatSEXP"])
+    y3[1501, 17] += 40
+    mu3[1502, 23] *= 3.0
+    a3 = dict(a, ySEXP=y3, mu_hatSEXP=mu3)
+    g3 = engine.fitDisp(**a3)
+    o3 = oracle.fitDisp(**a3, with_margin=True)
+    for gene in (1501, 1502):
+        assert g3["log_alpha"][gene] != g1["log_alpha"][gene]
+        assert abs(g3["initial_lp"][gene] - o3["initial_lp"][gene]) < 1e-9 * abs(o3["initial_lp"][gene])
+    other = np.ones(len(y3), bool)
+    other[[1501, 1502]] = False
+    assert np.array_equal(g3["log_alpha"][other], g1["log_alpha"][other])
+    # (3) nf: replicated size factors except one entry that none of the probed rows sees
+    alpha = np.clip(0.1 + 4.0 / c["baseMean"], 1e-8, 10)
+    b = beta_args(c, alpha)
+    r_vec = engine.fitBeta(**b)
+    nf2 = np.array(c["nf"], copy=True)
+    nf2[777, 5] *= 1.5
+    r_mat = engine.fitBeta(**beta_args(c, alpha, nf=nf2))
+    o_mat = oracle.fitBeta(**beta_args(c, alpha, nf=nf2))
+    assert np.max(rel_err(r_mat["beta_mat"], o_mat["beta_mat"], floor=1e-8)) < TOL
+    assert abs(r_mat["beta_mat"][777, 0] - r_vec["beta_mat"][777, 0]) > 1e-6
+    rest = np.arange(len(alpha)) != 777
+    assert np.max(rel_err(r_mat["beta_mat"][rest], r_vec["beta_mat"][rest], floor=1e-8)) < 1e-9
+    # (4) clear: the next call uploads again
+    L.b200nb_cache_clear()
+    s4 = _host_stats()
+    engine.fitDisp(**a)
+    s5 = _host_stats()
+    assert s5["misses"] - s4["misses"] == 2
