@@ -55,6 +55,8 @@ SIGNATURES = {
     "b200nb_kernel_launches": [],
     "b200nb_release_workspace": [],
     "b200nb_cache_clear": [],
+    "b200nb_host_alloc": [C.c_size_t],
+    "b200nb_host_free": [vp],
     "b200nb_host_stats": [vp, _I],
     "b200nb_version": [],
     "b200nb_test_special": [vp, _I, vp, vp, vp],
@@ -65,6 +67,8 @@ _RESTYPE = {
     "b200nb_kernel_launches": C.c_longlong,
     "b200nb_release_workspace": None,
     "b200nb_cache_clear": None,
+    "b200nb_host_alloc": C.c_void_p,
+    "b200nb_host_free": None,
 }
 
 

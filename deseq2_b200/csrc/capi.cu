@@ -155,12 +155,13 @@ void par_memcpy(void* dst, const void* src, size_t bytes) {
   });
 }
 
-hostrt::Hash128 par_hash(const void* src, size_t bytes) {
+// content hash of a column-major host matrix (elements of `elem` bytes, canonical index = position), by the pool
+hostrt::Hash128 par_hash(const void* src, size_t bytes, int elem) {
   const size_t nb = (bytes + kBlock - 1) / kBlock;
   std::vector<hostrt::Hash128> part(nb);
   pool().parallel_for(nb, [&](size_t b) {
     const size_t lo = b * kBlock, hi = (lo + kBlock < bytes) ? lo + kBlock : bytes;
-    part[b] = hostrt::hash_range(static_cast<const char*>(src) + lo, hi - lo, lo / 8);
+    part[b] = hostrt::hash_elems(static_cast<const char*>(src) + lo, (hi - lo) / elem, elem, lo / elem);
   });
   hostrt::Hash128 h;
   for (const auto& q : part) h.add(q);
@@ -168,41 +169,69 @@ hostrt::Hash128 par_hash(const void* src, size_t bytes) {
   return h;
 }
 
-// pageable host -> device through the pinned ring; when `hash` is given the content hash is computed on the way (each
-// task hashes the block it has just copied, from the pinned copy, while it is still in its cache)
-int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st, hostrt::Hash128* hash) {
-  if (hash) *hash = hostrt::Hash128();
+// wall time the calling thread spent (a) copying into the pinned ring, (b) waiting for ring slots / DMA (HOST_TIMING)
+std::atomic<long long> g_stage_copy_us{0}, g_stage_wait_us{0};
+static inline long long now_us() {
+  return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// pageable host -> device through the pinned ring
+int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return 0;
   if (stage_init()) return 1;
   size_t off = 0;
   for (int k = 0; off < bytes; k++) {
     const int b = k % kStageRing;
     const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
+    const long long t0 = now_us();
     if (k >= kStageRing) CU(cudaEventSynchronize(g_stage.ev[b]));
-    char* pin = static_cast<char*>(g_stage.buf[b]);
-    const char* s = static_cast<const char*>(src) + off;
-    const size_t nb = (len + kBlock - 1) / kBlock;
-    std::vector<hostrt::Hash128> part(hash ? nb : 0);
-    pool().parallel_for(nb, [&](size_t t) {
-      const size_t lo = t * kBlock, hi = (lo + kBlock < len) ? lo + kBlock : len;
-      memcpy(pin + lo, s + lo, hi - lo);
-      if (hash) part[t] = hostrt::hash_range(pin + lo, hi - lo, (off + lo) / 8);
-    });
-    if (hash)
-      for (const auto& q : part) hash->add(q);
-    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, pin, len, cudaMemcpyHostToDevice, st));
+    const long long t1 = now_us();
+    par_memcpy(g_stage.buf[b], static_cast<const char*>(src) + off, len);
+    const long long t2 = now_us();
+    g_stage_wait_us += t1 - t0;
+    g_stage_copy_us += t2 - t1;
+    CU(cudaMemcpyAsync(static_cast<char*>(dst) + off, g_stage.buf[b], len, cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(g_stage.ev[b], st));
     off += len;
   }
   // the ring is reused by the next transfer: drain it
+  const long long t0 = now_us();
   for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(g_stage.ev[b]));
+  g_stage_wait_us += now_us() - t0;
   g_h2d_bytes += (long long)bytes;
   return 0;
+}
+
+// ---------------------------------------------------------------- pinned result memory (b200nb_host_alloc)
+// A result matrix that the caller allocates with b200nb_host_alloc lives in page-locked memory: the device-to-host copy
+// is then ONE DMA straight into it -- no staging ring, no scatter by host threads and, above all, no first-touch page
+// faults (a freshly malloc'ed 40 MB hat-diagonal matrix costs ~3 ms of faults on the GPU box, more than the kernels).
+// Blocks are pooled: b200nb_host_free returns them for reuse; the pool keeps at most B200NB_PINNED_POOL_MB (default
+// 1024) of idle blocks.  R can place the REALSXP itself there through allocVector3's custom allocator (r_shim/).
+struct PinBlock {
+  void* p;
+  size_t cap;
+  bool in_use;
+};
+std::vector<PinBlock> g_pin;
+std::mutex g_pin_mu;
+bool pinned_contains(const void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  const char* q = static_cast<const char*>(p);
+  for (const auto& b : g_pin)
+    if (b.in_use && q >= static_cast<const char*>(b.p) && q + bytes <= static_cast<const char*>(b.p) + b.cap) return true;
+  return false;
 }
 
 // device -> pageable host through the pinned ring; synchronous on return
 int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return 0;
+  if (pinned_contains(dst, bytes)) {   // the caller's buffer is page-locked (b200nb_host_alloc): one DMA, no staging
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    g_d2h_bytes += (long long)bytes;
+    return 0;
+  }
   if (stage_init()) return 1;
   const size_t nchunk = (bytes + kStageChunk - 1) / kStageChunk;
   auto issue = [&](size_t k) -> int {
@@ -240,7 +269,9 @@ struct CacheEntry {
   bool valid = false;
   size_t n = 0;
   int m = 0, elem = 0;
-  hostrt::Hash128 hash;    // of every byte
+  hostrt::Hash128 hash;    // of every element (valid when hash_known)
+  bool hash_known = false; // false: the GPU is still computing it / it sits in the pinned slot g_hash_pin[index]
+  uint64_t upload_call = 0; // host call (g_call_seq) that uploaded it
   hostrt::Hash128 fprint;  // of ~64 sampled 4 KB blocks: cheap pre-filter before a speculative hit (see Speculation)
   void* dev = nullptr;     // gene-major n x ld
   size_t cap = 0;          // bytes allocated at dev
@@ -248,6 +279,29 @@ struct CacheEntry {
 };
 CacheEntry g_cache[kCacheEntries];
 uint64_t g_cache_clock = 0;
+// the hash of a freshly uploaded matrix is computed ON THE DEVICE from its gene-major copy (layout.cu) and lands in a
+// pinned slot with the stream synchronisation that ends the uploading call; the host never hashes what it uploads
+unsigned long long* g_hash_dev = nullptr;   // kCacheEntries x 2 (device)
+unsigned long long* g_hash_pin = nullptr;   // kCacheEntries x 2 (pinned host)
+int hash_slots_init() {
+  if (g_hash_dev) return 0;
+  CU(cudaMalloc(&g_hash_dev, sizeof(unsigned long long) * 2 * kCacheEntries));
+  CU(cudaHostAlloc(&g_hash_pin, sizeof(unsigned long long) * 2 * kCacheEntries, cudaHostAllocDefault));
+  return 0;
+}
+// entry's hash, fetching it from the pinned slot the first time (every host call ends with a stream synchronisation,
+// so the slot of an entry uploaded by an EARLIER call is final)
+uint64_t g_call_seq = 0;   // incremented by every host entry point (under g_call_mu)
+const hostrt::Hash128& entry_hash(CacheEntry& e) {
+  if (!e.hash_known) {
+    if (e.upload_call == g_call_seq && g_ws.stream) cudaStreamSynchronize(g_ws.stream);   // uploaded by THIS call
+    const int k = (int)(&e - g_cache);
+    e.hash.a = g_hash_pin[2 * k];
+    e.hash.b = g_hash_pin[2 * k + 1];
+    e.hash_known = true;
+  }
+  return e.hash;
+}
 size_t cache_limit_bytes() {
   static const size_t v = (size_t)hostrt::env_int("B200NB_CACHE_MB", 8192, 0, 1 << 20) << 20;
   return v;
@@ -269,14 +323,14 @@ long long ld_for(int m) { return ((long long)m + 3) & ~3LL; }
 hostrt::Hash128 fingerprint(const void* host, size_t bytes) {
   const char* s = static_cast<const char*>(host);
   const size_t blk = 4096;
-  if (bytes <= 80 * blk) return hostrt::hash_range(s, bytes, 0);
+  if (bytes <= 80 * blk) return hostrt::hash_elems(s, bytes / 8, 8, 0);
   hostrt::Hash128 h;
   const size_t nblk = bytes / blk;
   for (int k = 0; k < 64; k++) {
     const size_t b = nblk * k / 64;
-    h.add(hostrt::hash_range(s + b * blk, blk, b * (blk / 8)));
+    h.add(hostrt::hash_elems(s + b * blk, blk / 8, 8, b * (blk / 8)));
   }
-  h.add(hostrt::hash_range(s + bytes - blk, blk, (bytes - blk) / 16 * 2));
+  h.add(hostrt::hash_elems(s + ((bytes - blk) & ~(size_t)7), blk / 8, 8, (bytes - blk) / 8));
   return h;
 }
 
@@ -288,6 +342,7 @@ struct Pending {
   CacheEntry* e;
   const void* host;
   size_t bytes;
+  int elem;
 };
 struct CallInputs {
   bool speculate = true;
@@ -296,8 +351,8 @@ struct CallInputs {
   bool validate() {           // true when every speculative hit was a real one
     bool ok = true;
     for (const auto& q : pending) {
-      const hostrt::Hash128 h = par_hash(q.host, q.bytes);
-      if (h == q.e->hash) {
+      const hostrt::Hash128 h = par_hash(q.host, q.bytes, q.elem);
+      if (h == entry_hash(*q.e)) {
         g_cache_hits++;
         g_cache_hit_bytes += (long long)q.bytes;
       } else {
@@ -318,8 +373,8 @@ int upload_matrix(const void* host, int n, int m, int elem, cudaStream_t st, Cal
   const size_t bytes = (size_t)n * m * elem, dbytes = (size_t)n * ld * elem + 64;
   const bool use_cache = cache_limit_bytes() >= dbytes;
   hostrt::Hash128 h, fp;
-  bool have_hash = false;
   if (use_cache) {
+    if (hash_slots_init()) return 1;
     fp = fingerprint(host, bytes);
     CacheEntry* cand = nullptr;
     for (auto& e : g_cache)
@@ -328,15 +383,14 @@ int upload_matrix(const void* host, int n, int m, int elem, cudaStream_t st, Cal
         cand = &e;
     if (cand && ci.speculate) {
       cand->last_use = ++g_cache_clock;
-      ci.pending.push_back({cand, host, bytes});
+      ci.pending.push_back({cand, host, bytes, elem});
       *out = cand->dev;
       return 0;
     }
     if (cand) {
-      h = par_hash(host, bytes);
-      have_hash = true;
+      h = par_hash(host, bytes, elem);
       for (auto& e : g_cache)
-        if (e.valid && e.n == (size_t)n && e.m == m && e.elem == elem && e.hash == h) {
+        if (e.valid && e.n == (size_t)n && e.m == m && e.elem == elem && entry_hash(e) == h) {
           e.last_use = ++g_cache_clock;
           g_cache_hits++;
           g_cache_hit_bytes += (long long)bytes;
@@ -393,15 +447,20 @@ int upload_matrix(const void* host, int n, int m, int elem, cudaStream_t st, Cal
     CU(cudaMalloc(&d_dst, dbytes));
     ci.owned.push_back(d_dst);
   }
-  if (h2d_staged(d_raw, host, bytes, st, (use_cache && !have_hash) ? &h : nullptr)) return 1;
+  if (h2d_staged(d_raw, host, bytes, st)) return 1;
   CU(nb::launch_to_gene_major(d_raw, d_dst, n, m, ld, elem, st));
   g_launches++;
   if (dst) {
+    const int k = (int)(dst - g_cache);
+    CU(nb::launch_hash_gene_major(d_dst, n, m, ld, elem, g_hash_dev + 2 * k, st));
+    CU(cudaMemcpyAsync(g_hash_pin + 2 * k, g_hash_dev + 2 * k, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    g_launches++;
     dst->valid = true;
     dst->n = (size_t)n;
     dst->m = m;
     dst->elem = elem;
-    dst->hash = h;
+    dst->hash_known = false;
+    dst->upload_call = g_call_seq;
     dst->fprint = fp;
     dst->last_use = ++g_cache_clock;
   }
@@ -463,25 +522,6 @@ struct SmallOut {
     g_d2h_bytes += (long long)total;
     return 0;
   }
-};
-
-// Background population of a freshly allocated result matrix (see hostrt.h); joined before the scatter.
-struct Populate {
-  std::vector<std::thread> th;
-  void start(void* p, size_t bytes) {
-    if (!p || bytes < ((size_t)4 << 20) || !hostrt::env_int("B200NB_POPULATE", 1, 0, 1)) return;
-    const int T = hostrt::env_int("B200NB_POPULATE_THREADS", 8, 1, 32);
-    for (int t = 0; t < T; t++) {
-      char* lo = static_cast<char*>(p) + bytes * t / T;
-      char* hi = static_cast<char*>(p) + bytes * (t + 1) / T;
-      th.emplace_back([lo, hi] { hostrt::populate_write(lo, (size_t)(hi - lo)); });
-    }
-  }
-  void join() {
-    for (auto& t : th) t.join();
-    th.clear();
-  }
-  ~Populate() { join(); }
 };
 
 // device-side work-queue counters: a ring of slots, one per launch, so launches in flight on different
@@ -675,11 +715,12 @@ struct PhaseClock {
   int phase = 0;
   bool on;
   cudaStream_t st;
-  long long h2d0, d2h0, hit0, hashed0;
+  long long h2d0, d2h0, hit0, hashed0, copy0, wait0;
   explicit PhaseClock(cudaStream_t s) : on(host_timing()), st(s) {
     if (on) {
       t0 = std::chrono::steady_clock::now();
       h2d0 = g_h2d_bytes; d2h0 = g_d2h_bytes; hit0 = g_cache_hit_bytes; hashed0 = g_hashed_bytes;
+      copy0 = g_stage_copy_us; wait0 = g_stage_wait_us;
     }
   }
   void next() {   // close the current phase
@@ -692,9 +733,10 @@ struct PhaseClock {
   void report(const char* what, int n) {
     if (on)
       fprintf(stderr, "b200nb timing %s %d genes: hash+upload %.3f ms, kernels %.3f ms, download %.3f ms | H2D %.1f MB, "
-                      "D2H %.1f MB, hashed %.1f MB, served from the device cache %.1f MB\n", what, n, ms[0], ms[1], ms[2],
+                      "D2H %.1f MB, hashed %.1f MB, served from the device cache %.1f MB; upload staging: %.3f ms copying "
+                      "into the pinned ring, %.3f ms waiting for ring slots\n", what, n, ms[0], ms[1], ms[2],
               (g_h2d_bytes - h2d0) / 1e6, (g_d2h_bytes - d2h0) / 1e6, (g_hashed_bytes - hashed0) / 1e6,
-              (g_cache_hit_bytes - hit0) / 1e6);
+              (g_cache_hit_bytes - hit0) / 1e6, (g_stage_copy_us - copy0) / 1e3, (g_stage_wait_us - wait0) / 1e3);
   }
 };
 
@@ -713,6 +755,43 @@ int b200nb_device_count(void) {
     return 0;
   }
   return c;
+}
+
+void* b200nb_host_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  PinBlock* best = nullptr;
+  for (auto& b : g_pin)
+    if (!b.in_use && b.cap >= bytes && b.cap <= 2 * bytes + (1u << 20) && (!best || b.cap < best->cap)) best = &b;
+  if (best) {
+    best->in_use = true;
+    return best->p;
+  }
+  const size_t cap = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;   // the caller falls back to ordinary memory
+  }
+  g_pin.push_back({p, cap, true});
+  return p;
+}
+
+void b200nb_host_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  size_t idle = 0;
+  for (auto& b : g_pin) {
+    if (b.p == p) b.in_use = false;
+    if (!b.in_use) idle += b.cap;
+  }
+  const size_t limit = (size_t)hostrt::env_int("B200NB_PINNED_POOL_MB", 1024, 0, 1 << 20) << 20;
+  for (size_t i = g_pin.size(); i-- > 0 && idle > limit;)
+    if (!g_pin[i].in_use) {
+      idle -= g_pin[i].cap;
+      cudaFreeHost(g_pin[i].p);
+      g_pin.erase(g_pin.begin() + (long)i);
+    }
 }
 
 void b200nb_cache_clear(void) {
@@ -972,6 +1051,7 @@ int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu
   if (n == 0) return 0;
   if (use_weights && !weights) return fail("use_weights set but weights == NULL");
   std::lock_guard<std::mutex> lk(g_call_mu);
+  g_call_seq++;
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
   const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
@@ -1029,6 +1109,7 @@ int b200nb_fit_disp_grid(const void* y, int y_type, const double* x, const doubl
   if (use_weights && !weights) return fail("use_weights set but weights == NULL");
   if (disp_grid_n < 2) return fail("disp_grid needs at least 2 points");
   std::lock_guard<std::mutex> lk(g_call_mu);
+  g_call_seq++;
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
   const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
@@ -1104,12 +1185,9 @@ int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf
   if (n == 0) return 0;
   if (use_weights && !weights) return fail("use_weights set but weights == NULL");
   std::lock_guard<std::mutex> lk(g_call_mu);
+  g_call_seq++;
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
-  // the result matrices are fresh allocations of the caller: fault their pages in while the GPU works
-  Populate pop_h, pop_mu;
-  pop_h.start(out_hat_diagonals, sizeof(double) * (size_t)n * m);
-  pop_mu.start(out_mu, sizeof(double) * (size_t)n * m);
   const int ye = (y_type == B200NB_Y_F64) ? 8 : 4;
   const long long ld = ld_for(m);
   const bool sf_detect = hostrt::env_int("B200NB_SF_DETECT", 1, 0, 1) != 0;
@@ -1173,12 +1251,10 @@ int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf
       continue;
     }
     if (out_hat_diagonals) {
-      pop_h.join();
       if (d2h_staged(out_hat_diagonals, d_hc, sizeof(double) * (size_t)n * m, st)) return 1;
     }
     if (out_mu) {
       if (b200nb_to_col_major_dev((const double*)d_mu, (double*)d_hc, n, m, ld, st)) return 1;
-      pop_mu.join();
       if (d2h_staged(out_mu, d_hc, sizeof(double) * (size_t)n * m, st)) return 1;
     }
     if (out.download(dout, st)) return 1;
@@ -1192,6 +1268,7 @@ int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf
 int b200nb_test_special(const double* x, int n, double* out_lgamma, double* out_digamma, double* out_trigamma) {
   if (n <= 0) return 0;
   std::lock_guard<std::mutex> lk(g_call_mu);
+  g_call_seq++;
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
   SmallIn in;

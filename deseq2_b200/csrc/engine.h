@@ -55,18 +55,10 @@ struct DispArgs {
   const int* mode_lists;
 };
 
-#if defined(NB_EXP_TAB_BUCKETS)
 // experiment: [queue counter | 3 mode counters | 2 more queue counters | pad to 8 | 8 bucket counts | 8 bucket fills | pad],
 // then the three gene lists, one bucket code per gene and a scratch list for the bucket sort
 constexpr int kDispScratchHead = 32;
 constexpr int kDispScratchLists = 5;
-#elif defined(NB_EXP_SPLIT_MODES) || defined(NB_EXP_HALF_WARP)
-constexpr int kDispScratchHead = 8;   // experiment: [queue counter | 3 mode counters | second queue counter | pad]
-constexpr int kDispScratchLists = 3;
-#else
-constexpr int kDispScratchHead = 4;   // [queue counter | 3 mode counters], then the three per-mode gene lists
-constexpr int kDispScratchLists = 3;
-#endif
 inline size_t disp_scratch_bytes(int n) {
   return (kDispScratchHead + kDispScratchLists * (size_t)n) * sizeof(unsigned int);
 }
@@ -213,6 +205,9 @@ cudaError_t launch_to_gene_major(const void* src_colmajor, void* dst, int n, int
 // gene-major n x ld -> column-major n x m (f64)
 cudaError_t launch_to_col_major(const double* src, double* dst_colmajor, int n, int m, long long ld,
                                 cudaStream_t stream);
+// 128-bit content hash of a gene-major matrix into out2[0..1] (device); see hostrt.h::hash_elems
+cudaError_t launch_hash_gene_major(const void* src, int n, int m, long long ld, int elem_size,
+                                   unsigned long long* out2, cudaStream_t stream);
 cudaError_t launch_special_test(const double* x, int n, double* lg, double* dg, double* tg, cudaStream_t stream);
 
 int device_sm_count();

@@ -42,10 +42,9 @@ __device__ __forceinline__ double lgamma_diff(double y, double r, double lg_r) {
   return lgamma_pos(y + r) - lg_r;
 }
 
-// lgamma(y + 1) for the mu-independent part of the deviance.  NB_EXP_LFACT_TABLE (experiment, off by default): counts
+// lgamma(y + 1) for the mu-independent part of the deviance.  Counts
 // below 256 read log(y!) from a per-CTA shared table filled once with the very same lgamma_pos(k + 1), so the value --
 // and every result -- is bit-identical while one Stirling evaluation per sample and gene is saved.
-#ifdef NB_EXP_LFACT_TABLE
 __shared__ double s_lfact[256];
 __device__ __forceinline__ void init_lfact_table() {   // call before the first log_factorial; contains a __syncthreads
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lfact[i] = lgamma_pos((double)i + 1.0);
@@ -54,16 +53,12 @@ __device__ __forceinline__ void init_lfact_table() {   // call before the first 
 __device__ __forceinline__ double log_factorial(double y) {
   return (y < 256.0 && y == floor(y)) ? s_lfact[(int)y] : lgamma_pos(y + 1.0);
 }
-#else
-__device__ __forceinline__ void init_lfact_table() {}
-__device__ __forceinline__ double log_factorial(double y) { return lgamma_pos(y + 1.0); }
-#endif
 
 constexpr int pow2_ceil_b(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // One fused IRLS pass: mu (stored to shared memory), mu-dependent part of the deviance, X'WX and X'Wz.
 // Four samples per lane per trip (clamped index + validity factor) for instruction-level parallelism.
-// GL = lanes per gene: 32 in the product kernel; 16 in the NB_EXP_HALF_WARP experiment (`lane` is then the lane index
+// GL = lanes per gene: 32 (one warp per gene) or 16 / 8 (fit_beta_grp.cuh; `lane` is then the lane index
 // inside the group and the reduction stays inside the group).
 template <int P, bool USE_W, int GL = 32>
 __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta)[P], double alpha, double r,
@@ -139,11 +134,7 @@ __device__ __forceinline__ void beta_pass(const BetaRow& rv, const double (&beta
 
 #ifndef NB_LB_THREADS
 #define NB_LB_THREADS 256
-#ifdef NB_EXP_BETA_CTAS3   // experiment (off by default): 3 CTAs/SM; ptxas then spills 84 bytes at 80 registers
-#define NB_LB_CTAS 3
-#else
 #define NB_LB_CTAS 2
-#endif
 #endif
 template <int P, bool USE_W>
 __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_beta_kernel(const BetaArgs A, int warps_per_cta, int mpad) {
@@ -341,7 +332,6 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_beta_kernel(con
   }
 }
 
-#ifdef NB_EXP_HALF_WARP
 #include "fit_beta_grp.cuh"
 
 template <int P, bool USE_W, int GL>
@@ -370,7 +360,6 @@ cudaError_t launch_beta_grp(const BetaArgs& a, int mpad, size_t fixed, size_t ro
   launched = true;
   return cudaGetLastError();
 }
-#endif
 
 template <int P, bool USE_W>
 cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
@@ -407,7 +396,6 @@ cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
   if (grid < 1) grid = 1;
   e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
-#ifdef NB_EXP_HALF_WARP
   {
     const int gl = group_lanes_beta(a.m);
     bool launched = false;
@@ -415,7 +403,6 @@ cudaError_t launch_beta_t(const BetaArgs& a, cudaStream_t stream) {
     else if (gl == 16) e = launch_beta_grp<P, USE_W, 16>(a, mpad, fixed, rowbytes, sms, stream, launched);
     if (e != cudaSuccess || launched) return e;
   }
-#endif
   kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, warps, mpad);
   return cudaGetLastError();
 }

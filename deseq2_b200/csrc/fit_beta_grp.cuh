@@ -1,5 +1,5 @@
-// fit_beta_grp.cuh -- EXPERIMENT (compiled only with -DNB_EXP_HALF_WARP, never in the default build; parity-checked under
-// the SIMT emulator, not yet timed): several genes per warp for the IRLS kernel.  See fit_disp_grp.cuh for the idea;
+// fit_beta_grp.cuh -- several genes per warp for the IRLS kernel (the default for m <= ~330 samples; measured on B200,
+// C2 50k x 100: fitBeta 0.49 -> 0.42 ms with two genes per warp; 20k x 12: 0.24 -> 0.11 ms with four).  See fit_disp_grp.cuh for the idea;
 // included by fit_beta.cu inside namespace nb::{anonymous}.
 //
 // A warp holds NG = 32 / GL genes, GL lanes each.  Control flow is warp-uniform: a round loads one gene per group, all
@@ -13,11 +13,17 @@
 // threads, 3 CTAs per SM, so that 12 warps x 4 gene slices still fit in shared memory.
 #ifndef NB_GRP_SHAPE_DEFINED
 #define NB_GRP_SHAPE_DEFINED
+#ifndef NB_GRP16_CTAS
+#define NB_GRP16_CTAS 2   // resident CTAs per SM the register allocation is bounded for (A/B knobs of the build)
+#endif
+#ifndef NB_GRP8_CTAS
+#define NB_GRP8_CTAS 3
+#endif
 template <int GL>
 struct GrpShape {
   static_assert(GL == 16 || GL == 8, "group width must be 16 or 8 lanes");
   static constexpr int threads = (GL == 8) ? 128 : 256;
-  static constexpr int ctas = (GL == 8) ? 3 : 2;
+  static constexpr int ctas = (GL == 8) ? NB_GRP8_CTAS : NB_GRP16_CTAS;
 };
 #endif
 

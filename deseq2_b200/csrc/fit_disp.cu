@@ -51,7 +51,7 @@ struct DispScal {
 constexpr int pow2_ceil(int n) { int p = 1; while (p < n) p <<= 1; return p; }
 
 // One fused pass: lp (and dlp when WANT_D) at log-alpha `a`.
-// GL = lanes per gene: 32 (one warp per gene, the product path) or, in the NB_EXP_HALF_WARP experiment, 16 / 8 with
+// GL = lanes per gene: 32 (one warp per gene) or 16 / 8 (two / four genes per warp, fit_disp_grp.cuh) with
 // `lane` the lane index inside the group; reductions then stay inside the group.
 template <int N, int GL>
 __device__ __forceinline__ void group_allreduce_sum_n(double (&v)[N]) {
@@ -78,11 +78,7 @@ __device__ __forceinline__ void disp_eval_mode(const DispRow& rv, const DispScal
 
   if (MODE == MODE_TAB) {
     // shared factor table: sum_k c_k log(r+k), sum_k c_k/(r+k)
-#ifdef NB_EXP_TAB_UNROLL4   // experiment (off by default): four independent log/rcp chains in flight instead of two
-#pragma unroll 4
-#else
 #pragma unroll 2
-#endif
     for (int k = lane; k < rv.ntab; k += GL) {
       const double ck = rv.tab[k];
       const double xk = r + (double)k;
@@ -284,8 +280,7 @@ __device__ __forceinline__ double disp_d2(const DispRow& rv, const DispScal& sc,
 // one list per mode so the persistent kernel can work through one mode at a time (keeps the instruction
 // working set of an SM inside the instruction cache: the first fused version stalled 70% on instruction fetch,
 // profiles/r01b_*).  lists[mode * n + i], counts[mode].
-#ifdef NB_EXP_TAB_BUCKETS
-// EXPERIMENT (off by default): TAB genes ordered by the length of their count table, longest first (8 buckets of 32),
+// TAB genes ordered by the length of their count table, longest first (8 buckets of 32; used by the 8-lane kernels),
 // so that genes which share a warp in the narrow-group kernels wait for tables of similar length, and the launch ends
 // on the cheap genes.  classify_kernel records a bucket per TAB gene and counts the buckets; bucket_sort_kernel places
 // the TAB list into a scratch list in bucket order (counting sort); the launcher copies it back over the TAB list.
@@ -312,13 +307,10 @@ __global__ void __launch_bounds__(256) bucket_sort_kernel(const int* __restrict_
     sorted[base + atomicAdd(&bfill[b], 1u)] = g;
   }
 }
-#endif
 
 __global__ void __launch_bounds__(256) classify_kernel(const void* y, int y_is_f64, int n, int m, long long ld,
                                                        int* lists, unsigned int* counts
-#ifdef NB_EXP_TAB_BUCKETS
                                                        , int* code, unsigned int* bcount
-#endif
 ) {
   const int lane = threadIdx.x & 31;
   const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -341,13 +333,11 @@ __global__ void __launch_bounds__(256) classify_kernel(const void* y, int y_is_f
   if (lane == 0) {
     const unsigned int pos = atomicAdd(&counts[mode], 1u);
     lists[(size_t)mode * n + pos] = g;
-#ifdef NB_EXP_TAB_BUCKETS
     if (mode == MODE_TAB) {
       const int b = min(kTabBuckets - 1, (int)ymax / (kTabMax / kTabBuckets));
       code[g] = b;
       atomicAdd(&bcount[b], 1u);
     }
-#endif
   }
 }
 
@@ -520,18 +510,9 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(con
     if (q >= (unsigned int)A.n) break;
     int mode;
     unsigned int g;
-#ifdef NB_EXP_HEAVY_FIRST
-    // experiment (off by default): longest-processing-time-first order GEN | BIG | TAB, so that the persistent warps
-    // finish on the cheap table-mode genes instead of on the per-sample-lgamma ones (shorter tail of the launch)
-    const unsigned int n2 = (unsigned int)A.n - n0 - n1;
-    if (q < n2) { mode = MODE_GEN; g = A.mode_lists[2 * (size_t)A.n + q]; }
-    else if (q < n2 + n1) { mode = MODE_BIG; g = A.mode_lists[(size_t)A.n + (q - n2)]; }
-    else { mode = MODE_TAB; g = A.mode_lists[q - n2 - n1]; }
-#else
     if (q < n0) { mode = MODE_TAB; g = A.mode_lists[q]; }
     else if (q < n0 + n1) { mode = MODE_BIG; g = A.mode_lists[(size_t)A.n + (q - n0)]; }
     else { mode = MODE_GEN; g = A.mode_lists[2 * (size_t)A.n + (q - n0 - n1)]; }
-#endif
 
     double sum_wy, ymax;
     stage_row<USE_W>(A, g, mpad, lane, S, sum_wy, ymax);
@@ -548,66 +529,8 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(con
   }
 }
 
-#ifdef NB_EXP_HALF_WARP
 #include "fit_disp_grp.cuh"
-#endif
 
-#ifdef NB_EXP_SPLIT_MODES
-// EXPERIMENT (off by default, not yet timed): one kernel per evaluation-mode family instead of one kernel that walks
-// TAB | BIG | GEN.  ptxas needs 174 registers for the TAB-only body against 200 for all three; capped at 80 registers
-// (3 CTAs of 256 threads per SM = 24 warps instead of 16) the TAB-only kernel spills 40 bytes where the combined kernel
-// spills 416 -- 84 % of the evaluations of the C2 workload are TAB mode and 46 % of the issue slots are idle on
-// dependency / scoreboard stalls, which more resident warps should hide.  SPLIT = MODE_TAB: genes [0, n0) of the
-// queue on the first counter; SPLIT = MODE_GEN: BIG and GEN genes [n0, n) on the second counter.
-template <int P, bool USE_W, int SPLIT>
-__global__ void __launch_bounds__(256, SPLIT == MODE_TAB ? 3 : 2) fit_disp_split_kernel(const DispArgs A, int warps_per_cta,
-                                                                                      int mpad) {
-  extern __shared__ __align__(16) double smem[];
-  init_log_table();
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  constexpr int NROW = USE_W ? 3 : 2;
-  double* xs = smem;
-  double* rowbase = smem + (size_t)P * mpad + (size_t)warp * ((size_t)NROW * mpad + kTabMax);
-  DispWarpSmem S{rowbase, rowbase + mpad, USE_W ? rowbase + 2 * mpad : nullptr, rowbase + (size_t)NROW * mpad};
-  for (int idx = threadIdx.x; idx < P * A.m; idx += blockDim.x) {
-    const int k = idx / A.m, j = idx - k * A.m;
-    xs[k * mpad + j] = A.x[idx];
-  }
-  __syncthreads();
-  DispRow rv{S.ys, S.mus, S.wsm, xs, S.tab, A.m, mpad, 0};
-  const DispScal sc{A.prior_sigmasq, 1.0 / A.prior_sigmasq, A.weight_threshold, A.use_prior, A.use_cr};
-  const unsigned int n0 = A.mode_counts[MODE_TAB], n1 = A.mode_counts[MODE_BIG];
-  unsigned int* counter = (SPLIT == MODE_TAB) ? A.counter : A.counter + 4;
-  for (;;) {
-    unsigned int q = 0;
-    if (lane == 0) q = atomicAdd(counter, 1u);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    double sum_wy, ymax;
-    if (SPLIT == MODE_TAB) {
-      if (q >= n0) break;
-      const unsigned int g = A.mode_lists[q];
-      stage_row<USE_W>(A, g, mpad, lane, S, sum_wy, ymax);
-      build_table<USE_W>(S, A.m, lane);
-      rv.ntab = (int)ymax;
-      line_search_gene<P, USE_W, MODE_TAB>(A, rv, sc, g, sum_wy, lane);
-    } else {
-      q += n0;
-      if (q >= (unsigned int)A.n) break;
-      if (q < n0 + n1) {
-        const unsigned int g = A.mode_lists[(size_t)A.n + (q - n0)];
-        stage_row<USE_W>(A, g, mpad, lane, S, sum_wy, ymax);
-        line_search_gene<P, USE_W, MODE_BIG>(A, rv, sc, g, sum_wy, lane);
-      } else {
-        const unsigned int g = A.mode_lists[2 * (size_t)A.n + (q - n0 - n1)];
-        stage_row<USE_W>(A, g, mpad, lane, S, sum_wy, ymax);
-        line_search_gene<P, USE_W, MODE_GEN>(A, rv, sc, g, sum_wy, lane);
-      }
-    }
-    __syncwarp();
-  }
-}
-#endif
 
 // fitDispGrid (src/DESeq2.cpp:492-510): rare path (non-converged genes only); generic evaluation mode
 template <int P, bool USE_W>
@@ -658,7 +581,6 @@ __global__ void __launch_bounds__(256, 2) fit_disp_grid_kernel(const DispArgs A,
   }
 }
 
-#ifdef NB_EXP_HALF_WARP
 // launch the GL-lanes-per-gene experiment kernel if its shared-memory slices fit; `launched` tells
 template <int P, bool USE_W, int GL>
 cudaError_t launch_disp_grp(const DispArgs& a, int mpad, size_t xbytes, size_t rowbytes, int sms, cudaStream_t stream,
@@ -686,7 +608,6 @@ cudaError_t launch_disp_grp(const DispArgs& a, int mpad, size_t xbytes, size_t r
   launched = true;
   return cudaGetLastError();
 }
-#endif
 
 template <int P, bool USE_W>
 cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
@@ -730,26 +651,23 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
   a.mode_counts = a.scratch + 1;
   a.mode_lists = reinterpret_cast<int*>(a.scratch + kDispScratchHead);
   if (!grid_mode) {
-#ifdef NB_EXP_TAB_BUCKETS
     int* lists = reinterpret_cast<int*>(a.scratch + kDispScratchHead);
     int* code = lists + 3 * (size_t)a.n;
     int* sorted = lists + 4 * (size_t)a.n;
     classify_kernel<<<(a.n + 7) / 8, 256, 0, stream>>>(a.y, a.y_is_f64, a.n, a.m, a.ld, lists, a.scratch + 1, code, a.scratch + 8);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    bucket_sort_kernel<<<(a.n + 255) / 256 > 1184 ? 1184 : (a.n + 255) / 256, 256, 0, stream>>>(lists, code, a.scratch + 1 + MODE_TAB, a.scratch + 8, a.scratch + 16, sorted);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    // entries beyond the TAB count are never read by the kernels, so copying the whole n-entry region is harmless
-    e = cudaMemcpyAsync(lists, sorted, sizeof(int) * (size_t)a.n, cudaMemcpyDeviceToDevice, stream);
-    if (e != cudaSuccess) return e;
-#else
-    classify_kernel<<<(a.n + 7) / 8, 256, 0, stream>>>(a.y, a.y_is_f64, a.n, a.m, a.ld, reinterpret_cast<int*>(a.scratch + kDispScratchHead), a.scratch + 1);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-#endif
+    // Table-length ordering of the TAB list only pays when four genes share a warp (8 lanes per gene: they wait for the
+    // longest table of the four; measured on B200, 20k x 12: 0.46 -> 0.36 ms) and costs 10 % at two genes per warp
+    if (group_lanes_disp(a.m) == 8) {
+      bucket_sort_kernel<<<(a.n + 255) / 256 > 1184 ? 1184 : (a.n + 255) / 256, 256, 0, stream>>>(lists, code, a.scratch + 1 + MODE_TAB, a.scratch + 8, a.scratch + 16, sorted);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      // entries beyond the TAB count are never read by the kernels, so copying the whole n-entry region is harmless
+      e = cudaMemcpyAsync(lists, sorted, sizeof(int) * (size_t)a.n, cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess) return e;
+    }
   }
-#ifdef NB_EXP_HALF_WARP
   if (!grid_mode) {
     const int gl = group_lanes_disp(a.m);
     bool launched = false;
@@ -757,36 +675,6 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
     else if (gl == 16) e = launch_disp_grp<P, USE_W, 16>(a, mpad, xbytes, rowbytes, sms, stream, launched);
     if (e != cudaSuccess || launched) return e;
   }
-#endif
-#ifdef NB_EXP_SPLIT_MODES
-  if (!grid_mode && warps == 8) {
-    // per-family kernels, each sized to its own occupancy; an empty family costs one idle wave of CTAs
-    auto ktab = fit_disp_split_kernel<P, USE_W, MODE_TAB>;
-    auto kgen = fit_disp_split_kernel<P, USE_W, MODE_GEN>;
-    static size_t split_smem = 0;
-    static int split_ctas[2] = {0, 0};
-    if (split_smem != smem) {
-      e = cudaFuncSetAttribute(ktab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(kgen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split_ctas[0], ktab, 256, smem);
-      if (e != cudaSuccess) return e;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split_ctas[1], kgen, 256, smem);
-      if (e != cudaSuccess) return e;
-      if (split_ctas[0] < 1 || split_ctas[1] < 1) return cudaErrorLaunchOutOfResources;
-      split_smem = smem;
-    }
-    long long g0 = (long long)sms * split_ctas[0], g1 = (long long)sms * split_ctas[1];
-    if (g0 > want) g0 = want;
-    if (g1 > want) g1 = want;
-    ktab<<<(unsigned)(g0 < 1 ? 1 : g0), 256, smem, stream>>>(a, 8, mpad);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    kgen<<<(unsigned)(g1 < 1 ? 1 : g1), 256, smem, stream>>>(a, 8, mpad);
-    return cudaGetLastError();
-  }
-#endif
   kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, warps, mpad);
   return cudaGetLastError();
 }

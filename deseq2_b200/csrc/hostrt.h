@@ -6,12 +6,11 @@
 //               (/sys/bus/pci/devices/<bus id>/numa_node -> /sys/devices/system/node/nodeK/cpulist, intersected with the
 //               process affinity): 8 ranks on a two-socket box otherwise stage through the wrong socket's memory.
 //               Recreated after fork() (BiocParallel's multicore back-end forks R workers).
-//   hash_range  128-bit position-dependent content hash, commutative over blocks, so any partition of a buffer among
-//               threads gives the same value; it is what makes the device-side input cache safe (capi.cu): a hit
-//               requires every byte of the host buffer to hash to the cached value -- not a pointer comparison (R copies
-//               the count matrix for each of the three calls of one DESeq() run, and recycles addresses across runs).
-//   populate    MADV_POPULATE_WRITE of a freshly allocated result matrix, started while the GPU is busy, so that the
-//               device-to-host scatter does not take one page fault per 4 KB.
+//   hash_elems  128-bit position-dependent content hash, commutative over elements, so the host (column-major, split
+//               among threads) and the GPU (gene-major copy) compute the same value; it is what makes the device-side
+//               input cache safe (capi.cu): a hit requires every element of the caller's buffer to hash to the value of
+//               the resident copy -- not a pointer comparison (R copies the count matrix for each of the three calls of
+//               one DESeq() run, and recycles addresses across runs).
 #pragma once
 #include <pthread.h>
 #include <sched.h>
@@ -42,43 +41,50 @@ struct Hash128 {
   void add(const Hash128& o) { a += o.a; b += o.b; }
 };
 
-// Hash of the 8-byte words [first_word, first_word + bytes/8) of a buffer (the last partial word is zero-padded).
-// Word pairs are folded with one 64 x 64 -> 128 bit multiply each after being xored with keys derived from their global
-// position ("mum" mixing), and the folded values are SUMMED: block-order independent, so any split of the buffer among
-// threads gives the same value.  16 bytes per multiply: ~3x the rate of a multiply per word, which matters because a
-// cache hit costs exactly one such pass over the caller's buffer.  `first_word` must be even for every block but the
-// hash of a buffer does not depend on how it was split as long as the split points are multiples of 16 bytes.
-inline Hash128 hash_range(const void* p, size_t bytes, uint64_t first_word) {
+// Content hash of `count` elements of `elem` (4 or 8) bytes whose canonical indices are first_index, first_index + 1, ...
+// (the canonical index of entry (i, j) of an n x m matrix is i + n j, its position in R's column-major layout).
+// Every element is xored with a key derived from its index and folded with one 64 x 64 -> 128 bit multiply; the folded
+// values are SUMMED, so the hash does not depend on the order or grouping in which the elements are visited: the host
+// hashes the caller's column-major buffer split among threads, the GPU hashes its gene-major copy
+// (layout.cu::hash_gene_major_kernel) -- same value iff same content.
+constexpr uint64_t kHashK1 = 0x9E3779B97F4A7C15ull, kHashK2 = 0xD6E8FEB86659FD93ull;
+inline void hash_fold(uint64_t v, uint64_t key, uint64_t& a, uint64_t& b) {
+  const __uint128_t r = (__uint128_t)(v ^ key) * kHashK2;
+  const uint64_t lo = (uint64_t)r, hi = (uint64_t)(r >> 64);
+  a += lo ^ hi;
+  b += ((lo << 29) | (lo >> 35)) + hi;
+}
+inline Hash128 hash_elems(const void* p, size_t count, int elem, uint64_t first_index) {
   const unsigned char* s = static_cast<const unsigned char*>(p);
-  const uint64_t K1 = 0x9E3779B97F4A7C15ull, K2 = 0xD6E8FEB86659FD93ull;
   uint64_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-  uint64_t k = (first_word / 2 + 1) * K1;
-  auto fold = [](uint64_t x, uint64_t y, uint64_t& a, uint64_t& b) {
-    const __uint128_t r = (__uint128_t)x * y;
-    const uint64_t lo = (uint64_t)r, hi = (uint64_t)(r >> 64);
-    a += lo ^ hi;
-    b += ((lo << 29) | (lo >> 35)) + hi;
-  };
-  const size_t np = bytes / 16;
+  uint64_t k = (first_index + 1) * kHashK1;
   size_t i = 0;
-  for (; i + 2 <= np; i += 2) {
-    uint64_t w[4];
-    memcpy(w, s + 16 * i, 32);
-    fold(w[0] ^ k, w[1] ^ (k + K2), a0, b0);
-    k += K1;
-    fold(w[2] ^ k, w[3] ^ (k + K2), a1, b1);
-    k += K1;
-  }
-  for (; i < np; i++) {
-    uint64_t w[2];
-    memcpy(w, s + 16 * i, 16);
-    fold(w[0] ^ k, w[1] ^ (k + K2), a0, b0);
-    k += K1;
-  }
-  if (bytes & 15) {
-    uint64_t w[2] = {0, 0};
-    memcpy(w, s + 16 * np, bytes & 15);
-    fold(w[0] ^ k, w[1] ^ (k + K2), a0, b0);
+  if (elem == 8) {
+    for (; i + 2 <= count; i += 2) {
+      uint64_t w[2];
+      memcpy(w, s + 8 * i, 16);
+      hash_fold(w[0], k, a0, b0);
+      hash_fold(w[1], k + kHashK1, a1, b1);
+      k += 2 * kHashK1;
+    }
+    if (i < count) {
+      uint64_t w;
+      memcpy(&w, s + 8 * i, 8);
+      hash_fold(w, k, a0, b0);
+    }
+  } else {
+    for (; i + 2 <= count; i += 2) {
+      uint32_t w[2];
+      memcpy(w, s + 4 * i, 8);
+      hash_fold((uint64_t)w[0], k, a0, b0);
+      hash_fold((uint64_t)w[1], k + kHashK1, a1, b1);
+      k += 2 * kHashK1;
+    }
+    if (i < count) {
+      uint32_t w;
+      memcpy(&w, s + 4 * i, 4);
+      hash_fold((uint64_t)w, k, a0, b0);
+    }
   }
   Hash128 h;
   h.a = a0 + a1;
@@ -257,14 +263,5 @@ class Pool {
   size_t ntasks_ = 0;
   std::atomic<bool> stop_{false};
 };
-
-// fill the page tables of [p, p + bytes) for writing (the pages are about to be overwritten completely)
-inline void populate_write(void* p, size_t bytes) {
-  const uintptr_t a = ((uintptr_t)p + 4095) & ~(uintptr_t)4095, b = ((uintptr_t)p + bytes) & ~(uintptr_t)4095;
-  if (b <= a) return;
-  if (madvise(reinterpret_cast<void*>(a), b - a, MADV_POPULATE_WRITE) == 0) return;
-  // older kernels: touch one byte per page (zero is as good as anything: every byte is rewritten afterwards)
-  for (uintptr_t q = a; q < b; q += 4096) *reinterpret_cast<volatile char*>(q) = 0;
-}
 
 }  // namespace hostrt

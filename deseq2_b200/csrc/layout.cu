@@ -41,6 +41,36 @@ __global__ void __launch_bounds__(256) to_col_major_kernel(const double* __restr
   }
 }
 
+// Content hash of a gene-major matrix (hostrt.h::hash_elems computes the same value from the column-major host
+// buffer): element (i, j) has canonical index i + n j.  out[0], out[1] must be zero on entry.
+__global__ void __launch_bounds__(256) hash_gene_major_kernel(const void* __restrict__ src, int n, int m, long long ld,
+                                                              int elem, unsigned long long* __restrict__ out) {
+  const unsigned long long K1 = 0x9E3779B97F4A7C15ull, K2 = 0xD6E8FEB86659FD93ull;
+  unsigned long long a = 0, b = 0;
+  const long long total = (long long)n * ld;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / ld;
+    const int j = (int)(t - i * ld);
+    if (j >= m) continue;
+    const unsigned long long v = (elem == 8) ? static_cast<const unsigned long long*>(src)[t]
+                                             : (unsigned long long)static_cast<const unsigned int*>(src)[t];
+    const unsigned long long e = (unsigned long long)i + (unsigned long long)n * (unsigned long long)j;
+    const unsigned long long x = v ^ ((e + 1) * K1);
+    const unsigned long long lo = x * K2, hi = __umul64hi(x, K2);
+    a += lo ^ hi;
+    b += ((lo << 29) | (lo >> 35)) + hi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, a);
+    atomicAdd(out + 1, b);
+  }
+}
+
 __global__ void special_test_kernel(const double* x, int n, double* lg, double* dg, double* tg) {
   init_log_table();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,6 +103,18 @@ cudaError_t launch_to_col_major(const double* src, double* dst, int n, int m, lo
   if (n == 0 || m == 0) return cudaSuccess;
   dim3 grid((n + 31) / 32, (m + 31) / 32), block(32, 8);
   to_col_major_kernel<<<grid, block, 0, stream>>>(src, dst, n, m, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_hash_gene_major(const void* src, int n, int m, long long ld, int elem_size,
+                                   unsigned long long* out2, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(unsigned long long), stream);
+  if (e != cudaSuccess || n == 0 || m == 0) return e;
+  const long long total = (long long)n * ld;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)device_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  hash_gene_major_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, n, m, ld, elem_size, out2);
   return cudaGetLastError();
 }
 

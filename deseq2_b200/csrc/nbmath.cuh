@@ -42,19 +42,11 @@ __constant__ double kLn2[2] = {6.93147180369123816490e-01, 1.9082149292705877000
 __device__ __forceinline__ double rcp_fast(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-#ifdef NB_EXP_RCP_CUBIC
-  // experiment (off by default, not yet timed): one cubically convergent step r (1 + e + e^2) instead of two Newton
-  // steps -- 3 dependent FMAs instead of 4; error e^3 ~ 2^-60 from the 2^-20 seed
-  const double e = fma(-x, r, 1.0);
-  const double t = fma(e, e, e);
-  return fma(r, t, r);
-#else
   double e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   return r;
-#endif
 }
 
 // ---------------------------------------------------------------- table-driven log
@@ -85,22 +77,12 @@ __device__ __forceinline__ double log_pos(double x) {
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
   const double4 t = s_logtab[k];
   const double r = (m - t.w) * t.x;
-#ifdef NB_EXP_LOG_ESTRIN
-  // experiment (off by default, not yet timed): Estrin evaluation of the degree-5 polynomial -- dependency depth 3
-  // instead of 5 for one extra multiply (the kernel idles 46 % of its issue slots on dependency stalls)
-  const double r2 = r * r;
-  const double p01 = fma(kLogT[1], r, kLogT[0]);
-  const double p23 = fma(kLogT[3], r, kLogT[2]);
-  const double p45 = fma(kLogT[5], r, kLogT[4]);
-  const double p = fma(fma(p45, r2, p23), r2, p01);
-#else
   double p = kLogT[5];
   p = fma(p, r, kLogT[4]);
   p = fma(p, r, kLogT[3]);
   p = fma(p, r, kLogT[2]);
   p = fma(p, r, kLogT[1]);
   p = fma(p, r, kLogT[0]);
-#endif
   const double de = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
   const double h = fma(de, kLn2[0], t.y);
   const double l = fma(de, kLn2[1], t.z);

@@ -19,8 +19,10 @@
  */
 #include <R.h>
 #include <Rinternals.h>
+#include <R_ext/Rallocators.h>
 #include <R_ext/Rdynload.h>
 #include <R_ext/Utils.h>
+#include <stdlib.h>
 
 #include "../../include/b200nb.h"
 
@@ -31,6 +33,37 @@ static SEXP named_list(int n, const char **names) {
   Rf_setAttrib(l, R_NamesSymbol, nm);
   UNPROTECT(2);
   return l;
+}
+
+/* Large result matrices (hat_diagonals: n x m doubles) are allocated THROUGH R's custom-allocator hook
+ * (allocVector3, R >= 3.1.0) in the engine's pool of page-locked host memory: the device-to-host copy is then one DMA
+ * into the R object itself -- no staging, no first-touch page faults (a malloc'ed 40 MB matrix costs ~3 ms of faults).
+ * The block goes back to the pool when R's gc collects the object.  If page-locked memory cannot be had the block is
+ * ordinary malloc memory (a 16-byte prefix remembers which). */
+static void *pin_alloc(R_allocator_t *a, size_t size) {
+  (void)a;
+  char *p = (char *)b200nb_host_alloc(size + 16);
+  const int pinned = p != NULL;
+  if (!p) p = (char *)malloc(size + 16);
+  if (!p) return NULL;
+  *(int *)p = pinned;
+  return p + 16;
+}
+static void pin_free(R_allocator_t *a, void *q) {
+  (void)a;
+  char *p = (char *)q - 16;
+  if (*(int *)p) b200nb_host_free(p); else free(p);
+}
+static SEXP alloc_result_matrix(int n, int m) {
+  if ((double)n * (double)m * sizeof(double) < (double)(1 << 20)) return Rf_allocMatrix(REALSXP, n, m);
+  R_allocator_t al = {pin_alloc, pin_free, NULL, NULL};
+  SEXP s = PROTECT(Rf_allocVector3(REALSXP, (R_xlen_t)n * m, &al));
+  SEXP dim = PROTECT(Rf_allocVector(INTSXP, 2));
+  INTEGER(dim)[0] = n;
+  INTEGER(dim)[1] = m;
+  Rf_setAttrib(s, R_DimSymbol, dim);
+  UNPROTECT(2);
+  return s;
 }
 
 static const void *y_ptr(SEXP y, int *type) {
@@ -116,7 +149,7 @@ SEXP _DESeq2_fitBeta(SEXP ySEXP, SEXP xSEXP, SEXP nfSEXP, SEXP alpha_hatSEXP, SE
   SET_VECTOR_ELT(out, 0, Rf_allocMatrix(REALSXP, n, p));
   SET_VECTOR_ELT(out, 1, Rf_allocMatrix(REALSXP, n, p));
   SET_VECTOR_ELT(out, 2, Rf_allocVector(REALSXP, n));      /* NumericVector in the reference (:317) */
-  SET_VECTOR_ELT(out, 3, Rf_allocMatrix(REALSXP, n, m));
+  SET_VECTOR_ELT(out, 3, alloc_result_matrix(n, m));
   SET_VECTOR_ELT(out, 4, Rf_allocMatrix(REALSXP, n, 1));
   SET_VECTOR_ELT(out, 5, Rf_allocMatrix(REALSXP, n, 1));
   SET_VECTOR_ELT(out, 6, Rf_allocVector(REALSXP, n));

@@ -53,6 +53,37 @@ def _fmat(a):
     return np.asfortranarray(a, dtype=np.float64)
 
 
+class _PinnedBlock:
+    """A block of the engine's page-locked result memory (b200nb_host_alloc); returned to the pool when the numpy
+    arrays viewing it are gone.  The R shim does the same through allocVector3's custom allocator."""
+    __slots__ = ("ptr", "nbytes", "__weakref__")
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+
+    @property
+    def __array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            _lib.lib().b200nb_host_free(C.c_void_p(self.ptr))
+        except Exception:   # interpreter shutdown
+            pass
+
+
+def _result_matrix(n, m):
+    """Fresh n x m float64 column-major result matrix.  Large ones live in page-locked memory of the engine's pool: the
+    device-to-host copy is then one DMA into the array itself (no staging through host threads, no first-touch page
+    faults); small ones, or when page-locked memory cannot be had, are ordinary numpy arrays."""
+    nbytes = int(n) * int(m) * 8
+    if nbytes >= (1 << 20):
+        ptr = _lib.lib().b200nb_host_alloc(nbytes)
+        if ptr:
+            return np.asarray(_PinnedBlock(ptr, nbytes)).view(np.float64).reshape((n, m), order="F")
+    return np.empty((n, m), order="F")
+
+
 def _vec(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -145,8 +176,8 @@ def fitBeta(ySEXP, xSEXP, nfSEXP, alpha_hatSEXP, contrastSEXP, beta_matSEXP, lam
     beta = np.empty((n, p), order="F")
     var = np.empty((n, p), order="F")
     it = np.empty(n)
-    H = np.empty((n, m), order="F")
-    mu = np.empty((n, m), order="F") if return_mu else None
+    H = _result_matrix(n, m)
+    mu = _result_matrix(n, m) if return_mu else None
     cn = np.empty((n, 1))
     cd = np.empty((n, 1))
     dev = np.empty(n)

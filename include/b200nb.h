@@ -28,6 +28,7 @@
 #ifndef B200NB_H
 #define B200NB_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -163,6 +164,13 @@ void b200nb_release_workspace(void);      /* frees cached device / pinned buffer
  * matrix and the fitted means that one DESeq() run passes to fitDisp, fitDisp and fitBeta cross PCIe once.
  * b200nb_cache_clear() forgets them (the memory stays allocated for reuse); B200NB_CACHE_MB=0 disables the cache. */
 void b200nb_cache_clear(void);
+/* Page-locked memory for RESULT matrices (pooled).  A result buffer obtained here receives its data by one DMA; any
+ * other buffer is filled through the library's pinned staging ring by host threads and pays first-touch page faults
+ * when it is fresh (~3 ms for a 50 000 x 100 hat-diagonal matrix).  Returns NULL when page-locked memory cannot be had
+ * (use ordinary memory then).  In R: allocVector3(REALSXP, n, &allocator) with these two as mem_alloc / mem_free
+ * (deseq2_b200/r_shim/deseq2_b200_shim.c). */
+void* b200nb_host_alloc(size_t bytes);
+void b200nb_host_free(void* p);
 /* cumulative counters of the host entry points: out[0] bytes copied host->device, [1] device->host, [2] cache hits,
  * [3] cache misses, [4] bytes served from the cache instead of being uploaded, [5] bytes hashed / scanned on the host.
  * Writes min(n, 6) values, returns 6. */

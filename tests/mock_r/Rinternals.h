@@ -44,6 +44,7 @@ void Rf_unprotect(int);
 #define PROTECT(s) Rf_protect(s)
 #define UNPROTECT(n) Rf_unprotect(n)
 
+typedef long R_xlen_t;
 SEXP Rf_allocVector(SEXPTYPE, long);
 SEXP Rf_allocMatrix(SEXPTYPE, int, int);
 SEXP Rf_mkChar(const char *);

@@ -30,6 +30,23 @@ int oracle_fit_beta(const double *y, const double *x, const double *nf, const do
 static const char *last_error = "";
 const char *b200nb_last_error(void) { return last_error; }
 
+/* the pool of page-locked result memory: plain heap here; the counters let tests/test_r_shim.py see that the shim's
+ * custom allocator (allocVector3) obtains large result matrices from it and gives them back when R collects them */
+#include <stdlib.h>
+static int stub_allocs = 0, stub_frees = 0, stub_fail_alloc = 0;
+void *b200nb_host_alloc(size_t bytes) {
+  if (stub_fail_alloc) return NULL;
+  stub_allocs++;
+  return malloc(bytes);
+}
+void b200nb_host_free(void *p) {
+  stub_frees++;
+  free(p);
+}
+int stub_host_allocs(void) { return stub_allocs; }
+int stub_host_frees(void) { return stub_frees; }
+void stub_set_fail_alloc(int v) { stub_fail_alloc = v; }
+
 static double *y_as_double(const void *y, int y_type, size_t len, int *owned) {
   *owned = 0;
   if (y_type == B200NB_Y_F64) return (double *)y;

@@ -44,7 +44,16 @@ static void *track(void *p) {
   return p;
 }
 
+/* vectors whose data came from a custom allocator (Rf_allocVector3): released through it, like R's gc does */
+#include <R_ext/Rallocators.h>
+#define MOCK_HEADER 48   /* R places its vector header in front of the data inside the allocator's block */
+static struct { R_allocator_t al; void *block; } custom[256];
+static int n_custom = 0;
+int mock_custom_allocations(void) { return n_custom; }
+
 void mock_reset(void) {
+  for (int i = 0; i < n_custom; i++) custom[i].al.mem_free(&custom[i].al, custom[i].block);
+  n_custom = 0;
   for (int i = 0; i < n_alloc; i++) free(allocs[i]);
   n_alloc = 0;
   protect_depth = 0;
@@ -96,6 +105,26 @@ SEXP Rf_allocVector(SEXPTYPE t, long n) {
     for (long i = 0; i < n; i++) ((int *)s->data)[i] = -777777;
   if (t == STRSXP || t == VECSXP)
     for (long i = 0; i < n; i++) ((SEXP *)s->data)[i] = R_NilValue;
+  return s;
+}
+
+SEXP Rf_allocVector3(SEXPTYPE t, R_xlen_t n, R_allocator_t *al) {
+  if (!al) return Rf_allocVector(t, n);
+  if (t != REALSXP && t != INTSXP) Rf_error("mock R: allocVector3 of unsupported type %u", t);
+  if (n_custom == 256) Rf_error("mock R: too many custom allocations");
+  SEXP s = (SEXP)track(calloc(1, sizeof *s));
+  s->type = t;
+  s->length = n;
+  char *block = (char *)al->mem_alloc(al, MOCK_HEADER + (size_t)(n + 1) * elt_size(t));
+  if (!block) Rf_error("mock R: custom allocator returned NULL");
+  custom[n_custom].al = *al;
+  custom[n_custom].block = block;
+  n_custom++;
+  s->data = block + MOCK_HEADER;
+  if (t == REALSXP)
+    for (long i = 0; i < n; i++) ((double *)s->data)[i] = -7.7e77;
+  else
+    for (long i = 0; i < n; i++) ((int *)s->data)[i] = -777777;
   return s;
 }
 

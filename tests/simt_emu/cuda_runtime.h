@@ -129,6 +129,9 @@ inline void __threadfence_block() {}
 /* ------------------------------------------------------------------ memory / bit intrinsics */
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
+inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
+  return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+}
 inline int __double2hiint(double x) { uint64_t b; memcpy(&b, &x, 8); return (int)(b >> 32); }
 inline int __double2loint(double x) { uint64_t b; memcpy(&b, &x, 8); return (int)(b & 0xffffffffu); }
 inline double __hiloint2double(int hi, int lo) {

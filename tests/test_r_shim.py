@@ -272,3 +272,30 @@ def test_engine_through_R_boundary(r_engine, oracle):
     og = oracle.fitDispGrid(**g)["log_alpha"]
     assert np.mean(np.abs(gg["log_alpha"] - og) < 1e-9) > 0.995
     assert np.max(np.abs(gg["log_alpha"] - og)) < 2.0 * (grid[1] - grid[0]) / 9.5
+
+
+def test_large_hat_matrix_lives_in_the_engines_pinned_pool(r_oracle, oracle):
+    """hat_diagonals of >= 1 MB is allocated through allocVector3's custom allocator in the engine's page-locked pool
+    (b200nb_host_alloc), so that the device-to-host copy is one DMA into the R object; R's gc returns the block
+    (b200nb_host_free); if page-locked memory cannot be had the shim falls back to malloc.  Same numbers either way."""
+    L = r_oracle.lib
+    c = make_case(4200, 32, seed=6)                     # 4200 x 32 doubles > 1 MB
+    n = len(c["counts"])
+    ones = np.ones(c["counts"].shape)
+    a = beta_args(c, c["alpha0"], weights=ones)
+    ref = oracle.fitBeta(**a)
+    a0, f0 = L.stub_host_allocs(), L.stub_host_frees()
+    got, _ = r_oracle.dot_call("_DESeq2_fitBeta", *_ordered(a))
+    assert L.stub_host_allocs() == a0 + 1                 # exactly the one large matrix
+    assert got["hat_diagonals"].shape == (n, 32)
+    assert np.array_equal(got["hat_diagonals"], ref["hat_diagonals"])
+    L.mock_reset()                                        # R's gc
+    assert L.stub_host_frees() == f0 + 1 and L.mock_custom_allocations() == 0
+    L.stub_set_fail_alloc(1)                              # no page-locked memory: ordinary memory, same result
+    try:
+        got2, _ = r_oracle.dot_call("_DESeq2_fitBeta", *_ordered(a))
+        assert np.array_equal(got2["hat_diagonals"], ref["hat_diagonals"])
+        L.mock_reset()
+        assert L.stub_host_frees() == f0 + 1
+    finally:
+        L.stub_set_fail_alloc(0)
