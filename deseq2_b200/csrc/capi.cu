@@ -48,10 +48,13 @@ std::mutex g_arena_mu;   // guards the (re)allocation of the shared device arena
 enum Slot {
   S_RAW, S_SMALL_IN, S_SMALL_OUT, S_NF, S_H, S_MUO, S_HC, S_NSLOTS
 };
+constexpr int kMaxChunks = 8;
 struct Workspace {
   void* p[S_NSLOTS] = {};
   size_t bytes[S_NSLOTS] = {};
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // uploads, layout conversion, downloads
+  cudaStream_t compute = nullptr;    // kernels of the row-chunked path (overlap with the next chunk's upload)
+  cudaEvent_t chunk_ev[kMaxChunks + 1] = {};
 };
 Workspace g_ws;
 
@@ -73,6 +76,21 @@ int ws_stream(cudaStream_t* st) {
   if (!g_ws.stream) CU(cudaStreamCreateWithFlags(&g_ws.stream, cudaStreamNonBlocking));
   *st = g_ws.stream;
   return 0;
+}
+int ws_compute_stream(cudaStream_t* st) {
+  if (!g_ws.compute) {
+    CU(cudaStreamCreateWithFlags(&g_ws.compute, cudaStreamNonBlocking));
+    for (auto& e : g_ws.chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  *st = g_ws.compute;
+  return 0;
+}
+// Row chunks of a call whose inputs have to be uploaded: the kernels of chunk c run (second stream) while chunk c + 1
+// crosses PCIe.  B200NB_CHUNKS=1 disables; default: 4 chunks from 32768 genes, 2 from 16384.
+int plan_chunks(int n) {
+  const int forced = hostrt::env_int("B200NB_CHUNKS", 0, 0, kMaxChunks);   // read per call: tests toggle it
+  if (forced) return n >= 2 * forced ? forced : 1;
+  return n >= 32768 ? 4 : (n >= 16384 ? 2 : 1);
 }
 
 // ---------------------------------------------------------------- host worker pool (hostrt.h)
@@ -175,16 +193,23 @@ static inline long long now_us() {
   return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// pageable host -> device through the pinned ring
+// pageable host -> device through the pinned ring.  The ring position persists across transfers and a slot is only
+// waited for when it is about to be refilled, so back-to-back uploads (y, then mu) keep the DMA engine busy; every host
+// entry point ends with a stream synchronisation, which is what finally drains the ring.
+int g_ring_pos = 0;
+static int ring_next_slot() {
+  const int b = g_ring_pos % kStageRing;
+  g_ring_pos++;
+  return b;
+}
 int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return 0;
   if (stage_init()) return 1;
-  size_t off = 0;
-  for (int k = 0; off < bytes; k++) {
-    const int b = k % kStageRing;
+  for (size_t off = 0; off < bytes;) {
+    const int b = ring_next_slot();
     const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
     const long long t0 = now_us();
-    if (k >= kStageRing) CU(cudaEventSynchronize(g_stage.ev[b]));
+    CU(cudaEventSynchronize(g_stage.ev[b]));   // returns at once for a slot that is not in flight
     const long long t1 = now_us();
     par_memcpy(g_stage.buf[b], static_cast<const char*>(src) + off, len);
     const long long t2 = now_us();
@@ -194,11 +219,42 @@ int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     CU(cudaEventRecord(g_stage.ev[b], st));
     off += len;
   }
-  // the ring is reused by the next transfer: drain it
-  const long long t0 = now_us();
-  for (int b = 0; b < kStageRing; b++) CU(cudaEventSynchronize(g_stage.ev[b]));
-  g_stage_wait_us += now_us() - t0;
   g_h2d_bytes += (long long)bytes;
+  return 0;
+}
+
+// Rows [g0, g0 + gc) of a column-major host matrix with n_total rows -> a contiguous column-major gc x m block on the
+// device, staged in batches of whole column segments (one pool task per segment).
+int h2d_rows(void* dst, const void* host, size_t n_total, size_t g0, size_t gc, int m, int elem, cudaStream_t st) {
+  if (gc == n_total) return h2d_staged(dst, host, gc * m * elem, st);
+  if (gc == 0) return 0;
+  if (stage_init()) return 1;
+  const size_t col = gc * elem;
+  const char* src = static_cast<const char*>(host);
+  if (col > kStageChunk) {   // a single column segment exceeds a ring buffer: column by column
+    for (int j = 0; j < m; j++)
+      if (h2d_staged(static_cast<char*>(dst) + (size_t)j * col, src + ((size_t)j * n_total + g0) * elem, col, st)) return 1;
+    return 0;
+  }
+  const int cpc = (int)(kStageChunk / col);   // whole column segments per ring buffer (>= 1)
+  for (int j = 0; j < m;) {
+    const int b = ring_next_slot();
+    const int nc = (m - j < cpc) ? m - j : cpc;
+    const long long t0 = now_us();
+    CU(cudaEventSynchronize(g_stage.ev[b]));
+    const long long t1 = now_us();
+    char* pin = static_cast<char*>(g_stage.buf[b]);
+    pool().parallel_for((size_t)nc, [&](size_t c) {
+      memcpy(pin + c * col, src + ((size_t)(j + (int)c) * n_total + g0) * elem, col);
+    });
+    const long long t2 = now_us();
+    g_stage_wait_us += t1 - t0;
+    g_stage_copy_us += t2 - t1;
+    CU(cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)j * col, pin, (size_t)nc * col, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(g_stage.ev[b], st));
+    j += nc;
+  }
+  g_h2d_bytes += (long long)(col * m);
   return 0;
 }
 
@@ -238,6 +294,7 @@ int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     const int b = (int)(k % kStageRing);
     const size_t off = k * kStageChunk;
     const size_t len = (bytes - off < kStageChunk) ? bytes - off : kStageChunk;
+    // (an upload of this call may still be reading the slot: same stream, so the copy below is ordered after it)
     CU(cudaMemcpyAsync(g_stage.buf[b], static_cast<const char*>(src) + off, len, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(g_stage.ev[b], st));
     return 0;
@@ -347,6 +404,7 @@ struct Pending {
 struct CallInputs {
   bool speculate = true;
   std::vector<Pending> pending;
+  std::vector<CacheEntry*> filling;   // cache entries this call is uploading into
   std::vector<void*> owned;   // uncached uploads of this call (freed when the call ends)
   bool validate() {           // true when every speculative hit was a real one
     bool ok = true;
@@ -367,50 +425,64 @@ struct CallInputs {
   }
 };
 
-// Column-major host matrix (n x m, elem 4 or 8) -> gene-major device matrix, through the cache.
-int upload_matrix(const void* host, int n, int m, int elem, cudaStream_t st, CallInputs& ci, void** out) {
+// One input matrix of a host call: where its gene-major device copy is (or will be).
+struct MatIn {
+  const void* host = nullptr;
+  int n = 0, m = 0, elem = 0;
+  void* dev = nullptr;          // gene-major n x ld
+  bool resident = false;        // already on the device (verified or speculative hit): nothing to upload
+  CacheEntry* fresh = nullptr;  // cache entry being filled by this call (nullptr: uncached allocation owned by the call)
+  hostrt::Hash128 fp;
+};
+
+// Decide where the matrix comes from: a resident copy (speculatively, see Speculation) or a destination to upload into.
+int mat_acquire(MatIn& M, CallInputs& ci) {
+  const int n = M.n, m = M.m, elem = M.elem;
   const long long ld = ld_for(m);
   const size_t bytes = (size_t)n * m * elem, dbytes = (size_t)n * ld * elem + 64;
   const bool use_cache = cache_limit_bytes() >= dbytes;
-  hostrt::Hash128 h, fp;
   if (use_cache) {
     if (hash_slots_init()) return 1;
-    fp = fingerprint(host, bytes);
+    M.fp = fingerprint(M.host, bytes);
     CacheEntry* cand = nullptr;
     for (auto& e : g_cache)
-      if (e.valid && e.n == (size_t)n && e.m == m && e.elem == elem && e.fprint == fp &&
+      if (e.valid && e.n == (size_t)n && e.m == m && e.elem == elem && e.fprint == M.fp &&
           (!cand || e.last_use > cand->last_use))
         cand = &e;
     if (cand && ci.speculate) {
       cand->last_use = ++g_cache_clock;
-      ci.pending.push_back({cand, host, bytes, elem});
-      *out = cand->dev;
+      ci.pending.push_back({cand, M.host, bytes, elem});
+      M.dev = cand->dev;
+      M.resident = true;
       return 0;
     }
     if (cand) {
-      h = par_hash(host, bytes, elem);
+      const hostrt::Hash128 h = par_hash(M.host, bytes, elem);
       for (auto& e : g_cache)
         if (e.valid && e.n == (size_t)n && e.m == m && e.elem == elem && entry_hash(e) == h) {
           e.last_use = ++g_cache_clock;
           g_cache_hits++;
           g_cache_hit_bytes += (long long)bytes;
-          *out = e.dev;
+          M.dev = e.dev;
+          M.resident = true;
           return 0;
         }
     }
   }
   // miss: pick the destination (an invalid or the least recently used entry that no pending check of this call refers
   // to; evict while over the byte limit)
-  CacheEntry* dst = nullptr;
   if (use_cache) {
     g_cache_misses++;
+    CacheEntry* dst = nullptr;
     auto in_use = [&](const CacheEntry* e) {
       for (const auto& q : ci.pending)
         if (q.e == e) return true;
+      for (const CacheEntry* f : ci.filling)
+        if (f == e) return true;
       return false;
     };
     for (auto& e : g_cache)
-      if (!e.valid && (!dst || e.cap >= dbytes)) dst = &e;
+      if (!e.valid && !in_use(&e) && (!dst || e.cap >= dbytes)) dst = &e;
     if (!dst) {
       for (auto& e : g_cache)
         if (!in_use(&e) && (!dst || e.last_use < dst->last_use)) dst = &e;
@@ -437,34 +509,56 @@ int upload_matrix(const void* host, int n, int m, int elem, cudaStream_t st, Cal
       CU(cudaMalloc(&dst->dev, dbytes + dbytes / 16));
       dst->cap = dbytes + dbytes / 16;
     }
-  }
-  void *d_raw, *d_dst;
-  if (ws_get(S_RAW, bytes, &d_raw)) return 1;
-  if (dst) {
-    d_dst = dst->dev;
+    M.fresh = dst;
+    M.dev = dst->dev;
+    ci.filling.push_back(dst);
   } else {
     // cache disabled / matrix larger than the cache: its own allocation, freed when the call ends
-    CU(cudaMalloc(&d_dst, dbytes));
-    ci.owned.push_back(d_dst);
+    CU(cudaMalloc(&M.dev, dbytes));
+    ci.owned.push_back(M.dev);
   }
-  if (h2d_staged(d_raw, host, bytes, st)) return 1;
-  CU(nb::launch_to_gene_major(d_raw, d_dst, n, m, ld, elem, st));
+  return 0;
+}
+
+// upload rows [g0, g0 + gc) of a non-resident matrix and convert them to gene-major rows of its device copy
+int mat_fill_rows(MatIn& M, size_t g0, size_t gc, cudaStream_t st) {
+  if (M.resident || gc == 0) return 0;
+  void* d_raw;
+  if (ws_get(S_RAW, gc * M.m * M.elem, &d_raw)) return 1;
+  if (h2d_rows(d_raw, M.host, (size_t)M.n, g0, gc, M.m, M.elem, st)) return 1;
+  const long long ld = ld_for(M.m);
+  CU(nb::launch_to_gene_major(d_raw, static_cast<char*>(M.dev) + g0 * (size_t)ld * M.elem, (int)gc, M.m, ld, M.elem, st));
   g_launches++;
-  if (dst) {
-    const int k = (int)(dst - g_cache);
-    CU(nb::launch_hash_gene_major(d_dst, n, m, ld, elem, g_hash_dev + 2 * k, st));
-    CU(cudaMemcpyAsync(g_hash_pin + 2 * k, g_hash_dev + 2 * k, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    g_launches++;
-    dst->valid = true;
-    dst->n = (size_t)n;
-    dst->m = m;
-    dst->elem = elem;
-    dst->hash_known = false;
-    dst->upload_call = g_call_seq;
-    dst->fprint = fp;
-    dst->last_use = ++g_cache_clock;
-  }
-  *out = d_dst;
+  return 0;
+}
+
+// after the last rows: the device computes the content hash of the complete copy and the entry becomes valid
+int mat_finish(MatIn& M, cudaStream_t st) {
+  if (M.resident || !M.fresh) return 0;
+  CacheEntry* dst = M.fresh;
+  const int k = (int)(dst - g_cache);
+  CU(nb::launch_hash_gene_major(M.dev, M.n, M.m, ld_for(M.m), M.elem, g_hash_dev + 2 * k, st));
+  CU(cudaMemcpyAsync(g_hash_pin + 2 * k, g_hash_dev + 2 * k, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  g_launches++;
+  dst->valid = true;
+  dst->n = (size_t)M.n;
+  dst->m = M.m;
+  dst->elem = M.elem;
+  dst->hash_known = false;
+  dst->upload_call = g_call_seq;
+  dst->fprint = M.fp;
+  dst->last_use = ++g_cache_clock;
+  return 0;
+}
+
+// Column-major host matrix (n x m, elem 4 or 8) -> gene-major device matrix, through the cache, in one piece.
+int upload_matrix(const void* host, int n, int m, int elem, cudaStream_t st, CallInputs& ci, void** out) {
+  MatIn M;
+  M.host = host; M.n = n; M.m = m; M.elem = elem;
+  if (mat_acquire(M, ci)) return 1;
+  if (mat_fill_rows(M, 0, (size_t)n, st)) return 1;
+  if (mat_finish(M, st)) return 1;
+  *out = M.dev;
   return 0;
 }
 
@@ -513,6 +607,15 @@ struct SmallOut {
     return 0;
   }
   int download(const char* dev_base, cudaStream_t st) {
+    bool all_pinned = true;   // the caller's vectors are page-locked (b200nb_host_alloc): DMA straight into them
+    for (const auto& q : parts) all_pinned = all_pinned && (!q.host || pinned_contains(q.host, q.bytes));
+    if (all_pinned) {
+      for (const auto& q : parts)
+        if (q.host) CU(cudaMemcpyAsync(q.host, dev_base + q.off, q.bytes, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      g_d2h_bytes += (long long)total;
+      return 0;
+    }
     void* pin;
     if (stage_small(total, &pin)) return 1;
     CU(cudaMemcpyAsync(pin, dev_base, total, cudaMemcpyDeviceToHost, st));
@@ -1060,10 +1163,12 @@ int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu
     PhaseClock clk(st);
     CallInputs ci;
     ci.speculate = (attempt == 0) && speculation_on();
-    void *d_y, *d_mu, *d_w = nullptr;
-    if (upload_matrix(y, n, m, ye, st, ci, &d_y)) return 1;
-    if (upload_matrix(mu_hat, n, m, 8, st, ci, &d_mu)) return 1;
-    if (use_weights && upload_matrix(weights, n, m, 8, st, ci, &d_w)) return 1;
+    MatIn My, Mmu, Mw;
+    My.host = y; My.n = n; My.m = m; My.elem = ye;
+    Mmu.host = mu_hat; Mmu.n = n; Mmu.m = m; Mmu.elem = 8;
+    Mw.host = weights; Mw.n = n; Mw.m = m; Mw.elem = 8;
+    if (mat_acquire(My, ci) || mat_acquire(Mmu, ci)) return 1;
+    if (use_weights && mat_acquire(Mw, ci)) return 1;
     SmallIn in;
     const size_t o_x = in.add(x, sizeof(double) * m * p), o_la = in.add(log_alpha, sizeof(double) * n),
                  o_pm = in.add(log_alpha_prior_mean, sizeof(double) * n);
@@ -1077,15 +1182,46 @@ int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu
     const size_t oi = out.add(out_iter, sizeof(int32_t) * n), oia = out.add(out_iter_accept, sizeof(int32_t) * n);
     char* dout;
     if (out.device(&dout)) return 1;
-    clk.next();
     auto D = [&](size_t off) { return reinterpret_cast<double*>(dout + off); };
-    if (b200nb_fit_disp_dev(d_y, y_type, reinterpret_cast<const double*>(din + o_x), (const double*)d_mu,
-                            reinterpret_cast<const double*>(din + o_la), reinterpret_cast<const double*>(din + o_pm),
-                            log_alpha_prior_sigmasq, min_log_alpha, kappa_0, tol, maxit, use_prior, (const double*)d_w,
-                            use_weights, weight_threshold, use_cr, n, m, p, ld, D(od[0]),
-                            reinterpret_cast<int32_t*>(dout + oi), reinterpret_cast<int32_t*>(dout + oia), D(od[1]),
-                            D(od[2]), D(od[3]), D(od[4]), D(od[5]), D(od[6]), st))
-      return 1;
+    // kernels on rows [g0, g0 + gc) of the device copies
+    auto launch_rows = [&](size_t g0, int gc, cudaStream_t ks) -> int {
+      const char* yb = static_cast<const char*>(My.dev) + g0 * (size_t)ld * ye;
+      const double* mub = static_cast<const double*>(Mmu.dev) + g0 * (size_t)ld;
+      const double* wb = use_weights ? static_cast<const double*>(Mw.dev) + g0 * (size_t)ld : nullptr;
+      return b200nb_fit_disp_dev(yb, y_type, reinterpret_cast<const double*>(din + o_x), mub,
+                                 reinterpret_cast<const double*>(din + o_la) + g0,
+                                 reinterpret_cast<const double*>(din + o_pm) + g0, log_alpha_prior_sigmasq, min_log_alpha,
+                                 kappa_0, tol, maxit, use_prior, wb, use_weights, weight_threshold, use_cr, gc, m, p, ld,
+                                 D(od[0]) + g0, reinterpret_cast<int32_t*>(dout + oi) + g0,
+                                 reinterpret_cast<int32_t*>(dout + oia) + g0, D(od[1]) + g0, D(od[2]) + g0, D(od[3]) + g0,
+                                 D(od[4]) + g0, D(od[5]) + g0, D(od[6]) + g0, ks);
+    };
+    const bool any_miss = !My.resident || !Mmu.resident || (use_weights && !Mw.resident);
+    const int C = (any_miss && !use_generic(p)) ? plan_chunks(n) : 1;
+    if (C == 1) {
+      if (mat_fill_rows(My, 0, (size_t)n, st) || mat_fill_rows(Mmu, 0, (size_t)n, st)) return 1;
+      if (use_weights && mat_fill_rows(Mw, 0, (size_t)n, st)) return 1;
+      clk.next();
+      if (launch_rows(0, n, st)) return 1;
+    } else {
+      cudaStream_t ks;
+      if (ws_compute_stream(&ks)) return 1;
+      const size_t gc = (((size_t)n + C - 1) / C + 63) & ~(size_t)63;
+      int c = 0;
+      for (size_t g0 = 0; g0 < (size_t)n; g0 += gc, c++) {
+        const size_t cnt = (g0 + gc <= (size_t)n) ? gc : (size_t)n - g0;
+        if (mat_fill_rows(My, g0, cnt, st) || mat_fill_rows(Mmu, g0, cnt, st)) return 1;
+        if (use_weights && mat_fill_rows(Mw, g0, cnt, st)) return 1;
+        CU(cudaEventRecord(g_ws.chunk_ev[c], st));
+        CU(cudaStreamWaitEvent(ks, g_ws.chunk_ev[c], 0));
+        if (launch_rows(g0, (int)cnt, ks)) return 1;
+      }
+      CU(cudaEventRecord(g_ws.chunk_ev[kMaxChunks], ks));
+      CU(cudaStreamWaitEvent(st, g_ws.chunk_ev[kMaxChunks], 0));   // the download below follows the last kernel
+      clk.next();
+    }
+    if (mat_finish(My, st) || mat_finish(Mmu, st)) return 1;
+    if (use_weights && mat_finish(Mw, st)) return 1;
     const bool verified = ci.validate();   // host-side hashing while the kernels run
     clk.next();
     if (!verified) {

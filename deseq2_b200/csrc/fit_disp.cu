@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const void* y, int y_is_f
   if (lane == 0) {
     const unsigned int pos = atomicAdd(&counts[mode], 1u);
     lists[(size_t)mode * n + pos] = g;
-    if (mode == MODE_TAB) {
+    if (mode == MODE_TAB && code != nullptr) {   // bucket bookkeeping only for the 8-lane kernels (see the launcher)
       const int b = min(kTabBuckets - 1, (int)ymax / (kTabMax / kTabBuckets));
       code[g] = b;
       atomicAdd(&bcount[b], 1u);
@@ -654,12 +654,14 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
     int* lists = reinterpret_cast<int*>(a.scratch + kDispScratchHead);
     int* code = lists + 3 * (size_t)a.n;
     int* sorted = lists + 4 * (size_t)a.n;
-    classify_kernel<<<(a.n + 7) / 8, 256, 0, stream>>>(a.y, a.y_is_f64, a.n, a.m, a.ld, lists, a.scratch + 1, code, a.scratch + 8);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
     // Table-length ordering of the TAB list only pays when four genes share a warp (8 lanes per gene: they wait for the
     // longest table of the four; measured on B200, 20k x 12: 0.46 -> 0.36 ms) and costs 10 % at two genes per warp
-    if (group_lanes_disp(a.m) == 8) {
+    const bool buckets = group_lanes_disp(a.m) == 8;
+    classify_kernel<<<(a.n + 7) / 8, 256, 0, stream>>>(a.y, a.y_is_f64, a.n, a.m, a.ld, lists, a.scratch + 1,
+                                                       buckets ? code : nullptr, a.scratch + 8);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (buckets) {
       bucket_sort_kernel<<<(a.n + 255) / 256 > 1184 ? 1184 : (a.n + 255) / 256, 256, 0, stream>>>(lists, code, a.scratch + 1 + MODE_TAB, a.scratch + 8, a.scratch + 16, sorted);
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;

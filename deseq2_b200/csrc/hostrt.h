@@ -195,7 +195,7 @@ class Pool {
     for (size_t t; (t = next_.fetch_add(1, std::memory_order_relaxed)) < ntasks;) f(t);
     // wait for every worker to have left this generation (they may not touch `f` afterwards)
     for (long spin = 0; running_.load(std::memory_order_acquire) != 0; spin++) {
-      if (spin > 200000) std::this_thread::yield();
+      if (spin > 2000) std::this_thread::yield();   // an oversubscribed host: let the straggler run
       else cpu_relax();
     }
   }
@@ -218,7 +218,7 @@ class Pool {
     uint64_t seen = 0;
     for (;;) {
       // Wait for a new generation.  Host calls come in bursts (a staged upload is dozens of back-to-back parallel
-      // regions, separated by event waits): spin for ~1 ms before going to sleep -- a condvar wake-up per region costs
+      // regions, separated by event waits): poll for ~0.4 ms before going to sleep -- a condvar wake-up per region costs
       // more than the region itself (16 sleepers woken one after the other were measured to quadruple the upload time).
       uint64_t g = gen_.load(std::memory_order_acquire);
       if (g == seen) {
@@ -226,9 +226,10 @@ class Pool {
         for (long spin = 0; g == seen; spin++) {
           cpu_relax();
           g = gen_.load(std::memory_order_acquire);
-          if ((spin & 1023) == 1023 &&
-              std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(kSpinMicros))
-            break;
+          if ((spin & 255) == 255) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(kSpinMicros)) break;
+            if (spin > 4096) std::this_thread::yield();   // still polling, but not hogging a CPU somebody may need
+          }
         }
       }
       if (g == seen) {
@@ -248,7 +249,7 @@ class Pool {
     }
   }
 
-  static constexpr long kSpinMicros = 1000;
+  static constexpr long kSpinMicros = 400;
   int nworkers_;
   pid_t pid_;
   std::vector<int> cpus_;

@@ -299,7 +299,7 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
     full_pipeline times).  With a finite value the per-gene results of the refitted rows are overwritten in place
     and "replace" / "replaceable" / "n_replaced" are added.
     allgather: for the gene-sharded multi-GPU run (deseq2_b200/sharded.py::sharded_DESeq_device): a callable that
-    concatenates a per-gene 1-D device tensor over the ranks, in rank order.  It is used at the one point where the
+    concatenates each of a LIST of per-gene 1-D device tensors over the ranks, in rank order (one collective).  It is used at the one point where the
     reference needs every gene (R/parallel.R:25-28): the dispersion trend and the prior variance are then fitted,
     identically on every rank, to all genes' baseMean / dispGeneEst instead of the shard's."""
     dev = y.device
@@ -364,7 +364,8 @@ def DESeq_device(y, x, sizeFactors=None, minDisp=1e-8, kappa_0=1.0, dispTol=1e-6
     mark("rules+grid_mle")
 
     # ---- estimateDispersionsFit + dispersionFunction<- + PriorVar (R/core.R:864-940, R/methods.R:142-190, R/core.R:1135-1208)
-    bm_all, dge_all = (allgather(bm), allgather(dge)) if allgather is not None else (bm, dge)
+    # ONE packed collective for the two vectors the global step needs (sharded.PackedGather accepts a list)
+    bm_all, dge_all = allgather([bm, dge]) if allgather is not None else (bm, dge)
     tr = trend_fit(bm_all, dge_all, minDisp)
     dispFit = tr[0] + tr[1] / bm
     above = dge_all >= minDisp * 100

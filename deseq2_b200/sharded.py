@@ -92,35 +92,71 @@ def sharded_DESeq(counts, x, sizeFactors, engine=None):
             "WaldPvalue": allp[:, k + 3 * p:k + 4 * p], "dispPriorVar": dispPriorVar, "trendCoefs": tf["coefs"]}
 
 
+class PackedGather:
+    """ONE collective per exchange: several per-gene 1-D vectors of this rank (all of the same, rank-dependent length)
+    travel as one (1 + ncols) x cap buffer -- row 0 carries the shard's length -- through a single
+    all_gather_into_tensor, and come back concatenated over the ranks in rank order (R/parallel.R:54-66's rbind).
+    `cap` (rows of the largest shard) is agreed once per run with one 8-byte all-reduce."""
+
+    def __init__(self, n_local_rows: int, device):
+        self.world = dist.get_world_size()
+        c = torch.tensor([int(n_local_rows)], dtype=torch.int64, device=device)
+        dist.all_reduce(c, op=dist.ReduceOp.MAX)
+        self.cap = max(int(c.item()), 1)
+        self.collectives = 1
+
+    def __call__(self, cols):
+        single = isinstance(cols, torch.Tensor)
+        cols = [cols] if single else list(cols)
+        n = cols[0].numel()
+        dev = cols[0].device
+        buf = torch.zeros((len(cols) + 1, self.cap), dtype=torch.float64, device=dev)
+        buf[0, 0] = float(n)
+        for k, c in enumerate(cols):
+            buf[k + 1, :n] = c.to(torch.float64)
+        out = torch.empty((self.world * buf.shape[0], self.cap), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, buf)       # rank r's buffer = rows [r (1 + ncols), (r + 1)(1 + ncols))
+        out = out.view(self.world, buf.shape[0], self.cap)
+        self.collectives += 1
+        sizes = [int(v) for v in out[:, 0, 0].tolist()]
+        res = [torch.cat([out[r, k + 1, :sizes[r]] for r in range(self.world)]) for k in range(len(cols))]
+        return res[0] if single else res
+
+
 def allgather_1d(t: torch.Tensor) -> torch.Tensor:
-    """Concatenate a 1-D tensor of rank-dependent length over the ranks (rank order), on the tensor's device: sizes
-    first, then one all_gather_into_tensor of shards padded to the largest."""
-    world = dist.get_world_size()
-    n_local = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
-    sizes = torch.empty(world, dtype=torch.int64, device=t.device)
-    dist.all_gather_into_tensor(sizes, n_local)
-    sizes = [int(v) for v in sizes.tolist()]
-    cap = max(max(sizes), 1)
-    buf = torch.zeros(cap, dtype=t.dtype, device=t.device)
-    buf[: t.numel()] = t
-    out = torch.empty(world * cap, dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out, buf)
-    return torch.cat([out[r * cap: r * cap + sizes[r]] for r in range(world)])
+    """Concatenate a 1-D tensor of rank-dependent length over the ranks (rank order): a PackedGather of one column."""
+    return PackedGather(t.numel(), t.device)(t)
 
 
 def sharded_DESeq_device(y_local, x, sizeFactors, **kw):
     """Device-resident DESeq() on this rank's gene shard (y_local: gene-major counts of the shard, on the rank's GPU)
-    with the reference's global step on all genes (dispersion trend + prior variance, R/parallel.R:25-28) done through
-    one all-gather of two per-gene vectors; everything else -- and in particular the n x m matrices -- stays on the
-    shard.  Returns the shard's result dict (device tensors) plus "gathered": betaMatrix, betaSE, dispersion and
-    WaldPvalue of ALL genes on every rank (R/parallel.R:54-66's rbind), in rank order."""
+    with the reference's global step on all genes (dispersion trend + prior variance, R/parallel.R:25-28).  The whole run
+    issues TWO per-gene collectives: one packed all-gather of (baseMean, dispGeneEst) for the global step and ONE packed
+    all-gather of the results (dispersion, betaMatrix, betaSE, WaldPvalue: 1 + 3p doubles per gene), plus an 8-byte
+    all-reduce that agrees on the buffer size; the n x m matrices never leave their shard.  Returns the shard's result
+    dict (device tensors) plus "gathered": the results of ALL genes on every rank, in rank order, and "collectives"."""
     from . import device_pipeline as DP
-    res = DP.DESeq_device(y_local, x, sizeFactors, allgather=allgather_1d, **kw)
+    pg = PackedGather(y_local.shape[0], y_local.device)
+    res = DP.DESeq_device(y_local, x, sizeFactors, allgather=pg, **kw)
     p = res["betaMatrix"].shape[1]
-    cols = [res["dispersion"]] + [res["betaMatrix"][:, k].contiguous() for k in range(p)] \
-        + [res["betaSE"][:, k].contiguous() for k in range(p)] + [res["WaldPvalue"][:, k].contiguous() for k in range(p)]
-    g = [allgather_1d(c) for c in cols]
+    cols = [res["dispersion"]] + [res["betaMatrix"][:, k] for k in range(p)] \
+        + [res["betaSE"][:, k] for k in range(p)] + [res["WaldPvalue"][:, k] for k in range(p)]
+    g = pg(cols)
     res["gathered"] = {"dispersion": g[0], "betaMatrix": torch.stack(g[1:1 + p], dim=1),
                        "betaSE": torch.stack(g[1 + p:1 + 2 * p], dim=1),
                        "WaldPvalue": torch.stack(g[1 + 2 * p:1 + 3 * p], dim=1)}
+    res["collectives"] = pg.collectives
+    return res
+
+
+def sharded_nbinomLRT_device(y_local, x_full, x_reduced, sizeFactors, dispersion_local, **kw):
+    """nbinomLRT on this rank's shard (BASELINE config 5's call sequence: full and reduced IRLS fit, LRT statistic) and
+    ONE packed all-gather of (LRTStatistic, LRTPvalue, betaMatrix of the full model) to every rank."""
+    from . import device_pipeline as DP
+    pg = PackedGather(y_local.shape[0], y_local.device)
+    res = DP.nbinomLRT_device(y_local, x_full, x_reduced, sizeFactors, dispersion_local, **kw)
+    p = res["betaMatrix"].shape[1]
+    g = pg([res["LRTStatistic"], res["LRTPvalue"]] + [res["betaMatrix"][:, k] for k in range(p)])
+    res["gathered"] = {"LRTStatistic": g[0], "LRTPvalue": g[1], "betaMatrix": torch.stack(g[2:2 + p], dim=1)}
+    res["collectives"] = pg.collectives
     return res

@@ -72,6 +72,26 @@ class _PinnedBlock:
             pass
 
 
+def _result_vectors(spec):
+    """Fresh 1-D / small 2-D result arrays described by [(name, shape, dtype)], carved out of ONE block of the engine's
+    page-locked pool when together they are >= 256 KB (each then receives its data by DMA), else ordinary arrays."""
+    sizes = [int(np.prod(shape)) * np.dtype(dt).itemsize for _, shape, dt in spec]
+    offs = np.cumsum([0] + [(s + 63) & ~63 for s in sizes])
+    total = int(offs[-1])
+    block = None
+    if total >= (1 << 18):
+        ptr = _lib.lib().b200nb_host_alloc(total)
+        if ptr:
+            block = np.asarray(_PinnedBlock(ptr, total))
+    out = {}
+    for (name, shape, dt), off, sz in zip(spec, offs, sizes):
+        if block is None:
+            out[name] = np.empty(shape, dtype=dt, order="F")
+        else:
+            out[name] = block[off:off + sz].view(dt).reshape(shape, order="F")
+    return out
+
+
 def _result_matrix(n, m):
     """Fresh n x m float64 column-major result matrix.  Large ones live in page-locked memory of the engine's pool: the
     device-to-host copy is then one DMA into the array itself (no staging through host threads, no first-touch page
@@ -113,10 +133,9 @@ def fitDisp(ySEXP, xSEXP, mu_hatSEXP, log_alphaSEXP, log_alpha_prior_meanSEXP, l
     la = _vec_n(log_alphaSEXP, n, "log_alpha", "fitDisp")
     pm = _vec_n(log_alpha_prior_meanSEXP, n, "log_alpha_prior_mean", "fitDisp")
     w = _weights(weightsSEXP, useWeightsSEXP, (n, m), "fitDisp")
-    out = {k: np.empty(n) for k in ("log_alpha", "last_change", "initial_lp", "initial_dlp", "last_lp", "last_dlp",
-                                    "last_d2lp")}
-    out["iter"] = np.empty(n, dtype=np.int32)
-    out["iter_accept"] = np.empty(n, dtype=np.int32)
+    out = _result_vectors([(k, (n,), np.float64) for k in ("log_alpha", "last_change", "initial_lp", "initial_dlp",
+                                                           "last_lp", "last_dlp", "last_d2lp")]
+                          + [("iter", (n,), np.int32), ("iter_accept", (n,), np.int32)])
     rc = L.b200nb_fit_disp(_ptr(y), yt, _ptr(x), _ptr(mu), _ptr(la), _ptr(pm), float(log_alpha_prior_sigmasqSEXP),
                            float(min_log_alphaSEXP), float(kappa_0SEXP), float(tolSEXP), int(maxitSEXP),
                            int(bool(usePriorSEXP)), _ptr(w), int(w is not None), float(weightThresholdSEXP),
@@ -173,14 +192,11 @@ def fitBeta(ySEXP, xSEXP, nfSEXP, alpha_hatSEXP, contrastSEXP, beta_matSEXP, lam
     beta0 = _fmat(beta0.reshape(n, p))
     lam = _vec_n(lambdaSEXP, p, "lambda", "fitBeta", broadcast=True)
     w = _weights(weightsSEXP, useWeightsSEXP, (n, m), "fitBeta")
-    beta = np.empty((n, p), order="F")
-    var = np.empty((n, p), order="F")
-    it = np.empty(n)
+    sm = _result_vectors([("beta", (n, p), np.float64), ("var", (n, p), np.float64), ("it", (n,), np.float64),
+                          ("cn", (n, 1), np.float64), ("cd", (n, 1), np.float64), ("dev", (n,), np.float64)])
+    beta, var, it, cn, cd, dev = (sm[k] for k in ("beta", "var", "it", "cn", "cd", "dev"))
     H = _result_matrix(n, m)
     mu = _result_matrix(n, m) if return_mu else None
-    cn = np.empty((n, 1))
-    cd = np.empty((n, 1))
-    dev = np.empty(n)
     rc = L.b200nb_fit_beta(_ptr(y), yt, _ptr(x), _ptr(nf), _ptr(alpha), _ptr(contrast), _ptr(beta0), _ptr(lam),
                            _ptr(w), int(w is not None), float(tolSEXP), int(maxitSEXP), int(bool(useQRSEXP)),
                            float(minmuSEXP), n, m, p, _ptr(beta), _ptr(var), _ptr(it), _ptr(H), _ptr(cn), _ptr(cd),

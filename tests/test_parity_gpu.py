@@ -572,9 +572,23 @@ def test_host_cache_is_content_addressed_and_never_stale(engine, oracle):
     assert abs(r_mat["beta_mat"][777, 0] - r_vec["beta_mat"][777, 0]) > 1e-6
     rest = np.arange(len(alpha)) != 777
     assert np.max(rel_err(r_mat["beta_mat"][rest], r_vec["beta_mat"][rest], floor=1e-8)) < 1e-9
-    # (4) clear: the next call uploads again
+    # (4) clear: the next call uploads again -- here in 3 row chunks whose kernels overlap the next chunk's upload
+    # (the default for >= 16384 genes); bit-identical to the single-piece call, and the chunk-wise uploaded copy is a
+    # valid cache entry afterwards (its content hash is computed on the device from the assembled copy)
+    import os
     L.b200nb_cache_clear()
     s4 = _host_stats()
-    engine.fitDisp(**a)
+    os.environ["B200NB_CHUNKS"] = "3"
+    try:
+        g5 = engine.fitDisp(**a)
+    finally:
+        del os.environ["B200NB_CHUNKS"]
     s5 = _host_stats()
     assert s5["misses"] - s4["misses"] == 2
+    for k in DISP_KEYS + ("iter", "iter_accept"):
+        assert np.array_equal(g5[k], g1[k], equal_nan=True), k
+    g6 = engine.fitDisp(**a2)
+    s6 = _host_stats()
+    assert s6["hits"] - s5["hits"] == 2
+    for k in DISP_KEYS + ("iter", "iter_accept"):
+        assert np.array_equal(g6[k], g1[k], equal_nan=True), k
