@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=20000, help="genes in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3-5 block")
+    ap.add_argument("--quick-configs", action="store_true", help="configs block at 20%% of the stated sizes")
     ap.add_argument("--r-default-probe", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
@@ -282,6 +284,131 @@ def r_default_probe(n, m):
     print(json.dumps({"value": len(counts) / dt, "unit": "genes/s (one GPU)", "ms_per_step": dt * 1e3,
                       "genes_refitted": int(rr.get("n_replaced", 0)),
                       "what": "size factors on device + full_pipeline + outlier replacement and refit"}))
+
+
+def configs_block(world, rank, dev, peak_gbs, quick=False):
+    """BASELINE.json configs 3, 4, 5 through the device-resident pipeline (deseq2_b200.device_pipeline / sharded): the
+    whole DESeq() sequence of each config -- pre-steps, fitBeta for the GeneEst means where the design is not
+    group-wise (C3, C5), both dispersion fits, trend, grid refits, the Wald / LRT fits, Cook's -- with the counts
+    resident in HBM, timed with CUDA events (max over ranks), incl. the pipeline's few host syncs.
+      N = 1: C4 at its stated size (50k x 1000, 10-level factor) and C3 / C5 at their per-GPU shard size on 8 GPUs.
+      N > 1: C3 (200k x 500) and C5 (1M x 200, LRT) at their stated TOTAL size, gene-sharded over the N ranks with one
+             packed all-gather for the global step and ONE packed all-gather of the results (sharded.PackedGather),
+             plus C2 strong scaling (the 50k genes of config 2 split over the ranks, kernels only).
+    Algorithmic bytes per gene are SURVEY.md section 8(d)'s."""
+    import torch
+    import torch.distributed as dist
+    from deseq2_b200 import device as D, device_pipeline as DP, sharded, synth
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=3):
+        r = fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            a_, b_ = ev(), ev()
+            a_.record()
+            r = fn()
+            b_.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a_.elapsed_time(b_)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        return float(np.median(ts)), r
+
+    def total(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def common_sf(m, seed):     # the experiment's size factors: the same on every rank
+        sf = np.exp(np.random.Generator(np.random.PCG64(seed)).normal(0.0, 0.25, m))
+        return sf / np.exp(np.mean(np.log(sf)))
+
+    def shard(n_total, m, x, seed, **kw):
+        lo, hi = sharded.shard_bounds(n_total, world, rank)
+        sf = common_sf(m, seed)
+        d = synth.make_example_counts(hi - lo, m, x=x, seed=seed + 17 * (rank + 1), sizeFactors=sf, **kw)
+        return D.to_gene_major(d["counts"], dev), sf
+
+    out = {}
+    scale = 0.2 if quick else 1.0
+    specs = []
+    if world == 1:
+        specs.append(("C4", int(50000 * scale), 1000, synth.design_factor(1000, 10), "wald", 64 * 1000 + 24 * 21 + 256))
+        specs.append(("C3_shard_of_8", int(25000 * scale), 500, synth.design_batch_condition(500, 3), "wald", 64 * 500 + 48 * 4 + 256))
+        specs.append(("C5_shard_of_8", int(125000 * scale), 200, synth.design_batch_condition(200, 2), "lrt", 84 * 200 + 24 * 8 + 296))
+    else:
+        specs.append(("C3", int(200000 * scale), 500, synth.design_batch_condition(500, 3), "wald", 64 * 500 + 48 * 4 + 256))
+        specs.append(("C5", int(1000000 * scale), 200, synth.design_batch_condition(200, 2), "lrt", 84 * 200 + 24 * 8 + 296))
+    for name, n_total, m, x, kind, bytes_per_gene in specs:
+        try:
+            y, sf = shard(n_total, m, x, 20260923 + len(name), betaSD=0.5)
+            p = x.shape[1]
+            if world > 1:
+                run = lambda: sharded.sharded_DESeq_device(y, x, sf)
+            else:
+                run = lambda: DP.DESeq_device(y, x, sf)
+            ms, res = timed(run)
+            genes = total(res["idx"].numel())
+            rec = {"genes_total": int(genes), "genes_per_rank": int(y.shape[0]), "samples": m, "p": p, "n_gpus": world,
+                   "deseq_device_ms": ms, "genes_per_s": genes / (ms * 1e-3),
+                   "alg_bytes_per_gene": bytes_per_gene,
+                   "hbm_frac": genes * bytes_per_gene / (ms * 1e-3) / 1e9 / peak_gbs,
+                   "n_optim_rows": int(total(res.get("n_optim", 0)))}
+            if world > 1:
+                rec["per_gene_collectives"] = int(res["collectives"]) - 1
+            if kind == "lrt":
+                ynz = y[res["idx"]].contiguous()
+                xr = x[:, :2]
+                if world > 1:
+                    lrt = lambda: sharded.sharded_nbinomLRT_device(ynz, x, xr, sf, res["dispersion"])
+                else:
+                    lrt = lambda: DP.nbinomLRT_device(ynz, x, xr, sf, res["dispersion"])
+                ms2, _ = timed(lrt)
+                rec["nbinomLRT_device_ms"] = ms2
+                rec["genes_per_s_incl_lrt"] = genes / ((ms + ms2) * 1e-3)
+            if world == 1:
+                os.environ["B200NB_PIPE_DEBUG"] = "1"      # one extra run with a sync after every stage
+                try:
+                    rec["stage_ms"] = run()["stage_ms"]
+                finally:
+                    del os.environ["B200NB_PIPE_DEBUG"]
+            out[name] = rec
+            del y, res
+            torch.cuda.empty_cache()
+        except Exception as ex:  # pragma: no cover
+            out[name] = {"error": repr(ex)[:300]}
+    if world > 1:
+        # strong scaling of config 2: its 50 000 genes split over the ranks, the three kernels, device resident
+        try:
+            n2, m2 = int(50000 * scale), 100
+            x2 = synth.design_condition(m2)
+            lo, hi = sharded.shard_bounds(n2, world, rank)
+            sf2 = common_sf(m2, 20260925)
+            d = synth.make_example_counts(hi - lo, m2, x=x2, seed=20260923 + 2 + rank, sizeFactors=sf2)
+            y2 = D.to_gene_major(d["counts"], dev)
+            pr = DP.prep(y2, x2, sf2)
+            la0 = torch.log(pr["alpha0"])
+            lam = torch.full((2,), 1e-6 / np.log(2) ** 2, dtype=torch.float64, device=dev)
+            con = torch.tensor([1.0, 0.0], dtype=torch.float64, device=dev)
+
+            def three():
+                r1 = D.fit_disp(y2, pr["xd"], pr["mu_lin"], la0, la0, 1.0, MIN_LOG_ALPHA, 1.0, 1e-6, 100, False)
+                r2 = D.fit_disp(y2, pr["xd"], pr["mu_lin"], r1["log_alpha"], la0, 1.0, MIN_LOG_ALPHA, 1.0, 1e-6, 100, True)
+                return D.fit_beta(y2, pr["xd"], pr["sfd"], torch.exp(r2["log_alpha"]), con, pr["beta0"], lam, 1e-8, 100)
+            ms, _ = timed(three, reps=5)
+            out["C2_strong_scaling"] = {"genes_total": n2, "genes_per_rank": hi - lo, "n_gpus": world, "kernels_ms": ms,
+                                        "genes_per_s": n2 / (ms * 1e-3),
+                                        "what": "fitDisp + fitDisp(prior) + fitBeta on 1/N of config 2's genes per GPU, "
+                                                "device resident, CUDA events, max over ranks"}
+        except Exception as ex:  # pragma: no cover
+            out["C2_strong_scaling"] = {"error": repr(ex)[:300]}
+    return out
 
 
 def main():
@@ -575,6 +702,14 @@ def main():
         except Exception as ex:  # pragma: no cover
             full["r_default"] = {"error": repr(ex)[:200]}
 
+    cfgs = None
+    if not a.no_configs:
+        try:
+            pk = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+        except Exception:
+            pk = 6650.0
+        cfgs = configs_block(world, rank, dev, pk, quick=a.quick_configs)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -614,7 +749,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (makeExampleDESeqDataSet law, PCG64 seed 20260925)", "config": cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "full_pipeline": full, "genes_fitted": total_genes}
+            "full_pipeline": full, "genes_fitted": total_genes, "configs": cfgs}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -54,7 +54,7 @@ struct Workspace {
   size_t bytes[S_NSLOTS] = {};
   cudaStream_t stream = nullptr;     // uploads, layout conversion, downloads
   cudaStream_t compute = nullptr;    // kernels of the row-chunked path (overlap with the next chunk's upload)
-  cudaEvent_t chunk_ev[kMaxChunks + 1] = {};
+  cudaEvent_t up_ev[kMaxChunks] = {}, layout_ev[kMaxChunks] = {}, done_ev = nullptr;
 };
 Workspace g_ws;
 
@@ -80,7 +80,9 @@ int ws_stream(cudaStream_t* st) {
 int ws_compute_stream(cudaStream_t* st) {
   if (!g_ws.compute) {
     CU(cudaStreamCreateWithFlags(&g_ws.compute, cudaStreamNonBlocking));
-    for (auto& e : g_ws.chunk_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : g_ws.up_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : g_ws.layout_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g_ws.done_ev, cudaEventDisableTiming));
   }
   *st = g_ws.compute;
   return 0;
@@ -520,16 +522,27 @@ int mat_acquire(MatIn& M, CallInputs& ci) {
   return 0;
 }
 
-// upload rows [g0, g0 + gc) of a non-resident matrix and convert them to gene-major rows of its device copy
-int mat_fill_rows(MatIn& M, size_t g0, size_t gc, cudaStream_t st) {
+// rows [g0, g0 + gc) of a non-resident matrix: (1) host -> device as a column-major gc x m block at `d_raw` (copy
+// engine, stream `up`), (2) conversion to gene-major rows of the device copy (a kernel, stream `ks`).  The two halves
+// are separate because in the row-chunked path they run on different streams: a persistent fit kernel occupies every
+// SM, so a layout kernel queued on the UPLOAD stream would stall the next chunk's DMA behind the running compute.
+int mat_h2d_rows(MatIn& M, size_t g0, size_t gc, void* d_raw, cudaStream_t up) {
+  if (M.resident || gc == 0) return 0;
+  return h2d_rows(d_raw, M.host, (size_t)M.n, g0, gc, M.m, M.elem, up);
+}
+int mat_layout_rows(MatIn& M, size_t g0, size_t gc, const void* d_raw, cudaStream_t ks) {
+  if (M.resident || gc == 0) return 0;
+  const long long ld = ld_for(M.m);
+  CU(nb::launch_to_gene_major(d_raw, static_cast<char*>(M.dev) + g0 * (size_t)ld * M.elem, (int)gc, M.m, ld, M.elem, ks));
+  g_launches++;
+  return 0;
+}
+int mat_fill_rows(MatIn& M, size_t g0, size_t gc, cudaStream_t st) {   // both halves on one stream
   if (M.resident || gc == 0) return 0;
   void* d_raw;
   if (ws_get(S_RAW, gc * M.m * M.elem, &d_raw)) return 1;
-  if (h2d_rows(d_raw, M.host, (size_t)M.n, g0, gc, M.m, M.elem, st)) return 1;
-  const long long ld = ld_for(M.m);
-  CU(nb::launch_to_gene_major(d_raw, static_cast<char*>(M.dev) + g0 * (size_t)ld * M.elem, (int)gc, M.m, ld, M.elem, st));
-  g_launches++;
-  return 0;
+  if (mat_h2d_rows(M, g0, gc, d_raw, st)) return 1;
+  return mat_layout_rows(M, g0, gc, d_raw, st);
 }
 
 // after the last rows: the device computes the content hash of the complete copy and the entry becomes valid
@@ -1207,17 +1220,28 @@ int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu
       cudaStream_t ks;
       if (ws_compute_stream(&ks)) return 1;
       const size_t gc = (((size_t)n + C - 1) / C + 63) & ~(size_t)63;
+      // two sets of raw (column-major) chunk buffers: chunk c + 1 crosses PCIe into one while chunk c is converted
+      // from the other
+      const size_t ry = (gc * m * ye + 255) & ~(size_t)255, r8 = (gc * m * 8 + 255) & ~(size_t)255;
+      const size_t rset = ry + r8 + (use_weights ? r8 : 0);
+      void* rawbase;
+      if (ws_get(S_RAW, 2 * rset, &rawbase)) return 1;
       int c = 0;
       for (size_t g0 = 0; g0 < (size_t)n; g0 += gc, c++) {
         const size_t cnt = (g0 + gc <= (size_t)n) ? gc : (size_t)n - g0;
-        if (mat_fill_rows(My, g0, cnt, st) || mat_fill_rows(Mmu, g0, cnt, st)) return 1;
-        if (use_weights && mat_fill_rows(Mw, g0, cnt, st)) return 1;
-        CU(cudaEventRecord(g_ws.chunk_ev[c], st));
-        CU(cudaStreamWaitEvent(ks, g_ws.chunk_ev[c], 0));
+        char* raw = static_cast<char*>(rawbase) + (size_t)(c & 1) * rset;
+        if (c >= 2) CU(cudaStreamWaitEvent(st, g_ws.layout_ev[c - 2], 0));   // this buffer set has been consumed
+        if (mat_h2d_rows(My, g0, cnt, raw, st) || mat_h2d_rows(Mmu, g0, cnt, raw + ry, st)) return 1;
+        if (use_weights && mat_h2d_rows(Mw, g0, cnt, raw + ry + r8, st)) return 1;
+        CU(cudaEventRecord(g_ws.up_ev[c], st));
+        CU(cudaStreamWaitEvent(ks, g_ws.up_ev[c], 0));
+        if (mat_layout_rows(My, g0, cnt, raw, ks) || mat_layout_rows(Mmu, g0, cnt, raw + ry, ks)) return 1;
+        if (use_weights && mat_layout_rows(Mw, g0, cnt, raw + ry + r8, ks)) return 1;
+        CU(cudaEventRecord(g_ws.layout_ev[c], ks));
         if (launch_rows(g0, (int)cnt, ks)) return 1;
       }
-      CU(cudaEventRecord(g_ws.chunk_ev[kMaxChunks], ks));
-      CU(cudaStreamWaitEvent(st, g_ws.chunk_ev[kMaxChunks], 0));   // the download below follows the last kernel
+      CU(cudaEventRecord(g_ws.done_ev, ks));
+      CU(cudaStreamWaitEvent(st, g_ws.done_ev, 0));   // hashing and the download below follow the last kernel
       clk.next();
     }
     if (mat_finish(My, st) || mat_finish(Mmu, st)) return 1;

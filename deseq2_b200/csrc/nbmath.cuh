@@ -53,7 +53,7 @@ __device__ __forceinline__ double rcp_fast(double x) {
 // log(x) for positive, finite, normal x (no zero / denormal / inf / nan handling), Tang-style:
 //   x = 2^e m, m in [1, 2);  c = 1 + k/128 the grid point nearest to m (k = 0..128);  r = (m - c) / c, |r| <= 2^-8
 //   log x = e ln2 + log c + (r - r^2/2 + ... + r^7/7)
-// {1/c, hi(log c), lo(log c), c} come from a 129-entry table (gen_logtab.py) that every kernel using log_pos copies
+// {1/c, hi(log c), lo(log c)} come from a 129-entry table (gen_logtab.py) that every kernel using log_pos copies
 // into shared memory once per CTA (init_log_table): 3 integer ops for the index, one reciprocal-free reduction,
 // a degree-6 polynomial -- ~27 instructions against ~45 for the division-based fdlibm scheme (kept below as
 // log_pos_poly).  c = 1 and c = 2 are grid points, so results near x = 1 keep full relative accuracy.
@@ -61,12 +61,14 @@ __device__ __forceinline__ double rcp_fast(double x) {
 __device__ const double4 g_logtab[129] = {
 #include "logtab.inc"
 };
-#ifdef NB_LOGTAB_SPLIT
-// A/B variant: the grid point c is rebuilt from k with two integer instructions instead of being loaded, and the table is
-// split into {1/c, hi(log c)} (one LDS.128) and lo(log c) (one LDS.64): 24 instead of 32 bytes of shared-memory traffic
-// per call (the random-index fetch is the kernels' top short-scoreboard stall and bank-conflict source)
+// The grid point c is rebuilt from k with two integer instructions instead of being loaded, and the table is split into
+// {1/c, hi(log c)} (one LDS.128) and lo(log c) (one LDS.64): 24 instead of 32 bytes of shared-memory traffic per call.
+// The random-index fetch is the kernels' top short-scoreboard stall and bank-conflict source; measured on B200 (C2):
+// fitDisp 0.92 -> 0.87 ms against the single double4 table.
 __shared__ double2 s_logA[129];
 __shared__ double s_logL[129];
+
+// every thread of the CTA must call this before the first log_pos (contains a __syncthreads)
 __device__ __forceinline__ void init_log_table() {
   for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < 129; i += blockDim.x * blockDim.y) {
     const double4 t = g_logtab[i];
@@ -75,15 +77,6 @@ __device__ __forceinline__ void init_log_table() {
   }
   __syncthreads();
 }
-#else
-__shared__ double4 s_logtab[129];
-
-// every thread of the CTA must call this before the first log_pos (contains a __syncthreads)
-__device__ __forceinline__ void init_log_table() {
-  for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < 129; i += blockDim.x * blockDim.y) s_logtab[i] = g_logtab[i];
-  __syncthreads();
-}
-#endif
 
 __device__ __forceinline__ double log_pos(double x) {
   const int hi = __double2hiint(x);
@@ -91,12 +84,8 @@ __device__ __forceinline__ double log_pos(double x) {
   const int e = (hi >> 20) - 1023;
   const int k = ((hi >> 13) & 0x7f) + ((hi >> 12) & 1);
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-#ifdef NB_LOGTAB_SPLIT
   const double2 ta = s_logA[k];
   const double4 t = make_double4(ta.x, ta.y, s_logL[k], __hiloint2double(0x3ff00000 + (k << 13), 0));
-#else
-  const double4 t = s_logtab[k];
-#endif
   const double r = (m - t.w) * t.x;
   double p = kLogT[5];
   p = fma(p, r, kLogT[4]);

@@ -38,8 +38,10 @@ def design_factor_expanded(m: int, levels: int) -> np.ndarray:
 
 
 def make_example_counts(n: int, m: int, x: np.ndarray | None = None, seed: int = 20260923, betaSD: float = 1.0,
-                        interceptMean: float = 4.0, interceptSD: float = 2.0, size_factor_sd: float = 0.25):
-    """Returns dict(counts int32 n x m, x, sizeFactors, trueBeta (log2), trueDisp)."""
+                        interceptMean: float = 4.0, interceptSD: float = 2.0, size_factor_sd: float = 0.25,
+                        sizeFactors: np.ndarray | None = None):
+    """Returns dict(counts int32 n x m, x, sizeFactors, trueBeta (log2), trueDisp).  `sizeFactors` fixes the size
+    factors (gene shards of one experiment generated on different ranks share them)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     if x is None:
         x = design_condition(m)
@@ -51,6 +53,8 @@ def make_example_counts(n: int, m: int, x: np.ndarray | None = None, seed: int =
     disp = 4.0 / 2.0 ** beta[:, 0] + 0.1
     sf = np.exp(rng.normal(0.0, size_factor_sd, m)) if size_factor_sd > 0 else np.ones(m)
     sf = sf / np.exp(np.mean(np.log(sf)))
+    if sizeFactors is not None:
+        sf = np.asarray(sizeFactors, dtype=np.float64)
     mu = (2.0 ** (beta @ x.T)) * sf[None, :]
     size = 1.0 / disp[:, None]
     prob = size / (size + mu)

@@ -1,4 +1,4 @@
-"""Round-2 check on 2+ GPUs (NCCL): the gene-sharded device-resident pipeline equals the single-GPU run.
+"""Check on 2+ GPUs (NCCL; driven by tests/test_sharded_nccl_gpu.py): the gene-sharded device-resident pipeline equals the single-GPU run.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
         scripts/sharded_device_nccl.py
 The same logic runs on CPU in tests/test_sharded_gloo.py (gloo + emulated engine)."""
@@ -27,7 +27,8 @@ if rank == 0:
     ok = (torch.equal(r["trendCoefs"], whole["trendCoefs"]) and r["dispPriorVar"] == whole["dispPriorVar"]
           and torch.equal(r["gathered"]["dispersion"], whole["dispersion"])
           and torch.allclose(r["gathered"]["betaMatrix"], whole["betaMatrix"], rtol=0, atol=0, equal_nan=True))
-    print("sharded == whole:", ok, "| genes", int(whole["idx"].numel()), "| shard of rank 0:", int(r["idx"].numel()))
+    print("sharded == whole:", ok, "| genes", int(whole["idx"].numel()), "| shard of rank 0:", int(r["idx"].numel()),
+          "| per-gene collectives:", int(r["collectives"]) - 1, "(+ one 8-byte all-reduce)")
     assert ok
 dist.barrier()
 dist.destroy_process_group()
