@@ -42,6 +42,7 @@ struct DispArgs {
   const double* xg;   // G x (p|1) (grouped) or m x (p|1) (samplewise)
   const int* gid;     // m
   int G, grouped;
+  double* row_scratch;   // general-p path, long rows: per-warp global scratch for the sample rows (set by the launcher)
   // saturated design (G == p, distinct rows X_g invertible): X'WX = X_g' diag(W_g) X_g, so
   // log det = 2 log|det X_g| + sum_g log W_g and tr(B^-1 dB) = sum_g dW_g / W_g -- no p x p algebra at all
   int saturated;
@@ -95,6 +96,7 @@ struct BetaArgs {
   const double* xg;
   const int* gid;
   int G, grouped;
+  double* row_scratch;   // long rows: per-warp global scratch for the sample rows (set by the launcher)
 };
 
 // nbinomLogLike at the unclamped fitted mean (fit_beta.cu::nb_loglik_kernel)

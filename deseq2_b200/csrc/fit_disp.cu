@@ -530,6 +530,9 @@ __global__ void __launch_bounds__(NB_LB_THREADS, NB_LB_CTAS) fit_disp_kernel(con
 }
 
 #include "fit_disp_grp.cuh"
+#ifdef NB_EXP_TMA_ROWS
+#include "tma_rows_exp.cuinc"
+#endif
 
 
 // fitDispGrid (src/DESeq2.cpp:492-510): rare path (non-converged genes only); generic evaluation mode
@@ -677,6 +680,27 @@ cudaError_t launch_disp_t(const DispArgs& a0, cudaStream_t stream) {
     else if (gl == 16) e = launch_disp_grp<P, USE_W, 16>(a, mpad, xbytes, rowbytes, sms, stream, launched);
     if (e != cudaSuccess || launched) return e;
   }
+#ifdef NB_EXP_TMA_ROWS
+  if (!grid_mode) {   // experiment: one gene per warp with the mean row prefetched by TMA bulk copies (tma_rows_exp.cuinc)
+    const size_t trow = ((size_t)(NROW + 1) * mpad + kTabMax + 2) * sizeof(double);
+    int tw = NB_LB_THREADS / 32;
+    while (tw > 1 && xbytes + tw * trow > smem_cap / 2) tw >>= 1;
+    if (xbytes + tw * trow <= smem_cap) {
+      auto kt = fit_disp_tma_kernel<P, USE_W>;
+      const size_t tsm = xbytes + tw * trow;
+      e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+      if (e != cudaSuccess) return e;
+      int c = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kt, tw * 32, tsm);
+      if (e != cudaSuccess || c < 1) return e != cudaSuccess ? e : cudaErrorLaunchOutOfResources;
+      long long tg = (long long)sms * c;
+      const long long twant = ((long long)a.n + tw - 1) / tw;
+      if (tg > twant) tg = twant;
+      kt<<<(unsigned)(tg < 1 ? 1 : tg), tw * 32, tsm, stream>>>(a, tw, mpad);
+      return cudaGetLastError();
+    }
+  }
+#endif
   kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, warps, mpad);
   return cudaGetLastError();
 }

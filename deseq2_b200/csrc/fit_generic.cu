@@ -15,6 +15,8 @@
 //     triangular solves are cooperative with lanes = rows.
 // The per-sample arithmetic (fused lp/dlp pass, integer-count factor table, fused IRLS pass) is the same as in the
 // register-resident small-p kernels.
+#include <mutex>
+
 #include "engine.h"
 #include "nbmath.cuh"
 
@@ -127,24 +129,30 @@ struct GenWarp {
 // factor table (optional); `nacc` accumulator sets (3 for the dispersion kernel, 2 for IRLS).
 struct GenShape {
   int has_r1, has_r2, use_w, has_tab, nacc;
+  int rows_global;   // the sample rows live in a per-warp slice of a GLOBAL scratch buffer (L2-resident), not in shared memory
 };
+__host__ __device__ inline int gen_rows(GenShape sh) { return 1 + sh.has_r1 + sh.has_r2 + sh.use_w; }
 __host__ __device__ inline size_t gen_warp_doubles(int mpad, int p, int ps, int G, int grouped, GenShape sh) {
   const size_t terms = grouped ? (size_t)G : (size_t)mpad;
   const size_t acc = grouped ? (size_t)G * 32 : (size_t)mpad;
-  const size_t rows = 1 + sh.has_r1 + sh.has_r2 + sh.use_w;
+  const size_t rows = sh.rows_global ? 0 : (size_t)gen_rows(sh);
   return rows * mpad + (sh.has_tab ? kTabMaxG : 0) + sh.nacc * acc + (grouped ? sh.nacc * terms : 0) + terms +
          4 * (size_t)p * ps + 4 * 32;
 }
 
-__device__ __forceinline__ GenWarp carve(double* base, int mpad, int p, int ps, int G, int grouped, GenShape sh) {
+// `rowbase`: the warp's slice of the global row scratch when sh.rows_global, else ignored (rows come first in `base`)
+__device__ __forceinline__ GenWarp carve(double* base, double* rowbase, int mpad, int p, int ps, int G, int grouped,
+                                         GenShape sh) {
   GenWarp S;
   const size_t terms = grouped ? (size_t)G : (size_t)mpad;
   const size_t acc = grouped ? (size_t)G * 32 : (size_t)mpad;
   double* q = base;
-  S.ys = q; q += mpad;
-  S.r1 = sh.has_r1 ? q : nullptr; q += sh.has_r1 ? mpad : 0;
-  S.r2 = sh.has_r2 ? q : nullptr; q += sh.has_r2 ? mpad : 0;
-  S.wsm = sh.use_w ? q : nullptr; q += sh.use_w ? mpad : 0;
+  double* rq = sh.rows_global ? rowbase : base;
+  S.ys = rq; rq += mpad;
+  S.r1 = sh.has_r1 ? rq : nullptr; rq += sh.has_r1 ? mpad : 0;
+  S.r2 = sh.has_r2 ? rq : nullptr; rq += sh.has_r2 ? mpad : 0;
+  S.wsm = sh.use_w ? rq : nullptr; rq += sh.use_w ? mpad : 0;
+  if (!sh.rows_global) q = rq;
   S.tab = sh.has_tab ? q : nullptr; q += sh.has_tab ? kTabMaxG : 0;
   S.accA = q; q += acc;
   S.accB = q; q += acc;
@@ -421,7 +429,10 @@ __global__ void __launch_bounds__(256) fit_disp_generic_kernel(const DispArgs A,
   __syncthreads();
   GDispCtx C;
   C.D = Design{xg, gid, A.p, ps, A.G, A.grouped, A.m};
-  C.S = carve(wbase, mpad, A.p, ps, A.G, A.grouped, GenShape{1, 0, A.use_weights != 0, 1, 3});
+  const GenShape shp{1, 0, A.use_weights != 0, 1, 3, A.row_scratch != nullptr};
+  const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  C.S = carve(wbase, A.row_scratch ? A.row_scratch + gwarp * gen_rows(shp) * mpad : nullptr, mpad, A.p, ps, A.G, A.grouped,
+              shp);
   C.prior_sigmasq = A.prior_sigmasq;
   C.inv_sigmasq = 1.0 / A.prior_sigmasq;
   C.weight_threshold = A.weight_threshold;
@@ -628,7 +639,10 @@ __global__ void __launch_bounds__(256) fit_beta_generic_kernel(const BetaArgs A,
   __syncthreads();
   GBetaCtx C;
   C.D = Design{xg, gid, p, ps, A.G, A.grouped, A.m};
-  C.S = carve(wbase, mpad, p, ps, A.G, A.grouped, GenShape{A.nf_is_vector ? 0 : 1, 1, A.use_weights != 0, 0, 2});
+  const GenShape shp{A.nf_is_vector ? 0 : 1, 1, A.use_weights != 0, 0, 2, A.row_scratch != nullptr};
+  const size_t gwarp = (size_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  C.S = carve(wbase, A.row_scratch ? A.row_scratch + gwarp * gen_rows(shp) * mpad : nullptr, mpad, p, ps, A.G, A.grouped,
+              shp);
   C.use_w = A.use_weights;
   C.minmu = A.minmu;
   C.log_minmu = log(A.minmu);
@@ -788,19 +802,71 @@ __global__ void __launch_bounds__(256) fit_beta_generic_kernel(const BetaArgs A,
 struct GenLaunch {
   int mpad, ps, warps;
   size_t warp_doubles, smem;
+  int rows_global;
 };
 
-bool plan(int m, int p, int G, int grouped, GenShape sh, size_t extra_doubles, GenLaunch& out) {
+bool plan_one(int m, int p, int G, int grouped, GenShape sh, size_t extra_doubles, GenLaunch& out) {
   out.mpad = (m + 3) & ~3;
   out.ps = p | 1;
+  out.rows_global = sh.rows_global;
   out.warp_doubles = gen_warp_doubles(out.mpad, p, out.ps, G, grouped, sh);
   const size_t fixed = ((size_t)(grouped ? G : m) * out.ps + (m + 1) / 2 + extra_doubles) * sizeof(double);
   const size_t cap = 227 * 1024;
   int warps = 8;
   while (warps > 1 && fixed + warps * out.warp_doubles * sizeof(double) > cap) warps--;
+  // several CTAs per SM need room for each: prefer 8-warp CTAs that fit at least twice
+  while (warps > 4 && 2 * (fixed + warps * out.warp_doubles * sizeof(double)) > cap &&
+         fixed + (warps - 1) * out.warp_doubles * sizeof(double) <= cap / 2)
+    warps--;
   out.warps = warps;
   out.smem = fixed + warps * out.warp_doubles * sizeof(double);
   return out.smem <= cap;
+}
+
+// Shared-memory rows starve the SM of warps once the sample rows are long (config 4: m = 1000, two rows = 16 KB per
+// warp -> 7 warps per SM, 10 % warps active in the round-1 profile).  When the rows are more than ~40 % of a warp's
+// slice and fewer than 16 warps would be resident, the rows move to a per-warp slice of a global scratch buffer: a few
+// tens of MB that stay in the 126 MB L2, read with coalesced loads once per pass.
+bool plan(int m, int p, int G, int grouped, GenShape sh, size_t extra_doubles, GenLaunch& out) {
+  sh.rows_global = 0;
+  if (!plan_one(m, p, G, grouped, sh, extra_doubles, out)) {
+    sh.rows_global = 1;
+    return plan_one(m, p, G, grouped, sh, extra_doubles, out);
+  }
+  const size_t row_bytes = (size_t)gen_rows(sh) * out.mpad * sizeof(double);
+  const size_t per_sm_warps = (227 * 1024) / (out.warp_doubles * sizeof(double) + 1);
+  if (per_sm_warps < 16 && row_bytes * 10 > out.warp_doubles * sizeof(double) * 4) {
+    GenLaunch g;
+    GenShape sg = sh;
+    sg.rows_global = 1;
+    if (plan_one(m, p, G, grouped, sg, extra_doubles, g)) out = g;
+  }
+  return true;
+}
+
+// global row scratch: a small ring of grow-only device buffers (one per launch in flight)
+constexpr int kRowRing = 4;
+void* g_rowbuf[kRowRing] = {};
+size_t g_rowcap[kRowRing] = {};
+unsigned int g_rownext = 0;
+std::mutex g_rowmu;
+cudaError_t row_scratch(size_t bytes, double** out) {
+  std::lock_guard<std::mutex> lk(g_rowmu);
+  const int s = (int)(g_rownext++ % kRowRing);
+  if (g_rowcap[s] < bytes) {
+    if (g_rowbuf[s]) {
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) return e;
+      cudaFree(g_rowbuf[s]);
+      g_rowbuf[s] = nullptr;
+      g_rowcap[s] = 0;
+    }
+    cudaError_t e = cudaMalloc(&g_rowbuf[s], bytes + bytes / 8);
+    if (e != cudaSuccess) return e;
+    g_rowcap[s] = bytes + bytes / 8;
+  }
+  *out = static_cast<double*>(g_rowbuf[s]);
+  return cudaSuccess;
 }
 
 }  // namespace
@@ -808,7 +874,8 @@ bool plan(int m, int p, int G, int grouped, GenShape sh, size_t extra_doubles, G
 cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
   DispArgs a = a0;
   GenLaunch L;
-  if (!plan(a.m, a.p, a.G, a.grouped, GenShape{1, 0, a.use_weights != 0, 1, 3}, 0, L)) return cudaErrorInvalidValue;
+  const GenShape sh{1, 0, a.use_weights != 0, 1, 3, 0};
+  if (!plan(a.m, a.p, a.G, a.grouped, sh, 0, L)) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(fit_disp_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
   if (e != cudaSuccess) return e;
   int ctas_per_sm = 0;
@@ -819,6 +886,11 @@ cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
   long long grid = (long long)device_sm_count() * ctas_per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
+  a.row_scratch = nullptr;
+  if (L.rows_global) {
+    e = row_scratch((size_t)grid * L.warps * gen_rows(sh) * L.mpad * sizeof(double), &a.row_scratch);
+    if (e != cudaSuccess) return e;
+  }
   e = cudaMemsetAsync(a.scratch, 0, 4 * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
   a.counter = a.scratch;
@@ -826,11 +898,12 @@ cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_fit_beta_generic(const BetaArgs& a, cudaStream_t stream) {
+cudaError_t launch_fit_beta_generic(const BetaArgs& a0, cudaStream_t stream) {
+  BetaArgs a = a0;
   GenLaunch L;
   const int mpad = (a.m + 3) & ~3;
-  if (!plan(a.m, a.p, a.G, a.grouped, GenShape{a.nf_is_vector ? 0 : 1, 1, a.use_weights != 0, 0, 2}, (size_t)mpad + 64, L))
-    return cudaErrorInvalidValue;
+  const GenShape sh{a.nf_is_vector ? 0 : 1, 1, a.use_weights != 0, 0, 2, 0};
+  if (!plan(a.m, a.p, a.G, a.grouped, sh, (size_t)mpad + 64, L)) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(fit_beta_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
   if (e != cudaSuccess) return e;
   int ctas_per_sm = 0;
@@ -841,6 +914,11 @@ cudaError_t launch_fit_beta_generic(const BetaArgs& a, cudaStream_t stream) {
   long long grid = (long long)device_sm_count() * ctas_per_sm;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
+  a.row_scratch = nullptr;
+  if (L.rows_global) {
+    e = row_scratch((size_t)grid * L.warps * gen_rows(sh) * L.mpad * sizeof(double), &a.row_scratch);
+    if (e != cudaSuccess) return e;
+  }
   e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
   fit_beta_generic_kernel<<<(unsigned)grid, L.warps * 32, L.smem, stream>>>(a, L.mpad, L.ps, L.warp_doubles);
