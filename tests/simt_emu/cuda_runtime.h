@@ -214,6 +214,12 @@ template <typename T>
 inline cudaError_t cudaHostAlloc(T** p, size_t bytes, unsigned flags) {
   return cudaHostAlloc(reinterpret_cast<void**>(p), bytes, flags);
 }
+inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height,
+                                     cudaMemcpyKind, cudaStream_t = 0) {
+  for (size_t r = 0; r < height; r++)
+    memcpy(static_cast<char*>(d) + r * dpitch, static_cast<const char*>(s) + r * spitch, width);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) {
   if (n) memmove(d, s, n);
   return cudaSuccess;
