@@ -46,7 +46,7 @@ std::mutex g_arena_mu;   // guards the (re)allocation of the shared device arena
 // ---------------------------------------------------------------- device workspace of the host entry points
 // grow-only slots (one set per process; calls are serialised)
 enum Slot {
-  S_RAW, S_SMALL_IN, S_SMALL_OUT, S_NF, S_H, S_MUO, S_HC, S_BLK, S_NSLOTS
+  S_RAW, S_SMALL_IN, S_SMALL_OUT, S_NF, S_H, S_MUO, S_HC, S_NSLOTS
 };
 constexpr int kMaxChunks = 8;
 struct Workspace {
@@ -312,42 +312,6 @@ int d2h_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     par_memcpy(static_cast<char*>(dst) + off, g_stage.buf[b], len);
   }
   g_d2h_bytes += (long long)bytes;
-  return 0;
-}
-
-// A contiguous column-major gc x m block on the device -> rows [g0, g0 + gc) of the caller's column-major n_total x m
-// matrix.  Page-locked destination: one strided (2-D) DMA, asynchronous (the caller synchronises).  Otherwise: through
-// the pinned ring in batches of whole column segments, scattered by the pool; synchronous on return.
-int d2h_rows(void* host, const void* d_block, size_t n_total, size_t g0, size_t gc, int m, cudaStream_t st, bool pinned_dst) {
-  if (gc == 0) return 0;
-  const size_t col = gc * sizeof(double);
-  char* dst = static_cast<char*>(host) + g0 * sizeof(double);
-  if (pinned_dst) {
-    CU(cudaMemcpy2DAsync(dst, n_total * sizeof(double), d_block, col, col, (size_t)m, cudaMemcpyDeviceToHost, st));
-    g_d2h_bytes += (long long)(col * m);
-    return 0;
-  }
-  if (stage_init()) return 1;
-  if (col > kStageChunk) {
-    for (int j = 0; j < m; j++)
-      if (d2h_staged(dst + (size_t)j * n_total * sizeof(double), static_cast<const char*>(d_block) + (size_t)j * col, col, st))
-        return 1;
-    return 0;
-  }
-  const int cpc = (int)(kStageChunk / col);
-  for (int j = 0; j < m;) {
-    const int b = ring_next_slot();
-    const int nc = (m - j < cpc) ? m - j : cpc;
-    char* pin = static_cast<char*>(g_stage.buf[b]);
-    CU(cudaMemcpyAsync(pin, static_cast<const char*>(d_block) + (size_t)j * col, (size_t)nc * col, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(g_stage.ev[b], st));
-    CU(cudaEventSynchronize(g_stage.ev[b]));
-    pool().parallel_for((size_t)nc, [&](size_t c) {
-      memcpy(dst + (size_t)(j + (int)c) * n_total * sizeof(double), pin + c * col, col);
-    });
-    j += nc;
-  }
-  g_d2h_bytes += (long long)(col * m);
   return 0;
 }
 
@@ -1429,84 +1393,24 @@ int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf
     clk.next();
     auto Din = [&](size_t off) { return reinterpret_cast<const double*>(din + off); };
     auto Dout = [&](size_t off) { return reinterpret_cast<double*>(dout + off); };
-    // kernels on rows [g0, g0 + gc); bin / bo / bv: the chunk's gc x p column-major coefficient blocks
-    auto launch_rows = [&](size_t g0, int gc, cudaStream_t ks, double* bo, double* bv, const double* bin) -> int {
-      const char* yb = static_cast<const char*>(d_y) + g0 * (size_t)ld * ye;
-      const double* nfb = sfv.empty() ? static_cast<const double*>(d_nf) + g0 * (size_t)ld : Din(o_sf);
-      const double* wb = use_weights ? static_cast<const double*>(d_w) + g0 * (size_t)ld : nullptr;
-      return b200nb_fit_beta_dev(yb, y_type, Din(o_x), nfb, sfv.empty() ? 0 : 1, Din(o_alpha) + g0, Din(o_c), bin, Din(o_lam),
-                                 wb, use_weights, tol, maxit, use_qr, minmu, gc, m, p, ld, bo, bv, Dout(o_it) + g0,
-                                 d_h ? static_cast<double*>(d_h) + g0 * (size_t)ld : nullptr, Dout(o_cn) + g0,
-                                 Dout(o_cd) + g0, Dout(o_dev) + g0,
-                                 d_mu ? static_cast<double*>(d_mu) + g0 * (size_t)ld : nullptr, ks);
-    };
-    const bool h_pinned = out_hat_diagonals && pinned_contains(out_hat_diagonals, sizeof(double) * (size_t)n * m);
-    // Row chunks pay here through the DOWNLOAD: the hat diagonals of chunk c cross PCIe while chunk c + 1 is fitted.
-    // The coefficient matrices are column-major n x p: a chunk works on its own gc x p blocks, gathered afterwards.
-    const int CH = (out_hat_diagonals && !out_mu && !use_generic(p)) ? plan_chunks(n) : 1;
-    bool hat_done = false;
-    if (CH > 1) {
-      cudaStream_t ks;
-      if (ws_compute_stream(&ks)) return 1;
-      const size_t gc = (((size_t)n + CH - 1) / CH + 63) & ~(size_t)63;
-      void* d_blk;   // per chunk: beta_in, beta_out, beta_var blocks (gc x p each, column-major)
-      if (ws_get(S_BLK, sizeof(double) * 3 * gc * p * kMaxChunks, &d_blk)) return 1;
-      int c = 0;
-      for (size_t g0 = 0; g0 < (size_t)n; g0 += gc, c++) {
-        const size_t cnt = (g0 + gc <= (size_t)n) ? gc : (size_t)n - g0;
-        double* bin = static_cast<double*>(d_blk) + (size_t)c * 3 * gc * p;
-        double *bo = bin + gc * p, *bv = bo + gc * p;
-        // gather the chunk's start values: column k of the n x p matrix, rows g0.. -> column k of the gc x p block
-        CU(cudaMemcpy2DAsync(bin, cnt * sizeof(double), Din(o_b) + g0, (size_t)n * sizeof(double), cnt * sizeof(double),
-                             (size_t)p, cudaMemcpyDeviceToDevice, ks));
-        if (launch_rows(g0, (int)cnt, ks, bo, bv, bin)) return 1;
-        CU(cudaMemcpy2DAsync(Dout(o_bo) + g0, (size_t)n * sizeof(double), bo, cnt * sizeof(double), cnt * sizeof(double),
-                             (size_t)p, cudaMemcpyDeviceToDevice, ks));
-        CU(cudaMemcpy2DAsync(Dout(o_bv) + g0, (size_t)n * sizeof(double), bv, cnt * sizeof(double), cnt * sizeof(double),
-                             (size_t)p, cudaMemcpyDeviceToDevice, ks));
-        double* hc = static_cast<double*>(d_hc) + g0 * (size_t)m;   // the chunk's gc x m column-major block
-        if (b200nb_to_col_major_dev(static_cast<const double*>(d_h) + g0 * (size_t)ld, hc, (int)cnt, m, ld, ks)) return 1;
-        CU(cudaEventRecord(g_ws.layout_ev[c], ks));
-      }
-      CU(cudaEventRecord(g_ws.done_ev, ks));
-      bool verified = ci.validate();   // host-side hashing / scanning while the kernels run
-      if (sf_unverified) {
-        const bool same = rows_identical(nf, (size_t)n, m);
-        g_hashed_bytes += (long long)sizeof(double) * n * m;
-        verified = verified && same;
-      }
-      if (!verified) {
-        CU(cudaStreamSynchronize(ks));
-        CU(cudaStreamSynchronize(st));
-        continue;
-      }
-      c = 0;
-      for (size_t g0 = 0; g0 < (size_t)n; g0 += gc, c++) {
-        const size_t cnt = (g0 + gc <= (size_t)n) ? gc : (size_t)n - g0;
-        CU(cudaStreamWaitEvent(st, g_ws.layout_ev[c], 0));
-        if (d2h_rows(out_hat_diagonals, static_cast<const double*>(d_hc) + g0 * (size_t)m, (size_t)n, g0, cnt, m, st,
-                     h_pinned))
-          return 1;
-      }
-      CU(cudaStreamWaitEvent(st, g_ws.done_ev, 0));
-      hat_done = true;
-      clk.next();
-    } else {
-      if (launch_rows(0, n, st, Dout(o_bo), Dout(o_bv), Din(o_b))) return 1;
-      if (out_hat_diagonals && b200nb_to_col_major_dev((const double*)d_h, (double*)d_hc, n, m, ld, st)) return 1;
-      bool verified = ci.validate();   // host-side hashing / scanning while the kernels run
-      if (sf_unverified) {
-        const bool same = rows_identical(nf, (size_t)n, m);
-        g_hashed_bytes += (long long)sizeof(double) * n * m;
-        verified = verified && same;
-      }
-      clk.next();
-      if (!verified) {
-        CU(cudaStreamSynchronize(st));
-        continue;
-      }
+    if (b200nb_fit_beta_dev(d_y, y_type, Din(o_x), sfv.empty() ? (const double*)d_nf : Din(o_sf), sfv.empty() ? 0 : 1,
+                            Din(o_alpha), Din(o_c), Din(o_b), Din(o_lam), (const double*)d_w, use_weights, tol, maxit,
+                            use_qr, minmu, n, m, p, ld, Dout(o_bo), Dout(o_bv), Dout(o_it), (double*)d_h, Dout(o_cn),
+                            Dout(o_cd), Dout(o_dev), (double*)d_mu, st))
+      return 1;
+    if (out_hat_diagonals && b200nb_to_col_major_dev((const double*)d_h, (double*)d_hc, n, m, ld, st)) return 1;
+    bool verified = ci.validate();   // host-side hashing / scanning while the kernels run
+    if (sf_unverified) {
+      const bool same = rows_identical(nf, (size_t)n, m);
+      g_hashed_bytes += (long long)sizeof(double) * n * m;
+      verified = verified && same;
     }
-    if (out_hat_diagonals && !hat_done) {
+    clk.next();
+    if (!verified) {
+      CU(cudaStreamSynchronize(st));
+      continue;
+    }
+    if (out_hat_diagonals) {
       if (d2h_staged(out_hat_diagonals, d_hc, sizeof(double) * (size_t)n * m, st)) return 1;
     }
     if (out_mu) {

@@ -15,6 +15,8 @@
 //     triangular solves are cooperative with lanes = rows.
 // The per-sample arithmetic (fused lp/dlp pass, integer-count factor table, fused IRLS pass) is the same as in the
 // register-resident small-p kernels.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "engine.h"
@@ -828,6 +830,11 @@ bool plan_one(int m, int p, int G, int grouped, GenShape sh, size_t extra_double
 // slice and fewer than 16 warps would be resident, the rows move to a per-warp slice of a global scratch buffer: a few
 // tens of MB that stay in the 126 MB L2, read with coalesced loads once per pass.
 bool plan(int m, int p, int G, int grouped, GenShape sh, size_t extra_doubles, GenLaunch& out) {
+  const char* force = getenv("B200NB_GENERIC_ROWS");   // "smem" | "global": A/B switch for the measurement in profiles/
+  if (force && (force[0] == 's' || force[0] == 'g')) {
+    sh.rows_global = force[0] == 'g';
+    if (plan_one(m, p, G, grouped, sh, extra_doubles, out)) return true;
+  }
   sh.rows_global = 0;
   if (!plan_one(m, p, G, grouped, sh, extra_doubles, out)) {
     sh.rows_global = 1;

@@ -592,12 +592,3 @@ def test_host_cache_is_content_addressed_and_never_stale(engine, oracle):
     assert s6["hits"] - s5["hits"] == 2
     for k in DISP_KEYS + ("iter", "iter_accept"):
         assert np.array_equal(g6[k], g1[k], equal_nan=True), k
-    # fitBeta in row chunks (the hat diagonals of chunk c are downloaded while chunk c + 1 is fitted): bit-identical,
-    # into page-locked result memory (wrappers) and into an ordinary numpy array (raw C ABI call)
-    os.environ["B200NB_CHUNKS"] = "3"
-    try:
-        r_chunk = engine.fitBeta(**b)
-    finally:
-        del os.environ["B200NB_CHUNKS"]
-    for k in ("beta_mat", "beta_var_mat", "iter", "hat_diagonals", "contrast_num", "contrast_denom", "deviance"):
-        assert np.array_equal(r_chunk[k], r_vec[k], equal_nan=True), k
