@@ -1,6 +1,6 @@
 # Convenience targets (the driver uses __graft_entry__.build(), bench.py and pytest directly).
 PY ?= python
-.PHONY: build test-cpu test-gpu test-emulated bench experiments clean
+.PHONY: build test-cpu test-gpu test-emulated bench clean
 build:
 	$(PY) -c "import __graft_entry__ as g; g.build()"
 test-cpu: build
@@ -13,8 +13,6 @@ test-emulated: build
 	B200NB_LIB=$(CURDIR)/tests/simt_emu/_build/libb200nb_emu.so $(PY) -m pytest tests -q -m gpu
 bench: build
 	$(PY) bench.py
-experiments:
-	scripts/ab_experiments.sh build
 clean:
 	$(MAKE) -C deseq2_b200/csrc clean
 	$(MAKE) -C oracle clean || true

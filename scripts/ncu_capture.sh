@@ -10,7 +10,7 @@ tag=$1; kern=$2; lib=${3:-}
 mkdir -p gpurun_out
 [ -n "$lib" ] && export B200NB_LIB="$PWD/$lib"
 ncu --set full --clock-control none --import-source on -k "regex:$kern" -s 2 -c 1 -f -o "gpurun_out/$tag" \
-    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > "gpurun_out/$tag.log" 2>&1
+    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-configs > "gpurun_out/$tag.log" 2>&1
 ncu -i "gpurun_out/$tag.ncu-rep" --page raw --csv > "gpurun_out/${tag}_raw.csv"
 ncu -i "gpurun_out/$tag.ncu-rep" --page source --csv --print-source cuda,sass > "gpurun_out/${tag}_src.csv" || true
 python profiles/src_hot.py "gpurun_out/${tag}_src.csv" | head -40 > "gpurun_out/${tag}_hot_lines.txt" || true

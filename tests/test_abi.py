@@ -95,27 +95,3 @@ def test_product_refuses_the_emulated_engine():
     r = subprocess.run([sys.executable, "-c", "import deseq2_b200; deseq2_b200.lib()"], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "SIMT-emulated test build" in r.stderr
-
-
-def test_kernel_experiments_compile_for_sm100a(tmp_path):
-    """The compile-time kernel experiments are parity-checked under the emulator with g++; this keeps
-    them compiling with nvcc for sm_100a as well (objects only, nothing is linked or shipped)."""
-    import shutil
-    if os.environ.get("B200NB_TEST_NVCC_EXPERIMENTS") != "1":
-        pytest.skip("75 s of nvcc: set B200NB_TEST_NVCC_EXPERIMENTS=1 (scripts/ab_experiments.sh build compiles them anyway)")
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not available")
-    flags = ["-DNB_EXP_HALF_WARP", "-DNB_EXP_TAB_BUCKETS", "-DNB_EXP_SPLIT_MODES", "-DNB_EXP_LOG_ESTRIN",
-             "-DNB_EXP_RCP_CUBIC", "-DNB_EXP_TAB_UNROLL4", "-DNB_EXP_HEAVY_FIRST", "-DNB_EXP_LFACT_TABLE",
-             "-DNB_EXP_BETA_CTAS3"]
-    csrc = os.path.join(ROOT, "deseq2_b200", "csrc")
-    procs = []
-    for unit in ("fit_disp", "fit_beta"):
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
-               "-Xptxas", "-v", *flags, "-c", os.path.join(csrc, unit + ".cu"), "-o", str(tmp_path / (unit + ".o"))]
-        procs.append((unit, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for unit, p in procs:
-        out = p.communicate(timeout=900)[0]
-        assert p.returncode == 0, f"{unit}: {out[-2000:]}"
-        assert "_grp_kernel" in out, f"{unit}: the grouped experiment kernel was not compiled"

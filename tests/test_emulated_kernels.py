@@ -198,21 +198,18 @@ def test_emulated_engine_matches_golden(emu, path):
     TG.test_engine_matches_golden(emu, path)
 
 
-EXPERIMENT_FLAGS = ["-DNB_EXP_HALF_WARP", "-DNB_EXP_TAB_BUCKETS", "-DNB_EXP_SPLIT_MODES", "-DNB_EXP_LOG_ESTRIN", "-DNB_EXP_RCP_CUBIC",
-                    "-DNB_EXP_TAB_UNROLL4", "-DNB_EXP_HEAVY_FIRST", "-DNB_EXP_LFACT_TABLE"]
-
-
-def test_kernel_experiments_keep_parity(tmp_path):
-    """The kernel experiments of DESIGN.md section 8 (compile-time switches, all off in the product build) must stay
-    correct while they wait for GPU time: build the emulated engine with every switch on -- two genes per warp for
-    m up to ~330, per-mode-family kernels above that, Estrin log, cubic reciprocal step, 4-way table loop, heaviest mode
-    first -- and run a slice of the parity suite against it in a fresh process."""
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_every_group_width_keeps_parity(lanes):
+    """The small-p kernels run one, two or four genes per warp (32 / 16 / 8 lanes per gene; chosen from the number of
+    samples at run time, B200NB_GROUP_LANES forces one).  Whatever the width, results must be the oracle's: a slice of
+    the parity suite with each width forced, in a fresh process (the choice is read once per process)."""
     import subprocess
     import build_emu
-    lib = build_emu.build_experiment("ci_all", EXPERIMENT_FLAGS)
-    sel = "800-37 or 1500-6 or big_and_mixed or maxit0 or condition-51 or batch-61 or edge_shapes or divergence or C3"
+    lib = build_emu.build()
+    sel = "800-37 or 1500-6 or big_and_mixed or maxit0 or condition-51 or batch-61 or edge_shapes or divergence"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_parity_gpu.py"), "-q", "-m", "gpu", "-x",
-                        "-p", "no:cacheprovider", "-k", sel], env=dict(os.environ, B200NB_LIB=lib), capture_output=True,
+                        "-p", "no:cacheprovider", "-k", sel],
+                       env=dict(os.environ, B200NB_LIB=lib, B200NB_GROUP_LANES=str(lanes)), capture_output=True,
                        text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
@@ -236,6 +233,5 @@ def test_microbench_program_runs_against_the_emulated_engine(emu, tmp_path):
     lines = [l for l in r.stdout.splitlines() if "fitDisp" in l and "fitBeta" in l]
     assert len(lines) == 2 and "max|dlog_alpha| 0.00e+00" in lines[1] and "max|dbeta| 0.00e+00" in lines[1]
     r = subprocess.run([exe, "--host", "--genes", "150", "--samples", "24", "--reps", "1", lib],
-                       env=dict(env, B200NB_CHUNK_GENES="40", B200NB_DETECT_SF="1"), capture_output=True, text=True,
-                       timeout=600)
+                       env=dict(env, B200NB_CHUNKS="3"), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "end to end" in r.stdout, r.stdout + r.stderr
