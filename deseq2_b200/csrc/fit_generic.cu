@@ -825,10 +825,12 @@ bool plan_one(int m, int p, int G, int grouped, GenShape sh, size_t extra_double
   return out.smem <= cap;
 }
 
-// Shared-memory rows starve the SM of warps once the sample rows are long (config 4: m = 1000, two rows = 16 KB per
-// warp -> 7 warps per SM, 10 % warps active in the round-1 profile).  When the rows are more than ~40 % of a warp's
-// slice and fewer than 16 warps would be resident, the rows move to a per-warp slice of a global scratch buffer: a few
-// tens of MB that stay in the 126 MB L2, read with coalesced loads once per pass.
+// Rows in shared memory whenever they fit.  Config 4 (m = 1000, two rows = 16 KB per warp) leaves 7 warps per SM; moving
+// the rows to a per-warp slice of an L2-resident global scratch buffer (rows_global) doubles the resident warps but was
+// measured 5-10 % SLOWER on the B200 (profiles/r02_kernel_ab.md: 20k x 1000, p = 10: fitDisp 6.76 -> 7.43 ms, fitBeta
+// 4.87 -> 5.02 ms): the per-pass row reads turn from shared-memory into L2 latency and the kernel is not
+// occupancy-bound.  The global path remains for rows that do not fit in shared memory at all (m > ~6000) and as the
+// A/B switch B200NB_GENERIC_ROWS=global.
 bool plan(int m, int p, int G, int grouped, GenShape sh, size_t extra_doubles, GenLaunch& out) {
   const char* force = getenv("B200NB_GENERIC_ROWS");   // "smem" | "global": A/B switch for the measurement in profiles/
   if (force && (force[0] == 's' || force[0] == 'g')) {
@@ -836,19 +838,9 @@ bool plan(int m, int p, int G, int grouped, GenShape sh, size_t extra_doubles, G
     if (plan_one(m, p, G, grouped, sh, extra_doubles, out)) return true;
   }
   sh.rows_global = 0;
-  if (!plan_one(m, p, G, grouped, sh, extra_doubles, out)) {
-    sh.rows_global = 1;
-    return plan_one(m, p, G, grouped, sh, extra_doubles, out);
-  }
-  const size_t row_bytes = (size_t)gen_rows(sh) * out.mpad * sizeof(double);
-  const size_t per_sm_warps = (227 * 1024) / (out.warp_doubles * sizeof(double) + 1);
-  if (per_sm_warps < 16 && row_bytes * 10 > out.warp_doubles * sizeof(double) * 4) {
-    GenLaunch g;
-    GenShape sg = sh;
-    sg.rows_global = 1;
-    if (plan_one(m, p, G, grouped, sg, extra_doubles, g)) out = g;
-  }
-  return true;
+  if (plan_one(m, p, G, grouped, sh, extra_doubles, out)) return true;
+  sh.rows_global = 1;
+  return plan_one(m, p, G, grouped, sh, extra_doubles, out);
 }
 
 // global row scratch: a small ring of grow-only device buffers (one per launch in flight)

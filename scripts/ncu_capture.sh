@@ -6,10 +6,10 @@
 #   scripts/ncu_capture.sh r02a_half fit_disp_grp_kernel deseq2_b200/libb200nb_exp_half_warp.so
 set -e
 cd "$(dirname "$0")/.."
-tag=$1; kern=$2; lib=${3:-}
+tag=$1; kern=$2; lib=${3:-}; skip=${NCU_SKIP:-8}   # skip the (row-chunked) launches of the workload build: land in the device-resident steps
 mkdir -p gpurun_out
 [ -n "$lib" ] && export B200NB_LIB="$PWD/$lib"
-ncu --set full --clock-control none --import-source on -k "regex:$kern" -s 2 -c 1 -f -o "gpurun_out/$tag" \
+ncu --set full --clock-control none --import-source on -k "regex:$kern" -s $skip -c 1 -f -o "gpurun_out/$tag" \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-configs > "gpurun_out/$tag.log" 2>&1
 ncu -i "gpurun_out/$tag.ncu-rep" --page raw --csv > "gpurun_out/${tag}_raw.csv"
 ncu -i "gpurun_out/$tag.ncu-rep" --page source --csv --print-source cuda,sass > "gpurun_out/${tag}_src.csv" || true
