@@ -415,6 +415,11 @@ def main():
     a = parse()
     if a.r_default_probe:
         return r_default_probe(a.genes, a.samples)
+    # NCCL's own log (version banner, communicator init lines with nranks) must not land on stdout, where the ONE JSON
+    # line goes -- and must not be hidden either: it goes to stderr at INFO/INIT level unless the caller chose otherwise
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

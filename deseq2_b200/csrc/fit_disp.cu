@@ -392,9 +392,18 @@ template <bool USE_W>
 __device__ __forceinline__ void build_table(const DispWarpSmem& S, int m, int lane) {
   for (int k = lane; k < kTabMax; k += 32) S.tab[k] = 0.0;
   __syncwarp();
-  for (int j = lane; j < m; j += 32) {
-    const int v = (int)S.ys[j];
-    if (v >= 1) atomicAdd(&S.tab[v - 1], USE_W ? S.wsm[j] : 1.0);
+  if (USE_W) {
+    // weighted histogram in a FIXED order (bin k belongs to lane k % 32, which adds its samples in index order):
+    // floating-point atomics would make c_k -- and with it `iter` on knife-edge genes -- vary from run to run
+    for (int j = 0; j < m; j++) {
+      const int v = (int)S.ys[j];
+      if (v >= 1 && ((v - 1) & 31) == lane) S.tab[v - 1] += S.wsm[j];
+    }
+  } else {
+    for (int j = lane; j < m; j += 32) {
+      const int v = (int)S.ys[j];
+      if (v >= 1) atomicAdd(&S.tab[v - 1], 1.0);   // integer-valued sums: exact in any order
+    }
   }
   __syncwarp();
   constexpr int PER = kTabMax / 32;

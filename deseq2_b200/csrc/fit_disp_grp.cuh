@@ -110,9 +110,17 @@ template <bool USE_W, int GL>
 __device__ __forceinline__ void build_table_g(const DispWarpSmem& S, int m, int lg) {
   for (int k = lg; k < kTabMax; k += GL) S.tab[k] = 0.0;
   __syncwarp();
-  for (int j = lg; j < m; j += GL) {
-    const int v = (int)S.ys[j];
-    if (v >= 1 && v <= kTabMax) atomicAdd(&S.tab[v - 1], USE_W ? S.wsm[j] : 1.0);
+  if (USE_W) {
+    // weighted histogram in a fixed order (bin k belongs to lane k % GL of the group): see build_table
+    for (int j = 0; j < m; j++) {
+      const int v = (int)S.ys[j];
+      if (v >= 1 && v <= kTabMax && ((v - 1) % GL) == lg) S.tab[v - 1] += S.wsm[j];
+    }
+  } else {
+    for (int j = lg; j < m; j += GL) {
+      const int v = (int)S.ys[j];
+      if (v >= 1 && v <= kTabMax) atomicAdd(&S.tab[v - 1], 1.0);
+    }
   }
   __syncwarp();
   constexpr int PER = kTabMax / GL;

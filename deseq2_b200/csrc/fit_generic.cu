@@ -391,9 +391,17 @@ __device__ __forceinline__ void gstage_disp(const DispArgs& A, unsigned int g, i
 __device__ __forceinline__ void gbuild_table(const GenWarp& S, int m, bool use_w, int lane) {
   for (int k = lane; k < kTabMaxG; k += 32) S.tab[k] = 0.0;
   __syncwarp();
-  for (int j = lane; j < m; j += 32) {
-    const int v = (int)S.ys[j];
-    if (v >= 1) atomicAdd(&S.tab[v - 1], use_w ? S.wsm[j] : 1.0);
+  if (use_w) {
+    // weighted histogram in a fixed order (bin k belongs to lane k % 32): see fit_disp.cu::build_table
+    for (int j = 0; j < m; j++) {
+      const int v = (int)S.ys[j];
+      if (v >= 1 && ((v - 1) & 31) == lane) S.tab[v - 1] += S.wsm[j];
+    }
+  } else {
+    for (int j = lane; j < m; j += 32) {
+      const int v = (int)S.ys[j];
+      if (v >= 1) atomicAdd(&S.tab[v - 1], 1.0);
+    }
   }
   __syncwarp();
   constexpr int PER = kTabMaxG / 32;
