@@ -286,6 +286,32 @@ def r_default_probe(n, m):
                       "what": "size factors on device + full_pipeline + outlier replacement and refit"}))
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """One process per GPU: run this rank (and so first-touch its host buffers, its pinned staging ring and its result
+    arrays) on the CPUs of the NUMA node the GPU hangs off -- what `numactl --cpunodebind` does for an R worker per
+    GPU.  torchrun starts the ranks unpinned; round 1's e2e fell to 0.475 efficiency at 8 GPUs with every rank staging
+    through whichever socket it happened to run on.  B200NB_BENCH_NUMA=0 switches it off."""
+    if os.environ.get("B200NB_BENCH_NUMA", "1") == "0":
+        return "off"
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "unknown node"
+        cpus = set()
+        for tok in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = tok.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no usable cpu on node %d" % node
+        os.sched_setaffinity(0, cpus)
+        return "rank bound to NUMA node %d (%d CPUs)" % (node, len(cpus))
+    except Exception as ex:  # pragma: no cover
+        return "not bound: " + repr(ex)[:80]
+
+
 def configs_block(world, rank, dev, peak_gbs, quick=False):
     """BASELINE.json configs 3, 4, 5 through the device-resident pipeline (deseq2_b200.device_pipeline / sharded): the
     whole DESeq() sequence of each config -- pre-steps, fitBeta for the GeneEst means where the design is not
@@ -417,8 +443,10 @@ def main():
         return r_default_probe(a.genes, a.samples)
     # NCCL's own log (version banner, communicator init lines with nranks) must not land on stdout, where the ONE JSON
     # line goes -- and must not be hidden either: it goes to stderr at INFO/INIT level unless the caller chose otherwise
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    # (NCCL ignores NCCL_DEBUG_FILE at the VERSION level some images preset, and then prints its banner on stdout)
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -456,6 +484,7 @@ def main():
     from deseq2_b200 import device as D
     from deseq2_b200 import wrappers as W
     torch.cuda.set_device(local_rank)
+    cfg["numa"] = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
@@ -647,6 +676,11 @@ def main():
             res = three_calls_host(w, W)
             per.append(time.perf_counter() - t0)
             del res                         # the results are released outside the timed region (R's gc runs later too)
+        allt = torch.tensor([float(np.median(per))], dtype=torch.float64, device=dev)
+        if world > 1:
+            gl = [torch.zeros_like(allt) for _ in range(world)]
+            dist.all_gather(gl, allt)
+            cfg["e2e_ms_per_rank"] = [round(float(t.item()) * 1e3, 2) for t in gl]
         st1 = (ctypes.c_longlong * 6)()
         L.b200nb_host_stats(st1, 6)
         dt = float(np.median(per))      # median step
