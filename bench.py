@@ -484,6 +484,7 @@ def main():
     from deseq2_b200 import device as D
     from deseq2_b200 import wrappers as W
     torch.cuda.set_device(local_rank)
+    affinity_at_start = os.sched_getaffinity(0)
     cfg["numa"] = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         import datetime
@@ -781,6 +782,7 @@ def main():
 
     cpu = None
     if not a.no_cpu_baseline:
+        os.sched_setaffinity(0, affinity_at_start)     # the CPU baseline gets every host thread, not one NUMA node
         cpu = cpu_baseline_record(w, a.cpu_sample, 3, 1)
 
     line = {"metric": "genes/sec, DESeq2 Wald hot path (fitDisp MLE + fitDisp MAP + fitBeta)", "value": value,
