@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200nb_host_stats": [vp, _I],
     "b200nb_version": [],
     "b200nb_test_special": [vp, _I, vp, vp, vp],
+    "b200nb_test_hash": [vp, _LL, _I, _LL, vp],
 }
 _RESTYPE = {
     "b200nb_last_error": C.c_char_p,

@@ -20,6 +20,9 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <unistd.h>
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#endif
 
 #include <atomic>
 #include <chrono>
@@ -43,53 +46,103 @@ struct Hash128 {
 
 // Content hash of `count` elements of `elem` (4 or 8) bytes whose canonical indices are first_index, first_index + 1, ...
 // (the canonical index of entry (i, j) of an n x m matrix is i + n j, its position in R's column-major layout).
-// Every element is xored with a key derived from its index and folded with one 64 x 64 -> 128 bit multiply; the folded
-// values are SUMMED, so the hash does not depend on the order or grouping in which the elements are visited: the host
-// hashes the caller's column-major buffer split among threads, the GPU hashes its gene-major copy
-// (layout.cu::hash_gene_major_kernel) -- same value iff same content.
+// Every element v (zero-extended to 64 bits) is xored with two keys derived from its index, and each keyed word
+// x contributes lo32(x) * hi32(x) + swap32(x) to one of two 64-bit accumulators (the NH construction of UMAC / XXH3:
+// one 32 x 32 -> 64 bit multiply per word, which SIMD units have -- the 64 x 64 -> 128 bit multiply of round 2's first
+// hash ran at 3-4 GB/s per thread and was the critical path of every cache hit with eight ranks on one host).  The
+// contributions are SUMMED, so the hash does not depend on the order or grouping in which the elements are visited: the
+// host hashes the caller's column-major buffer split among threads, the GPU hashes its gene-major copy
+// (layout.cu::hash_gene_major_kernel) -- same value iff same content (up to a 2^-64 accident; the keys are public,
+// this is a cache key, not a MAC).
 constexpr uint64_t kHashK1 = 0x9E3779B97F4A7C15ull, kHashK2 = 0xD6E8FEB86659FD93ull;
-inline void hash_fold(uint64_t v, uint64_t key, uint64_t& a, uint64_t& b) {
-  const __uint128_t r = (__uint128_t)(v ^ key) * kHashK2;
-  const uint64_t lo = (uint64_t)r, hi = (uint64_t)(r >> 64);
-  a += lo ^ hi;
-  b += ((lo << 29) | (lo >> 35)) + hi;
+inline void hash_fold(uint64_t v, uint64_t index, uint64_t& a, uint64_t& b) {
+  const uint64_t x1 = v ^ ((index + 1) * kHashK1), x2 = v ^ ((index + 1) * kHashK2);
+  a += (x1 & 0xffffffffull) * (x1 >> 32) + ((x1 << 32) | (x1 >> 32));
+  b += (x2 & 0xffffffffull) * (x2 >> 32) + ((x2 << 32) | (x2 >> 32));
 }
-inline Hash128 hash_elems(const void* p, size_t count, int elem, uint64_t first_index) {
-  const unsigned char* s = static_cast<const unsigned char*>(p);
-  uint64_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-  uint64_t k = (first_index + 1) * kHashK1;
-  size_t i = 0;
-  if (elem == 8) {
-    for (; i + 2 <= count; i += 2) {
-      uint64_t w[2];
-      memcpy(w, s + 8 * i, 16);
-      hash_fold(w[0], k, a0, b0);
-      hash_fold(w[1], k + kHashK1, a1, b1);
-      k += 2 * kHashK1;
-    }
-    if (i < count) {
-      uint64_t w;
-      memcpy(&w, s + 8 * i, 8);
-      hash_fold(w, k, a0, b0);
-    }
-  } else {
-    for (; i + 2 <= count; i += 2) {
-      uint32_t w[2];
-      memcpy(w, s + 4 * i, 8);
-      hash_fold((uint64_t)w[0], k, a0, b0);
-      hash_fold((uint64_t)w[1], k + kHashK1, a1, b1);
-      k += 2 * kHashK1;
-    }
-    if (i < count) {
+inline Hash128 hash_elems_scalar(const unsigned char* s, size_t i, size_t count, int elem, uint64_t first_index, Hash128 h) {
+  for (; i < count; i++) {
+    uint64_t v;
+    if (elem == 8) {
+      memcpy(&v, s + 8 * i, 8);
+    } else {
       uint32_t w;
       memcpy(&w, s + 4 * i, 4);
-      hash_fold((uint64_t)w, k, a0, b0);
+      v = w;
     }
+    hash_fold(v, first_index + i, h.a, h.b);
   }
-  Hash128 h;
-  h.a = a0 + a1;
-  h.b = b0 + b1;
   return h;
+}
+#if (defined(__x86_64__) || defined(__i386__)) && defined(__GNUC__)
+#define B200NB_HASH_AVX2 1
+__attribute__((target("avx2"))) inline Hash128 hash_elems_avx2(const unsigned char* s, size_t count, int elem,
+                                                                uint64_t first_index) {
+  const uint64_t f = first_index + 1;
+  __m256i k1 = _mm256_set_epi64x((long long)((f + 3) * kHashK1), (long long)((f + 2) * kHashK1),
+                                 (long long)((f + 1) * kHashK1), (long long)(f * kHashK1));
+  __m256i k2 = _mm256_set_epi64x((long long)((f + 3) * kHashK2), (long long)((f + 2) * kHashK2),
+                                 (long long)((f + 1) * kHashK2), (long long)(f * kHashK2));
+  const __m256i s1 = _mm256_set1_epi64x((long long)(4 * kHashK1)), s2 = _mm256_set1_epi64x((long long)(4 * kHashK2));
+  __m256i a = _mm256_setzero_si256(), b = _mm256_setzero_si256();
+  size_t i = 0;
+  for (; i + 4 <= count; i += 4) {
+    const __m256i v = (elem == 8) ? _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 8 * i))
+                                  : _mm256_cvtepu32_epi64(_mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 4 * i)));
+    const __m256i x1 = _mm256_xor_si256(v, k1), x2 = _mm256_xor_si256(v, k2);
+    a = _mm256_add_epi64(a, _mm256_add_epi64(_mm256_mul_epu32(x1, _mm256_srli_epi64(x1, 32)), _mm256_shuffle_epi32(x1, 0xB1)));
+    b = _mm256_add_epi64(b, _mm256_add_epi64(_mm256_mul_epu32(x2, _mm256_srli_epi64(x2, 32)), _mm256_shuffle_epi32(x2, 0xB1)));
+    k1 = _mm256_add_epi64(k1, s1);
+    k2 = _mm256_add_epi64(k2, s2);
+  }
+  uint64_t la[4], lb[4];
+  _mm256_storeu_si256(reinterpret_cast<__m256i*>(la), a);
+  _mm256_storeu_si256(reinterpret_cast<__m256i*>(lb), b);
+  Hash128 h;
+  h.a = la[0] + la[1] + la[2] + la[3];
+  h.b = lb[0] + lb[1] + lb[2] + lb[3];
+  return hash_elems_scalar(s, i, count, elem, first_index, h);
+}
+__attribute__((target("avx512f"))) inline Hash128 hash_elems_avx512(const unsigned char* s, size_t count, int elem,
+                                                                    uint64_t first_index) {
+  const uint64_t f = first_index + 1;
+  uint64_t i1[8], i2[8];
+  for (int l = 0; l < 8; l++) {
+    i1[l] = (f + l) * kHashK1;
+    i2[l] = (f + l) * kHashK2;
+  }
+  __m512i k1 = _mm512_loadu_si512(i1), k2 = _mm512_loadu_si512(i2);
+  const __m512i s1 = _mm512_set1_epi64((long long)(8 * kHashK1)), s2 = _mm512_set1_epi64((long long)(8 * kHashK2));
+  __m512i a = _mm512_setzero_si512(), b = _mm512_setzero_si512();
+  size_t i = 0;
+  for (; i + 8 <= count; i += 8) {
+    const __m512i v = (elem == 8) ? _mm512_loadu_si512(s + 8 * i)
+                                  : _mm512_cvtepu32_epi64(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + 4 * i)));
+    const __m512i x1 = _mm512_xor_si512(v, k1), x2 = _mm512_xor_si512(v, k2);
+    a = _mm512_add_epi64(a, _mm512_add_epi64(_mm512_mul_epu32(x1, _mm512_srli_epi64(x1, 32)), _mm512_rol_epi64(x1, 32)));
+    b = _mm512_add_epi64(b, _mm512_add_epi64(_mm512_mul_epu32(x2, _mm512_srli_epi64(x2, 32)), _mm512_rol_epi64(x2, 32)));
+    k1 = _mm512_add_epi64(k1, s1);
+    k2 = _mm512_add_epi64(k2, s2);
+  }
+  uint64_t la[8], lb[8];
+  _mm512_storeu_si512(la, a);
+  _mm512_storeu_si512(lb, b);
+  Hash128 h;
+  for (int l = 0; l < 8; l++) {
+    h.a += la[l];
+    h.b += lb[l];
+  }
+  return hash_elems_scalar(s, i, count, elem, first_index, h);
+}
+#endif
+inline Hash128 hash_elems(const void* p, size_t count, int elem, uint64_t first_index) {
+  const unsigned char* s = static_cast<const unsigned char*>(p);
+#ifdef B200NB_HASH_AVX2
+  static const int isa = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+  if (isa == 2) return hash_elems_avx512(s, count, elem, first_index);
+  if (isa == 1) return hash_elems_avx2(s, count, elem, first_index);
+#endif
+  return hash_elems_scalar(s, 0, count, elem, first_index, Hash128());
 }
 
 inline int env_int(const char* name, int dflt, int lo, int hi) {

@@ -55,10 +55,9 @@ __global__ void __launch_bounds__(256) hash_gene_major_kernel(const void* __rest
     const unsigned long long v = (elem == 8) ? static_cast<const unsigned long long*>(src)[t]
                                              : (unsigned long long)static_cast<const unsigned int*>(src)[t];
     const unsigned long long e = (unsigned long long)i + (unsigned long long)n * (unsigned long long)j;
-    const unsigned long long x = v ^ ((e + 1) * K1);
-    const unsigned long long lo = x * K2, hi = __umul64hi(x, K2);
-    a += lo ^ hi;
-    b += ((lo << 29) | (lo >> 35)) + hi;
+    const unsigned long long x1 = v ^ ((e + 1) * K1), x2 = v ^ ((e + 1) * K2);
+    a += (unsigned long long)(unsigned int)x1 * (unsigned long long)(unsigned int)(x1 >> 32) + ((x1 << 32) | (x1 >> 32));
+    b += (unsigned long long)(unsigned int)x2 * (unsigned long long)(unsigned int)(x2 >> 32) + ((x2 << 32) | (x2 >> 32));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -10,6 +10,8 @@
 //   parametricDispersionFit   R/core.R:2166-2189      Gamma GLM (identity link) disp ~ a0 + a1/mean, iterated trimming
 // prep_kernel: one warp per gene; the projection P = (X'X)^-1 X' (p x m) is computed once on the host.
 // trend_fit_kernel: ONE CTA runs the whole iteratively re-trimmed IRLS on the device (no host round trips).
+#include <mutex>
+
 #include "engine.h"
 #include "nbmath.cuh"
 
@@ -92,24 +94,74 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs A) {
   }
 }
 
-// ---------------------------------------------------------------- dispersion trend (single CTA)
-__device__ __forceinline__ double block_sum(double v, double* red, int tid, int nthreads) {
-  v = warp_allreduce_sum(v);
+// ---------------------------------------------------------------- dispersion trend (one CTA per SM, grid barrier)
+// The fit is a sequence of full passes over all genes (five weighted sums, then the deviance), dozens of them, each
+// needing the previous one's result: a single CTA spends ~0.25 ms per pass at a million genes (config 5 on 8 GPUs: the
+// global step is on ALL genes, 15 ms).  Here every CTA reduces a slice, writes its partial sums to a double-buffered
+// global slot, the grid meets at a counter barrier, and every CTA then adds the partials in the same fixed order, so
+// all CTAs carry bit-identical coefficients and take the same branches.  The launch is cooperative (co-residency is
+// guaranteed or the launch fails; no spinning on CTAs that were never scheduled).
+constexpr int kTrendVals = 5;
+struct TrendGrid {
+  double* part;          // [2][gridDim.x][kTrendVals]
+  unsigned int* bar;     // arrival counter, zeroed before the launch
+  double* red;           // shared: 32 * kTrendVals + kTrendVals
+  unsigned int phase;
+};
+
+// v[0..K) summed over the whole grid; every thread of every CTA returns with the same totals in v
+template <int K>
+__device__ __forceinline__ void grid_sum(TrendGrid& G, double (&v)[K]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int ncta = gridDim.x;
+#pragma unroll
+  for (int k = 0; k < K; k++) v[k] = warp_allreduce_sum(v[k]);
+  __syncthreads();   // the previous call's totals in red[] have been read by everybody
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < K; k++) G.red[warp * kTrendVals + k] = v[k];
   __syncthreads();
-  if ((tid & 31) == 0) red[tid >> 5] = v;
+  double* slot = G.part + ((size_t)(G.phase & 1u) * ncta + blockIdx.x) * kTrendVals;
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double t = (lane < nw) ? G.red[lane * kTrendVals + k] : 0.0;
+      t = warp_allreduce_sum(t);
+      if (lane == 0) slot[k] = t;
+    }
+    if (ncta > 1) {
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(G.bar, 1u);
+        const unsigned int want = (G.phase + 1u) * (unsigned int)ncta;
+        while (*reinterpret_cast<volatile unsigned int*>(G.bar) < want) {}
+        __threadfence();
+      }
+      __syncwarp();
+    }
+    const double* base = G.part + (size_t)(G.phase & 1u) * ncta * kTrendVals;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double t = 0.0;
+      for (int c = lane; c < ncta; c += 32) t += __ldcg(base + (size_t)c * kTrendVals + k);
+      t = warp_allreduce_sum(t);
+      if (lane == 0) G.red[32 * kTrendVals + k] = t;
+    }
+  }
   __syncthreads();
-  double t = 0.0;
-  for (int w = 0; w < (nthreads >> 5); w++) t += red[w];
-  return t;
+#pragma unroll
+  for (int k = 0; k < K; k++) v[k] = G.red[32 * kTrendVals + k];
+  G.phase++;
 }
 
 // out[0..1] = coefficients (asymptDisp, extraPois); out[2] = status (0 ok, 1 not converged, 2 non-positive
 // coefficients, 3 no usable genes); out[3] = outer iterations used.
-__global__ void __launch_bounds__(1024) trend_fit_kernel(const double* __restrict__ means,
+__global__ void __launch_bounds__(512) trend_fit_kernel(const double* __restrict__ means,
                                                          const double* __restrict__ disps, int n, double min_disp,
-                                                         double* __restrict__ out) {
-  __shared__ double red[32];
-  const int tid = threadIdx.x, nt = blockDim.x;
+                                                         double* __restrict__ out, double* part, unsigned int* bar) {
+  __shared__ double red[33 * kTrendVals];
+  TrendGrid G{part, bar, red, 0u};
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gnt = gridDim.x * blockDim.x;
   double c0 = 0.1, c1 = 1.0;
   int status = 1, outer = 0;
   for (; outer <= 10; outer++) {   // R: iter > 10 => "dispersion fit did not converge"
@@ -118,24 +170,24 @@ __global__ void __launch_bounds__(1024) trend_fit_kernel(const double* __restric
     double b0 = c0, b1 = c1;
     double dev_old;
     {
-      double dv = 0.0, cnt = 0.0;
-      for (int i = tid; i < n; i += nt) {
+      double a[2] = {0.0, 0.0};   // deviance, count
+      for (int i = gtid; i < n; i += gnt) {
         const double d = disps[i], mn = means[i];
         if (!(d > 100.0 * min_disp)) continue;
         const double resid = d / (t0 + t1 / mn);
         if (!(resid > 1e-4 && resid < 15.0)) continue;
         const double mu = b0 + b1 / mn;
-        dv += -log(d / mu) + (d - mu) / mu;
-        cnt += 1.0;
+        a[0] += -log(d / mu) + (d - mu) / mu;
+        a[1] += 1.0;
       }
-      dev_old = 2.0 * block_sum(dv, red, tid, nt);
-      cnt = block_sum(cnt, red, tid, nt);
-      if (cnt < 2.0) { status = 3; break; }
+      grid_sum(G, a);
+      dev_old = 2.0 * a[0];
+      if (a[1] < 2.0) { status = 3; break; }
     }
     bool converged = false, bad = false;
     for (int it = 0; it < 25; it++) {
-      double sw = 0.0, swx = 0.0, swxx = 0.0, swy = 0.0, swxy = 0.0;
-      for (int i = tid; i < n; i += nt) {
+      double sv[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // sw, swx, swxx, swy, swxy
+      for (int i = gtid; i < n; i += gnt) {
         const double d = disps[i], mn = means[i];
         if (!(d > 100.0 * min_disp)) continue;
         const double resid = d / (t0 + t1 / mn);
@@ -143,29 +195,26 @@ __global__ void __launch_bounds__(1024) trend_fit_kernel(const double* __restric
         const double xi = 1.0 / mn;
         const double mu = b0 + b1 * xi;
         const double w = 1.0 / (mu * mu);
-        sw += w; swx += w * xi; swxx += w * xi * xi; swy += w * d; swxy += w * xi * d;
+        sv[0] += w; sv[1] += w * xi; sv[2] += w * xi * xi; sv[3] += w * d; sv[4] += w * xi * d;
       }
-      sw = block_sum(sw, red, tid, nt);
-      swx = block_sum(swx, red, tid, nt);
-      swxx = block_sum(swxx, red, tid, nt);
-      swy = block_sum(swy, red, tid, nt);
-      swxy = block_sum(swxy, red, tid, nt);
+      grid_sum(G, sv);
+      const double sw = sv[0], swx = sv[1], swxx = sv[2], swy = sv[3], swxy = sv[4];
       const double det = sw * swxx - swx * swx;
       b0 = (swxx * swy - swx * swxy) / det;
       b1 = (sw * swxy - swx * swy) / det;
-      double dv = 0.0, neg = 0.0;
-      for (int i = tid; i < n; i += nt) {
+      double a[2] = {0.0, 0.0};   // deviance, number of non-positive means
+      for (int i = gtid; i < n; i += gnt) {
         const double d = disps[i], mn = means[i];
         if (!(d > 100.0 * min_disp)) continue;
         const double resid = d / (t0 + t1 / mn);
         if (!(resid > 1e-4 && resid < 15.0)) continue;
         const double mu = b0 + b1 / mn;
-        if (!(mu > 0.0)) neg += 1.0;
-        dv += -log(d / mu) + (d - mu) / mu;
+        if (!(mu > 0.0)) a[1] += 1.0;
+        a[0] += -log(d / mu) + (d - mu) / mu;
       }
-      const double dev = 2.0 * block_sum(dv, red, tid, nt);
-      neg = block_sum(neg, red, tid, nt);
-      if (neg > 0.0) { bad = true; break; }
+      grid_sum(G, a);
+      const double dev = 2.0 * a[0];
+      if (a[1] > 0.0) { bad = true; break; }
       if (fabs(dev - dev_old) / (fabs(dev) + 0.1) < 1e-8) { converged = true; break; }
       dev_old = dev;
     }
@@ -175,7 +224,7 @@ __global__ void __launch_bounds__(1024) trend_fit_kernel(const double* __restric
     c1 = b1;
     if ((l0 * l0 + l1 * l1 < 1e-6) && converged) { status = 0; break; }
   }
-  if (tid == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     out[0] = c0;
     out[1] = c1;
     out[2] = (double)status;
@@ -200,10 +249,40 @@ cudaError_t launch_prep(const PrepArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// scratch of the grid reduction: partial sums of every CTA (double-buffered) + the barrier counter.  One buffer per
+// process (the device pipeline runs on one stream); trend fits on two streams at once are serialised by the mutex only
+// up to the launch, so callers must not overlap them.
 cudaError_t launch_trend_fit(const double* means, const double* disps, int n, double min_disp, double* out,
                              cudaStream_t stream) {
-  trend_fit_kernel<<<1, 1024, 0, stream>>>(means, disps, n, min_disp, out);
+  static std::mutex mu;
+  static void* scratch = nullptr;
+  constexpr int kMaxCtas = 256;
+  constexpr size_t kPartBytes = 2 * (size_t)kMaxCtas * kTrendVals * sizeof(double);
+  std::lock_guard<std::mutex> lk(mu);
+  if (scratch == nullptr) {
+    cudaError_t e = cudaMalloc(&scratch, kPartBytes + 256);
+    if (e != cudaSuccess) return e;
+  }
+  double* part = static_cast<double*>(scratch);
+  unsigned int* bar = reinterpret_cast<unsigned int*>(static_cast<char*>(scratch) + kPartBytes);
+  cudaError_t e = cudaMemsetAsync(bar, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+#ifdef SIMT_EMU
+  // the emulator runs the CTAs of a grid one after the other: a grid barrier needs the one-CTA grid
+  trend_fit_kernel<<<1, 512, 0, stream>>>(means, disps, n, min_disp, out, part, bar);
   return cudaGetLastError();
+#else
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trend_fit_kernel, 512, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  int grid = (n + 2047) / 2048;                 // at least four genes per thread before another CTA pays its barrier
+  const int cap = device_sm_count() < kMaxCtas ? device_sm_count() : kMaxCtas;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  void* args[] = {(void*)&means, (void*)&disps, (void*)&n, (void*)&min_disp, (void*)&out, (void*)&part, (void*)&bar};
+  return cudaLaunchCooperativeKernel((const void*)trend_fit_kernel, dim3(grid), dim3(512), args, 0, stream);
+#endif
 }
 
 }  // namespace nb

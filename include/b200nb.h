@@ -179,6 +179,10 @@ const char* b200nb_version(void);
 
 /* test hook: lgamma / digamma / trigamma of the device math on host arrays x[0..n) (x > 0) */
 int b200nb_test_special(const double* x, int n, double* out_lgamma, double* out_digamma, double* out_trigamma);
+/* test hook: the host content hash of `count` elements of `elem` (4 | 8) bytes at p, canonical indices first_index...,
+ * by every instruction-set variant this CPU can run (scalar, AVX2, AVX-512): out[0..1] receive the scalar value;
+ * returns the number of variants compared, or -1 if two of them disagree. */
+int b200nb_test_hash(const void* p, long long count, int elem, long long first_index, unsigned long long* out2);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,19 @@ import deseq2_b200
 from deseq2_b200 import wrappers as W
 
 n, m = int(os.environ.get("PROBE_GENES", 50000)), int(os.environ.get("PROBE_SAMPLES", 100))
+REPS = int(os.environ.get("PROBE_REPS", 9))
+NUMA = ""
+if os.environ.get("PROBE_WORLD"):   # one of several concurrent single-GPU processes (scripts/contention_probe.sh)
+    try:   # the main thread (first touch of the buffers) on the GPU's NUMA node, like bench.bind_to_gpu_numa_node
+        node = int(open(f"/sys/bus/pci/devices/{os.environ['PROBE_PCI'].lower()[-12:]}/numa_node").read())
+        cpus = set()
+        for tok in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = tok.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus & os.sched_getaffinity(0))
+        NUMA = f"node{node}"
+    except Exception as ex:
+        NUMA = "unbound(" + repr(ex)[:60] + ")"
 w = bench.build_workload(n, m, 20260925, W)
 L = deseq2_b200.lib()
 c, x, mu = w["counts"], w["x"], w["mu"]
@@ -70,9 +83,20 @@ def step_raw():
     return t1 - t0, t2 - t1, t3 - t2, 0.0
 
 
-def run(f, reps=9):
+def barrier(tag):
+    d, world = os.environ.get("PROBE_BARRIER_DIR"), int(os.environ.get("PROBE_WORLD", 0))
+    if not d or world < 2:
+        return
+    open(os.path.join(d, f"{tag}.{os.environ.get('CUDA_VISIBLE_DEVICES', '0')}"), "w").close()
+    t0 = time.time()
+    while len([f for f in os.listdir(d) if f.startswith(tag + ".")]) < world and time.time() - t0 < 120:
+        time.sleep(0.002)
+
+
+def run(f, reps=REPS):
     for _ in range(3):
         f()
+    barrier(f.__name__)
     t = np.array([f() for _ in range(reps)])
     return np.median(t, axis=0) * 1e3
 
@@ -83,9 +107,9 @@ a = run(step_wrappers)
 st1 = (C.c_longlong * 6)()
 L.b200nb_host_stats(st1, 6)
 b = run(step_raw)
-per_step = [(st1[i] - st0[i]) / 12 for i in range(6)]
+per_step = [(st1[i] - st0[i]) / (REPS + 3) for i in range(6)]
 knobs = " ".join(f"{k[7:]}={v}" for k, v in sorted(os.environ.items()) if k.startswith("B200NB_") and k != "B200NB_LIB")
-print(f"{knobs or 'default'} | wrappers: disp {a[0]:.2f} disp {a[1]:.2f} beta {a[2]:.2f} free {a[3]:.2f} total {a[:3].sum():.2f} ms"
+print(f"{NUMA + ' ' if NUMA else ''}{knobs or 'default'} | wrappers: disp {a[0]:.2f} disp {a[1]:.2f} beta {a[2]:.2f} free {a[3]:.2f} total {a[:3].sum():.2f} ms"
       f" | raw preallocated: disp {b[0]:.2f} disp {b[1]:.2f} beta {b[2]:.2f} total {b[:3].sum():.2f} ms"
       f" | per step: H2D {per_step[0] / 1e6:.1f} MB, D2H {per_step[1] / 1e6:.1f} MB, cache hits {per_step[2]:.1f}, "
       f"served from cache {per_step[4] / 1e6:.1f} MB, hashed {per_step[5] / 1e6:.1f} MB", flush=True)

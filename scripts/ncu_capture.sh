@@ -3,6 +3,7 @@
 # the GPU box under gpurun with ONE GPU; writes gpurun_out/<tag>.ncu-rep plus the raw / source CSV exports that
 # profiles/src_hot.py and profiles/sass_hist.py read.
 #   scripts/ncu_capture.sh <tag> <kernel regex> [library]      e.g.  scripts/ncu_capture.sh r02a_fit_disp fit_disp_kernel
+#   NCU_CMD='python scripts/c4_ab.py 8000' NCU_SKIP=0 scripts/ncu_capture.sh r02h_generic_disp fit_disp_generic_kernel
 #   scripts/ncu_capture.sh r02a_half fit_disp_grp_kernel deseq2_b200/libb200nb_exp_half_warp.so
 set -e
 cd "$(dirname "$0")/.."
@@ -10,7 +11,7 @@ tag=$1; kern=$2; lib=${3:-}; skip=${NCU_SKIP:-8}   # skip the (row-chunked) laun
 mkdir -p gpurun_out
 [ -n "$lib" ] && export B200NB_LIB="$PWD/$lib"
 ncu --set full --clock-control none --import-source on -k "regex:$kern" -s $skip -c 1 -f -o "gpurun_out/$tag" \
-    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-configs > "gpurun_out/$tag.log" 2>&1
+    ${NCU_CMD:-python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-configs} > "gpurun_out/$tag.log" 2>&1
 ncu -i "gpurun_out/$tag.ncu-rep" --page raw --csv > "gpurun_out/${tag}_raw.csv"
 ncu -i "gpurun_out/$tag.ncu-rep" --page source --csv --print-source cuda,sass > "gpurun_out/${tag}_src.csv" || true
 python profiles/src_hot.py "gpurun_out/${tag}_src.csv" | head -40 > "gpurun_out/${tag}_hot_lines.txt" || true

@@ -123,6 +123,8 @@ inline int __any_sync(unsigned mask, int pred) { return simt_emu::ballot(mask, p
 inline int __all_sync(unsigned mask, int pred) { return simt_emu::ballot(mask, !pred) == 0; }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { simt_emu::barrier_warp(mask); }
 inline void __syncthreads() { simt_emu::barrier_cta(); }
+template <typename T>
+inline T __ldcg(const T* p) { return *p; }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 

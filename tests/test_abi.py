@@ -95,3 +95,48 @@ def test_product_refuses_the_emulated_engine():
     r = subprocess.run([sys.executable, "-c", "import deseq2_b200; deseq2_b200.lib()"], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "SIMT-emulated test build" in r.stderr
+
+
+def test_host_content_hash_variants_agree_and_match_definition():
+    """The cache key of the host entry points (hostrt.h::hash_elems): every SIMD variant this CPU can run equals the
+    scalar one, the value is independent of how the buffer is split, and it matches a restatement of the definition
+    in Python integers (lo32 * hi32 + swap32 of the keyed word, two key streams, summed mod 2^64)."""
+    import ctypes as C
+    import numpy as np
+    import deseq2_b200
+    L = deseq2_b200.lib()
+    K1, K2, M = 0x9E3779B97F4A7C15, 0xD6E8FEB86659FD93, (1 << 64) - 1
+    rng = np.random.Generator(np.random.PCG64(5))
+
+    def py_hash(words, first):
+        a = b = 0
+        for i, v in enumerate(words):
+            for which, K in ((0, K1), (1, K2)):
+                x = int(v) ^ (((first + i + 1) * K) & M)
+                t = ((x & 0xffffffff) * (x >> 32) + (((x << 32) | (x >> 32)) & M)) & M
+                if which == 0:
+                    a = (a + t) & M
+                else:
+                    b = (b + t) & M
+        return a, b
+
+    def lib_hash(arr, elem, first):
+        out = (C.c_ulonglong * 2)()
+        rc = L.b200nb_test_hash(C.c_void_p(arr.ctypes.data), arr.size, elem, first, out)
+        assert rc >= 1, rc
+        return (out[0], out[1]), rc
+
+    for elem, dt in ((4, np.uint32), (8, np.uint64)):
+        for count in (0, 1, 7, 8, 9, 31, 257):
+            arr = rng.integers(0, np.iinfo(dt).max, size=count, dtype=dt, endpoint=True)
+            h, variants = lib_hash(arr, elem, 1000)
+            assert h == py_hash(arr, 1000), (elem, count)
+        big = rng.integers(0, np.iinfo(dt).max, size=100003, dtype=dt, endpoint=True)
+        whole, variants = lib_hash(big, elem, 0)
+        left, _ = lib_hash(big[:40001], elem, 0)
+        right, _ = lib_hash(np.ascontiguousarray(big[40001:]), elem, 40001)
+        assert whole == ((left[0] + right[0]) & M, (left[1] + right[1]) & M)
+        flipped = big.copy()
+        flipped[77777] ^= dt(1)
+        assert lib_hash(flipped, elem, 0)[0] != whole
+    assert variants >= 1
