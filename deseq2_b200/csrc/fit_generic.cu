@@ -22,10 +22,22 @@
 #include "engine.h"
 #include "nbmath.cuh"
 
+// Unroll factors of the two per-sample loops.  These kernels are instruction-cache bound, not latency bound (ncu of the
+// config-4 shape: 34 % of the stall samples no_instructions at 19k SASS instructions, 7 warps per SM): on the B200
+// unroll 1 | 2 | 4 | 8 of the dispersion loop gave 4.98 | 5.18 | 6.91 | 10.5 ms for 20 000 genes x 1000 samples, and
+// __noinline__ evaluation functions or a 128-register cap made it slower (profiles/r02_kernel_ab.md).
+#ifndef NB_EXP_GEN_UNROLL_DISP
+#define NB_EXP_GEN_UNROLL_DISP 1
+#endif
+#ifndef NB_EXP_GEN_UNROLL_BETA
+#define NB_EXP_GEN_UNROLL_BETA 1
+#endif
+
 namespace nb {
 namespace {
 
 constexpr int kTabMaxG = 256;
+constexpr int kUnrollDisp = NB_EXP_GEN_UNROLL_DISP, kUnrollBeta = NB_EXP_GEN_UNROLL_BETA;
 
 // ---------------------------------------------------------------- cooperative dense helpers (lanes = rows)
 
@@ -226,7 +238,7 @@ __device__ __forceinline__ void gdisp_eval(const GDispCtx& C, double a, double p
   }
   const double* ys = S.ys;
   const double* mus = S.r1;
-#pragma unroll 4
+#pragma unroll kUnrollDisp
   for (int j = lane; j < D.m; j += 32) {
     const double y = ys[j], mu = mus[j];
     // wd = 1/(1/mu + alpha) = mu/(1 + mu alpha); 1/mu never needed: y/mu - 1 = (y - mu)/mu cancels against wd
@@ -425,7 +437,7 @@ __device__ __forceinline__ void gbuild_table(const GenWarp& S, int m, bool use_w
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(256) fit_disp_generic_kernel(const DispArgs A, int mpad, int ps, size_t warp_doubles) {
+__global__ void __launch_bounds__(256, 1) fit_disp_generic_kernel(const DispArgs A, int mpad, int ps, size_t warp_doubles) {
   extern __shared__ __align__(16) double smem[];
   init_log_table();
   const int lane = threadIdx.x & 31;
@@ -575,7 +587,7 @@ __device__ __forceinline__ double gbeta_pass(const GBetaCtx& C, const double* be
   __syncwarp();
   double dev = 0.0;
   double* mus = S.r2;
-#pragma unroll 2
+#pragma unroll kUnrollBeta
   for (int j = lane; j < D.m; j += 32) {
     const int t = D.grouped ? D.gid[j] : j;
     const double lnf = C.lnf[j];
@@ -625,7 +637,7 @@ __device__ __forceinline__ double lgamma_diff_g(double y, double r, double lg_r)
   return lgamma_pos(y + r) - lg_r;
 }
 
-__global__ void __launch_bounds__(256) fit_beta_generic_kernel(const BetaArgs A, int mpad, int ps, size_t warp_doubles) {
+__global__ void __launch_bounds__(256, 1) fit_beta_generic_kernel(const BetaArgs A, int mpad, int ps, size_t warp_doubles) {
   extern __shared__ __align__(16) double smem[];
   init_log_table();
   const int lane = threadIdx.x & 31;

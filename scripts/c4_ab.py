@@ -42,11 +42,11 @@ def t(fn, reps=3):
     return best
 
 
-for mode in ("smem", "global"):
+for mode in os.environ.get("C4_AB_MODES", "smem,global").split(","):
     os.environ["B200NB_GENERIC_ROWS"] = mode
     t1 = t(lambda: D.fit_disp(y, pr["xd"], pr["mu_lin"], la0, la0, 1.0, float(np.log(1e-9)), 1.0, 1e-6, 100, False))
     t2 = t(lambda: D.fit_disp(y, pr["xd"], pr["mu_lin"], torch.log(res["dispGeneEst"]), lfit, res["dispPriorVar"],
                               float(np.log(1e-9)), 1.0, 1e-6, 100, True))
     t3 = t(lambda: D.fit_beta(y, pr["xd"], pr["sfd"], res["dispersion"], con, pr["beta0"], lam, 1e-8, 100))
     print(f"rows in {mode:6s}: fitDisp MLE {t1:.2f} ms, fitDisp MAP {t2:.2f} ms, fitBeta {t3:.2f} ms  ({n} genes x {m})")
-del os.environ["B200NB_GENERIC_ROWS"]
+os.environ.pop("B200NB_GENERIC_ROWS", None)
