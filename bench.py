@@ -187,6 +187,28 @@ def host_threads():
     return int(os.environ.get("B200NB_REF_THREADS", n))
 
 
+def limit_library_thread_pools():
+    """numpy's OpenBLAS and torch's OpenMP pool start one worker per CPU of the affinity mask (64-128 on the GPU
+    hosts) and those workers busy-wait after every call; inside a container with a CPU quota (1-GPU lease: 16 CPUs) the
+    spin exhausts the quota and the kernel throttles the whole process for the rest of the 100 ms period -- holes of
+    40-90 ms in a device pipeline whose host glue is a few numpy calls (profiles/r02_pipeline_host_stalls.md).  The GPU
+    arm needs none of those pools: one thread each.  (torchrun does the same with OMP_NUM_THREADS=1 for N > 1.)"""
+    done = []
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+        done.append("threadpoolctl: 1")
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(1)
+        done.append("torch: 1")
+    except Exception:
+        pass
+    return ", ".join(done) or "unchanged"
+
+
 class RefEngine:
     """The CPU arm's engine: the REFERENCE'S OWN src/DESeq2.cpp (oracle/_ref, compiled unchanged against stand-in
     headers; kind = "reference") with `threads` BiocParallel-style gene chunks (R/parallel.R:9-10); if the prebuilt
@@ -485,6 +507,7 @@ def main():
     from deseq2_b200 import wrappers as W
     torch.cuda.set_device(local_rank)
     affinity_at_start = os.sched_getaffinity(0)
+    cfg["host_library_threads"] = limit_library_thread_pools()
     cfg["numa"] = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         import datetime

@@ -116,6 +116,13 @@ hostrt::Pool& pool() {
     const int local_ranks = hostrt::env_int("LOCAL_WORLD_SIZE", 1, 1, 64);
     const int ranks_here = cpus.empty() ? local_ranks : (local_ranks + 1) / 2;
     int dflt = avail / 2 / (ranks_here > 0 ? ranks_here : 1);
+    // ... and no more than the container's CPU quota leaves after the calling thread and the driver's helper threads
+    // (the quota is shared by every rank of the container)
+    const int quota = hostrt::cgroup_cpu_quota();
+    if (quota > 0) {
+      const int share = quota / local_ranks - 2;
+      if (dflt > share) dflt = share;
+    }
     if (dflt > 16) dflt = 16;
     if (dflt < 2) dflt = avail >= 2 ? 2 : 1;
     g_pool.reset(new hostrt::Pool(hostrt::env_int("B200NB_HOST_THREADS", dflt, 1, 128), cpus));

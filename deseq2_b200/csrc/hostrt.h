@@ -194,6 +194,27 @@ inline int pci_numa_node(const char* pci_bus_id) {   // "0000:1b:00.0" (any case
   return node;
 }
 
+// CPUs the container may burn per scheduling period (cgroup v2 cpu.max, v1 cpu.cfs_quota_us / cfs_period_us), rounded
+// up; 0 = no quota.  A process whose runnable (spinning!) threads exceed it is throttled as a whole for the rest of the
+// 100 ms period -- measured on the 1-GPU lease (affinity 128 CPUs, quota 16): holes of 40-90 ms in the host timeline.
+inline int cgroup_cpu_quota() {
+  long long q = -1, per = 100000;
+  if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    char a[64] = "";
+    if (fscanf(f, "%63s %lld", a, &per) >= 1 && strcmp(a, "max") != 0) q = atoll(a);
+    fclose(f);
+  } else if (FILE* g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+    if (fscanf(g, "%lld", &q) != 1) q = -1;
+    fclose(g);
+    if (FILE* h = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+      if (fscanf(h, "%lld", &per) != 1) per = 100000;
+      fclose(h);
+    }
+  }
+  if (q <= 0 || per <= 0) return 0;
+  return (int)((q + per - 1) / per);
+}
+
 inline int affinity_count() {
   cpu_set_t s;
   CPU_ZERO(&s);

@@ -70,6 +70,30 @@ def size_factors(y, m, type="ratio"):
     return out
 
 
+def _projection(x):
+    """(X'X)^-1 X' (p x m) WITHOUT a BLAS / LAPACK call.  numpy hands `x.T @ x` and linalg.solve to OpenBLAS, whose
+    worker threads (one per CPU the process may run on: 64-128 on the GPU hosts) then busy-wait for ~100 ms; under a
+    container CPU quota (the 1-GPU lease: cpu.max = 16 CPUs) that spin exhausts the quota and the kernel throttles the
+    WHOLE process for the rest of the period -- measured: DESeq_device on the config-4 shape took 100-170 ms instead of
+    54 ms, with random 40-90 ms holes in the host timeline (profiles/r02_pipeline_host_stalls.md).  The matrices
+    are p x p with p <= 32: einsum's own loops and a Gauss-Jordan sweep with partial pivoting are plenty."""
+    x = np.asarray(x, dtype=np.float64)
+    m, p = x.shape
+    a = np.einsum("ik,il->kl", x, x)                       # X'X (c_einsum loops, no BLAS)
+    aug = np.concatenate([a, np.ascontiguousarray(x.T)], axis=1)   # [X'X | X']
+    for c in range(p):
+        piv = c + int(np.argmax(np.abs(aug[c:, c])))
+        if aug[piv, c] == 0.0:
+            raise np.linalg.LinAlgError("singular design matrix")
+        if piv != c:
+            aug[[c, piv]] = aug[[piv, c]]
+        aug[c] /= aug[c, c]
+        f = aug[:, c].copy()
+        f[c] = 0.0
+        aug -= f[:, None] * aug[c][None, :]
+    return np.ascontiguousarray(aug[:, p:])
+
+
 def prep(y, x, sizeFactors, minDisp=1e-8, minmu=0.5, want_mu=True, want_beta0=True):
     """b200nb_prep_dev.  y: gene-major (n, ld) int32/float64 device tensor; x: (m, p) numpy; sizeFactors: (m,) numpy."""
     L = _lib.lib()
@@ -77,7 +101,7 @@ def prep(y, x, sizeFactors, minDisp=1e-8, minmu=0.5, want_mu=True, want_beta0=Tr
     n, ld = y.shape
     x = np.asarray(x, dtype=np.float64)
     m, p = x.shape
-    proj = np.linalg.solve(x.T @ x, x.T)                       # (X'X)^-1 X', p x m
+    proj = _projection(x)                                      # (X'X)^-1 X', p x m
     xd = D.x_to_device(x, dev)
     projd = torch.as_tensor(np.ascontiguousarray(proj), device=dev)
     sfd = torch.as_tensor(np.asarray(sizeFactors, dtype=np.float64), device=dev)
