@@ -137,10 +137,18 @@ std::atomic<long long> g_h2d_bytes{0}, g_d2h_bytes{0}, g_cache_hits{0}, g_cache_
 // ---------------------------------------------------------------- pinned staging ring
 // R hands over ordinary (pageable) memory; cudaMemcpy from pageable memory runs at ~9 GB/s on the GPU box.  A ring of
 // pinned buffers filled by the pool while the previous buffer is in flight reaches PCIe speed.
-// B200NB_STAGE_KB / B200NB_STAGE_BLOCK_KB: size of one ring buffer / of one pool task (read once, when the library loads)
-const size_t kStageChunk = (size_t)hostrt::env_int("B200NB_STAGE_KB", 8192, 64, 262144) << 10;
+// Size of one ring buffer and of one pool task.  One rank per host: 8 MB buffers (fewest synchronisations; 4.8 ms per C2
+// step vs 5.1 ms with 2 MB).  Several ranks per host: the four buffers of every rank should stay resident in the shared
+// last-level cache between the staging copy and the DMA that reads them -- with 8 ranks on a 2 x 60 MB-L3 host, 2 MB
+// buffers took 1.2 ms off the 9 ms step (profiles/r02_host_path.md) -- so 4 MB from two local ranks, 2 MB from four.
+// B200NB_STAGE_KB / B200NB_STAGE_BLOCK_KB override (read once, when the library loads).
+static size_t default_stage_kb() {
+  const int local_ranks = hostrt::env_int("LOCAL_WORLD_SIZE", 1, 1, 64);
+  return local_ranks >= 4 ? 2048 : (local_ranks >= 2 ? 4096 : 8192);
+}
+const size_t kStageChunk = (size_t)hostrt::env_int("B200NB_STAGE_KB", (int)default_stage_kb(), 64, 262144) << 10;
 constexpr int kStageRing = 4;
-const size_t kBlock = (size_t)hostrt::env_int("B200NB_STAGE_BLOCK_KB", 512, 16, 65536) << 10;   // unit of work of one pool task
+const size_t kBlock = (size_t)hostrt::env_int("B200NB_STAGE_BLOCK_KB", (int)(default_stage_kb() / 16), 16, 65536) << 10;   // unit of work of one pool task
 struct Staging {
   void* buf[kStageRing] = {};
   cudaEvent_t ev[kStageRing] = {};

@@ -14,6 +14,10 @@ ncu --set full --clock-control none --import-source on -k "regex:$kern" -s $skip
     ${NCU_CMD:-python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-configs} > "gpurun_out/$tag.log" 2>&1
 ncu -i "gpurun_out/$tag.ncu-rep" --page raw --csv > "gpurun_out/${tag}_raw.csv"
 ncu -i "gpurun_out/$tag.ncu-rep" --page source --csv --print-source cuda,sass > "gpurun_out/${tag}_src.csv" || true
-python profiles/src_hot.py "gpurun_out/${tag}_src.csv" | head -40 > "gpurun_out/${tag}_hot_lines.txt" || true
+python profiles/src_hot.py "gpurun_out/${tag}_src.csv" > "gpurun_out/${tag}_hot_lines_all.txt"; head -40 "gpurun_out/${tag}_hot_lines_all.txt" > "gpurun_out/${tag}_hot_lines.txt" || true
 grep -E "gpu__time_duration.sum|sm__pipe_fp64_cycles_active.avg.pct|smsp__issue_active.avg.pct|sm__warps_active.avg.pct|launch__registers_per_thread|smsp__inst_executed.sum|dram__bytes_(read|write).sum" \
     "gpurun_out/${tag}_raw.csv" | head -20 || true
+python profiles/ncu_summary.py "gpurun_out/${tag}_raw.csv" > "gpurun_out/${tag}_ncu_summary.txt" 2>&1 || true
+python profiles/sass_hist.py "gpurun_out/${tag}_src.csv" > "gpurun_out/${tag}_sass_hist.txt" 2>&1 || true
+# gpurun copies at most 64 MiB back: NCU_KEEP=0 drops the report and the source export once the summaries exist
+if [ "${NCU_KEEP:-1}" = "0" ]; then rm -f "gpurun_out/$tag.ncu-rep" "gpurun_out/${tag}_src.csv" "gpurun_out/${tag}_hot_lines_all.txt"; fi
