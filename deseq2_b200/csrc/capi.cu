@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <sys/mman.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <memory>
@@ -728,7 +729,58 @@ struct DesignDev {
   int G, grouped;
   int saturated;       // G == p and the distinct rows form an invertible p x p matrix
   double sat_logdet;   // 2 log|det X_g|
+  nb::SegLayout seg;   // sorted lane-chunk sample layout (grouped designs with m <= 65535), else seg.pos == nullptr
 };
+void apply_design(const DesignDev& dd, int use_weights, nb::DispArgs* a) {
+  a->xg = dd.xg; a->gid = dd.gid; a->G = dd.G; a->grouped = dd.grouped;
+  a->saturated = dd.saturated && !use_weights; a->sat_logdet = dd.sat_logdet;
+  a->seg = dd.seg;
+}
+void apply_design(const DesignDev& dd, nb::BetaArgs* a) {
+  a->xg = dd.xg; a->gid = dd.gid; a->G = dd.G; a->grouped = dd.grouped;
+  a->seg = dd.seg;
+}
+
+// engine.h::SegLayout on the host: samples sorted by group (stable), dealt to the lanes in contiguous chunks
+struct SegHost {
+  std::vector<unsigned short> pos, inv, seg_end;
+  std::vector<unsigned char> gfirst, glo, ghi;
+  int kmax = 0;
+};
+void build_seg_layout(const std::vector<int>& gid, int m, int G, SegHost* h) {
+  std::vector<int> order(m);
+  {
+    std::vector<int> start(G + 1, 0);
+    for (int j = 0; j < m; j++) start[gid[j] + 1]++;
+    for (int g = 0; g < G; g++) start[g + 1] += start[g];
+    for (int j = 0; j < m; j++) order[start[gid[j]]++] = j;
+  }
+  const int q = m / 32, rem = m % 32;
+  h->pos.assign(m, 0);
+  h->inv.assign(m, 0);
+  h->gfirst.assign(32, 0);
+  h->glo.assign(G, 255);
+  h->ghi.assign(G, 0);
+  std::vector<std::vector<int>> ends(32);
+  for (int l = 0; l < 32; l++) {
+    const int n_l = q + (l < rem ? 1 : 0);
+    const int s0 = l * q + (l < rem ? l : rem);
+    for (int i = 0; i < n_l; i++) {
+      const int j = order[s0 + i], g = gid[j];
+      h->pos[j] = (unsigned short)(i * 32 + l);
+      h->inv[i * 32 + l] = (unsigned short)j;
+      if (i == 0) h->gfirst[l] = (unsigned char)g;
+      if (l < h->glo[g]) h->glo[g] = (unsigned char)l;
+      if (l > h->ghi[g]) h->ghi[g] = (unsigned char)l;
+      if (i + 1 == n_l || gid[order[s0 + i + 1]] != g) ends[l].push_back(i + 1);
+    }
+  }
+  h->kmax = 1;
+  for (int l = 0; l < 32; l++) h->kmax = std::max(h->kmax, (int)ends[l].size());
+  h->seg_end.assign((size_t)h->kmax * 32, 0xffff);
+  for (int l = 0; l < 32; l++)
+    for (size_t r = 0; r < ends[l].size(); r++) h->seg_end[r * 32 + l] = (unsigned short)ends[l][r];
+}
 constexpr int kDesignRing = 16;
 void* g_design_arena = nullptr;
 size_t g_design_slot = 0;
@@ -779,16 +831,44 @@ int prepare_design(const double* x_host, int m, int p, cudaStream_t st, DesignDe
   }
   if (!grouped)
     for (int j = 0; j < m; j++) gid[j] = j;
+  // one packed upload: [xg | gid | segment layout (pos, inv, seg_end, gfirst, glo, ghi)]
   const size_t xbytes = xg.size() * sizeof(double), gbytes = (size_t)m * sizeof(int);
-  const size_t need = ((xbytes + 15) & ~(size_t)15) + gbytes;
+  const bool with_seg = grouped && m <= 65535;
+  SegHost sh;
+  if (with_seg) build_seg_layout(gid, m, (int)rep.size(), &sh);
+  auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  const size_t o_gid = up16(xbytes), o_pos = up16(o_gid + gbytes);
+  const size_t o_inv = up16(o_pos + sh.pos.size() * 2), o_end = up16(o_inv + sh.inv.size() * 2);
+  const size_t o_gf = up16(o_end + sh.seg_end.size() * 2), o_lo = up16(o_gf + sh.gfirst.size());
+  const size_t o_hi = up16(o_lo + sh.glo.size()), need = up16(o_hi + sh.ghi.size());
+  std::vector<char> pack(need, 0);
+  memcpy(pack.data(), xg.data(), xbytes);
+  memcpy(pack.data() + o_gid, gid.data(), gbytes);
+  if (with_seg) {
+    memcpy(pack.data() + o_pos, sh.pos.data(), sh.pos.size() * 2);
+    memcpy(pack.data() + o_inv, sh.inv.data(), sh.inv.size() * 2);
+    memcpy(pack.data() + o_end, sh.seg_end.data(), sh.seg_end.size() * 2);
+    memcpy(pack.data() + o_gf, sh.gfirst.data(), sh.gfirst.size());
+    memcpy(pack.data() + o_lo, sh.glo.data(), sh.glo.size());
+    memcpy(pack.data() + o_hi, sh.ghi.data(), sh.ghi.size());
+  }
   char* base = nullptr;
   if (next_design_slot(need, &base)) return 1;
-  // pageable H2D copies are staged before cudaMemcpyAsync returns, so the vectors may die at scope exit
-  CU(cudaMemcpyAsync(base, xg.data(), xbytes, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(base + ((xbytes + 15) & ~(size_t)15), gid.data(), gbytes, cudaMemcpyHostToDevice, st));
+  // pageable H2D copies are staged before cudaMemcpyAsync returns, so the vector may die at scope exit
+  CU(cudaMemcpyAsync(base, pack.data(), need, cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
   out->xg = reinterpret_cast<const double*>(base);
-  out->gid = reinterpret_cast<const int*>(base + ((xbytes + 15) & ~(size_t)15));
+  out->gid = reinterpret_cast<const int*>(base + o_gid);
+  out->seg = nb::SegLayout{};
+  if (with_seg) {
+    out->seg.pos = reinterpret_cast<const unsigned short*>(base + o_pos);
+    out->seg.inv = reinterpret_cast<const unsigned short*>(base + o_inv);
+    out->seg.seg_end = reinterpret_cast<const unsigned short*>(base + o_end);
+    out->seg.gfirst = reinterpret_cast<const unsigned char*>(base + o_gf);
+    out->seg.glo = reinterpret_cast<const unsigned char*>(base + o_lo);
+    out->seg.ghi = reinterpret_cast<const unsigned char*>(base + o_hi);
+    out->seg.kmax = sh.kmax;
+  }
   out->G = grouped ? (int)rep.size() : m;
   out->grouped = grouped ? 1 : 0;
   out->saturated = 0;
@@ -1023,8 +1103,7 @@ int b200nb_fit_disp_dev(const void* y, int y_type, const double* x, const double
   if (use_generic(p)) {
     DesignDev dd;
     if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
-    a.xg = dd.xg; a.gid = dd.gid; a.G = dd.G; a.grouped = dd.grouped;
-    a.saturated = dd.saturated && !use_weights; a.sat_logdet = dd.sat_logdet;
+    apply_design(dd, use_weights, &a);
     CU(nb::launch_fit_disp_generic(a, (cudaStream_t)stream));
     g_launches += 1;
     return 0;
@@ -1053,8 +1132,7 @@ int b200nb_fit_disp_grid_dev(const void* y, int y_type, const double* x, const d
   if (use_generic(p)) {
     DesignDev dd;
     if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
-    a.xg = dd.xg; a.gid = dd.gid; a.G = dd.G; a.grouped = dd.grouped;
-    a.saturated = dd.saturated && !use_weights; a.sat_logdet = dd.sat_logdet;
+    apply_design(dd, use_weights, &a);
     CU(nb::launch_fit_disp_generic(a, (cudaStream_t)stream));
     g_launches++;
     return 0;
@@ -1088,7 +1166,7 @@ int b200nb_fit_beta_dev(const void* y, int y_type, const double* x, const double
     if (n == 0) return 0;
     DesignDev dd;
     if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
-    a.xg = dd.xg; a.gid = dd.gid; a.G = dd.G; a.grouped = dd.grouped;
+    apply_design(dd, &a);
     CU(nb::launch_fit_beta_generic(a, (cudaStream_t)stream));
     g_launches++;
     return 0;

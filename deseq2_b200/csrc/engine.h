@@ -11,6 +11,22 @@ namespace nb {
 constexpr int kMaxSmallP = 4;    // register-resident normal equations
 constexpr int kMaxP = 32;        // shared-memory path upper bound
 
+// Sample layout of the segmented general-p kernels (fit_generic_seg.cuh; grouped designs, m <= 65535).  The samples are
+// sorted by design group and dealt to the 32 lanes as contiguous chunks of the sorted sequence (lane l gets sorted
+// samples [l q + min(l, rem), ...), q = m / 32, rem = m % 32); the sample that lane l visits in trip i of the loop
+// `for (j = lane; j < m; j += 32)` sits at position i * 32 + l.  A lane therefore sees a short run of consecutive
+// groups ("segments"), accumulates the per-group sums of a pass in registers and stores one value per segment.
+// All arrays are device pointers prepared by the C-ABI layer together with xg / gid; `pos == nullptr`: no layout.
+struct SegLayout {
+  const unsigned short* pos;      // m: position of sample j
+  const unsigned short* inv;      // m: sample at position q
+  const unsigned short* seg_end;  // kmax x 32: trip count after which segment r of lane l ends (0xffff: no such segment)
+  const unsigned char* gfirst;    // 32: group of lane l's first segment
+  const unsigned char* glo;       // G: first lane holding samples of group g
+  const unsigned char* ghi;       // G: last lane holding samples of group g
+  int kmax;                       // most segments any lane has
+};
+
 struct DispArgs {
   // inputs (device pointers)
   const void* y;        // gene-major counts, int32 or f64
@@ -47,6 +63,7 @@ struct DispArgs {
   // log det = 2 log|det X_g| + sum_g log W_g and tr(B^-1 dB) = sum_g dW_g / W_g -- no p x p algebra at all
   int saturated;
   double sat_logdet;  // 2 log|det X_g|
+  SegLayout seg;
   // device scratch supplied by the caller: (4 + 3 n) 32-bit words
   // [work-queue counter | 3 per-mode gene counts | 3 per-mode gene lists]; the launcher zeroes the header
   unsigned int* scratch;
@@ -97,6 +114,7 @@ struct BetaArgs {
   const int* gid;
   int G, grouped;
   double* row_scratch;   // long rows: per-warp global scratch for the sample rows (set by the launcher)
+  SegLayout seg;
 };
 
 // nbinomLogLike at the unclamped fitted mean (fit_beta.cu::nb_loglik_kernel)

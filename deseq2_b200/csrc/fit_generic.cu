@@ -400,6 +400,29 @@ __device__ __forceinline__ void gstage_disp(const DispArgs& A, unsigned int g, i
   __syncwarp();
 }
 
+// histogram tab[v] = #{y == v + 1} (weighted) -> tab[k] = c_k = sum_j w_j [y_j > k], in place
+__device__ __forceinline__ void tab_suffix_sums(double* tab, int lane) {
+  constexpr int PER = kTabMaxG / 32;
+  double loc[PER];
+  double run = 0.0;
+#pragma unroll
+  for (int q = PER - 1; q >= 0; q--) {
+    run += tab[lane * PER + q];
+    loc[q] = run;
+  }
+  double above = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_down_sync(0xffffffffu, above, o);
+    if (lane + o < 32) above += t;
+  }
+  above -= run;
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < PER; q++) tab[lane * PER + q] = loc[q] + above;
+  __syncwarp();
+}
+
 __device__ __forceinline__ void gbuild_table(const GenWarp& S, int m, bool use_w, int lane) {
   for (int k = lane; k < kTabMaxG; k += 32) S.tab[k] = 0.0;
   __syncwarp();
@@ -416,25 +439,7 @@ __device__ __forceinline__ void gbuild_table(const GenWarp& S, int m, bool use_w
     }
   }
   __syncwarp();
-  constexpr int PER = kTabMaxG / 32;
-  double loc[PER];
-  double run = 0.0;
-#pragma unroll
-  for (int q = PER - 1; q >= 0; q--) {
-    run += S.tab[lane * PER + q];
-    loc[q] = run;
-  }
-  double above = run;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double t = __shfl_down_sync(0xffffffffu, above, o);
-    if (lane + o < 32) above += t;
-  }
-  above -= run;
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < PER; q++) S.tab[lane * PER + q] = loc[q] + above;
-  __syncwarp();
+  tab_suffix_sums(S.tab, lane);
 }
 
 __global__ void __launch_bounds__(256, 1) fit_disp_generic_kernel(const DispArgs A, int mpad, int ps, size_t warp_doubles) {
@@ -821,6 +826,8 @@ __global__ void __launch_bounds__(256, 1) fit_beta_generic_kernel(const BetaArgs
   }
 }
 
+#include "fit_generic_seg.cuh"
+
 struct GenLaunch {
   int mpad, ps, warps;
   size_t warp_doubles, smem;
@@ -888,10 +895,81 @@ cudaError_t row_scratch(size_t bytes, double** out) {
   return cudaSuccess;
 }
 
+// ---- segmented kernels: launch plan.  One CTA per SM of up to 16 warps; the kernels are compiled for 256 / 384 / 512
+// threads (255 / 168 / 128 registers).  B200NB_GENERIC_SEG=0 keeps the kernels above (A/B switch, read per launch),
+// B200NB_GENERIC_WARPS=<n> caps the warps per CTA.
+struct SegPlan {
+  int warps, mpad, ps;
+  size_t warp_bytes, smem;
+};
+bool seg_enabled(const SegLayout& L) {
+  if (L.pos == nullptr) return false;
+  const char* e = getenv("B200NB_GENERIC_SEG");
+  return !(e && e[0] == '0');
+}
+bool plan_seg(size_t fixed, size_t warp_bytes, SegPlan& out) {
+  const size_t cap = 227 * 1024;
+  if (fixed + warp_bytes > cap) return false;
+  int warps = (int)((cap - fixed) / warp_bytes);
+  if (warps > 16) warps = 16;
+  const char* e = getenv("B200NB_GENERIC_WARPS");
+  if (e && atoi(e) >= 1 && atoi(e) < warps) warps = atoi(e);
+  out.warps = warps;
+  out.warp_bytes = warp_bytes;
+  out.smem = fixed + (size_t)warps * warp_bytes;
+  return true;
+}
+template <typename K>
+cudaError_t seg_grid(K kernel, const SegPlan& P, int n, long long* grid) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem);
+  if (e != cudaSuccess) return e;
+  int ctas_per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, P.warps * 32, P.smem);
+  if (e != cudaSuccess) return e;
+  if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+  const long long want = ((long long)n + P.warps - 1) / P.warps;
+  long long g = (long long)device_sm_count() * ctas_per_sm;
+  if (g > want) g = want;
+  *grid = g < 1 ? 1 : g;
+  return cudaSuccess;
+}
+template <int MAXT>
+cudaError_t launch_disp_seg_t(const DispArgs& a, const SegPlan& P, cudaStream_t stream) {
+  long long grid = 1;
+  cudaError_t e = seg_grid(fit_disp_seg_kernel<MAXT>, P, a.n, &grid);
+  if (e != cudaSuccess) return e;
+  fit_disp_seg_kernel<MAXT><<<(unsigned)grid, P.warps * 32, P.smem, stream>>>(a, P.mpad, P.ps, P.warp_bytes);
+  return cudaGetLastError();
+}
+template <int MAXT>
+cudaError_t launch_beta_seg_t(const BetaArgs& a, const SegPlan& P, cudaStream_t stream) {
+  long long grid = 1;
+  cudaError_t e = seg_grid(fit_beta_seg_kernel<MAXT>, P, a.n, &grid);
+  if (e != cudaSuccess) return e;
+  fit_beta_seg_kernel<MAXT><<<(unsigned)grid, P.warps * 32, P.smem, stream>>>(a, P.mpad, P.ps, P.warp_bytes);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
   DispArgs a = a0;
+  if (a.grouped && !a.use_weights && a.grid == nullptr && seg_enabled(a.seg)) {
+    SegPlan P;
+    P.mpad = (a.m + 7) & ~7;
+    P.ps = a.p | 1;
+    const int sat = a.saturated && a.G == a.p;
+    const size_t fixed = (size_t)a.G * P.ps * sizeof(double) + seg_table_bytes(a.seg.kmax, a.G);
+    if (plan_seg(fixed, sdisp_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, sat), P)) {
+      cudaError_t e = cudaMemsetAsync(a.scratch, 0, 4 * sizeof(unsigned int), stream);
+      if (e != cudaSuccess) return e;
+      a.counter = a.scratch;
+      a.row_scratch = nullptr;
+      if (P.warps <= 8) return launch_disp_seg_t<256>(a, P, stream);
+      if (P.warps <= 12) return launch_disp_seg_t<384>(a, P, stream);
+      return launch_disp_seg_t<512>(a, P, stream);
+    }
+  }
   GenLaunch L;
   const GenShape sh{1, 0, a.use_weights != 0, 1, 3, 0};
   if (!plan(a.m, a.p, a.G, a.grouped, sh, 0, L)) return cudaErrorInvalidValue;
@@ -919,6 +997,21 @@ cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
 
 cudaError_t launch_fit_beta_generic(const BetaArgs& a0, cudaStream_t stream) {
   BetaArgs a = a0;
+  if (a.grouped && !a.use_weights && seg_enabled(a.seg)) {
+    SegPlan P;
+    P.mpad = (a.m + 7) & ~7;
+    P.ps = a.p | 1;
+    const size_t fixed = ((size_t)a.G * P.ps + (a.nf_is_vector ? P.mpad : 0) + 64) * sizeof(double) +
+                         seg_table_bytes(a.seg.kmax, a.G);
+    if (plan_seg(fixed, sbeta_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, a.nf_is_vector), P)) {
+      cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream);
+      if (e != cudaSuccess) return e;
+      a.row_scratch = nullptr;
+      if (P.warps <= 8) return launch_beta_seg_t<256>(a, P, stream);
+      if (P.warps <= 12) return launch_beta_seg_t<384>(a, P, stream);
+      return launch_beta_seg_t<512>(a, P, stream);
+    }
+  }
   GenLaunch L;
   const int mpad = (a.m + 3) & ~3;
   const GenShape sh{a.nf_is_vector ? 0 : 1, 1, a.use_weights != 0, 0, 2, 0};

@@ -77,6 +77,10 @@ CASES = [
     ("general p: 10-level factor", lambda e, o: TP.test_general_p_parity(e, o, "factor10", 81, n=60)),
     ("general p: expanded 11 columns + ridge", lambda e, o: TP.test_general_p_parity(e, o, "expanded11", 82, n=60)),
     ("general p: continuous covariates", lambda e, o: TP.test_general_p_parity(e, o, "covariates7", 83, n=60)),
+    ("segmented general p: m=7, 6 groups (saturated)", lambda e, o: TP.test_segmented_general_p_kernels(e, o, 7, 6, 1)),
+    ("segmented general p: m=33, 6 groups", lambda e, o: TP.test_segmented_general_p_kernels(e, o, 33, 6, 3)),
+    ("segmented general p: m=64, 12 groups", lambda e, o: TP.test_segmented_general_p_kernels(e, o, 64, 12, 4)),
+    ("segmented general p: m=40, 32 groups", lambda e, o: TP.test_segmented_general_p_kernels(e, o, 40, 32, 7)),
     ("config 4 shape m=1000", lambda e, o: TP.test_config_shapes_spot_check(e, o, "C4", 48, 1000)),
     ("config 3 shape m=500", lambda e, o: TP.test_config_shapes_spot_check(e, o, "C3", 60, 500)),
     ("edge 1x4", lambda e, o: TP.test_edge_shapes(e, o, 1, 4)),

@@ -344,6 +344,75 @@ def test_general_p_parity(engine, oracle, kind, seed, n=400):
     assert np.mean(np.abs(gg - og) < 1e-9) > 0.9
 
 
+@pytest.mark.parametrize("m,G,seed", [(7, 6, 1), (31, 5, 2), (33, 6, 3), (64, 12, 4), (100, 7, 5), (257, 10, 6), (40, 32, 7),
+                                      (1000, 10, 8)])
+def test_segmented_general_p_kernels(engine, oracle, m, G, seed):
+    """The segmented general-p kernels (csrc/fit_generic_seg.cuh: samples sorted by design group, lane chunks, per-lane
+    segment sums) on grouped designs of every shape: unequal group sizes in shuffled sample order, m below / across /
+    far above the warp width, as many groups as lanes, a genuine (not replicated) normalisation-factor matrix, rows
+    with counts beyond 8 and 16 bits (gathered from global memory), double-typed counts.  Checked against the oracle
+    and against the kernels of fit_generic.cu (B200NB_GENERIC_SEG=0, read per launch) on the same inputs."""
+    import os
+    from deseq2_b200 import synth
+    rng = np.random.default_rng(900 + seed)
+    sizes = rng.multinomial(m - G, rng.dirichlet(np.full(G, 0.7))) + 1      # every group at least one sample
+    gid = rng.permutation(np.repeat(np.arange(G), sizes))
+    levels = min(G, 6)                                                      # p = levels (+1 covariate-like column)
+    x = np.zeros((m, levels))
+    x[:, 0] = 1.0
+    for k in range(1, levels):
+        x[:, k] = (gid % levels == k)
+    if G > levels:
+        x = np.c_[x, (gid // levels).astype(float)]                         # distinguishes the remaining groups
+    assert len(np.unique(x, axis=0)) == G and np.linalg.matrix_rank(x) == x.shape[1]
+    p = x.shape[1]
+    assert p > 4          # the general-p kernels (p <= 4 runs on the register-resident kernels)
+    n = 40 if m >= 1000 else 150
+    c = make_case(n, m, x=synth.design_condition(m), seed=seed, betaSD=0.5)
+    n = len(c["counts"])
+    counts = c["counts"].copy()
+    counts[0] = np.minimum(counts[0] * 0 + rng.integers(300, 5000, m), 2 ** 31 - 1)    # beyond 8 bits
+    counts[1] = rng.integers(70000, 400000, m)                                          # beyond 16 bits
+    c["counts"] = counts
+    c["x"] = x
+    nf = c["nf"] * np.exp(rng.normal(0, 0.1, c["nf"].shape))                            # a real matrix
+    nf /= np.exp(np.mean(np.log(nf), axis=1, keepdims=True))
+    alpha = np.clip(0.1 + 4 / np.maximum(c["baseMean"], 1.0), 1e-8, max(10, m))
+    beta0 = np.zeros((n, p))
+    beta0[:, 0] = np.log(np.maximum(counts.mean(axis=1), 0.1))
+    lam = np.full(p, 1e-6) / np.log(2) ** 2
+    for variant in ("nf-matrix", "sf-vector", "f64-counts"):
+        a = beta_args(c, alpha, x=x, lam=lam, beta0=beta0, contrast=np.r_[np.zeros(p - 1), 1.0],
+                      nf=nf if variant == "nf-matrix" else None,
+                      y=counts.astype(np.float64) if variant == "f64-counts" else None)
+        g = engine.fitBeta(**a, return_mu=True)
+        o = oracle.fitBeta(**a)
+        _compare_beta(g, o, f"seg beta {variant} m={m} G={G}")
+        os.environ["B200NB_GENERIC_SEG"] = "0"
+        try:
+            g0 = engine.fitBeta(**a, return_mu=True)
+        finally:
+            os.environ.pop("B200NB_GENERIC_SEG")
+        assert np.array_equal(g["iter"], g0["iter"])
+        for k in ("beta_mat", "beta_var_mat", "hat_diagonals", "mu", "deviance"):
+            assert np.nanmax(rel_err(g[k], g0[k], floor=1e-9)) < 1e-8, (variant, k)
+    mu = np.maximum(nf * np.exp(o["beta_mat"] @ x.T), 0.5)
+    for variant in ("mle", "map", "f64-counts, no CR"):
+        d = disp_args(c, mu, np.log(c["alpha0"]), prior_mean=np.log(alpha), sigmasq=0.7, usePrior=variant == "map",
+                      useCR=variant != "f64-counts, no CR", y=counts.astype(np.float64) if "f64" in variant else None)
+        g = engine.fitDisp(**d)
+        _compare_disp(g, oracle.fitDisp(**d, with_margin=True), f"seg disp {variant} m={m} G={G}", min_robust=0.7)
+        os.environ["B200NB_GENERIC_SEG"] = "0"
+        try:
+            g0 = engine.fitDisp(**d)
+        finally:
+            os.environ.pop("B200NB_GENERIC_SEG")
+        same = (g["iter"] == g0["iter"]) & (g["iter_accept"] == g0["iter_accept"])
+        assert same.mean() > 0.9
+        assert np.nanmax(rel_err(g["initial_lp"], g0["initial_lp"])) < 1e-9
+        assert np.nanmax(rel_err(g["log_alpha"][same], g0["log_alpha"][same], floor=1e-3)) < 1e-6
+
+
 def test_generic_kernels_on_small_p_designs():
     """Cross-check: force the general-p (shared-memory) kernels onto the p <= 4 cases above in a fresh process
     (the switch is read once per process) -- both kernel families must agree with the oracle on the same inputs."""
