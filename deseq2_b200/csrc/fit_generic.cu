@@ -959,7 +959,7 @@ cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
     P.mpad = (a.m + 7) & ~7;
     P.ps = a.p | 1;
     const int sat = a.saturated && a.G == a.p;
-    const size_t fixed = (size_t)a.G * P.ps * sizeof(double) + seg_table_bytes(a.seg.kmax, a.G);
+    const size_t fixed = (size_t)a.G * P.ps * sizeof(double) + seg_table_bytes(a.seg.kmax, a.G) + pair_table_bytes(a.p);
     if (plan_seg(fixed, sdisp_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, sat), P)) {
       cudaError_t e = cudaMemsetAsync(a.scratch, 0, 4 * sizeof(unsigned int), stream);
       if (e != cudaSuccess) return e;
@@ -1001,8 +1001,8 @@ cudaError_t launch_fit_beta_generic(const BetaArgs& a0, cudaStream_t stream) {
     SegPlan P;
     P.mpad = (a.m + 7) & ~7;
     P.ps = a.p | 1;
-    const size_t fixed = ((size_t)a.G * P.ps + (a.nf_is_vector ? P.mpad : 0) + 64) * sizeof(double) +
-                         seg_table_bytes(a.seg.kmax, a.G);
+    const size_t fixed = ((size_t)a.G * P.ps + (a.nf_is_vector ? 2 * P.mpad : 0) + 64) * sizeof(double) +
+                         seg_table_bytes(a.seg.kmax, a.G) + pair_table_bytes(a.p);
     if (plan_seg(fixed, sbeta_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, a.nf_is_vector), P)) {
       cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream);
       if (e != cudaSuccess) return e;

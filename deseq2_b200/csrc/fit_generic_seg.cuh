@@ -51,6 +51,41 @@ __device__ __forceinline__ double seg_group_sum(const SegTables& T, const double
   return s;
 }
 
+// (a, b), a >= b, of the lower-triangle entry `idx`: the p (p + 1) / 2 entries of X'WX are dealt to the 32 lanes
+struct PairTable {
+  const unsigned char* a;
+  const unsigned char* b;
+  int n;
+};
+__host__ __device__ inline size_t pair_table_bytes(int p) { return ((size_t)p * (p + 1) + 15) & ~(size_t)15; }
+__device__ __forceinline__ PairTable stage_pair_table(int p, unsigned char* dst) {
+  const int n = p * (p + 1) / 2;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    int a = 0, rem = idx;
+    while (rem > a) {
+      rem -= a + 1;
+      a++;
+    }
+    dst[idx] = (unsigned char)a;
+    dst[n + idx] = (unsigned char)rem;
+  }
+  return PairTable{dst, dst + n, n};
+}
+// M = sum_g W[g] x_g x_g' (full symmetric storage), one entry per lane and trip, sums kept in registers
+__device__ __forceinline__ void build_xtwx_pairs(const Design& D, const PairTable& P, const double* W, double* M, int lane) {
+  for (int idx = lane; idx < P.n; idx += 32) {
+    const int a = P.a[idx], b = P.b[idx];
+    double s = 0.0;
+    for (int g = 0; g < D.G; g++) {
+      const double* xr = D.xg + (size_t)g * D.ps;
+      s = fma(W[g] * xr[a], xr[b], s);
+    }
+    M[a * D.ps + b] = s;
+    M[b * D.ps + a] = s;
+  }
+  __syncwarp();
+}
+
 // ================================================================ dispersion
 
 struct SDispWarp {
@@ -92,6 +127,7 @@ __device__ __forceinline__ SDispWarp sdisp_carve(double* base, int mpad, int p, 
 struct SDispCtx {
   Design D;
   SegTables T;
+  PairTable P;
   SDispWarp S;
   const unsigned short* inv;   // global: sample at position q (genes that cannot use the byte row)
   const void* yrow;            // the gene's row of counts in global memory
@@ -223,7 +259,7 @@ __device__ __forceinline__ void sdisp_eval(const SDispCtx& C, double a, double p
       }
       __syncwarp();
       double* B = S.M0;
-      build_xtwx(D, S.WA, B, lane);
+      build_xtwx_pairs(D, C.P, S.WA, B, lane);
       chol_smem(B, D.p, D.ps, lane);
       double ld = (lane < D.p) ? log(B[lane * D.ps + lane]) : 0.0;
       ld = warp_allreduce_sum(ld);
@@ -242,7 +278,7 @@ __device__ __forceinline__ void sdisp_eval(const SDispCtx& C, double a, double p
         tr3 = warp_allreduce_sum(tr3);
         double* dB = S.M2;
         double* Mm = S.M3;
-        build_xtwx(D, S.WB, dB, lane);
+        build_xtwx_pairs(D, C.P, S.WB, dB, lane);
         if (lane < D.p)
           for (int c = 0; c < D.p; c++) {
             double s = 0.0;
@@ -284,11 +320,13 @@ __global__ void __launch_bounds__(MAXT, 1) fit_disp_seg_kernel(const DispArgs A,
   for (int i = threadIdx.x; i < A.G * ps; i += blockDim.x) xg[i] = A.xg[i];
   SDispCtx C;
   C.T = stage_seg_tables(A.seg, A.G, tabs);
+  C.P = stage_pair_table(A.p, tabs + seg_table_bytes(A.seg.kmax, A.G));
   __syncthreads();
   C.D = Design{xg, nullptr, A.p, ps, A.G, 1, A.m};
   C.saturated = A.saturated && A.G == A.p;
-  C.S = sdisp_carve(reinterpret_cast<double*>(tabs + seg_table_bytes(A.seg.kmax, A.G) + (size_t)warp * warp_bytes), mpad,
-                    A.p, ps, A.G, A.seg.kmax, C.saturated);
+  C.S = sdisp_carve(reinterpret_cast<double*>(tabs + seg_table_bytes(A.seg.kmax, A.G) + pair_table_bytes(A.p) +
+                                              (size_t)warp * warp_bytes),
+                    mpad, A.p, ps, A.G, A.seg.kmax, C.saturated);
   C.inv = A.seg.inv;
   C.y_is_f64 = A.y_is_f64;
   C.inv_sigmasq = 1.0 / A.prior_sigmasq;
@@ -393,27 +431,29 @@ __global__ void __launch_bounds__(MAXT, 1) fit_disp_seg_kernel(const DispArgs A,
 
 struct SBetaWarp {
   unsigned short* y16;   // mpad, position order (genes with counts that do not fit gather y from global memory)
-  double* lnf;           // mpad, position order: the gene's log normalisation factors (nf matrix only)
+  double *nf, *lnf;      // mpad each, position order: the gene's normalisation factors and their logs (nf matrix only)
   double *segA, *segB;   // kmax x 32
-  double *WA, *WB, *eta, *q;   // G
+  double *WA, *WB, *eta, *eeta, *q;   // G
   double *M0, *M1, *M2, *M3;   // p x ps
   double *v0, *v1, *v2, *v3;   // 32
 };
 __host__ __device__ inline size_t sbeta_warp_bytes(int mpad, int p, int ps, int G, int kmax, int nf_is_vector) {
   const size_t Gp = (size_t)(G + 1) & ~(size_t)1;
-  return 8 * ((nf_is_vector ? 0 : (size_t)mpad) + 2 * (size_t)kmax * 32 + 4 * Gp + 4 * (size_t)p * ps + 4 * 32) +
+  return 8 * ((nf_is_vector ? 0 : 2 * (size_t)mpad) + 2 * (size_t)kmax * 32 + 5 * Gp + 4 * (size_t)p * ps + 4 * 32) +
          2 * (size_t)mpad;
 }
 __device__ __forceinline__ SBetaWarp sbeta_carve(double* base, int mpad, int p, int ps, int G, int kmax, int nf_is_vector) {
   SBetaWarp S;
   const size_t Gp = (size_t)(G + 1) & ~(size_t)1;
   double* q = base;
+  S.nf = nf_is_vector ? nullptr : q; q += nf_is_vector ? 0 : mpad;
   S.lnf = nf_is_vector ? nullptr : q; q += nf_is_vector ? 0 : mpad;
   S.segA = q; q += (size_t)kmax * 32;
   S.segB = q; q += (size_t)kmax * 32;
   S.WA = q; q += Gp;
   S.WB = q; q += Gp;
   S.eta = q; q += Gp;
+  S.eeta = q; q += Gp;
   S.q = q; q += Gp;
   S.M0 = q; q += (size_t)p * ps;
   S.M1 = q; q += (size_t)p * ps;
@@ -430,8 +470,9 @@ __device__ __forceinline__ SBetaWarp sbeta_carve(double* base, int mpad, int p, 
 struct SBetaCtx {
   Design D;
   SegTables T;
+  PairTable P;
   SBetaWarp S;
-  const double* lnfp;          // position order: shared (size-factor vector) or the warp's row
+  const double *nfp, *lnfp;    // position order: shared (size-factor vector) or the warp's rows
   const unsigned short* inv;   // global
   const void* yrow;
   int y_is_f64, y_gather;
@@ -443,6 +484,10 @@ __device__ __forceinline__ double sbeta_y(const SBetaCtx& C, int j) {
   const int jj = C.inv[j];
   return C.y_is_f64 ? static_cast<const double*>(C.yrow)[jj] : (double)static_cast<const int32_t*>(C.yrow)[jj];
 }
+
+// mu of a sample of group g: nf * exp(eta_g), the exponential taken once per group and pass (1 ulp from
+// exp(eta_g + log nf), far below what the stop rule at 1e-8 can see); log mu = eta_g + log nf unless clamped
+__device__ __forceinline__ double sbeta_exp(double e) { return (fabs(e) < 700.0) ? exp_fast(e) : exp(e); }
 
 // one fused pass: eta per group -> mu, deviance part, per-group sums W = sum w, WZ = sum w z (src/DESeq2.cpp:324-373)
 template <bool WANT_DEV>
@@ -456,27 +501,29 @@ __device__ __forceinline__ double sbeta_pass(const SBetaCtx& C, const double* be
     double e = 0.0;
     for (int k = 0; k < D.p; k++) e = fma(xr[k], beta[k], e);
     S.eta[lane] = e;
+    S.eeta[lane] = sbeta_exp(e);
   }
   __syncwarp();
   int seg = 0;
   int end = C.T.seg_end[lane];
   int g = C.T.gfirst[lane];
-  double e = S.eta[g];
+  double e = S.eta[g], ee = S.eeta[g];
   double aW = 0.0, aB = 0.0, dev = 0.0;
   for (int i = 1, j = lane; j < D.m; i++, j += 32) {
-    const double lnf = C.lnfp[j];
-    const double le = e + lnf;
-    const double mu = fmax((fabs(le) < 700.0) ? exp_fast(le) : exp(le), C.minmu);
-    const double lmu = (mu == C.minmu) ? C.log_minmu : le;
+    const double mu = fmax(ee * C.nfp[j], C.minmu);
     const double y = sbeta_y(C, j);
     const double am = mu * alpha;
     const double u1 = 1.0 + am;
     const double iu1 = rcp_fast(u1);
     const double w = mu * iu1;
-    const double z = (lmu - lnf) + fma(y, rcp_fast(mu), -1.0);
+    double lmu_lnf = e;   // log(mu / nf)
+    double lnf = 0.0;
+    if (WANT_DEV || mu == C.minmu) lnf = C.lnfp[j];
+    if (mu == C.minmu) lmu_lnf = C.log_minmu - lnf;
+    const double z = lmu_lnf + fma(y, rcp_fast(mu), -1.0);
     if (WANT_DEV) {
       const double l1p = log_pos(u1) + (am - (u1 - 1.0)) * iu1;   // log1p(am)
-      dev += fma(y, lmu + log_alpha, -(y + r) * l1p);
+      dev += fma(y, (lmu_lnf + lnf) + log_alpha, -(y + r) * l1p);
     }
     aW += w;
     aB = fma(w, z, aB);
@@ -488,6 +535,7 @@ __device__ __forceinline__ double sbeta_pass(const SBetaCtx& C, const double* be
       end = (seg < C.T.kmax) ? (int)C.T.seg_end[seg * 32 + lane] : 0xffff;
       g = (g + 1 < D.G) ? g + 1 : g;
       e = S.eta[g];
+      ee = S.eeta[g];
     }
   }
   __syncwarp();
@@ -507,27 +555,35 @@ __global__ void __launch_bounds__(MAXT, 1) fit_beta_seg_kernel(const BetaArgs A,
   const int warp = threadIdx.x >> 5;
   const int p = A.p;
   double* xg = smem;                                         // G x ps
-  double* lnf_shared = xg + (size_t)A.G * ps;                // mpad (size-factor vector only), position order
+  double* nf_shared = xg + (size_t)A.G * ps;                 // mpad (size-factor vector only), position order
+  double* lnf_shared = nf_shared + (A.nf_is_vector ? mpad : 0);   // mpad, their logs
   double* lam = lnf_shared + (A.nf_is_vector ? mpad : 0);    // 32
   double* contrast = lam + 32;                               // 32
   unsigned char* tabs = reinterpret_cast<unsigned char*>(contrast + 32);
   for (int i = threadIdx.x; i < A.G * ps; i += blockDim.x) xg[i] = A.xg[i];
   if (A.nf_is_vector)
-    for (int j = threadIdx.x; j < A.m; j += blockDim.x) lnf_shared[A.seg.pos[j]] = log(A.nf[j]);
+    for (int j = threadIdx.x; j < A.m; j += blockDim.x) {
+      const int q = A.seg.pos[j];
+      nf_shared[q] = A.nf[j];
+      lnf_shared[q] = log(A.nf[j]);
+    }
   for (int k = threadIdx.x; k < p; k += blockDim.x) {
     lam[k] = A.lambda[k];
     contrast[k] = A.contrast[k];
   }
   SBetaCtx C;
   C.T = stage_seg_tables(A.seg, A.G, tabs);
+  C.P = stage_pair_table(p, tabs + seg_table_bytes(A.seg.kmax, A.G));
   __syncthreads();
   C.D = Design{xg, nullptr, p, ps, A.G, 1, A.m};
-  C.S = sbeta_carve(reinterpret_cast<double*>(tabs + seg_table_bytes(A.seg.kmax, A.G) + (size_t)warp * warp_bytes), mpad, p,
-                    ps, A.G, A.seg.kmax, A.nf_is_vector);
+  C.S = sbeta_carve(reinterpret_cast<double*>(tabs + seg_table_bytes(A.seg.kmax, A.G) + pair_table_bytes(p) +
+                                              (size_t)warp * warp_bytes),
+                    mpad, p, ps, A.G, A.seg.kmax, A.nf_is_vector);
   C.inv = A.seg.inv;
   C.y_is_f64 = A.y_is_f64;
   C.minmu = A.minmu;
   C.log_minmu = log(A.minmu);
+  C.nfp = A.nf_is_vector ? nf_shared : C.S.nf;
   C.lnfp = A.nf_is_vector ? lnf_shared : C.S.lnf;
   const SBetaWarp& S = C.S;
   double* B = S.M0;      // X'WX
@@ -554,7 +610,11 @@ __global__ void __launch_bounds__(MAXT, 1) fit_beta_seg_kernel(const BetaArgs A,
       const int q = A.seg.pos[j];
       fits = fits && (y >= 0.0) && (y <= 65535.0) && (y == floor(y));
       S.y16[q] = (unsigned short)fmin(fmax(y, 0.0), 65535.0);
-      if (!A.nf_is_vector) S.lnf[q] = log(A.nf[off + j]);
+      if (!A.nf_is_vector) {
+        const double f = A.nf[off + j];
+        S.nf[q] = f;
+        S.lnf[q] = log(f);
+      }
     }
     C.y_gather = !__all_sync(0xffffffffu, fits);
     if (lane < p) beta[lane] = A.beta_in[(size_t)g + (size_t)A.n * lane];
@@ -578,7 +638,7 @@ __global__ void __launch_bounds__(MAXT, 1) fit_beta_seg_kernel(const BetaArgs A,
     for (int t = 0; t < A.maxit; t++) {
       it += 1.0;
       // normal equations (X'WX + Lambda) b = X'Wz, Jacobi-equilibrated Cholesky
-      build_xtwx(C.D, S.WA, B, lane);
+      build_xtwx_pairs(C.D, C.P, S.WA, B, lane);
       if (lane < p) {
         double s = 0.0;
         for (int q = 0; q < A.G; q++) s = fma(S.WB[q], xg[(size_t)q * ps + lane], s);
@@ -622,7 +682,7 @@ __global__ void __launch_bounds__(MAXT, 1) fit_beta_seg_kernel(const BetaArgs A,
       dev_old = dev;
     }
     // ---- post-loop block (src/DESeq2.cpp:429-455): the W sums and eta belong to the last pass
-    build_xtwx(C.D, S.WA, B, lane);
+    build_xtwx_pairs(C.D, C.P, S.WA, B, lane);
     if (lane < p) sc[lane] = rsqrt(B[lane * ps + lane] + lam[lane]);
     __syncwarp();
     if (lane < p)
@@ -637,8 +697,7 @@ __global__ void __launch_bounds__(MAXT, 1) fit_beta_seg_kernel(const BetaArgs A,
     if (A.hat_diag != nullptr || A.mu_out != nullptr) {
       for (int j = lane; j < A.m; j += 32) {   // sample order: coalesced stores
         const int q = A.seg.pos[j], gj = A.gid[j];
-        const double le = S.eta[gj] + C.lnfp[q];
-        const double mu = fmax((fabs(le) < 700.0) ? exp_fast(le) : exp(le), C.minmu);   // the last pass's mu, bit for bit
+        const double mu = fmax(S.eeta[gj] * C.nfp[q], C.minmu);   // the last pass's mu, bit for bit
         if (A.mu_out != nullptr) A.mu_out[off + j] = mu;
         if (A.hat_diag != nullptr) A.hat_diag[off + j] = mu * rcp_fast(fma(alpha, mu, 1.0)) * S.q[gj];
       }
