@@ -895,8 +895,8 @@ cudaError_t row_scratch(size_t bytes, double** out) {
   return cudaSuccess;
 }
 
-// ---- segmented kernels: launch plan.  One CTA per SM of up to 16 warps; the kernels are compiled for 256 / 384 / 512
-// threads (255 / 168 / 128 registers).  B200NB_GENERIC_SEG=0 keeps the kernels above (A/B switch, read per launch),
+// ---- segmented kernels: launch plan.  One CTA per SM of up to 16 warps (dispersion) / 20 warps (IRLS, 96 registers);
+// the kernels are compiled for 256 / 384 / 512 [/ 640] threads (255 / 168 / 128 / 102 registers at most).  B200NB_GENERIC_SEG=0 keeps the kernels above (A/B switch, read per launch),
 // B200NB_GENERIC_WARPS=<n> caps the warps per CTA.
 struct SegPlan {
   int warps, mpad, ps;
@@ -907,11 +907,11 @@ bool seg_enabled(const SegLayout& L) {
   const char* e = getenv("B200NB_GENERIC_SEG");
   return !(e && e[0] == '0');
 }
-bool plan_seg(size_t fixed, size_t warp_bytes, SegPlan& out) {
-  const size_t cap = 227 * 1024;
+bool plan_seg(size_t fixed, size_t warp_bytes, int max_warps, SegPlan& out) {
+  const size_t cap = 227 * 1024 - 4096;   // the kernels' static shared memory (log tables, 3.1 KB) counts against the 227 KB
   if (fixed + warp_bytes > cap) return false;
   int warps = (int)((cap - fixed) / warp_bytes);
-  if (warps > 16) warps = 16;
+  if (warps > max_warps) warps = max_warps;
   const char* e = getenv("B200NB_GENERIC_WARPS");
   if (e && atoi(e) >= 1 && atoi(e) < warps) warps = atoi(e);
   out.warps = warps;
@@ -960,7 +960,7 @@ cudaError_t launch_fit_disp_generic(const DispArgs& a0, cudaStream_t stream) {
     P.ps = a.p | 1;
     const int sat = a.saturated && a.G == a.p;
     const size_t fixed = (size_t)a.G * P.ps * sizeof(double) + seg_table_bytes(a.seg.kmax, a.G) + pair_table_bytes(a.p);
-    if (plan_seg(fixed, sdisp_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, sat), P)) {
+    if (plan_seg(fixed, sdisp_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, sat), 16, P)) {
       cudaError_t e = cudaMemsetAsync(a.scratch, 0, 4 * sizeof(unsigned int), stream);
       if (e != cudaSuccess) return e;
       a.counter = a.scratch;
@@ -1001,15 +1001,16 @@ cudaError_t launch_fit_beta_generic(const BetaArgs& a0, cudaStream_t stream) {
     SegPlan P;
     P.mpad = (a.m + 7) & ~7;
     P.ps = a.p | 1;
-    const size_t fixed = ((size_t)a.G * P.ps + (a.nf_is_vector ? 2 * P.mpad : 0) + 64) * sizeof(double) +
+    const size_t fixed = ((size_t)a.G * P.ps + (a.nf_is_vector ? 2 * P.mpad : 0) + 64 + 256) * sizeof(double) +
                          seg_table_bytes(a.seg.kmax, a.G) + pair_table_bytes(a.p);
-    if (plan_seg(fixed, sbeta_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, a.nf_is_vector), P)) {
+    if (plan_seg(fixed, sbeta_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, a.nf_is_vector), 20, P)) {
       cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream);
       if (e != cudaSuccess) return e;
       a.row_scratch = nullptr;
       if (P.warps <= 8) return launch_beta_seg_t<256>(a, P, stream);
       if (P.warps <= 12) return launch_beta_seg_t<384>(a, P, stream);
-      return launch_beta_seg_t<512>(a, P, stream);
+      if (P.warps <= 16) return launch_beta_seg_t<512>(a, P, stream);
+      return launch_beta_seg_t<640>(a, P, stream);
     }
   }
   GenLaunch L;

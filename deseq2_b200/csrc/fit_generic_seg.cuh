@@ -50,6 +50,19 @@ __device__ __forceinline__ double seg_group_sum(const SegTables& T, const double
   for (int l = lo; l <= hi; l++) s += seg[(g - (int)T.gfirst[l]) * 32 + l];
   return s;
 }
+// the same for two or three slot arrays at once (one index computation per contributing lane)
+template <bool THREE>
+__device__ __forceinline__ void seg_group_sums(const SegTables& T, const double* sa, const double* sb, const double* sc, int g,
+                                               double& a, double& b, double& c) {
+  a = b = c = 0.0;
+  const int lo = T.glo[g], hi = T.ghi[g];
+  for (int l = lo; l <= hi; l++) {
+    const int idx = (g - (int)T.gfirst[l]) * 32 + l;
+    a += sa[idx];
+    b += sb[idx];
+    if (THREE) c += sc[idx];
+  }
+}
 
 // (a, b), a >= b, of the lower-triangle entry `idx`: the p (p + 1) / 2 entries of X'WX are dealt to the 32 lanes
 struct PairTable {
@@ -88,24 +101,34 @@ __device__ __forceinline__ void build_xtwx_pairs(const Design& D, const PairTabl
 
 // ================================================================ dispersion
 
+// Factor table of the segmented dispersion kernel: c_k = #{j : y_j > k} as 16-bit counts (m <= 65535), kTabSeg entries.
+// A table of T entries costs T / 32 log + reciprocal pairs per lane and evaluation, the lgamma / digamma pair it
+// replaces about twice that per SAMPLE: the table pays while max(y) < 2 m, so long rows (config 4: m = 1000) take it
+// up to max(y) = 1023 where the 256-entry fp64 table of fit_generic.cu left 23 % of the evaluations on the per-sample path.
+constexpr int kTabSeg = 1024;
+__host__ __device__ inline int seg_tab_limit(int m) {
+  const int lim = 2 * m > 256 ? 2 * m : 256;
+  return lim < kTabSeg ? lim : kTabSeg;
+}
+
 struct SDispWarp {
-  double* mu;            // mpad, position order
-  unsigned char* y8;     // mpad, position order (min(y, 255); exact whenever the factor table is used)
-  double* tab;           // kTabMaxG
+  double* mu;             // mpad, position order
+  unsigned short* y16;    // mpad, position order (min(y, 65535); exact unless the gene gathers y from global memory)
+  unsigned short* tab;    // kTabSeg
   double *segA, *segB, *segC;   // kmax x 32
   double *WA, *WB, *WC, *q;     // G (not saturated)
   double *M0, *M1, *M2, *M3;    // p x ps (not saturated)
 };
 __host__ __device__ inline size_t sdisp_warp_bytes(int mpad, int p, int ps, int G, int kmax, int saturated) {
   const size_t Gp = (size_t)(G + 1) & ~(size_t)1;
-  return 8 * ((size_t)mpad + kTabMaxG + 3 * (size_t)kmax * 32 + (saturated ? 0 : 4 * Gp + 4 * (size_t)p * ps)) + (size_t)mpad;
+  return 8 * ((size_t)mpad + 3 * (size_t)kmax * 32 + (saturated ? 0 : 4 * Gp + 4 * (size_t)p * ps)) + 2 * (size_t)kTabSeg +
+         2 * (size_t)mpad;
 }
 __device__ __forceinline__ SDispWarp sdisp_carve(double* base, int mpad, int p, int ps, int G, int kmax, int saturated) {
   SDispWarp S;
   const size_t Gp = (size_t)(G + 1) & ~(size_t)1;
   double* q = base;
   S.mu = q; q += mpad;
-  S.tab = q; q += kTabMaxG;
   S.segA = q; q += (size_t)kmax * 32;
   S.segB = q; q += (size_t)kmax * 32;
   S.segC = q; q += (size_t)kmax * 32;
@@ -120,8 +143,37 @@ __device__ __forceinline__ SDispWarp sdisp_carve(double* base, int mpad, int p, 
     S.M2 = q; q += (size_t)p * ps;
     S.M3 = q; q += (size_t)p * ps;
   }
-  S.y8 = reinterpret_cast<unsigned char*>(q);
+  S.tab = reinterpret_cast<unsigned short*>(q);
+  S.y16 = S.tab + kTabSeg;
   return S;
+}
+
+// tab[k] = #{y == k + 1} (packed 16-bit counters, built with 32-bit shared-memory atomics) -> c_k = #{y > k}, in place.
+// Lane l owns entries 32 l .. 32 l + 31 (16 words): its total, an exclusive suffix scan over the lanes, a second sweep.
+__device__ __forceinline__ void seg_tab_suffix_sums(unsigned short* tab, int lane) {
+  unsigned int* w = reinterpret_cast<unsigned int*>(tab) + lane * (kTabSeg / 64);
+  unsigned int tot = 0;
+#pragma unroll
+  for (int q = 0; q < kTabSeg / 64; q++) {
+    const unsigned int v = w[q];
+    tot += (v & 0xffffu) + (v >> 16);
+  }
+  unsigned int above = tot;   // inclusive suffix sum over lanes >= lane
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_down_sync(0xffffffffu, above, o);
+    if (lane + o < 32) above += t;
+  }
+  unsigned int run = above - tot;   // counts in the lanes above
+#pragma unroll
+  for (int q = kTabSeg / 64 - 1; q >= 0; q--) {
+    const unsigned int v = w[q];
+    const unsigned int hi = run + (v >> 16);
+    const unsigned int lo = hi + (v & 0xffffu);
+    w[q] = (hi << 16) | lo;
+    run = lo;
+  }
+  __syncwarp();
 }
 
 struct SDispCtx {
@@ -129,9 +181,9 @@ struct SDispCtx {
   SegTables T;
   PairTable P;
   SDispWarp S;
-  const unsigned short* inv;   // global: sample at position q (genes that cannot use the byte row)
+  const unsigned short* inv;   // global: sample at position q (genes whose counts do not fit the 16-bit row)
   const void* yrow;            // the gene's row of counts in global memory
-  int y_is_f64;
+  int y_is_f64, y_gather;
   double inv_sigmasq;
   int use_prior, use_cr;
   int tab_mode, ntab;
@@ -141,7 +193,7 @@ struct SDispCtx {
 };
 
 // The sample pass: likelihood sums and the per-segment Cox-Reid weight sums.  TAB: the lgamma / digamma differences
-// come from the factor table (integer counts < 256), y is read from the byte row; else per sample, y from global.
+// come from the factor table (integer counts below seg_tab_limit); else per sample.
 template <bool TAB, bool WANT2>
 __device__ __forceinline__ void sdisp_samples(const SDispCtx& C, double alpha, double r, double r2, int lane, double& s_ll,
                                               double& s_dl, double& s_d2) {
@@ -152,16 +204,19 @@ __device__ __forceinline__ void sdisp_samples(const SDispCtx& C, double alpha, d
     lgamma_digamma_pos(r, lg_r, dg_r);
     if (WANT2) tg_r = trigamma_pos(r);
   }
-  int seg = 0;
+  int slot = lane;   // seg * 32 + lane of the lane's current segment
   int end = C.T.seg_end[lane];
+  const int slot_last = (C.T.kmax - 1) * 32;
   double aW = 0.0, aB = 0.0, aC = 0.0;
   const double* mus = S.mu;
-  const unsigned char* y8 = S.y8;
+  const unsigned short* y16 = S.y16;
+  // (a uniform full-trip loop with a guarded tail sample, and running stores instead of the segment-end test, were
+  // measured on the B200: both slower than this plain loop, profiles/r02_kernel_ab.md)
   for (int i = 1, j = lane; j < m; i++, j += 32) {
     const double mu = mus[j];
     double y;
-    if (TAB) {
-      y = (double)y8[j];
+    if (TAB || !C.y_gather) {
+      y = (double)y16[j];
     } else {
       const int jj = C.inv[j];
       y = C.y_is_f64 ? static_cast<const double*>(C.yrow)[jj] : (double)static_cast<const int32_t*>(C.yrow)[jj];
@@ -190,12 +245,12 @@ __device__ __forceinline__ void sdisp_samples(const SDispCtx& C, double alpha, d
     aB = fma(-wd, wd, aB);
     if (WANT2) aC = fma(2.0 * wd * wd, wd, aC);
     if (i == end) {   // last sample of this lane's current group: one store per sum
-      S.segA[seg * 32 + lane] = aW;
-      S.segB[seg * 32 + lane] = aB;
-      if (WANT2) S.segC[seg * 32 + lane] = aC;
+      S.segA[slot] = aW;
+      S.segB[slot] = aB;
+      if (WANT2) S.segC[slot] = aC;
       aW = aB = aC = 0.0;
-      seg++;
-      end = (seg < C.T.kmax) ? (int)C.T.seg_end[seg * 32 + lane] : 0xffff;
+      end = (slot < slot_last) ? (int)C.T.seg_end[slot + 32] : 0xffff;
+      slot += 32;
     }
   }
 }
@@ -213,7 +268,7 @@ __device__ __forceinline__ void sdisp_eval(const SDispCtx& C, double a, double p
   __syncwarp();   // the previous evaluation's reads of the segment slots are done
   if (C.tab_mode) {
     for (int k = lane; k < C.ntab; k += 32) {
-      const double ck = S.tab[k];
+      const double ck = (double)S.tab[k];
       const double xk = r + (double)k;
       const double ik = rcp_fast(xk);
       s_ll = fma(ck, log_pos(xk), s_ll);
@@ -229,17 +284,14 @@ __device__ __forceinline__ void sdisp_eval(const SDispCtx& C, double a, double p
   warp_allreduce_sum_n(red);
   double cr = 0.0, dcr = 0.0, cr2 = 0.0;
   if (C.use_cr) {
+    // ONE divergent region (lane g owns group g), then warp-uniform code: with the group sums and the per-group terms
+    // in two `if (lane < G)` blocks the compiler threaded the branches and the warp reached the reduction split in
+    // two (ncu: every shuffle through the WARPSYNC.COLLECTIVE slow path, 25 % of the stall samples)
     double W = 0.0, dW = 0.0, d2W = 0.0;
-    if (lane < D.G) {   // lane g owns group g
-      W = seg_group_sum(C.T, S.segA, lane);
-      dW = seg_group_sum(C.T, S.segB, lane);
-      if (WANT2) d2W = seg_group_sum(C.T, S.segC, lane);
-    }
-    if (C.saturated) {
-      // log det B = 2 log|det X_g| + sum log W_g, tr(B^-1 dB) = sum dW/W, tr(B^-1 dB B^-1 dB) = sum (dW/W)^2,
-      // tr(B^-1 d2B) = sum d2W/W
-      double rr[4] = {0.0, 0.0, 0.0, 0.0};
-      if (lane < D.G) {
+    double rr[4] = {0.0, 0.0, 0.0, 0.0};
+    if (lane < D.G) {
+      seg_group_sums<WANT2>(C.T, S.segA, S.segB, S.segC, lane, W, dW, d2W);
+      if (C.saturated) {
         const double iw = rcp_fast(W);
         const double q = dW * iw;
         rr[0] = log_pos(W);
@@ -247,6 +299,11 @@ __device__ __forceinline__ void sdisp_eval(const SDispCtx& C, double a, double p
         rr[2] = q * q;
         if (WANT2) rr[3] = d2W * iw;
       }
+    }
+    __syncwarp();
+    if (C.saturated) {
+      // log det B = 2 log|det X_g| + sum log W_g, tr(B^-1 dB) = sum dW/W, tr(B^-1 dB B^-1 dB) = sum (dW/W)^2,
+      // tr(B^-1 d2B) = sum d2W/W
       warp_allreduce_sum_n(rr);
       cr = -0.5 * (rr[0] + C.sat_logdet);
       dcr = -0.5 * rr[1];
@@ -335,6 +392,7 @@ __global__ void __launch_bounds__(MAXT, 1) fit_disp_seg_kernel(const DispArgs A,
   C.sat_logdet = A.sat_logdet;
   const SDispWarp& S = C.S;
   const double epsilon = 1.0e-4;
+  const int tab_limit = seg_tab_limit(A.m);
 
   for (;;) {
     unsigned int g = 0;
@@ -351,7 +409,7 @@ __global__ void __launch_bounds__(MAXT, 1) fit_disp_seg_kernel(const DispArgs A,
       const double y = A.y_is_f64 ? static_cast<const double*>(A.y)[off + j] : (double)static_cast<const int32_t*>(A.y)[off + j];
       const int q = A.seg.pos[j];
       S.mu[q] = A.mu[off + j];
-      S.y8[q] = (unsigned char)fmin(fmax(y, 0.0), 255.0);
+      S.y16[q] = (unsigned short)fmin(fmax(y, 0.0), 65535.0);
       sy += y;
       ym = fmax(ym, y);
       ymin = fmin(ymin, y);
@@ -360,17 +418,20 @@ __global__ void __launch_bounds__(MAXT, 1) fit_disp_seg_kernel(const DispArgs A,
     C.sum_y = warp_allreduce_sum(sy);
     const double ymax = warp_allreduce_max(ym);
     ymin = -warp_allreduce_max(-ymin);
-    C.tab_mode = __all_sync(0xffffffffu, integ) && (ymin >= 0.0) && (ymax < (double)kTabMaxG);
+    const bool counts = __all_sync(0xffffffffu, integ) && (ymin >= 0.0);
+    C.y_gather = !(counts && ymax <= 65535.0);
+    C.tab_mode = counts && (ymax < (double)tab_limit);
     C.ntab = 0;
-    for (int k = lane; k < kTabMaxG; k += 32) S.tab[k] = 0.0;
-    __syncwarp();
     if (C.tab_mode) {
+      unsigned int* tw = reinterpret_cast<unsigned int*>(S.tab);
+      for (int k = lane; k < kTabSeg / 2; k += 32) tw[k] = 0u;
+      __syncwarp();
       for (int j = lane; j < A.m; j += 32) {
-        const int v = S.y8[j];
-        if (v >= 1) atomicAdd(&S.tab[v - 1], 1.0);   // counts: exact in any order
+        const int v = S.y16[j];
+        if (v >= 1) atomicAdd(&tw[(v - 1) >> 1], 1u << (((v - 1) & 1) * 16));   // counts <= m <= 65535: no carry
       }
       __syncwarp();
-      tab_suffix_sums(S.tab, lane);
+      seg_tab_suffix_sums(S.tab, lane);
       C.ntab = (int)ymax;
     }
     const double pm = A.prior_mean[g];
@@ -504,8 +565,9 @@ __device__ __forceinline__ double sbeta_pass(const SBetaCtx& C, const double* be
     S.eeta[lane] = sbeta_exp(e);
   }
   __syncwarp();
-  int seg = 0;
+  int slot = lane;
   int end = C.T.seg_end[lane];
+  const int slot_last = (C.T.kmax - 1) * 32;
   int g = C.T.gfirst[lane];
   double e = S.eta[g], ee = S.eeta[g];
   double aW = 0.0, aB = 0.0, dev = 0.0;
@@ -528,11 +590,11 @@ __device__ __forceinline__ double sbeta_pass(const SBetaCtx& C, const double* be
     aW += w;
     aB = fma(w, z, aB);
     if (i == end) {
-      S.segA[seg * 32 + lane] = aW;
-      S.segB[seg * 32 + lane] = aB;
+      S.segA[slot] = aW;
+      S.segB[slot] = aB;
       aW = aB = 0.0;
-      seg++;
-      end = (seg < C.T.kmax) ? (int)C.T.seg_end[seg * 32 + lane] : 0xffff;
+      end = (slot < slot_last) ? (int)C.T.seg_end[slot + 32] : 0xffff;
+      slot += 32;
       g = (g + 1 < D.G) ? g + 1 : g;
       e = S.eta[g];
       ee = S.eeta[g];
@@ -540,8 +602,10 @@ __device__ __forceinline__ double sbeta_pass(const SBetaCtx& C, const double* be
   }
   __syncwarp();
   if (lane < D.G) {
-    S.WA[lane] = seg_group_sum(C.T, S.segA, lane);
-    S.WB[lane] = seg_group_sum(C.T, S.segB, lane);
+    double wa, wb, unused;
+    seg_group_sums<false>(C.T, S.segA, S.segB, nullptr, lane, wa, wb, unused);
+    S.WA[lane] = wa;
+    S.WB[lane] = wb;
   }
   __syncwarp();
   return WANT_DEV ? warp_allreduce_sum(dev) : 0.0;
@@ -559,7 +623,9 @@ __global__ void __launch_bounds__(MAXT, 1) fit_beta_seg_kernel(const BetaArgs A,
   double* lnf_shared = nf_shared + (A.nf_is_vector ? mpad : 0);   // mpad, their logs
   double* lam = lnf_shared + (A.nf_is_vector ? mpad : 0);    // 32
   double* contrast = lam + 32;                               // 32
-  unsigned char* tabs = reinterpret_cast<unsigned char*>(contrast + 32);
+  double* lfact = contrast + 32;                             // 256: log y! of small counts (the same lgamma_pos, bit for bit)
+  unsigned char* tabs = reinterpret_cast<unsigned char*>(lfact + 256);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lfact[i] = lgamma_pos((double)i + 1.0);
   for (int i = threadIdx.x; i < A.G * ps; i += blockDim.x) xg[i] = A.xg[i];
   if (A.nf_is_vector)
     for (int j = threadIdx.x; j < A.m; j += blockDim.x) {
@@ -628,7 +694,8 @@ __global__ void __launch_bounds__(MAXT, 1) fit_beta_seg_kernel(const BetaArgs A,
       double c = 0.0;
       for (int j = lane; j < A.m; j += 32) {
         const double y = sbeta_y(C, j);
-        c += lgamma_diff_g(y, r, lg_r) - lgamma_pos(y + 1.0);
+        const double lf = (y >= 0.0 && y < 256.0 && y == floor(y)) ? lfact[(int)y] : lgamma_pos(y + 1.0);
+        c += lgamma_diff_g(y, r, lg_r) - lf;
       }
       devc = warp_allreduce_sum(c);
     }

@@ -20,4 +20,6 @@ grep -E "gpu__time_duration.sum|sm__pipe_fp64_cycles_active.avg.pct|smsp__issue_
 python profiles/ncu_summary.py "gpurun_out/${tag}_raw.csv" > "gpurun_out/${tag}_ncu_summary.txt" 2>&1 || true
 python profiles/sass_hist.py "gpurun_out/${tag}_src.csv" > "gpurun_out/${tag}_sass_hist.txt" 2>&1 || true
 # gpurun copies at most 64 MiB back: NCU_KEEP=0 drops the report and the source export once the summaries exist
+# (NCU_KEEP=src keeps the per-instruction source export, gzipped, but not the report)
 if [ "${NCU_KEEP:-1}" = "0" ]; then rm -f "gpurun_out/$tag.ncu-rep" "gpurun_out/${tag}_src.csv" "gpurun_out/${tag}_hot_lines_all.txt"; fi
+if [ "${NCU_KEEP:-1}" = "src" ]; then rm -f "gpurun_out/$tag.ncu-rep"; gzip -f "gpurun_out/${tag}_src.csv"; fi
