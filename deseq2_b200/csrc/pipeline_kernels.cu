@@ -336,6 +336,51 @@ __device__ __forceinline__ double trimmed_mean_list(const double* vals, const in
   return (tot - removed) / (double)(n - 2 * k);
 }
 
+// The same trimmed mean for a COMPACT list cv[0..n), n <= 32 NQ <= 256, by rank counting: every lane owns NQ entries
+// and counts, for each, the entries that precede it in the total order (value, index) -- one broadcast load and NQ
+// integer compares per visited entry, all independent, no warp reduction per removed value (the extraction above is a
+// serial chain of k five-level shuffle reductions: ncu on the config-4 shape, 100 samples per cell, showed the
+// Cook's kernel bound by that latency).  Values are non-negative doubles, so their bit patterns order like the
+// values; "v_j precedes v_i" is bits_j < bits_i + [j < i], and [j < i] depends only on the 32-entry blocks of j and i
+// and, inside the same block, on the lanes.  Entries of rank in [k, n - k) are kept and summed.
+template <int NQ>
+__device__ __forceinline__ double trimmed_mean_rank(const double* cv, int n, int k, int lane) {
+  unsigned long long thr0[NQ], thr1[NQ];
+  double own[NQ];
+  int rank[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int i = lane + 32 * q;
+    own[q] = (i < n) ? cv[i] : 0.0;
+    thr0[q] = (unsigned long long)__double_as_longlong(own[q]);
+    thr1[q] = thr0[q] + 1ull;
+    rank[q] = 0;
+  }
+#pragma unroll
+  for (int b = 0; b < NQ; b++) {
+    const int jn = (n - 32 * b < 32) ? n - 32 * b : 32;   // warp-uniform
+    for (int jl = 0; jl < jn; jl++) {
+      const unsigned long long vb = (unsigned long long)__double_as_longlong(cv[32 * b + jl]);
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const unsigned long long thr = (q > b) ? thr1[q] : ((q < b) ? thr0[q] : ((jl < lane) ? thr1[q] : thr0[q]));
+        rank[q] += (vb < thr) ? 1 : 0;
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < NQ; q++)
+    if (lane + 32 * q < n && rank[q] >= k && rank[q] < n - k) s += own[q];
+  return warp_allreduce_sum(s) / (double)(n - 2 * k);
+}
+__device__ __forceinline__ double trimmed_mean_compact(const double* cv, int n, int k, int lane) {
+  if (n <= 32) return trimmed_mean_rank<1>(cv, n, k, lane);
+  if (n <= 64) return trimmed_mean_rank<2>(cv, n, k, lane);
+  if (n <= 128) return trimmed_mean_rank<4>(cv, n, k, lane);
+  return trimmed_mean_rank<8>(cv, n, k, lane);
+}
+
 __device__ __forceinline__ int trim_bin(int n) { return n <= 3 ? 0 : (n <= 23 ? 1 : 2); }
 
 __global__ void __launch_bounds__(128) cooks_kernel(const CooksArgs A) {
@@ -378,26 +423,42 @@ __global__ void __launch_bounds__(128) cooks_kernel(const CooksArgs A) {
     any3 = true;
     const int tb = trim_bin(nc);
     const int k = (int)floor((double)nc * trimratio[tb]);
-    const double cm = trimmed_mean_list(vn, cell_samples + lo, nc, k, taken, lane);
-    for (int i = lane; i < nc; i += 32) {
-      const int j = cell_samples[lo + i];
-      const double d = vn[j] - cm;
-      sq[j] = d * d;
+    double ve;
+    if (nc <= 256) {
+      // the cell's values, compact, in the `sq` row; squared errors in place for the second trimmed mean
+      __syncwarp();
+      for (int i = lane; i < nc; i += 32) sq[i] = vn[cell_samples[lo + i]];
+      __syncwarp();
+      const double cm = trimmed_mean_compact(sq, nc, k, lane);
+      for (int i = lane; i < nc; i += 32) {
+        const double d = sq[i] - cm;
+        sq[i] = d * d;
+      }
+      __syncwarp();
+      ve = scale_c[tb] * trimmed_mean_compact(sq, nc, k, lane);
+    } else {
+      const double cm = trimmed_mean_list(vn, cell_samples + lo, nc, k, taken, lane);
+      for (int i = lane; i < nc; i += 32) {
+        const int j = cell_samples[lo + i];
+        const double d = vn[j] - cm;
+        sq[j] = d * d;
+      }
+      __syncwarp();
+      ve = scale_c[tb] * trimmed_mean_list(sq, cell_samples + lo, nc, k, taken, lane);
     }
-    __syncwarp();
-    const double ve = scale_c[tb] * trimmed_mean_list(sq, cell_samples + lo, nc, k, taken, lane);
     vmax = fmax(vmax, ve);
   }
   if (!any3) {
     // trimmedVariance over all samples (R/core.R:2327-2332); cell_samples is a permutation of 0..m-1
     const int k = (int)floor((double)A.m / 8.0);
-    const double rm = trimmed_mean_list(vn, cell_samples, A.m, k, taken, lane);
+    const bool small = A.m <= 256;   // vn[0..m) is the compact list itself
+    const double rm = small ? trimmed_mean_compact(vn, A.m, k, lane) : trimmed_mean_list(vn, cell_samples, A.m, k, taken, lane);
     for (int j = lane; j < A.m; j += 32) {
       const double d = vn[j] - rm;
       sq[j] = d * d;
     }
     __syncwarp();
-    vmax = 1.51 * trimmed_mean_list(sq, cell_samples, A.m, k, taken, lane);
+    vmax = 1.51 * (small ? trimmed_mean_compact(sq, A.m, k, lane) : trimmed_mean_list(sq, cell_samples, A.m, k, taken, lane));
   }
   const double alpha_r = fmax((vmax - mean) / (mean * mean), 0.04);
   // Cook's distance and its maximum over samples in cells with >= 3 replicates

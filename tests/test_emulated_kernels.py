@@ -128,6 +128,10 @@ DEVICE_CASES = [
     ("cooks ~batch+condition", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "batch", 36, n=150)),
     ("cooks covariate (one cell per sample)", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "covariate", 20, n=150)),
     ("cooks 10-level factor", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "factor10", 200, n=60)),
+    ("cooks cells of 75 (4 entries per lane)", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "condition", 150, n=40)),
+    ("cooks cells of 200 (8 entries per lane)", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "condition", 400, n=30)),
+    ("cooks cells of 350 (extraction path)", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "condition", 700, n=20)),
+    ("cooks covariate m=100 (one cell per sample)", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "covariate", 100, n=40)),
     ("DESeq on device ~condition", lambda T, e, o: T.test_device_pipeline_matches_host_pipeline(e, o, "condition", 240, 40)),
     ("DESeq on device ~condition m=6", lambda T, e, o: T.test_device_pipeline_matches_host_pipeline(e, o, "condition", 300, 6)),
     ("DESeq on device ~batch+condition", lambda T, e, o: T.test_device_pipeline_matches_host_pipeline(e, o, "batch", 160, 36)),
