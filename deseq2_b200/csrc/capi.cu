@@ -1235,6 +1235,13 @@ int b200nb_prep_dev(const void* y, int y_type, const double* x, const double* pr
   a.min_disp = min_disp; a.max_disp = max_disp; a.minmu = minmu; a.n = n; a.m = m; a.p = p; a.ld = ld;
   a.base_mean = base_mean; a.base_var = base_var; a.all_zero = all_zero; a.alpha0 = alpha0; a.mu_lin = mu_lin;
   a.beta0 = beta0;
+  a.gid = nullptr; a.xg = nullptr; a.G = 0;
+  if (n > 0 && (long long)m * p >= 1024) {
+    // long rows: a design with few distinct rows is handled per group (this fetches the m x p design: one stream sync)
+    DesignDev dd;
+    if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
+    if (dd.grouped) { a.gid = dd.gid; a.xg = dd.xg; a.G = dd.G; }
+  }
   CU(nb::launch_prep(a, (cudaStream_t)stream));
   if (n > 0) g_launches++;
   return 0;

@@ -174,6 +174,11 @@ struct PrepArgs {
   double* alpha0;              // n: min(rough, moments) dispersion, clamped
   double* mu_lin;              // gene-major n x ld or nullptr: linear-model mu * size factor, clamped at minmu
   double* beta0;               // n x p column-major or nullptr: least-squares start values on log(K/s + 0.1)
+  // grouped designs (G <= 32 distinct rows; G == 0: not used): P = (X'X)^-1 X' has one distinct column per design
+  // group, so P v = sum_g P_g (sum_{j in g} v_j) and the fitted value of a sample is its group's
+  const int* gid;              // m: design group of sample j
+  const double* xg;            // G x (p|1): the distinct design rows
+  int G;
 };
 cudaError_t launch_prep(const PrepArgs& a, cudaStream_t stream);
 

@@ -94,6 +94,115 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs A) {
   }
 }
 
+// The same pre-steps for a design with G <= 32 distinct rows (factor designs: config 4 has m = 1000, p = 10, G = 10).
+// prep_kernel streams the p x m projection and the m x p design through every gene (2 p m loads and FMAs per gene,
+// L2 latency bound at 8 warps per SM: 5 ms for 50 000 x 1000); here a sample only adds its value and its log to its
+// group's lane-private slot, the projection is applied to the G group sums and the fitted value is read per group.
+__global__ void __launch_bounds__(256) prep_grouped_kernel(const PrepArgs A, int mpad, int ps) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int G = A.G, p = A.p;
+  double* sf = smem;                                   // mpad
+  double* Pg = sf + mpad;                              // p x G: the projection's column of each group
+  double* xg = Pg + (size_t)p * G;                     // G x ps
+  int* rep = reinterpret_cast<int*>(xg + (size_t)G * ps);          // 32: one sample of each group
+  unsigned char* gidb = reinterpret_cast<unsigned char*>(rep + 32);   // mpad
+  double* wrow = reinterpret_cast<double*>(gidb + mpad) + (size_t)warp * (mpad + 2 * (size_t)G * 32 + 3 * 32 + 2 * 32);
+  double* vn = wrow;                                   // normalised counts
+  double* accN = wrow + mpad;                          // G x 32 lane-private sums of the normalised counts
+  double* accL = accN + (size_t)G * 32;                // G x 32: of log(norm + 0.1)
+  double* gsN = accL + (size_t)G * 32;                 // 32: group sums
+  double* gsL = gsN + 32;
+  double* fit = gsL + 32;                              // 32: fitted value of each group
+  double* coef = fit + 32;                             // 32: P * norm
+  double* coefl = coef + 32;                           // 32: P * log(norm + .1)
+  for (int j = threadIdx.x; j < A.m; j += blockDim.x) {
+    sf[j] = A.size_factors[j];
+    const int g = A.gid[j];
+    gidb[j] = (unsigned char)g;
+    rep[g] = j;                                        // any sample of the group (racing writers, all valid)
+  }
+  for (int i = threadIdx.x; i < G * ps; i += blockDim.x) xg[i] = A.xg[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < p * G; i += blockDim.x) Pg[i] = A.proj[(size_t)(i / G) * A.m + rep[i % G]];
+  __syncthreads();
+  const int g = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (g >= A.n) return;
+  const size_t off = (size_t)g * A.ld;
+  for (int t = 0; t < G; t++) {
+    accN[t * 32 + lane] = 0.0;
+    accL[t * 32 + lane] = 0.0;
+  }
+  double s = 0.0, s2 = 0.0, raw = 0.0;
+  for (int j = lane; j < A.m; j += 32) {
+    const double y = A.y_is_f64 ? static_cast<const double*>(A.y)[off + j] : (double)static_cast<const int32_t*>(A.y)[off + j];
+    const double v = y / sf[j];
+    vn[j] = v;
+    const int slot = gidb[j] * 32 + lane;
+    accN[slot] += v;
+    accL[slot] += log(v + 0.1);
+    s += v;
+    raw += y;
+  }
+  s = warp_allreduce_sum(s);
+  raw = warp_allreduce_sum(raw);
+  const double bm = s / (double)A.m;
+  for (int j = lane; j < A.m; j += 32) {
+    const double d = vn[j] - bm;
+    s2 = fma(d, d, s2);
+  }
+  s2 = warp_allreduce_sum(s2);
+  const double bv = s2 / (double)(A.m - 1);
+  __syncwarp();
+  if (lane < G) {
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < 32; l++) {
+      a += accN[lane * 32 + ((l + lane) & 31)];
+      b += accL[lane * 32 + ((l + lane) & 31)];
+    }
+    gsN[lane] = a;
+    gsL[lane] = b;
+  }
+  __syncwarp();
+  if (lane < p) {
+    double c = 0.0, cl = 0.0;
+    for (int t = 0; t < G; t++) {
+      c = fma(Pg[lane * G + t], gsN[t], c);
+      cl = fma(Pg[lane * G + t], gsL[t], cl);
+    }
+    coef[lane] = c;
+    coefl[lane] = cl;
+    if (A.beta0 != nullptr) A.beta0[(size_t)g + (size_t)A.n * lane] = cl;
+  }
+  __syncwarp();
+  if (lane < G) {
+    double f = 0.0;
+    for (int k = 0; k < p; k++) f = fma(xg[lane * ps + k], coef[k], f);
+    fit[lane] = f;
+  }
+  __syncwarp();
+  double rs = 0.0;
+  for (int j = lane; j < A.m; j += 32) {
+    const double f = fit[gidb[j]];
+    const double mu1 = fmax(1.0, f);
+    const double d = vn[j] - mu1;
+    rs += (d * d - mu1) / (mu1 * mu1);
+    if (A.mu_lin != nullptr) A.mu_lin[off + j] = fmax(f * sf[j], A.minmu);
+  }
+  rs = warp_allreduce_sum(rs);
+  if (lane == 0) {
+    const double rough = fmax(rs / (double)(A.m - A.p), 0.0);
+    const double moments = (bv - A.xim * bm) / (bm * bm);
+    double a0 = fmin(rough, moments);
+    a0 = fmin(fmax(A.min_disp, a0), A.max_disp);   // pmin(pmax(minDisp, alpha_hat), maxDisp): NaN -> minDisp like pmax
+    A.base_mean[g] = bm;
+    A.base_var[g] = bv;
+    A.alpha0[g] = a0;
+    A.all_zero[g] = (raw == 0.0) ? 1 : 0;
+  }
+}
+
 // ---------------------------------------------------------------- dispersion trend (one CTA per SM, grid barrier)
 // The fit is a sequence of full passes over all genes (five weighted sums, then the deviance), dozens of them, each
 // needing the previous one's result: a single CTA spends ~0.25 ms per pass at a million genes (config 5 on 8 GPUs: the
@@ -236,6 +345,18 @@ __global__ void __launch_bounds__(512) trend_fit_kernel(const double* __restrict
 
 cudaError_t launch_prep(const PrepArgs& a, cudaStream_t stream) {
   if (a.n == 0) return cudaSuccess;
+  if (a.G > 0 && a.G <= 32) {
+    const int mpad = (a.m + 7) & ~7, ps = a.p | 1, warps = 8;
+    const size_t fixed = ((size_t)mpad + (size_t)a.p * a.G + (size_t)a.G * ps) * sizeof(double) + 32 * sizeof(int) + mpad;
+    const size_t per_warp = ((size_t)mpad + 2 * (size_t)a.G * 32 + 5 * 32) * sizeof(double);
+    const size_t smem = fixed + warps * per_warp;
+    if (smem <= 200 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(prep_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      prep_grouped_kernel<<<(a.n + warps - 1) / warps, warps * 32, smem, stream>>>(a, mpad, ps);
+      return cudaGetLastError();
+    }
+  }
   const int mpad = (a.m + 3) & ~3;
   int warps = 8;
   size_t smem = ((size_t)mpad + (size_t)warps * (2 * mpad + 64)) * sizeof(double);

@@ -17,11 +17,22 @@ def _setup(n, m, x=None, seed=1):
     return d, y
 
 
-@pytest.mark.parametrize("design", ["condition", "batch"])
+@pytest.mark.parametrize("design", ["condition", "batch", "batch-long-rows", "factor10-long-rows", "covariates-long-rows"])
 def test_prep_kernel_matches_numpy(engine, design, n=2000):
+    """The `-long-rows` designs (m p >= 1024) take the per-group kernel when the design has <= 32 distinct rows
+    (prep_grouped_kernel) and the streaming kernel otherwise (continuous covariates)."""
     from deseq2_b200 import device_pipeline as DP, pipeline, synth
     m = 30
-    x = synth.design_condition(m) if design == "condition" else synth.design_batch_condition(m, 3)
+    if design.endswith("long-rows"):
+        m, n = 300, min(n, 300)
+    if design == "condition":
+        x = synth.design_condition(m)
+    elif design.startswith("batch"):
+        x = synth.design_batch_condition(m, 3)
+    elif design.startswith("factor10"):
+        x = synth.design_factor(m, 10)
+    else:
+        x = np.c_[synth.design_condition(m), np.random.default_rng(8).normal(0, 1, (m, 2))]
     d, y = _setup(n, m, x=x, seed=3)
     sf = d["sizeFactors"]
     pr = DP.prep(y, x, sf)

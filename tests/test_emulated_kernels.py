@@ -123,6 +123,9 @@ def emu_device(emu, monkeypatch):
 DEVICE_CASES = [
     ("prep ~condition", lambda T, e: T.test_prep_kernel_matches_numpy(e, "condition", n=300)),
     ("prep ~batch+condition", lambda T, e: T.test_prep_kernel_matches_numpy(e, "batch", n=300)),
+    ("prep per group: ~batch+condition m=300", lambda T, e: T.test_prep_kernel_matches_numpy(e, "batch-long-rows", n=120)),
+    ("prep per group: 10-level factor m=300", lambda T, e: T.test_prep_kernel_matches_numpy(e, "factor10-long-rows", n=120)),
+    ("prep streaming: covariates m=300", lambda T, e: T.test_prep_kernel_matches_numpy(e, "covariates-long-rows", n=120)),
     ("trend fit", lambda T, e: T.test_trend_kernel_matches_numpy(e, n=3000)),
     ("cooks m=12", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "condition", 12, n=200)),
     ("cooks ~batch+condition", lambda T, e: T.test_cooks_kernel_matches_numpy(e, "batch", 36, n=150)),
