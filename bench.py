@@ -426,6 +426,11 @@ def configs_block(world, rank, dev, peak_gbs, quick=False):
                     rec["stage_ms"] = run()["stage_ms"]
                 finally:
                     del os.environ["B200NB_PIPE_DEBUG"]
+                hot = [rec["stage_ms"].get(k) for k in ("fit_disp_mle", "fit_disp_map", "fit_beta")]
+                if all(v is not None for v in hot):
+                    # the three native calls of the Wald path inside this run (stage wall times with a sync after each)
+                    rec["hot_path_ms"] = round(sum(hot), 3)
+                    rec["hot_path_genes_per_s"] = genes / (sum(hot) * 1e-3)
             out[name] = rec
             del y, res
             torch.cuda.empty_cache()

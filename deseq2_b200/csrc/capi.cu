@@ -1236,7 +1236,8 @@ int b200nb_prep_dev(const void* y, int y_type, const double* x, const double* pr
   a.base_mean = base_mean; a.base_var = base_var; a.all_zero = all_zero; a.alpha0 = alpha0; a.mu_lin = mu_lin;
   a.beta0 = beta0;
   a.gid = nullptr; a.xg = nullptr; a.G = 0;
-  if (n > 0 && (long long)m * p >= 1024) {
+  const char* pg = getenv("B200NB_PREP_GROUPED");   // "0": always the streaming kernel (A/B switch, read per call)
+  if (n > 0 && (long long)m * p >= 1024 && !(pg && pg[0] == '0')) {
     // long rows: a design with few distinct rows is handled per group (this fetches the m x p design: one stream sync)
     DesignDev dd;
     if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
