@@ -1266,6 +1266,15 @@ int b200nb_cooks_dev(const void* y, int y_type, const double* mu, const double* 
   a.y = y; a.y_is_f64 = (y_type == B200NB_Y_F64); a.mu = mu; a.hat = hat; a.size_factors = size_factors;
   a.cell_ptr = cell_ptr; a.cell_samples = cell_samples; a.ncell = ncell; a.n = n; a.m = m; a.p = p; a.ld = ld;
   a.cooks = cooks; a.max_cooks = max_cooks; a.robust_disp = robust_disp;
+  a.max_cell = 0;
+  if (n > 0 && m > 256) {
+    // long rows: the size of the largest cell decides how much per-warp scratch the trimmed means need (one small
+    // device-to-host copy and a stream sync; short rows need none of it)
+    std::vector<int32_t> cp((size_t)ncell + 1);
+    CU(cudaMemcpyAsync(cp.data(), cell_ptr, cp.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int c = 0; c < ncell; c++) a.max_cell = std::max(a.max_cell, (int)(cp[c + 1] - cp[c]));
+  }
   CU(nb::launch_cooks(a, (cudaStream_t)stream));
   if (n > 0) g_launches++;
   return 0;

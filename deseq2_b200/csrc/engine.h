@@ -207,6 +207,7 @@ struct CooksArgs {
   const int* cell_ptr;         // ncell + 1: samples of cell c are cell_samples[cell_ptr[c] .. cell_ptr[c+1])
   const int* cell_samples;     // m: a permutation of 0..m-1 grouped by cell
   int ncell, n, m, p;
+  int max_cell;                // samples in the largest cell (the launcher sizes the per-warp scratch by it); 0: unknown
   long long ld;
   double* cooks;               // gene-major n x ld or nullptr
   double* max_cooks;           // n

@@ -504,18 +504,30 @@ __device__ __forceinline__ double trimmed_mean_compact(const double* cv, int n, 
 
 __device__ __forceinline__ int trim_bin(int n) { return n <= 3 ? 0 : (n <= 23 ? 1 : 2); }
 
-__global__ void __launch_bounds__(128) cooks_kernel(const CooksArgs A) {
+// per-warp scratch: the row of normalised counts, `sqlen` doubles for the values / squared errors of one cell (the whole
+// row when a cell has more than 256 samples or the cell sizes are unknown: extraction path), `taken` flags likewise
+__host__ __device__ inline int cooks_sqlen(int m, int mpad, int max_cell) {
+  // max_cell < 3: no cell has three replicates and the whole row is trimmed at once (needs the full scratch)
+  return (max_cell >= 3 && max_cell <= 256 && m > 256) ? 256 : mpad;
+}
+__host__ __device__ inline size_t cooks_warp_doubles(int m, int mpad, int max_cell) {
+  const int sqlen = cooks_sqlen(m, mpad, max_cell);
+  return (size_t)mpad + sqlen + (sqlen == mpad ? (mpad + 7) / 8 : 0);
+}
+
+__global__ void __launch_bounds__(256) cooks_kernel(const CooksArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int mpad = (A.m + 3) & ~3;
+  const int sqlen = cooks_sqlen(A.m, mpad, A.max_cell);
   int* cell_ptr = reinterpret_cast<int*>(smem);                 // ncell + 1
   int* cell_samples = cell_ptr + A.ncell + 1;                   // m
   double* sf = smem + ((A.ncell + 1 + A.m + 1) / 2 + 1);        // mpad
-  double* wbase = sf + mpad + (size_t)warp * (2 * mpad + (mpad + 7) / 8);
+  double* wbase = sf + mpad + (size_t)warp * cooks_warp_doubles(A.m, mpad, A.max_cell);
   double* vn = wbase;                                           // normalised counts
-  double* sq = wbase + mpad;                                    // squared errors
-  unsigned char* taken = reinterpret_cast<unsigned char*>(wbase + 2 * mpad);
+  double* sq = wbase + mpad;                                    // one cell's values, then its squared errors
+  unsigned char* taken = reinterpret_cast<unsigned char*>(wbase + mpad + sqlen);   // extraction path only
   for (int i = threadIdx.x; i <= A.ncell; i += blockDim.x) cell_ptr[i] = A.cell_ptr[i];
   for (int i = threadIdx.x; i < A.m; i += blockDim.x) {
     cell_samples[i] = A.cell_samples[i];
@@ -609,10 +621,12 @@ __global__ void __launch_bounds__(128) cooks_kernel(const CooksArgs A) {
 cudaError_t launch_cooks(const CooksArgs& a, cudaStream_t stream) {
   if (a.n == 0) return cudaSuccess;
   const int mpad = (a.m + 3) & ~3;
-  int warps = 4;
   auto bytes = [&](int w) {
-    return (((size_t)(a.ncell + 1 + a.m + 1) / 2 + 1) + mpad + (size_t)w * (2 * mpad + (mpad + 7) / 8)) * sizeof(double);
+    return (((size_t)(a.ncell + 1 + a.m + 1) / 2 + 1) + mpad + (size_t)w * cooks_warp_doubles(a.m, mpad, a.max_cell)) *
+           sizeof(double);
   };
+  // several CTAs per SM: 4 warps each, 8 when the per-warp scratch is small enough for two such CTAs
+  int warps = (2 * bytes(8) <= 220 * 1024) ? 8 : 4;
   while (warps > 1 && bytes(warps) > 200 * 1024) warps >>= 1;
   const size_t smem = bytes(warps);
   cudaError_t e = cudaFuncSetAttribute(cooks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
