@@ -99,6 +99,46 @@ __device__ __forceinline__ void build_xtwx_pairs(const Design& D, const PairTabl
   __syncwarp();
 }
 
+// In-place lower Cholesky as fit_generic.cu::chol_smem, with the reciprocal diagonal kept in dinv[0..p): one rsqrt per
+// column instead of a square root and a division, and the triangular solves multiply instead of dividing.
+__device__ __forceinline__ void chol_smem_d(double* A, double* dinv, int p, int ps, int lane) {
+  for (int c = 0; c < p; c++) {
+    __syncwarp();
+    const double d = A[c * ps + c];
+    const double il = rsqrt(d);
+    __syncwarp();
+    if (lane == c) {
+      A[c * ps + c] = d * il;
+      dinv[c] = il;
+    }
+    if (lane > c && lane < p) A[lane * ps + c] *= il;
+    __syncwarp();
+    if (lane > c && lane < p) {
+      const double arc = A[lane * ps + c];
+      for (int k = c + 1; k <= lane; k++) A[lane * ps + k] -= arc * A[k * ps + c];
+    }
+  }
+  __syncwarp();
+}
+// inv = (L L')^-1, full symmetric storage; lane c computes column c
+__device__ __forceinline__ void chol_inverse_smem_d(const double* L, const double* dinv, double* inv, int p, int ps, int lane) {
+  if (lane < p) {
+    const int c = lane;
+    for (int k = 0; k < c; k++) inv[k * ps + c] = 0.0;
+    for (int k = c; k < p; k++) {
+      double s = (k == c) ? 1.0 : 0.0;
+      for (int i = c; i < k; i++) s -= L[k * ps + i] * inv[i * ps + c];
+      inv[k * ps + c] = s * dinv[k];
+    }
+    for (int k = p - 1; k >= 0; k--) {
+      double s = inv[k * ps + c];
+      for (int i = k + 1; i < p; i++) s -= L[i * ps + k] * inv[i * ps + c];
+      inv[k * ps + c] = s * dinv[k];
+    }
+  }
+  __syncwarp();
+}
+
 // ================================================================ dispersion
 
 // Factor table of the segmented dispersion kernel: c_k = #{j : y_j > k} as 16-bit counts (m <= 65535), kTabSeg entries.
@@ -118,10 +158,11 @@ struct SDispWarp {
   double *segA, *segB, *segC;   // kmax x 32
   double *WA, *WB, *WC, *q;     // G (not saturated)
   double *M0, *M1, *M2, *M3;    // p x ps (not saturated)
+  double* dv;                   // 32 (not saturated): reciprocal Cholesky diagonal
 };
 __host__ __device__ inline size_t sdisp_warp_bytes(int mpad, int p, int ps, int G, int kmax, int saturated) {
   const size_t Gp = (size_t)(G + 1) & ~(size_t)1;
-  return 8 * ((size_t)mpad + 3 * (size_t)kmax * 32 + (saturated ? 0 : 4 * Gp + 4 * (size_t)p * ps)) + 2 * (size_t)kTabSeg +
+  return 8 * ((size_t)mpad + 3 * (size_t)kmax * 32 + (saturated ? 0 : 4 * Gp + 4 * (size_t)p * ps + 32)) + 2 * (size_t)kTabSeg +
          2 * (size_t)mpad;
 }
 __device__ __forceinline__ SDispWarp sdisp_carve(double* base, int mpad, int p, int ps, int G, int kmax, int saturated) {
@@ -132,7 +173,7 @@ __device__ __forceinline__ SDispWarp sdisp_carve(double* base, int mpad, int p, 
   S.segA = q; q += (size_t)kmax * 32;
   S.segB = q; q += (size_t)kmax * 32;
   S.segC = q; q += (size_t)kmax * 32;
-  S.WA = S.WB = S.WC = S.q = S.M0 = S.M1 = S.M2 = S.M3 = nullptr;
+  S.WA = S.WB = S.WC = S.q = S.M0 = S.M1 = S.M2 = S.M3 = S.dv = nullptr;
   if (!saturated) {
     S.WA = q; q += Gp;
     S.WB = q; q += Gp;
@@ -142,6 +183,7 @@ __device__ __forceinline__ SDispWarp sdisp_carve(double* base, int mpad, int p, 
     S.M1 = q; q += (size_t)p * ps;
     S.M2 = q; q += (size_t)p * ps;
     S.M3 = q; q += (size_t)p * ps;
+    S.dv = q; q += 32;
   }
   S.tab = reinterpret_cast<unsigned short*>(q);
   S.y16 = S.tab + kTabSeg;
@@ -317,12 +359,12 @@ __device__ __forceinline__ void sdisp_eval(const SDispCtx& C, double a, double p
       __syncwarp();
       double* B = S.M0;
       build_xtwx_pairs(D, C.P, S.WA, B, lane);
-      chol_smem(B, D.p, D.ps, lane);
+      chol_smem_d(B, S.dv, D.p, D.ps, lane);
       double ld = (lane < D.p) ? log(B[lane * D.ps + lane]) : 0.0;
       ld = warp_allreduce_sum(ld);
       cr = -0.5 * (2.0 * ld);
       double* Bi = S.M1;
-      chol_inverse_smem(B, Bi, D.p, D.ps, lane);
+      chol_inverse_smem_d(B, S.dv, Bi, D.p, D.ps, lane);
       quad_forms(D, Bi, S.q, lane);
       double tr1 = 0.0, tr3 = 0.0;
       if (lane < D.G) {
@@ -720,16 +762,16 @@ __global__ void __launch_bounds__(MAXT, 1) fit_beta_seg_kernel(const BetaArgs A,
         }
         rhs[lane] *= sc[lane];
       }
-      chol_smem(L, p, ps, lane);
+      chol_smem_d(L, tmp, p, ps, lane);   // tmp: reciprocal diagonal
       // forward / backward substitution, column oriented (lane = row)
       for (int c = 0; c < p; c++) {
-        if (lane == c) rhs[c] /= L[c * ps + c];
+        if (lane == c) rhs[c] *= tmp[c];
         __syncwarp();
         if (lane > c && lane < p) rhs[lane] -= L[lane * ps + c] * rhs[c];
         __syncwarp();
       }
       for (int c = p - 1; c >= 0; c--) {
-        if (lane == c) rhs[c] /= L[c * ps + c];
+        if (lane == c) rhs[c] *= tmp[c];
         __syncwarp();
         if (lane < c) rhs[lane] -= L[c * ps + lane] * rhs[c];
         __syncwarp();
@@ -755,8 +797,8 @@ __global__ void __launch_bounds__(MAXT, 1) fit_beta_seg_kernel(const BetaArgs A,
     if (lane < p)
       for (int b = 0; b < p; b++)
         L[lane * ps + b] = (B[lane * ps + b] + ((b == lane) ? lam[lane] : 0.0)) * sc[lane] * sc[b];
-    chol_smem(L, p, ps, lane);
-    chol_inverse_smem(L, Ainv, p, ps, lane);
+    chol_smem_d(L, tmp, p, ps, lane);
+    chol_inverse_smem_d(L, tmp, Ainv, p, ps, lane);
     if (lane < p)
       for (int b = 0; b < p; b++) Ainv[lane * ps + b] *= sc[lane] * sc[b];
     __syncwarp();
