@@ -895,8 +895,8 @@ cudaError_t row_scratch(size_t bytes, double** out) {
   return cudaSuccess;
 }
 
-// ---- segmented kernels: launch plan.  One CTA per SM of up to 16 warps (dispersion) / 20 warps (IRLS, 96 registers);
-// the kernels are compiled for 256 / 384 / 512 [/ 640] threads (255 / 168 / 128 / 102 registers at most).  B200NB_GENERIC_SEG=0 keeps the kernels above (A/B switch, read per launch),
+// ---- segmented kernels: launch plan.  One CTA per SM of up to 16 warps; the kernels are compiled for 256 / 384 / 512
+// threads (255 / 168 / 128 registers at most; 20 warps of the 92-register IRLS kernel were measured: no gain over 16).  B200NB_GENERIC_SEG=0 keeps the kernels above (A/B switch, read per launch),
 // B200NB_GENERIC_WARPS=<n> caps the warps per CTA.
 struct SegPlan {
   int warps, mpad, ps;
@@ -1003,14 +1003,13 @@ cudaError_t launch_fit_beta_generic(const BetaArgs& a0, cudaStream_t stream) {
     P.ps = a.p | 1;
     const size_t fixed = ((size_t)a.G * P.ps + (a.nf_is_vector ? 2 * P.mpad : 0) + 64 + 256) * sizeof(double) +
                          seg_table_bytes(a.seg.kmax, a.G) + pair_table_bytes(a.p);
-    if (plan_seg(fixed, sbeta_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, a.nf_is_vector), 20, P)) {
+    if (plan_seg(fixed, sbeta_warp_bytes(P.mpad, a.p, P.ps, a.G, a.seg.kmax, a.nf_is_vector), 16, P)) {
       cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), stream);
       if (e != cudaSuccess) return e;
       a.row_scratch = nullptr;
       if (P.warps <= 8) return launch_beta_seg_t<256>(a, P, stream);
       if (P.warps <= 12) return launch_beta_seg_t<384>(a, P, stream);
-      if (P.warps <= 16) return launch_beta_seg_t<512>(a, P, stream);
-      return launch_beta_seg_t<640>(a, P, stream);
+      return launch_beta_seg_t<512>(a, P, stream);
     }
   }
   GenLaunch L;

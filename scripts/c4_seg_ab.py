@@ -64,7 +64,7 @@ def clone(o):
 
 
 ref = None
-MODES = (("1", "16"), ("1", "20")) if os.environ.get("C4_SEG_ONLY") else (("0", ""), ("1", "8"), ("1", "12"), ("1", "16"), ("1", "20"))
+MODES = (("1", "12"), ("1", "16")) if os.environ.get("C4_SEG_ONLY") else (("0", ""), ("1", "8"), ("1", "12"), ("1", "16"))
 for seg, warps in MODES:
     os.environ["B200NB_GENERIC_SEG"] = seg
     if warps:
