@@ -723,6 +723,26 @@ bool use_generic(int p) {
   return force || p > nb::kMaxSmallP;
 }
 
+// Long rows on the small-p designs too: from m = 400 samples on the segmented general-p kernels (fit_generic_seg.cuh:
+// one gene per warp, per-segment sums, 1024-entry factor table) beat the register-resident small-p kernels, whose
+// per-sample X'WX accumulation and 256-entry table are sized for short rows -- measured on the B200
+// (profiles/r02_kernel_ab.md: 25 000 x 500, p = 4: fitDisp 3.00 -> 2.38 ms, fitBeta 1.08 -> 0.99 ms; 10 000 x 1000, p = 2:
+// 1.42 -> 1.00 ms, 0.76 -> 0.59 ms; at m = 300 and below the small-p kernels win).  Only the device entry points called
+// directly take this route (it fetches the design matrix: one stream sync per call); the host entry points keep the
+// small-p kernels, whose launches per row chunk overlap the uploads.  B200NB_LONG_ROWS=<m> moves the threshold, 0 = off.
+thread_local int t_in_host_call = 0;
+struct HostCallScope {
+  HostCallScope() { t_in_host_call++; }
+  ~HostCallScope() { t_in_host_call--; }
+};
+bool long_rows(int m, int use_weights) {
+  if (t_in_host_call || use_weights) return false;
+  int thr = 400;
+  const char* e = getenv("B200NB_LONG_ROWS");
+  if (e) thr = atoi(e);
+  return thr > 0 && m >= thr;
+}
+
 struct DesignDev {
   const double* xg;
   const int* gid;
@@ -1100,13 +1120,15 @@ int b200nb_fit_disp_dev(const void* y, int y_type, const double* x, const double
   a.last_d2lp = out_last_d2lp; a.grid = nullptr; a.grid_n = 0;
   if (n == 0) return 0;
   if (next_scratch(nb::disp_scratch_bytes(n), &a.scratch)) return 1;
-  if (use_generic(p)) {
+  if (use_generic(p) || long_rows(m, use_weights)) {
     DesignDev dd;
     if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
-    apply_design(dd, use_weights, &a);
-    CU(nb::launch_fit_disp_generic(a, (cudaStream_t)stream));
-    g_launches += 1;
-    return 0;
+    if (use_generic(p) || dd.seg.pos != nullptr) {   // long rows: only designs the segmented kernels take
+      apply_design(dd, use_weights, &a);
+      CU(nb::launch_fit_disp_generic(a, (cudaStream_t)stream));
+      g_launches += 1;
+      return 0;
+    }
   }
   CU(nb::launch_fit_disp(a, (cudaStream_t)stream));
   g_launches += 2;   // classify + line search
@@ -1162,14 +1184,16 @@ int b200nb_fit_beta_dev(const void* y, int y_type, const double* x, const double
   a.n = n; a.m = m; a.p = p; a.ld = ld; a.beta_out = out_beta_mat; a.beta_var = out_beta_var_mat; a.iter = out_iter;
   a.hat_diag = out_hat_diagonals; a.mu_out = out_mu; a.contrast_num = out_contrast_num;
   a.contrast_denom = out_contrast_denom; a.deviance = out_deviance; a.counter = ctr;
-  if (use_generic(p)) {
+  if (use_generic(p) || long_rows(m, use_weights)) {
     if (n == 0) return 0;
     DesignDev dd;
     if (prepare_design_from_device(x, m, p, (cudaStream_t)stream, &dd)) return 1;
-    apply_design(dd, &a);
-    CU(nb::launch_fit_beta_generic(a, (cudaStream_t)stream));
-    g_launches++;
-    return 0;
+    if (use_generic(p) || dd.seg.pos != nullptr) {
+      apply_design(dd, &a);
+      CU(nb::launch_fit_beta_generic(a, (cudaStream_t)stream));
+      g_launches++;
+      return 0;
+    }
   }
   CU(nb::launch_fit_beta(a, (cudaStream_t)stream));
   if (n > 0) g_launches++;
@@ -1316,6 +1340,7 @@ int b200nb_fit_disp(const void* y, int y_type, const double* x, const double* mu
   if (n == 0) return 0;
   if (use_weights && !weights) return fail("use_weights set but weights == NULL");
   std::lock_guard<std::mutex> lk(g_call_mu);
+  HostCallScope host_scope;   // the row-chunked path keeps the small-p kernels (see long_rows)
   g_call_seq++;
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
@@ -1419,6 +1444,7 @@ int b200nb_fit_disp_grid(const void* y, int y_type, const double* x, const doubl
   if (use_weights && !weights) return fail("use_weights set but weights == NULL");
   if (disp_grid_n < 2) return fail("disp_grid needs at least 2 points");
   std::lock_guard<std::mutex> lk(g_call_mu);
+  HostCallScope host_scope;   // the row-chunked path keeps the small-p kernels (see long_rows)
   g_call_seq++;
   cudaStream_t st;
   if (ws_stream(&st)) return 1;
@@ -1496,6 +1522,7 @@ int b200nb_fit_beta(const void* y, int y_type, const double* x, const double* nf
   if (n == 0) return 0;
   if (use_weights && !weights) return fail("use_weights set but weights == NULL");
   std::lock_guard<std::mutex> lk(g_call_mu);
+  HostCallScope host_scope;   // the row-chunked path keeps the small-p kernels (see long_rows)
   g_call_seq++;
   cudaStream_t st;
   if (ws_stream(&st)) return 1;

@@ -3,7 +3,7 @@ DESeq() Wald path against the numpy restatement of the R callers (deseq2_b200/pi
 import numpy as np
 import pytest
 
-from helpers import DEV, rel_err
+from helpers import DEV, beta_args, disp_args, make_case, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -82,8 +82,54 @@ class _MarginOracle:
         return r
 
 
+def test_long_rows_take_the_segmented_kernels(engine, oracle):
+    """From m = 400 samples on, the DEVICE entry points run designs with p <= 4 on the segmented general-p kernels
+    (capi.cu::long_rows; the host entry points keep the small-p kernels): one launch instead of classify + line search,
+    switched off by B200NB_LONG_ROWS=0 (read per call), results equal to the small-p kernels' and the oracle's."""
+    import os
+    import torch
+    from deseq2_b200 import _lib, device as D, synth
+    m, n = 448, 160
+    x = synth.design_batch_condition(m, 3)
+    c = make_case(n, m, x=x, seed=77, betaSD=0.5)
+    dev = torch.device(DEV)
+    y = D.to_gene_major(c["counts"], dev)
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=dev)
+    alpha = np.clip(0.1 + 4 / c["baseMean"], 1e-8, m)
+    o = oracle.fitBeta(**beta_args(c, alpha))
+    mu = np.maximum(c["nf"] * np.exp(o["beta_mat"] @ x.T), 0.5)
+    mud, la0 = D.to_gene_major(mu, dev), T(np.log(c["alpha0"]))
+    L = _lib.lib()
+
+    def disp():
+        k0 = L.b200nb_kernel_launches()
+        r = D.fit_disp(y, x, mud, la0, la0, 1.0, float(np.log(1e-9)), 1.0, 1e-6, 100, False)
+        return {k: v.cpu().numpy() for k, v in r.items()}, L.b200nb_kernel_launches() - k0
+
+    seg, n_seg = disp()
+    os.environ["B200NB_LONG_ROWS"] = "0"
+    try:
+        small, n_small = disp()
+    finally:
+        os.environ.pop("B200NB_LONG_ROWS")
+    assert (n_seg, n_small) == (1, 2)
+    od = oracle.fitDisp(**disp_args(c, mu, np.log(c["alpha0"])), with_margin=True)
+    same = (seg["iter"] == od["iter"]) & (seg["iter_accept"] == od["iter_accept"])
+    assert np.all(same | (od["margin"] <= 64.0))
+    assert np.max(rel_err(seg["log_alpha"][same], od["log_alpha"][same], floor=1e-3)) < 1e-6
+    both = (seg["iter"] == small["iter"]) & (seg["iter_accept"] == small["iter_accept"])
+    assert both.mean() > 0.97
+    assert np.max(rel_err(seg["log_alpha"][both], small["log_alpha"][both], floor=1e-3)) < 1e-6
+    lam = T(np.full(4, 1e-6) / np.log(2) ** 2)
+    con = T(np.r_[1.0, 0, 0, 0])
+    b = D.fit_beta(y, x, T(c["sf"]), T(alpha), con, T(c["beta0"].T), lam, 1e-8, 100)
+    assert np.array_equal(b["iter"].cpu().numpy(), o["iter"])
+    assert np.max(np.abs(b["beta_mat"].cpu().numpy().T - o["beta_mat"])) < 1e-6
+    assert np.max(rel_err(b["hat_diagonals"].cpu().numpy()[:, :m], o["hat_diagonals"])) < 1e-6
+
+
 @pytest.mark.parametrize("design,n,m", [("condition", 6000, 40), ("condition", 4000, 6), ("condition", 3000, 12),
-                                        ("batch", 3000, 36), ("factor10", 1500, 120)])
+                                        ("batch", 3000, 36), ("factor10", 1500, 120), ("batch", 600, 420)])
 def test_device_pipeline_matches_host_pipeline(engine, oracle, design, n, m):
     """The device-resident DESeq() against the numpy restatement of the R glue driving the same engine through the C ABI:
     EVERY gene within 1e-6 on dispGeneEst / dispMAP / dispersion / beta / SE, unless its line search took a different
