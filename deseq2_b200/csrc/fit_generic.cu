@@ -21,7 +21,6 @@
 
 #include "engine.h"
 #include "nbmath.cuh"
-#include "smallp.cuh"
 
 // Unroll factors of the two per-sample loops.  These kernels are instruction-cache bound, not latency bound (ncu of the
 // config-4 shape: 34 % of the stall samples no_instructions at 19k SASS instructions, 7 warps per SM): on the B200

@@ -297,32 +297,6 @@ __device__ __forceinline__ void sdisp_samples(const SDispCtx& C, double alpha, d
   }
 }
 
-// Cox-Reid term and its derivative for p <= 4 (long rows of small designs that are not saturated, e.g. ~batch+condition):
-// every lane builds B = X'WX and dB from the G group sums in registers and takes det / tr(B^-1 dB) from smallp.cuh
-// (adjugate for p <= 3, unrolled Cholesky for p = 4) -- no shared-memory matrices, no warp synchronisation.
-template <int P>
-__device__ __forceinline__ void sdisp_cr_small(const Design& D, const double* WA, const double* WB, double& cr, double& dcr) {
-  SymP<P> B, dB;
-  B.zero();
-  dB.zero();
-  for (int g = 0; g < D.G; g++) {
-    const double* xr = D.xg + (size_t)g * D.ps;
-    const double w = WA[g], dw = WB[g];
-#pragma unroll
-    for (int a = 0; a < P; a++)
-#pragma unroll
-      for (int b = 0; b <= a; b++) {
-        const double xx = xr[a] * xr[b];
-        B.v[a * (a + 1) / 2 + b] = fma(w, xx, B.v[a * (a + 1) / 2 + b]);
-        dB.v[a * (a + 1) / 2 + b] = fma(dw, xx, dB.v[a * (a + 1) / 2 + b]);
-      }
-  }
-  double det, tr;
-  cr_det_trace<P, true>(B, dB, det, tr);
-  cr = -0.5 * log(det);
-  dcr = -0.5 * tr;
-}
-
 // lp, dlp (and, when WANT2, the second derivative) at log-alpha a.  src/DESeq2.cpp:31-158.
 template <bool WANT2>
 __device__ __forceinline__ void sdisp_eval(const SDispCtx& C, double a, double pm, int lane, double& lp, double& dlp,
@@ -383,14 +357,6 @@ __device__ __forceinline__ void sdisp_eval(const SDispCtx& C, double a, double p
         if (WANT2) S.WC[lane] = d2W;
       }
       __syncwarp();
-      if (!WANT2 && D.p <= 4) {
-        switch (D.p) {
-          case 1: sdisp_cr_small<1>(D, S.WA, S.WB, cr, dcr); break;
-          case 2: sdisp_cr_small<2>(D, S.WA, S.WB, cr, dcr); break;
-          case 3: sdisp_cr_small<3>(D, S.WA, S.WB, cr, dcr); break;
-          default: sdisp_cr_small<4>(D, S.WA, S.WB, cr, dcr); break;
-        }
-      } else {
       double* B = S.M0;
       build_xtwx_pairs(D, C.P, S.WA, B, lane);
       chol_smem_d(B, S.dv, D.p, D.ps, lane);
@@ -424,7 +390,6 @@ __device__ __forceinline__ void sdisp_eval(const SDispCtx& C, double a, double p
           for (int k = 0; k < D.p; k++) tr2 = fma(Mm[lane * D.ps + k], Mm[k * D.ps + lane], tr2);
         tr2 = warp_allreduce_sum(tr2);
         cr2 = 0.5 * tr1 * tr1 - 0.5 * (tr1 * tr1 - tr2 + tr3);
-      }
       }
     }
   }
