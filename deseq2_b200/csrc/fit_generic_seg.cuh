@@ -9,13 +9,17 @@
 //     (engine.h::SegLayout, prepared once per call on the host): a lane meets one or two groups per pass, keeps the
 //     per-group sums in REGISTERS and stores one value per segment (kmax x 32 slots instead of G x 32, no
 //     read-modify-write of shared memory and no group-id load per sample);
-//   * counts are kept as bytes (dispersion kernel: the factor-table mode needs y < 256 anyway; other genes gather y
-//     from global memory) or 16-bit (IRLS kernel); the IRLS kernel keeps no row of fitted means at all (the post-loop
-//     block recomputes mu from the per-group linear predictor of the last pass, bit for bit);
-//   * the saturated-design dispersion kernel carries no p x p matrices;
-//   * the sample loops are specialised at compile time (factor table or not, second derivative or not).
-// Config 4 then needs 13 KB (dispersion) / 9 KB (IRLS) per warp and the kernels are built for up to 16 warps per SM
-// at 128 registers.  Weights, the grid search and samplewise designs stay on the kernels of fit_generic.cu.
+//   * counts are kept as 16-bit values (a gene with a count beyond 65535, or with non-integer "counts", gathers y from
+//     global memory through the inverse permutation); the IRLS kernel keeps no row of fitted means at all (the
+//     post-loop block recomputes mu from the per-group linear predictor of the last pass, bit for bit);
+//   * the factor table is 1024 16-bit counts (used while max y < 2 m) instead of 256 doubles;
+//   * the saturated-design dispersion kernel carries no p x p matrices; the others factor with the reciprocal diagonal;
+//   * the sample loops are specialised at compile time (factor table or not, second derivative or not), and the
+//     per-group work sits in ONE divergent region ahead of the warp reductions.
+// Config 4 then needs 13.6 KB (dispersion) / 9 KB (IRLS) per warp and the kernels run 16 warps per SM at <= 128
+// registers: fitDisp 5.00 -> 1.82 ms, fitBeta 3.91 -> 1.69 ms for 20 000 genes (profiles/r02_kernel_ab.md).  Weights, the
+// grid search and samplewise designs stay on the kernels of fit_generic.cu.  The device entry points also send long
+// rows (m >= 400) of designs with p <= 4 here (capi.cu::long_rows).
 
 // per-CTA shared-memory copies of SegLayout's small tables
 struct SegTables {
